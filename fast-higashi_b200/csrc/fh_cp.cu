@@ -1,0 +1,266 @@
+// Inner CP-ALS on the projected tensor of one chromosome (reference: parafac_integrative.py:12-112)
+// and the core norm (parafac2_intergrative.py:623-632). The big contractions (two MTTKRP GEMMs per
+// iteration) go through fh_gemm_batched; everything r x r (Hadamard of Grams, ridge, SPD inverse,
+// column norms, balance) is fused into small single-CTA kernels in fp64.
+#include "fh_common.cuh"
+#include "../../include/fh_b200.h"
+#include <math.h>
+
+namespace {
+
+// H = G1 * G2 (Hadamard) + ridge I, inverted in place in shared memory by the symmetric sweep
+// operator (Gauss-Jordan without pivoting: H is SPD), fp64. One CTA.
+__global__ void __launch_bounds__(1024)
+hadamard_inverse_kernel(const double* __restrict__ G1, const double* __restrict__ G2, int r, double ridge,
+                        double* __restrict__ Hinv) {
+	extern __shared__ double H[];  // r x ld
+	const int ld = r | 1;
+	double* colk = H + (size_t)r * ld;  // r: column k before the step
+	const int tid = threadIdx.x, nt = blockDim.x;
+	for (int i = tid; i < r * r; i += nt) {
+		int a = i / r, b = i - a * r;
+		H[a * ld + b] = G1[i] * G2[i] + (a == b ? ridge : 0.0);
+	}
+	__syncthreads();
+	for (int k = 0; k < r; ++k) {
+		const double d = H[k * ld + k];
+		for (int i = tid; i < r; i += nt) colk[i] = H[i * ld + k];
+		__syncthreads();
+		const double inv = 1.0 / d;
+		// row k <- row k / d
+		for (int j = tid; j < r; j += nt) H[k * ld + j] = (j == k) ? inv : H[k * ld + j] * inv;
+		__syncthreads();
+		// rows i != k: a_ij -= a_ik * a_kj (j != k); a_ik = -a_ik / d
+		for (int i = tid; i < r * r; i += nt) {
+			int a = i / r, b = i - a * r;
+			if (a == k) continue;
+			double f = colk[a];
+			H[a * ld + b] = (b == k) ? -f * inv : H[a * ld + b] - f * H[k * ld + b];
+		}
+		__syncthreads();
+	}
+	for (int i = tid; i < r * r; i += nt) {
+		int a = i / r, b = i - a * r;
+		Hinv[i] = H[a * ld + b];
+	}
+}
+
+// column 2-norms of A (n x r), B (r x r), D (R x r): grid 3, thread per column. fp32 result like
+// torch.norm on fp32 tensors.
+__global__ void __launch_bounds__(256)
+col_norms_kernel(const float* __restrict__ A, int n, const float* __restrict__ B, const float* __restrict__ D,
+                 int R, int r, float* __restrict__ norms /* 3 x r */) {
+	const float* F = blockIdx.x == 0 ? A : (blockIdx.x == 1 ? B : D);
+	const int rows = blockIdx.x == 0 ? n : (blockIdx.x == 1 ? r : R);
+	for (int c = threadIdx.x; c < r; c += blockDim.x) {
+		double s = 0.0;
+		for (int i = 0; i < rows; ++i) {
+			double v = F[(size_t)i * r + c];
+			s += v * v;
+		}
+		norms[blockIdx.x * r + c] = (float)sqrt(s);
+	}
+}
+
+// balance_norm (parafac_integrative.py:19-26): unit columns; product of the norms into D
+__global__ void balance_kernel(float* __restrict__ A, int n, float* __restrict__ B, float* __restrict__ D,
+                               int R, int r, const float* __restrict__ norms) {
+	const long long total = (long long)(n + r + R) * r;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+	     i += (long long)gridDim.x * blockDim.x) {
+		long long row = i / r;
+		int c = (int)(i - row * r);
+		float na = norms[c], nb = norms[r + c], nd = norms[2 * r + c];
+		if (row < n) A[i] = A[i] / (na + 1e-15f);
+		else if (row < n + r) { long long j = i - (long long)n * r; B[j] = B[j] / (nb + 1e-15f); }
+		else {
+			long long j = i - (long long)(n + r) * r;
+			float prod = (na * nb) * nd;
+			D[j] = (D[j] / (nd + 1e-15f)) * (prod + 1e-15f);
+		}
+	}
+}
+
+// M0[i,p] = sum_j Z[(i*r+j), p] * B[j,p]
+__global__ void mode0_reduce_kernel(const float* __restrict__ Z, const float* __restrict__ B, int n, int r,
+                                    float* __restrict__ M0) {
+	const int i = blockIdx.x;
+	for (int p = threadIdx.x; p < r; p += blockDim.x) {
+		float s = 0.f;
+		for (int j = 0; j < r; ++j) s += Z[((size_t)i * r + j) * r + p] * B[j * r + p];
+		M0[(size_t)i * r + p] = s;
+	}
+}
+// M1[j,p] = sum_i Z[(i*r+j), p] * A[i,p]
+__global__ void mode1_reduce_kernel(const float* __restrict__ Z, const float* __restrict__ A, int n, int r,
+                                    float* __restrict__ M1) {
+	const int j = blockIdx.x;
+	for (int p = threadIdx.x; p < r; p += blockDim.x) {
+		double s = 0.0;
+		for (int i = 0; i < n; ++i) s += (double)Z[((size_t)i * r + j) * r + p] * (double)A[(size_t)i * r + p];
+		M1[(size_t)j * r + p] = (float)s;
+	}
+}
+// KR[(i*r + j), p] = A[i,p] * B[j,p]
+__global__ void khatri_rao_kernel(const float* __restrict__ A, const float* __restrict__ B, int n, int r,
+                                  float* __restrict__ KR) {
+	const long long total = (long long)n * r * r;
+	for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+	     t += (long long)gridDim.x * blockDim.x) {
+		int p = (int)(t % r);
+		long long ij = t / r;
+		int j = (int)(ij % r);
+		long long i = ij / r;
+		KR[t] = A[i * r + p] * B[j * r + p];
+	}
+}
+// acc += sum(G1 * G2 * G3)
+__global__ void __launch_bounds__(1024)
+triple_hadamard_sum_kernel(const double* __restrict__ G1, const double* __restrict__ G2,
+                           const double* __restrict__ G3, int nn, double* __restrict__ acc) {
+	__shared__ double red[32];
+	double s = 0.0;
+	for (int i = threadIdx.x; i < nn; i += blockDim.x) s += G1[i] * G2[i] * G3[i];
+	s = fh_block_sum(s, red);
+	if (threadIdx.x == 0) *acc += s;
+}
+
+int gemm(int dtype, int M, int N, int K, const void* A, long long sa_m, long long sa_k, const void* B,
+         long long sb_k, long long sb_n, void* C, long long ldc, void* stream) {
+	fh_gemm_desc g;
+	memset(&g, 0, sizeof(g));
+	g.M = M; g.N = N; g.K = K; g.batch = 1;
+	g.sa_m = sa_m; g.sa_k = sa_k; g.sb_k = sb_k; g.sb_n = sb_n; g.ldc = ldc;
+	g.alpha = 1.0; g.dtype = dtype;
+	return fh_gemm_batched(&g, A, B, C, stream);
+}
+// G = F^T F in fp64 (F rows x r, fp32)
+int gram(const float* F, int rows, int r, double* G, void* stream) {
+	return gemm(FH_GEMM_F32_ACC64, r, r, rows, F, 1, r, F, r, 1, G, r, stream);
+}
+
+size_t al(size_t x) { return (x + 255) / 256 * 256; }
+struct CpWs {
+	float *Z, *M, *norms;
+	double *Ga, *Gb, *Gd, *Hinv, *scal;
+	size_t bytes;
+};
+CpWs carve(int n, int r, int R, void* ws) {
+	CpWs c;
+	char* b = (char*)ws;
+	c.Z = (float*)b; b += al((size_t)n * r * r * 4);
+	int mx = n > R ? n : R; mx = mx > r ? mx : r;
+	c.M = (float*)b; b += al((size_t)mx * r * 4);
+	c.norms = (float*)b; b += al((size_t)3 * r * 4);
+	c.Ga = (double*)b; b += al((size_t)r * r * 8);
+	c.Gb = (double*)b; b += al((size_t)r * r * 8);
+	c.Gd = (double*)b; b += al((size_t)r * r * 8);
+	c.Hinv = (double*)b; b += al((size_t)r * r * 8);
+	c.scal = (double*)b; b += 256;
+	c.bytes = (size_t)(b - (char*)ws);
+	return c;
+}
+
+int balance(float* A, int n, float* B, float* D, int R, int r, float* norms, cudaStream_t st) {
+	col_norms_kernel<<<3, 256, 0, st>>>(A, n, B, D, R, r, norms);
+	FH_LAUNCH_CHECK();
+	long long total = (long long)(n + r + R) * r;
+	balance_kernel<<<fh_cdiv(total, 256), 256, 0, st>>>(A, n, B, D, R, r, norms);
+	FH_LAUNCH_CHECK();
+	return FH_OK;
+}
+
+// F = M * (G1 * G2 + ridge I)^{-1}
+int solve_update(const float* M, int rows, const double* G1, const double* G2, int r, double* Hinv, float* out,
+                 cudaStream_t st) {
+	size_t smem = ((size_t)r * (r | 1) + r) * 8;
+	FH_CHECK_ARG(smem <= 227 * 1024, "fh_cp_als: r=%d too large for the shared-memory SPD inverse", r);
+	FH_CUDA(cudaFuncSetAttribute(hadamard_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int threads = r * r >= 1024 ? 1024 : ((r * r + 31) / 32 * 32);
+	hadamard_inverse_kernel<<<1, threads, smem, st>>>(G1, G2, r, 1e-10, Hinv);
+	FH_LAUNCH_CHECK();
+	return gemm(FH_GEMM_F32xF64_F32, rows, r, r, M, r, 1, Hinv, r, 1, out, r, (void*)st);
+}
+
+}  // namespace
+
+extern "C" size_t fh_cp_als_workspace_bytes(int n, int r, int R) { return carve(n, r, R, nullptr).bytes; }
+
+extern "C" int fh_cp_als(const float* Y, int n, int r, int R, float* A, float* B, float* D, int n_iter_max,
+                         void* workspace, size_t workspace_bytes, double* host_out, void* stream) {
+	FH_CHECK_ARG(n > 0 && r > 0 && R > 0, "fh_cp_als: bad shape");
+	FH_CHECK_ARG(workspace && workspace_bytes >= fh_cp_als_workspace_bytes(n, r, R), "fh_cp_als: workspace too small");
+	cudaStream_t st = (cudaStream_t)stream;
+	CpWs w = carve(n, r, R, workspace);
+	int rc;
+	if (host_out) host_out[0] = host_out[1] = 0.0;
+	rc = balance(A, n, B, D, R, r, w.norms, st);
+	if (rc) return rc;
+	double prev_loss = -1.0, ynorm = 0.0;
+	const bool need_loss = n_iter_max > 1;
+	if (need_loss) {
+		FH_CUDA(cudaMemsetAsync(w.scal, 0, 64, st));
+		rc = fh_sqnorm_accum(Y, 1, (long long)n * r * R, (long long)n * r * R, w.scal, stream);
+		if (rc) return rc;
+	}
+	for (int it = 0; it < n_iter_max; ++it) {
+		// Z = Y_(n r x R) D : shared by the A and B updates (D is unchanged between them)
+		rc = gemm(FH_GEMM_F32, n * r, r, R, Y, R, 1, D, r, 1, w.Z, r, stream);
+		if (rc) return rc;
+		// mode 0: A = M0 ((B^T B) * (D^T D))^{-1}
+		if ((rc = gram(B, r, r, w.Gb, stream))) return rc;
+		if ((rc = gram(D, R, r, w.Gd, stream))) return rc;
+		mode0_reduce_kernel<<<n, 128, 0, st>>>(w.Z, B, n, r, w.M);
+		FH_LAUNCH_CHECK();
+		if ((rc = solve_update(w.M, n, w.Gb, w.Gd, r, w.Hinv, A, st))) return rc;
+		// mode 1: B = M1 ((A^T A) * (D^T D))^{-1}
+		if ((rc = gram(A, n, r, w.Ga, stream))) return rc;
+		mode1_reduce_kernel<<<r, 128, 0, st>>>(w.Z, A, n, r, w.M);
+		FH_LAUNCH_CHECK();
+		if ((rc = solve_update(w.M, r, w.Ga, w.Gd, r, w.Hinv, B, st))) return rc;
+		// mode 2: D = M2 ((A^T A) * (B^T B))^{-1},  M2 = Y_(R x n r) KhatriRao(A, B)
+		if ((rc = gram(B, r, r, w.Gb, stream))) return rc;
+		khatri_rao_kernel<<<fh_cdiv((long long)n * r * r, 256) > 4096 ? 4096 : fh_cdiv((long long)n * r * r, 256), 256, 0, st>>>(A, B, n, r, w.Z);
+		FH_LAUNCH_CHECK();
+		rc = gemm(FH_GEMM_F32, R, r, n * r, Y, 1, R, w.Z, r, 1, w.M, r, stream);
+		if (rc) return rc;
+		if ((rc = solve_update(w.M, R, w.Ga, w.Gb, r, w.Hinv, D, st))) return rc;
+		if (need_loss) {
+			// loss = ||Y||^2 - 2 <Y, Xhat> + ||Xhat||^2 ; <Y, Xhat> = <M2, D>
+			FH_CUDA(cudaMemsetAsync(w.scal + 1, 0, 16, st));
+			if ((rc = fh_dot_accum(w.M, D, R, r, r, r, w.scal + 1, stream))) return rc;
+			if ((rc = gram(D, R, r, w.Gd, stream))) return rc;
+			triple_hadamard_sum_kernel<<<1, 1024, 0, st>>>(w.Ga, w.Gb, w.Gd, r * r, w.scal + 2);
+			FH_LAUNCH_CHECK();
+			double h[3];
+			FH_CUDA(cudaMemcpyAsync(h, w.scal, 24, cudaMemcpyDeviceToHost, st));
+			FH_CUDA(cudaStreamSynchronize(st));
+			ynorm = h[0];
+			double loss = ynorm - 2.0 * h[1] + h[2];
+			if (host_out) { host_out[0] = h[2]; host_out[1] = h[1]; }
+			bool stop = false;
+			if (prev_loss >= 0.0) {
+				double wdiff = (prev_loss - loss) / prev_loss;
+				stop = wdiff < 1e-5;
+			}
+			prev_loss = loss;
+			if (stop) break;
+		}
+		rc = balance(A, n, B, D, R, r, w.norms, st);
+		if (rc) return rc;
+	}
+	return FH_OK;
+}
+
+extern "C" int fh_cp_core_sqnorm(const float* A, int n, const float* B, const float* D, int R, int r,
+                                 double* ws, double* acc, void* stream) {
+	FH_CHECK_ARG(ws && acc, "fh_cp_core_sqnorm: null workspace");
+	int rc;
+	double* Ga = ws; double* Gb = ws + (size_t)r * r; double* Gd = Gb + (size_t)r * r;
+	if ((rc = gram(A, n, r, Ga, stream))) return rc;
+	if ((rc = gram(B, r, r, Gb, stream))) return rc;
+	if ((rc = gram(D, R, r, Gd, stream))) return rc;
+	triple_hadamard_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(Ga, Gb, Gd, r * r, acc);
+	FH_LAUNCH_CHECK();
+	return FH_OK;
+}

@@ -1,0 +1,517 @@
+// Partial RWR imputation of one bin-block (reference: sparse_for_schic.py:279-320 densify,
+// partial_rwr.py:45-175). The block-CSR of a range of cells is read once from HBM with 128-bit
+// loads, staged through shared memory, and the imputed dense nb x w panel of every cell is written
+// once; everything in between (conv'd panel A, A A^T, transition matrix P, the Q iterates) lives in
+// an L2-sized workspace that is reused chunk after chunk.
+#include "fh_common.cuh"
+#include "../../include/fh_b200.h"
+
+#define FH_FLOOR 1e-8f
+#define FH_EPS 1e-15f
+
+namespace {
+
+constexpr int RT = 16;  // output rows per CTA in densify/conv
+
+// ---------------------------------------------------------------------------------------------
+// K1+K2: CSR -> dense (floor 1e-8) [-> 3x3 mean, zero padding counted, floor 1e-8]
+// grid (ceil(nb/RT), ncell), 256 threads, smem (RT+2) x (w+2) floats + rowptr slice
+// ---------------------------------------------------------------------------------------------
+template <bool FROM_DENSE>
+__global__ void __launch_bounds__(256)
+densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restrict__ col,
+                    const float* __restrict__ val, long long nnz_total,
+                    const float* __restrict__ dense_in, long long in_cell_stride,
+                    int cell0, int nb, int w, int ldw, int do_conv,
+                    float* __restrict__ out, long long out_cell_stride) {
+	extern __shared__ float smem[];
+	const int tw = w + 2;
+	float* tile = smem;                                   // (RT+2) x tw
+	int* rp = (int*)(smem + (RT + 2) * tw);               // RT+3 row pointers
+	const int cell = blockIdx.y;
+	const int r0 = blockIdx.x * RT;
+	const int halo = do_conv ? 1 : 0;
+	const int ra = max(r0 - halo, 0), rb = min(r0 + RT + halo, nb);  // staged global rows [ra, rb)
+	const int tid = threadIdx.x;
+
+	// 1. background: floor inside the block, 0 in the zero padding ring
+	for (int i = tid; i < (RT + 2) * tw; i += blockDim.x) {
+		int tr = i / tw, tc = i - tr * tw;
+		int gr = r0 - 1 + tr, gc = tc - 1;
+		tile[i] = (gr >= 0 && gr < nb && gc >= 0 && gc < w) ? FH_FLOOR : 0.f;
+	}
+	if (!FROM_DENSE) {
+		const long long base = (long long)(cell0 + cell) * nb;
+		for (int i = tid; i <= rb - ra; i += blockDim.x) rp[i] = rowptr[base + ra + i];
+	}
+	__syncthreads();
+	if (FROM_DENSE) {
+		const float* src = dense_in + (long long)cell * in_cell_stride;
+		for (int i = tid; i < (rb - ra) * w; i += blockDim.x) {
+			int rr = i / w, c = i - rr * w;
+			int gr = ra + rr;
+			tile[(gr - r0 + 1) * tw + c + 1] = fmaxf(src[(long long)gr * ldw + c], FH_FLOOR);
+		}
+	} else {
+		// 2. scatter the CSR entries of rows [ra, rb): 8 entries per thread and step through one
+		// 128-bit load of column indices and two 128-bit loads of values
+		const int lo = rp[0], hi = rp[rb - ra];
+		const int nrow = rb - ra;
+		const long long start = (long long)lo & ~7LL;
+		for (long long u = start + 8LL * tid; u < hi; u += 8LL * blockDim.x) {
+			short c8[8];
+			float v8[8];
+			if (u + 8 <= nnz_total) {
+				*reinterpret_cast<int4*>(c8) = __ldg(reinterpret_cast<const int4*>(col + u));
+				*reinterpret_cast<float4*>(v8) = __ldg(reinterpret_cast<const float4*>(val + u));
+				*reinterpret_cast<float4*>(v8 + 4) = __ldg(reinterpret_cast<const float4*>(val + u + 4));
+			} else {
+#pragma unroll
+				for (int e = 0; e < 8; ++e) {
+					bool ok = u + e < nnz_total;
+					c8[e] = ok ? col[u + e] : (short)0;
+					v8[e] = ok ? val[u + e] : 0.f;
+				}
+			}
+			// row of the first in-range entry by binary search, then walk
+			long long first = u < lo ? lo : u;
+			int r = 0;
+			{
+				int a = 0, b = nrow;  // find r with rp[r] <= first < rp[r+1]
+				while (b - a > 1) {
+					int m = (a + b) >> 1;
+					if (rp[m] <= first) a = m; else b = m;
+				}
+				r = a;
+			}
+#pragma unroll
+			for (int e = 0; e < 8; ++e) {
+				long long idx = u + e;
+				if (idx < lo || idx >= hi) continue;
+				while (rp[r + 1] <= idx) ++r;
+				int gr = ra + r;
+				tile[(gr - r0 + 1) * tw + (int)c8[e] + 1] = fmaxf(v8[e], FH_FLOOR);
+			}
+		}
+	}
+	__syncthreads();
+	// 3. stencil + write (coalesced rows); pad columns [w, ldw) are written as 0
+	float* dst = out + (long long)cell * out_cell_stride;
+	const int rows = min(RT, nb - r0);
+	for (int i = tid; i < rows * ldw; i += blockDim.x) {
+		int tr = i / ldw, c = i - tr * ldw;
+		float v = 0.f;
+		if (c < w) {
+			const float* t = tile + (tr + 1) * tw + (c + 1);
+			if (do_conv) {
+				float s = t[-tw - 1];
+				s += t[-tw]; s += t[-tw + 1];
+				s += t[-1]; s += t[0]; s += t[1];
+				s += t[tw - 1]; s += t[tw]; s += t[tw + 1];
+				v = fmaxf(s / 9.0f, FH_FLOOR);
+			} else {
+				v = t[0];
+			}
+		}
+		dst[(long long)(r0 + tr) * ldw + c] = v;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: second-order affinity S2 = A A^T (diagonal ignored) + first-order block of A -> column
+// stochastic P, in place over S2. grid (ncell), thread per column.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+transition_kernel(const float* __restrict__ A, long long a_cell_stride, int ldw, int s,
+                  float* __restrict__ SP, int nb, int ldp) {
+	const int cell = blockIdx.x;
+	const float* a = A + (long long)cell * a_cell_stride + s;
+	float* p = SP + (long long)cell * nb * ldp;
+	for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+		float cs1 = 0.f, cs2 = 0.f;
+		for (int i = 0; i < nb; ++i) {
+			cs1 += a[(long long)i * ldw + j];
+			if (i != j) cs2 += p[i * ldp + j];
+		}
+		cs1 += FH_EPS; cs2 += FH_EPS;
+		float csl = 0.f;
+		for (int i = 0; i < nb; ++i) {
+			float f = (a[(long long)i * ldw + j] / cs1) * 0.75f;
+			float g = (i != j) ? (p[i * ldp + j] / cs2) * 0.25f : 0.f;
+			float l = f + g;
+			p[i * ldp + j] = l;
+			csl += l;
+		}
+		if (csl == 0.f) {  // unreachable after the 1e-8 floor, kept for parity (partial_rwr.py:96-97)
+			p[j * ldp + j] += 1.f;
+			csl += 1.f;
+		}
+		csl += FH_EPS;
+		for (int i = 0; i < nb; ++i) p[i * ldp + j] = p[i * ldp + j] / csl;
+	}
+	// pad columns [nb, ldp) must stay zero for the GEMMs that read P/Q with K = nb only: they are
+	// never read, nothing to do.
+}
+
+// Q = 0.5 * P + 0.5 * I  (first RWR step: Q0 = I so bmm(Q0, P) = P exactly)
+__global__ void first_step_kernel(const float* __restrict__ P, float* __restrict__ Q, int nb, int ldp,
+                                  long long total) {
+	long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (i >= total) return;
+	int c = (int)(i % ldp);
+	int r = (int)((i / ldp) % nb);
+	float v = 0.5f * P[i];
+	if (r == c) v += 0.5f;
+	Q[i] = (c < nb) ? v : 0.f;
+}
+
+__global__ void identity_kernel(float* __restrict__ Q, int nb, int ldp, long long total) {
+	long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (i >= total) return;
+	int c = (int)(i % ldp);
+	int r = (int)((i / ldp) % nb);
+	Q[i] = (r == c) ? 1.f : 0.f;
+}
+
+// per-cell Frobenius norm of Qa - Qb (Qa == nullptr: identity)
+__global__ void __launch_bounds__(256)
+delta_kernel(const float* __restrict__ Qa, const float* __restrict__ Qb, int nb, int ldp,
+             float* __restrict__ delta) {
+	__shared__ float red[32];
+	const int cell = blockIdx.x;
+	const long long base = (long long)cell * nb * ldp;
+	float acc = 0.f;
+	for (int i = threadIdx.x; i < nb * ldp; i += blockDim.x) {
+		int c = i % ldp, r = i / ldp;
+		if (c >= nb) continue;
+		float a = Qa ? Qa[base + i] : (r == c ? 1.f : 0.f);
+		float d = a - Qb[base + i];
+		acc += d * d;
+	}
+	acc = fh_block_sum(acc, red);
+	if (threadIdx.x == 0) delta[cell] = sqrtf(acc);
+}
+
+// do_col: Q <- rownorm(clamp0((Q + Q^T)/2))   (partial_rwr.py:132-134). warp per row.
+__global__ void __launch_bounds__(256)
+symnorm_kernel(const float* __restrict__ Q, float* __restrict__ out, int nb, int ldp) {
+	const int cell = blockIdx.x;
+	const float* q = Q + (long long)cell * nb * ldp;
+	float* o = out + (long long)cell * nb * ldp;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+	for (int i = wid; i < nb; i += nw) {
+		float rs = 0.f;
+		for (int j = lane; j < nb; j += 32) {
+			float v = fmaxf((q[i * ldp + j] + q[j * ldp + i]) * 0.5f, 0.f);
+			rs += v;
+		}
+		rs = fh_warp_sum(rs) + FH_EPS;
+		for (int j = lane; j < ldp; j += 32) {
+			float v = 0.f;
+			if (j < nb) v = fmaxf((q[i * ldp + j] + q[j * ldp + i]) * 0.5f, 0.f) / rs;
+			o[i * ldp + j] = v;
+		}
+	}
+}
+
+__global__ void colsum_accum_kernel(const float* __restrict__ x, int nb, int w, int ldw,
+                                    long long cell_stride, float* __restrict__ cov, long long cov_ld) {
+	const int cell = blockIdx.y;
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= w) return;
+	const float* p = x + (long long)cell * cell_stride + c;
+	float s = 0.f;
+	for (int r = 0; r < nb; ++r) s += p[(long long)r * ldw];
+	cov[(long long)cell * cov_ld + c] += s;
+}
+
+__global__ void avgpool_kernel(const float* __restrict__ x, int nb, int w, int ldw, long long cell_stride,
+                               int ll, int orow, int ocol, float* __restrict__ out, long long out_cell_stride) {
+	const int cell = blockIdx.y;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= orow * ocol) return;
+	int pr = i / ocol, pc = i - pr * ocol;
+	const float* p = x + (long long)cell * cell_stride + (long long)(pr * ll) * ldw + pc * ll;
+	float s = 0.f;
+	for (int a = 0; a < ll; ++a)
+		for (int b = 0; b < ll; ++b) s += p[(long long)a * ldw + b];
+	out[(long long)cell * out_cell_stride + i] = s / (float)(ll * ll);
+}
+
+__global__ void __launch_bounds__(256)
+sqnorm_kernel(const float* __restrict__ x, const float* __restrict__ y, long long rows, long long cols,
+              long long ldx, long long ldy, double* __restrict__ acc) {
+	__shared__ double red[32];
+	double a = 0.0;
+	const long long total = rows * cols;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+	     i += (long long)gridDim.x * blockDim.x) {
+		long long r = i / cols, c = i - r * cols;
+		float xv = x[r * ldx + c];
+		float yv = y ? y[r * ldy + c] : xv;
+		a += (double)xv * (double)yv;
+	}
+	a = fh_block_sum(a, red);
+	if (threadIdx.x == 0) atomicAdd(acc, a);
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct RwrWs {
+	float *A, *P, *Q0, *Q1, *delta;
+	size_t bytes;
+};
+
+RwrWs carve(const fh_rwr_desc* d, void* ws) {
+	RwrWs r;
+	const int ldp = (d->nb + 3) & ~3;
+	size_t a = align_up((size_t)d->ncell * d->nb * d->ldw * 4, 256);
+	size_t p = align_up((size_t)d->ncell * d->nb * ldp * 4, 256);
+	char* b = (char*)ws;
+	r.A = (float*)b; b += a;
+	r.P = (float*)b; b += p;
+	r.Q0 = (float*)b; b += p;
+	r.Q1 = (float*)b; b += p;
+	r.delta = (float*)b; b += align_up((size_t)d->ncell * 4, 256);
+	r.bytes = (size_t)(b - (char*)ws);
+	return r;
+}
+
+int gemm_f32(int use_tc, int M, int N, int K, int batch, const float* A, long long sa_m, long long sa_k,
+             long long ba, const float* B, long long sb_k, long long sb_n, long long bb, float* C,
+             long long ldc, long long bc, double alpha, int epi, double diag, const float* cscale,
+             long long cs_batch, int recip, void* stream) {
+	fh_gemm_desc g;
+	memset(&g, 0, sizeof(g));
+	g.M = M; g.N = N; g.K = K; g.batch = batch;
+	g.sa_m = sa_m; g.sa_k = sa_k; g.sb_k = sb_k; g.sb_n = sb_n; g.ldc = ldc;
+	g.batch_a = ba; g.batch_b = bb; g.batch_c = bc;
+	g.alpha = alpha; g.beta = 0.0; g.dtype = use_tc ? FH_GEMM_TF32X3 : FH_GEMM_F32;
+	g.epilogue = epi; g.diag = diag;
+	g.cscale = cscale; g.cscale_batch = cs_batch; g.cscale_recip = recip;
+	// batches are limited to 65535 per launch by gridDim.z
+	for (int b0 = 0; b0 < batch; b0 += 32768) {
+		int nbt = batch - b0 < 32768 ? batch - b0 : 32768;
+		g.batch = nbt;
+		g.cscale = cscale ? cscale + (long long)b0 * cs_batch : nullptr;
+		int rc = fh_gemm_batched(&g, A + (long long)b0 * ba, B + (long long)b0 * bb, C + (long long)b0 * bc, stream);
+		if (rc) return rc;
+	}
+	return FH_OK;
+}
+
+// the RWR pipeline from the conv'd panel A (in ws.A, or already in `out` when !do_rwr)
+int rwr_from_panel(const fh_rwr_desc* d, const RwrWs& ws, const float* bin_cov, long long bin_cov_ld,
+                   float* out, long long out_cell_stride, int* host_n_iter, cudaStream_t st) {
+	const int nb = d->nb, w = d->w, ldw = d->ldw, nc = d->ncell;
+	const int ldp = (nb + 3) & ~3;
+	const long long acs = (long long)nb * ldw, pcs = (long long)nb * ldp;
+	const long long ptotal = (long long)nc * pcs;
+	const int tc = d->use_tensor_cores;
+	int rc;
+	// S2 = A A^T  (partial_rwr.py:85)
+	rc = gemm_f32(tc, nb, nb, w, nc, ws.A, ldw, 1, acs, ws.A, 1, ldw, acs, ws.P, ldp, pcs, 1.0, FH_EPI_NONE, 0.0,
+	              nullptr, 0, 0, st);
+	if (rc) return rc;
+	transition_kernel<<<nc, 256, 0, st>>>(ws.A, acs, ldw, d->s, ws.P, nb, ldp);
+	FH_LAUNCH_CHECK();
+	float* Q = ws.Q0;
+	float* Qn = ws.Q1;
+	int n_iter = 0;
+	const int tpb = 256;
+	const int nblk = fh_cdiv(ptotal, tpb);
+	if (d->k >= 0) {
+		if (d->k == 0) {
+			identity_kernel<<<nblk, tpb, 0, st>>>(Q, nb, ldp, ptotal);
+			FH_LAUNCH_CHECK();
+		} else {
+			first_step_kernel<<<nblk, tpb, 0, st>>>(ws.P, Q, nb, ldp, ptotal);
+			FH_LAUNCH_CHECK();
+			for (int it = 1; it < d->k; ++it) {
+				rc = gemm_f32(tc, nb, nb, nb, nc, Q, ldp, 1, pcs, ws.P, ldp, 1, pcs, Qn, ldp, pcs, 0.5,
+				              FH_EPI_DIAG_ADD, 0.5, nullptr, 0, 0, st);
+				if (rc) return rc;
+				float* t = Q; Q = Qn; Qn = t;
+			}
+		}
+		n_iter = d->k;
+	} else {
+		// auto-stop (partial_rwr.py:99-126): apply the step, then stop once the largest per-cell
+		// Frobenius change is < 0.01; the reported count excludes the breaking step.
+		float* hdelta = (float*)malloc(sizeof(float) * nc);
+		if (!hdelta) { fh_set_error("fh_rwr: host malloc failed"); return FH_ERR_ARG; }
+		const float* prev = nullptr;  // identity
+		int count = 0;
+		for (int it = 0; it < 60; ++it) {
+			if (it == 0) {
+				first_step_kernel<<<nblk, tpb, 0, st>>>(ws.P, Qn, nb, ldp, ptotal);
+				FH_LAUNCH_CHECK();
+			} else {
+				rc = gemm_f32(tc, nb, nb, nb, nc, Q, ldp, 1, pcs, ws.P, ldp, 1, pcs, Qn, ldp, pcs, 0.5,
+				              FH_EPI_DIAG_ADD, 0.5, nullptr, 0, 0, st);
+				if (rc) { free(hdelta); return rc; }
+			}
+			delta_kernel<<<nc, 256, 0, st>>>(prev, Qn, nb, ldp, ws.delta);
+			fh_count_launch(1);
+			cudaError_t e = cudaMemcpyAsync(hdelta, ws.delta, sizeof(float) * nc, cudaMemcpyDeviceToHost, st);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+			if (e != cudaSuccess) { free(hdelta); fh_set_error("fh_rwr auto-stop: %s", cudaGetErrorString(e)); return FH_ERR_CUDA; }
+			float mx = 0.f;
+			for (int c = 0; c < nc; ++c) mx = hdelta[c] > mx ? hdelta[c] : mx;
+			float* t = Q; Q = Qn; Qn = t;
+			prev = Q;
+			if (mx < 0.01f) break;
+			count++;
+		}
+		free(hdelta);
+		n_iter = count;
+	}
+	if (host_n_iter) *host_n_iter = n_iter;
+	const float* Qfin = Q;
+	if (d->do_col) {
+		symnorm_kernel<<<nc, 256, 0, st>>>(Q, Qn, nb, ldp);
+		FH_LAUNCH_CHECK();
+		Qfin = Qn;
+	}
+	// x = Q A (/ bin_cov per window column when do_col)   (partial_rwr.py:135,138)
+	rc = gemm_f32(tc, nb, w, nb, nc, Qfin, ldp, 1, pcs, ws.A, ldw, 1, acs, out, ldw, out_cell_stride, 1.0,
+	              FH_EPI_NONE, 0.0, d->do_col ? bin_cov : nullptr, bin_cov_ld, 1, st);
+	if (rc) return rc;
+	if (ldw > w) {
+		if (out_cell_stride == acs) {
+			FH_CUDA(cudaMemset2DAsync(out + w, (size_t)ldw * 4, 0, (size_t)(ldw - w) * 4, (size_t)nc * nb, st));
+		} else {
+			for (int c = 0; c < nc; ++c)
+				FH_CUDA(cudaMemset2DAsync(out + (long long)c * out_cell_stride + w, (size_t)ldw * 4, 0,
+				                          (size_t)(ldw - w) * 4, (size_t)nb, st));
+		}
+	}
+	return FH_OK;
+}
+
+int check_desc(const fh_rwr_desc* d) {
+	FH_CHECK_ARG(d != nullptr, "fh_rwr: null descriptor");
+	FH_CHECK_ARG(d->nb > 0 && d->w > 0 && d->ncell >= 0, "fh_rwr: bad sizes nb=%d w=%d ncell=%d", d->nb, d->w, d->ncell);
+	FH_CHECK_ARG(d->ldw >= d->w && d->ldw % 4 == 0, "fh_rwr: ldw=%d must be >= w=%d and a multiple of 4", d->ldw, d->w);
+	FH_CHECK_ARG(d->s >= 0 && d->s + d->nb <= d->w, "fh_rwr: diagonal block [%d,%d) outside window %d", d->s, d->s + d->nb, d->w);
+	FH_CHECK_ARG(d->ncell <= 65535, "fh_rwr: ncell %d > 65535 per call", d->ncell);
+	FH_CHECK_ARG((size_t)((RT + 2) * (d->w + 2) + RT + 4) * 4 <= 200 * 1024, "fh_rwr: window %d too wide", d->w);
+	return FH_OK;
+}
+
+int launch_densify(const fh_rwr_desc* d, bool from_dense, const int32_t* rowptr, const int16_t* col,
+                   const float* val, const float* dense_in, long long in_cs, int do_conv, float* out,
+                   long long out_cs, cudaStream_t st) {
+	size_t smem = (size_t)((RT + 2) * (d->w + 2) + RT + 4) * 4;
+	dim3 grid(fh_cdiv(d->nb, RT), d->ncell);
+	if (from_dense) {
+		if (smem > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(densify_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		densify_conv_kernel<true><<<grid, 256, smem, st>>>(nullptr, nullptr, nullptr, 0, dense_in, in_cs, 0, d->nb, d->w,
+		                                                  d->ldw, do_conv, out, out_cs);
+	} else {
+		if (smem > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(densify_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		densify_conv_kernel<false><<<grid, 256, smem, st>>>(rowptr, col, val, d->nnz, nullptr, 0, d->cell0, d->nb, d->w,
+		                                                   d->ldw, do_conv, out, out_cs);
+	}
+	FH_LAUNCH_CHECK();
+	return FH_OK;
+}
+
+}  // namespace
+
+extern "C" size_t fh_rwr_workspace_bytes(const fh_rwr_desc* d) {
+	if (!d) return 0;
+	return carve(d, nullptr).bytes;
+}
+
+extern "C" int fh_densify(const fh_rwr_desc* d, const int32_t* rowptr, const int16_t* col, const float* val,
+                          float* out, long long out_cell_stride, void* stream) {
+	int rc = check_desc(d);
+	if (rc) return rc;
+	if (d->ncell == 0) return FH_OK;
+	return launch_densify(d, false, rowptr, col, val, nullptr, 0, 0, out, out_cell_stride, (cudaStream_t)stream);
+}
+
+extern "C" int fh_rwr_batched(const fh_rwr_desc* d, const int32_t* rowptr, const int16_t* col, const float* val,
+                              const float* bin_cov, long long bin_cov_ld, float* out, long long out_cell_stride,
+                              void* workspace, size_t workspace_bytes, int* host_n_iter, void* stream) {
+	int rc = check_desc(d);
+	if (rc) return rc;
+	if (host_n_iter) *host_n_iter = 0;
+	if (d->ncell == 0) return FH_OK;
+	cudaStream_t st = (cudaStream_t)stream;
+	const int conv = d->do_conv && d->nb > 1;  // partial_rwr.py:77
+	if (!d->do_rwr)  // conv only, or neither: the (floored) densified block
+		return launch_densify(d, false, rowptr, col, val, nullptr, 0, conv, out, out_cell_stride, st);
+	FH_CHECK_ARG(workspace != nullptr && workspace_bytes >= fh_rwr_workspace_bytes(d),
+	             "fh_rwr_batched: workspace too small (%zu < %zu)", workspace_bytes, fh_rwr_workspace_bytes(d));
+	FH_CHECK_ARG(!d->do_col || bin_cov != nullptr, "fh_rwr_batched: do_col needs bin_cov");
+	RwrWs ws = carve(d, workspace);
+	rc = launch_densify(d, false, rowptr, col, val, nullptr, 0, conv, ws.A, (long long)d->nb * d->ldw, st);
+	if (rc) return rc;
+	return rwr_from_panel(d, ws, bin_cov, bin_cov_ld, out, out_cell_stride, host_n_iter, st);
+}
+
+extern "C" int fh_rwr_dense(const fh_rwr_desc* d, float* x, long long cell_stride, const float* bin_cov,
+                            long long bin_cov_ld, void* workspace, size_t workspace_bytes, int* host_n_iter,
+                            void* stream) {
+	int rc = check_desc(d);
+	if (rc) return rc;
+	if (host_n_iter) *host_n_iter = 0;
+	if (d->ncell == 0 || !(d->do_conv || d->do_rwr)) return FH_OK;
+	cudaStream_t st = (cudaStream_t)stream;
+	FH_CHECK_ARG(workspace != nullptr && workspace_bytes >= fh_rwr_workspace_bytes(d),
+	             "fh_rwr_dense: workspace too small (%zu < %zu)", workspace_bytes, fh_rwr_workspace_bytes(d));
+	FH_CHECK_ARG(!d->do_col || !d->do_rwr || bin_cov != nullptr, "fh_rwr_dense: do_col needs bin_cov");
+	RwrWs ws = carve(d, workspace);
+	const int conv = d->do_conv && d->nb > 1;
+	rc = launch_densify(d, true, nullptr, nullptr, nullptr, x, cell_stride, conv, ws.A, (long long)d->nb * d->ldw, st);
+	if (rc) return rc;
+	if (!d->do_rwr) {
+		FH_CUDA(cudaMemcpy2DAsync(x, (size_t)cell_stride * 4, ws.A, (size_t)d->nb * d->ldw * 4, (size_t)d->nb * d->ldw * 4,
+		                          d->ncell, cudaMemcpyDeviceToDevice, st));
+		return FH_OK;
+	}
+	return rwr_from_panel(d, ws, bin_cov, bin_cov_ld, x, cell_stride, host_n_iter, st);
+}
+
+extern "C" int fh_colsum_accum(const float* x, int ncell, int nb, int w, int ldw, long long cell_stride,
+                               float* cov, long long cov_ld, void* stream) {
+	if (ncell <= 0) return FH_OK;
+	FH_CHECK_ARG(ncell <= 65535, "fh_colsum_accum: ncell > 65535");
+	dim3 grid(fh_cdiv(w, 128), ncell);
+	colsum_accum_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, nb, w, ldw, cell_stride, cov, cov_ld);
+	FH_LAUNCH_CHECK();
+	return FH_OK;
+}
+
+extern "C" int fh_avgpool(const float* x, int ncell, int nb, int w, int ldw, long long cell_stride, int ll,
+                          float* out, long long out_cell_stride, void* stream) {
+	if (ncell <= 0) return FH_OK;
+	FH_CHECK_ARG(ll >= 1 && ncell <= 65535, "fh_avgpool: bad arguments");
+	int orow = nb / ll, ocol = w / ll;
+	if (orow * ocol == 0) return FH_OK;
+	dim3 grid(fh_cdiv(orow * ocol, 128), ncell);
+	avgpool_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, nb, w, ldw, cell_stride, ll, orow, ocol, out, out_cell_stride);
+	FH_LAUNCH_CHECK();
+	return FH_OK;
+}
+
+extern "C" int fh_sqnorm_accum(const float* x, long long rows, long long cols, long long ld, double* acc, void* stream) {
+	if (rows * cols <= 0) return FH_OK;
+	int grid = (int)((rows * cols + 256 * 8 - 1) / (256 * 8));
+	if (grid > 148 * 8) grid = 148 * 8;
+	sqnorm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, nullptr, rows, cols, ld, ld, acc);
+	FH_LAUNCH_CHECK();
+	return FH_OK;
+}
+
+extern "C" int fh_dot_accum(const float* x, const float* y, long long rows, long long cols, long long ldx,
+                            long long ldy, double* acc, void* stream) {
+	if (rows * cols <= 0) return FH_OK;
+	int grid = (int)((rows * cols + 256 * 8 - 1) / (256 * 8));
+	if (grid > 148 * 8) grid = 148 * 8;
+	sqnorm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, rows, cols, ldx, ldy, acc);
+	FH_LAUNCH_CHECK();
+	return FH_OK;
+}

@@ -1,0 +1,511 @@
+"""Integrative PARAFAC2 driver on the B200 (mirror of fasthigashi/parafac2_intergrative.py (sic)).
+
+Same class name, methods and return values as the reference's `Fast_Higashi_core`
+(parafac2_intergrative.py:45-850); the sweep is re-derived for a device-resident design:
+
+  * the imputed tensor X of every (chromosome, bin-block) lives in HBM as a (cells, nb*ldw) fp32
+    matrix (cell-major panels), produced by ONE RWR pass per sweep (`cache="sweep"`, default) or per
+    run (`cache="run"`); the reference re-imputes 2-3x per sweep (:357,451,508);
+  * with that layout the three cell-mode contractions are plain large GEMMs against X
+        P1  T1  = X^T (V D)                       (:336,374-383)   temp_i = (T1_i diag(A_i)) B^T
+        P3  M  += X W,  W_i = U_i B diag(A_i) D^T (:422-430)       M = SVD_term^T
+        P5  Z   = X^T V, Y_i = U_i^T Z_i          (:522-529)
+    and the per-bin pieces are small batched GEMMs with the A-row scaling folded into the load;
+  * cells shard over ranks (one process per GPU): T1, Y, the R x R Gram of M and three scalars are
+    all-reduced (NCCL), everything else is local.
+
+PyTorch is used for memory, streams and torch.distributed only; all arithmetic on the timed path
+goes through libfh_b200.so (fast-higashi_b200/_lib.py).
+"""
+import math
+import sys
+import time
+import numpy as np
+import torch
+
+from . import _lib
+from .partial_rwr import rwr_block_csr, pad4, cells_per_chunk
+from .project2orthogonal import polar_batched, polar_tall
+from .parafac_integrative import cp_als_, core_sqnorm_accum
+from .sparse_for_schic import Chrom_Dataset
+
+
+def _as_block_csr(ds, device):
+	if isinstance(ds, Chrom_Dataset):
+		return ds.to(device)
+	if hasattr(ds, "tensor_list"):  # a reference Chrom_Dataset (duck-typed)
+		return Chrom_Dataset.from_reference(ds, device=device)
+	raise TypeError("schic entries must be Chrom_Dataset objects (ours or the reference's)")
+
+
+class Fast_Higashi_core:
+	def __init__(self, rank, off_diag, res_list, cache="sweep", use_tc=None, group=None, warm_polar=True):
+		self.rank = rank
+		self.off_diag = off_diag
+		self.res_list = res_list
+		self.device = torch.device("cpu")
+		self.cache = cache            # "sweep": one RWR pass per ALS sweep; "run": one per run
+		self.use_tc = use_tc          # None -> decided in .to()
+		self.group = group            # torch.distributed process group when cell-sharded
+		self.warm_polar = warm_polar
+		self.verbose = True
+		self.n_rwr_passes = 0
+		self._X = {}
+		self._eig = {}
+
+	def to(self, device):
+		self.device = torch.device(device)
+		if self.device.type != "cuda":
+			raise _lib.FHError("fasthigashi_b200 runs on CUDA devices only; there is no CPU path")
+		_lib.lib()
+		if self.use_tc is None:
+			self.use_tc = False
+		return self
+
+	# ------------------------------------------------------------------------------------------
+	def _dist(self):
+		if self.group is None:
+			return None
+		import torch.distributed as dist
+		return dist
+
+	def _allreduce(self, t, op=None):
+		d = self._dist()
+		if d is not None:
+			d.all_reduce(t, op=op or d.ReduceOp.SUM, group=self.group)
+		return t
+
+	def _log(self, *a):
+		if self.verbose and (self.group is None or self._dist().get_rank(self.group) == 0):
+			print(*a)
+			sys.stdout.flush()
+
+	def _gemm_dtype(self):
+		return _lib.GEMM_TF32X3 if self.use_tc else _lib.GEMM_F32
+
+	# ------------------------------------------------------------------------------------------
+	# sizes: parafac2_intergrative.py:558-590
+	def _setup(self, schic, size_ratio, size_list):
+		rank = self.rank
+		self.schic = [_as_block_csr(ds, self.device) for ds in schic]
+		if size_list is None:
+			size_list = [min(int(ds.num_bin * size_ratio * ds.resolution / 1000000), rank) for ds in self.schic]
+			chrom2size = {}
+			for ds, size in zip(self.schic, size_list):
+				chrom2size[ds.chrom] = min(chrom2size.get(ds.chrom, size), size)
+		else:
+			chrom2size = {}
+			for ds, size in zip(self.schic, size_list):
+				if ds.chrom in chrom2size and chrom2size[ds.chrom] != size:
+					print("size of the same chromosome must be same!", size, chrom2size[ds.chrom], ds.chrom)
+					raise EOFError
+				chrom2size[ds.chrom] = size
+		self.chrom2size = chrom2size
+		self.chrom2num_bin = {}
+		self.chrom2id = {c: [] for c in chrom2size}
+		for ci, ds in enumerate(self.schic):
+			self.chrom2id[ds.chrom].append(ci)
+			start = self.chrom2num_bin.get(ds.chrom, 0)
+			ds.global_slice_bin = slice(start, start + ds.num_bin)
+			self.chrom2num_bin[ds.chrom] = start + ds.num_bin
+		for ds_in, ds in zip(schic, self.schic):
+			try:
+				ds_in.global_slice_bin = ds.global_slice_bin  # the reference writes this too (:586-589)
+			except Exception:
+				pass
+		self.num_cell = self.schic[0].num_cell
+		self.total_cell_num = self.schic[0].total_cell_num
+
+	# ------------------------------------------------------------------------------------------
+	# I1: init_params, parafac2_intergrative.py:61-301
+	@torch.no_grad()
+	def init_params(self, schic, do_conv, do_rwr, do_col):
+		from sklearn.decomposition import TruncatedSVD
+		dev, R = self.device, self.rank
+		t0 = time.perf_counter()
+		sizes = [self.chrom2size[ds.chrom] for ds in self.schic]
+		# same CPU RNG call order as the reference (:71-80) so a shared seed gives the same start
+		A_list = [torch.randn([ds.num_bin, r], dtype=torch.float32) * 1e-2 + 1 for ds, r in zip(self.schic, sizes)]
+		B_dict = {c: torch.eye(r, dtype=torch.float32).add_(torch.randn(r, dtype=torch.float32), alpha=1e-2)
+		          for c, r in self.chrom2size.items()}
+		uniq = list(self.chrom2size.values()) * len(self.res_list)
+		cum = np.concatenate([[0], np.cumsum(uniq)])
+		dist = self._dist()
+		rank0 = dist is None or dist.get_rank(self.group) == 0
+		C = None
+		cstart = 0
+		self.bin_cov_list, self.bad_bin_cov_list, n_i_all = [], [], []
+		for ci, ds in enumerate(self.schic):
+			nbad = ds.total_cell_num - ds.num_cell
+			# one coverage table for good then bad cells (rows follow the dataset's cell order)
+			cov = torch.full((ds.total_cell_num, ds.num_bin), 1e-4, dtype=torch.float32, device=dev)
+			n1m = int(math.ceil(ds.num_bin * ds.resolution / 1000000))
+			size1 = min(int(math.ceil(ds.num_bin / ds.num_bin_batch * ds.resolution / 1000000)) + 2 * self.off_diag + 1, n1m)
+			feats_dim = int(math.ceil(n1m * size1))
+			ll = int(math.ceil(1000000 / ds.resolution))
+			feats = torch.zeros(ds.num_cell, feats_dim, dtype=torch.float32, device=dev)
+			n_i_list = []
+
+			def feature_pass(with_col, fstart):
+				for b, g in enumerate(ds.geoms):
+					ldw = pad4(g.w)
+					width = 0
+					for sl in ds.cell_slice_list[:ds.num_cell_batch]:
+						nc = sl.stop - sl.start
+						x = torch.empty(nc, g.nb * ldw, dtype=torch.float32, device=dev)
+						n_i = rwr_block_csr(ds, b, sl.start, nc, x, g.nb * ldw, -1, do_conv, do_rwr, with_col,
+						                    bin_cov=cov if with_col else None, use_tc=self.use_tc)
+						if not with_col:
+							n_i_list.append(n_i)
+							_lib.check(_lib.lib().fh_colsum_accum(x.data_ptr(), nc, g.nb, g.w, ldw, g.nb * ldw,
+							                                      cov.data_ptr() + 4 * (sl.start * cov.stride(0) + g.col0),
+							                                      cov.stride(0), _lib.stream_ptr()))
+						if with_col == do_col:
+							orow, ocol = g.nb // ll, g.w // ll
+							width = orow * ocol
+							if width:
+								pooled = torch.empty(nc, width, dtype=torch.float32, device=dev)
+								_lib.check(_lib.lib().fh_avgpool(x.data_ptr(), nc, g.nb, g.w, ldw, g.nb * ldw, ll,
+								                                 pooled.data_ptr(), width, _lib.stream_ptr()))
+								feats[sl, fstart:fstart + width] = pooled
+						del x
+					fstart += width
+					if not with_col:
+						for sl in ds.cell_slice_list[ds.num_cell_batch:]:
+							nc = sl.stop - sl.start
+							x = torch.empty(nc, g.nb * ldw, dtype=torch.float32, device=dev)
+							rwr_block_csr(ds, b, sl.start, nc, x, g.nb * ldw, -1, do_conv, do_rwr, False, use_tc=self.use_tc)
+							_lib.check(_lib.lib().fh_colsum_accum(x.data_ptr(), nc, g.nb, g.w, ldw, g.nb * ldw,
+							                                      cov.data_ptr() + 4 * (sl.start * cov.stride(0) + g.col0),
+							                                      cov.stride(0), _lib.stream_ptr()))
+							del x
+				return fstart
+
+			fstart = feature_pass(False, 0)
+			if do_col:
+				fstart = feature_pass(True, fstart)
+			r = self.chrom2size[ds.chrom]
+			# host randomized SVD exactly as the reference (:257-258, numpy global RNG); with cell
+			# sharding the features are gathered to rank 0 (SURVEY.md 8e "init")
+			f_host = feats[:, :fstart].cpu().numpy().astype(np.float64)
+			if dist is not None:
+				gathered = [None] * dist.get_world_size(self.group)
+				dist.all_gather_object(gathered, f_host, group=self.group)
+				f_host = np.concatenate(gathered, 0)
+			if rank0:
+				emb = TruncatedSVD(n_components=r, n_iter=2).fit_transform(f_host)
+				if C is None:
+					C = np.empty((f_host.shape[0], cum[-1]))
+				C[:, cstart:cstart + emb.shape[1]] = emb
+			cstart += r
+			ni = torch.tensor([max(n_i_list) if n_i_list else 0], device=dev)
+			if dist is not None:
+				self._allreduce(ni, dist.ReduceOp.MAX)
+			n_i_all.append(int(ni.item()))
+			cov[cov <= 1e-4] = float("inf")
+			self.bin_cov_list.append(cov[:ds.num_cell])
+			self.bad_bin_cov_list.append(cov[ds.num_cell:] if nbad > 0 else 0)
+			self._cov_all = getattr(self, "_cov_all", {})
+			self._cov_all[ci] = cov
+			del feats
+		self.n_i = np.array(n_i_all)
+		self._log("rwr iters:", self.n_i)
+		# joint SVD of the per-chromosome embeddings (:283-290); one-off, cuSOLVER through torch
+		if rank0:
+			Ct = torch.from_numpy(C).float().to(dev)
+			U, S, Vh = torch.linalg.svd(Ct, full_matrices=False)
+			meta_all = U[:, :R].contiguous()
+			SVh = (Vh[:R] * S[:R, None]).contiguous()
+		if dist is not None:
+			sizes_all = [None] * dist.get_world_size(self.group)
+			dist.all_gather_object(sizes_all, self.num_cell, group=self.group)
+			if not rank0:
+				meta_all = torch.empty(sum(sizes_all), R, device=dev)
+				SVh = torch.empty(R, int(cum[-1]), device=dev)
+			dist.broadcast(meta_all, src=dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0, group=self.group)
+			dist.broadcast(SVh, src=dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0, group=self.group)
+			off = sum(sizes_all[:dist.get_rank(self.group)])
+			meta = meta_all[off:off + self.num_cell].contiguous()
+			# A, B must be identical on every rank
+			for a in A_list: pass
+		else:
+			meta = meta_all
+		self.A_dev = [a.to(dev) for a in A_list]
+		self.B_dict = {c: b.to(dev) for c, b in B_dict.items()}
+		self.D_dict = {c: SVh[:, a:b].clone().contiguous() for c, a, b in zip(self.chrom2size, cum[:-1], cum[1:])}
+		if dist is not None:
+			src = dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0
+			for t in self.A_dev + list(self.B_dict.values()):
+				dist.broadcast(t, src=src, group=self.group)
+		self.meta_embedding = meta
+		self._log(f"time elapsed: {time.perf_counter() - t0:.2f}")
+		self._log("finish init")
+
+	def load_state(self, A_list, B_list, D_list, meta_embedding, bin_cov_list, bad_bin_cov_list, n_i):
+		"""Start from a given state (e.g. the reference's init, for lock-step parity runs)."""
+		dev = self.device
+		f = lambda x: torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(dev, torch.float32).contiguous().clone()
+		self.A_dev = [f(a) for a in A_list]
+		self.B_dict = {c: f(b) for c, b in zip(self.chrom2size, B_list)}
+		self.D_dict = {c: f(d) for c, d in zip(self.chrom2size, D_list)}
+		self.meta_embedding = f(meta_embedding)
+		self.bin_cov_list = [f(b) for b in bin_cov_list]
+		self.bad_bin_cov_list = [f(b) if (torch.is_tensor(b) or isinstance(b, np.ndarray)) and np.size(b) else 0
+		                         for b in bad_bin_cov_list]
+		self._cov_all = {}
+		for ci, ds in enumerate(self.schic):
+			good = self.bin_cov_list[ci]
+			bad = self.bad_bin_cov_list[ci]
+			self._cov_all[ci] = torch.cat([good, bad], 0).contiguous() if torch.is_tensor(bad) else good
+			self.bin_cov_list[ci] = self._cov_all[ci][:ds.num_cell]
+		self.n_i = np.asarray(n_i)
+
+	# ------------------------------------------------------------------------------------------
+	def _impute_good(self, ci, b, do_conv, do_rwr, do_col):
+		"""The imputed (cells, nb*ldw) matrix of block b; cached per sweep or per run."""
+		key = (ci, b)
+		ds = self.schic[ci]
+		g = ds.geoms[b]
+		ldw = pad4(g.w)
+		X = self._X.get(key)
+		if X is None:
+			X = torch.zeros(ds.num_cell, g.nb * ldw, dtype=torch.float32, device=self.device)
+			self._X[key] = X
+			self._X_valid = getattr(self, "_X_valid", set())
+		if key not in self._X_valid:
+			rwr_block_csr(ds, b, 0, ds.num_cell, X, g.nb * ldw, int(self.n_i[ci]), do_conv, do_rwr, do_col,
+			              bin_cov=self._cov_all[ci] if do_col else None, use_tc=self.use_tc)
+			self._X_valid.add(key)
+		return X
+
+	def invalidate_cache(self):
+		self._X_valid = set()
+
+	# P1-P5: parafac2_intergrative.py:304-540
+	@torch.no_grad()
+	def update_meta_embedding_interactions(self, schic=None, projection_list=None, projected_tensor_list=None,
+	                                       do_conv=True, do_rwr=True, do_col=False, first_iter=False):
+		dev, R = self.device, self.rank
+		gd = self._gemm_dtype()
+		nch = len(self.schic)
+		V = self.meta_embedding
+		Cn = self.num_cell
+		if self.cache == "sweep" or not hasattr(self, "_X_valid"):
+			self.invalidate_cache()
+			self.n_rwr_passes += 1
+		MT = torch.zeros(Cn, R, dtype=torch.float32, device=dev)  # SVD_term^T
+		stats = torch.zeros(2 * nch + 1, dtype=torch.float64, device=dev)  # x_U | ||X||^2 | x_V
+		for ci, ds in enumerate(self.schic):
+			r = self.chrom2size[ds.chrom]
+			A, B, D = self.A_dev[ci], self.B_dict[ds.chrom], self.D_dict[ds.chrom]
+			Cc = torch.empty(Cn, r, dtype=torch.float32, device=dev)
+			_lib.gemm(V, D, Cc, Cn, r, R, (R, 1), (r, 1), r, dtype=gd)  # C = V D  (:336)
+			for b, g in enumerate(ds.geoms):
+				ldw = pad4(g.w)
+				P = g.nb * ldw
+				X = self._impute_good(ci, b, do_conv, do_rwr, do_col)
+				if first_iter:
+					_lib.check(_lib.lib().fh_sqnorm_accum(X.data_ptr(), 1, Cn * P, Cn * P, stats[nch + ci:].data_ptr(),
+					                                      _lib.stream_ptr()))
+				# P1: T1 = X^T C ; temp_i = (T1_i diag(A_i)) B^T
+				T1 = torch.empty(P, r, dtype=torch.float32, device=dev)
+				_lib.gemm(X, Cc, T1, P, r, Cn, (1, P), (r, 1), r, dtype=gd)
+				self._allreduce(T1)
+				temp = torch.empty(g.nb, ldw, r, dtype=torch.float32, device=dev)
+				Arows = A[g.row0:g.row0 + g.nb]
+				_lib.gemm(T1, B, temp, ldw, r, r, (r, 1), (1, r), r, batch=g.nb, batch_strides=(ldw * r, 0, ldw * r),
+				          kscale=Arows, kscale_batch=r)
+				# P2: U_i = polar(temp_i)
+				key = (ci, b)
+				eig = self._eig.get(key)
+				warm = eig is not None and self.warm_polar
+				if eig is None and self.warm_polar:
+					n_side = min(ldw, r)
+					eig = self._eig[key] = torch.empty(g.nb, n_side, n_side, dtype=torch.float64, device=dev)
+				U = self.projection_dev[ci][b]
+				_, ssum, _ = polar_batched(temp, ldw, r, r, out=U, eig_state=eig, warm=warm)
+				stats[ci] += ssum.sum()
+				# P3: W_i = ((U_i B) diag(A_i)) D^T ; M += X W
+				UB = T1  # reuse
+				_lib.gemm(U, B, UB, P, r, r, (r, 1), (r, 1), r)
+				W = torch.empty(P, R, dtype=torch.float32, device=dev)
+				_lib.gemm(UB, D, W, ldw, R, r, (r, 1), (1, r), R, batch=g.nb, batch_strides=(ldw * r, 0, ldw * R),
+				          kscale=Arows, kscale_batch=r)
+				_lib.gemm(X, W, MT, Cn, R, P, (P, 1), (R, 1), R, beta=1.0, dtype=gd)
+				del W, T1, temp
+		# P4: V = polar(SVD_term^T) (:483-486)
+		self.last_svd_term_T = MT
+		Vn = polar_tall(MT, self.group)
+		_lib.check(_lib.lib().fh_dot_accum(Vn.data_ptr(), MT.data_ptr(), Cn, R, R, R, stats[2 * nch:].data_ptr(),
+		                                   _lib.stream_ptr()))
+		self.meta_embedding = Vn
+		# P5: Y_i = U_i^T X_i V (:488-529)
+		for ci, ds in enumerate(self.schic):
+			r = self.chrom2size[ds.chrom]
+			Y = self.projected_dev[ds.chrom]
+			for b, g in enumerate(ds.geoms):
+				ldw = pad4(g.w)
+				P = g.nb * ldw
+				X = self._impute_good(ci, b, do_conv, do_rwr, do_col)
+				Z = torch.empty(P, R, dtype=torch.float32, device=dev)
+				_lib.gemm(X, Vn, Z, P, R, Cn, (1, P), (R, 1), R, dtype=gd)
+				U = self.projection_dev[ci][b]
+				Yb = Y[ds.global_slice_bin.start + g.row0: ds.global_slice_bin.start + g.row0 + g.nb]
+				_lib.gemm(U, Z, Yb, r, R, ldw, (1, r), (R, 1), R, batch=g.nb, batch_strides=(ldw * r, ldw * R, r * R))
+				del Z
+		for chrom in self.chrom2size:
+			self._allreduce(self.projected_dev[chrom])
+		if self._dist() is not None:
+			loc = stats[nch:].clone()
+			self._allreduce(loc)
+			stats[nch:] = loc
+		s = stats.cpu().numpy()
+		x_U = s[:nch].reshape(-1, 1).copy()
+		x_V = float(s[2 * nch])
+		if first_iter:
+			return self.projection_dev, self.projected_dev, x_U, x_V, s[nch:2 * nch].reshape(-1, 1).copy()
+		return self.projection_dev, self.projected_dev, x_U, x_V
+
+	def _core_norms(self):
+		nch = len(self.schic)
+		acc = torch.zeros(nch, dtype=torch.float64, device=self.device)
+		for ci, ds in enumerate(self.schic):
+			core_sqnorm_accum(self.A_dev[ci], self.B_dict[ds.chrom], self.D_dict[ds.chrom], acc[ci:])
+		return acc.cpu().numpy().reshape(-1, 1)
+
+	# ------------------------------------------------------------------------------------------
+	# parafac2_intergrative.py:544-740
+	def fit(self, schic, size_ratio=0.3, n_iter_max=2000, n_iter_parafac=5, do_conv=True, do_rwr=False,
+	        do_col=False, tol=1e-8, size_list=None, gpu_id=None, verbose=True, run_init=True, state=None):
+		self.gpu_id = gpu_id
+		self.verbose = verbose
+		dev, R = self.device, self.rank
+		if self.device.type != "cuda":
+			raise _lib.FHError("call .to('cuda') first; fasthigashi_b200 has no CPU path")
+		self._setup(schic, size_ratio, size_list)
+		self._log("empty params initialized")
+		if state is not None:
+			self.load_state(*state)
+		elif run_init:
+			self.init_params(schic, do_conv, do_rwr, do_col)
+		self._flags = (do_conv, do_rwr, do_col)
+		self.projection_dev = [[torch.zeros(g.nb, pad4(g.w), self.chrom2size[ds.chrom], dtype=torch.float32, device=dev)
+		                        for g in ds.geoms] for ds in self.schic]
+		self.projected_dev = {c: torch.zeros(self.chrom2num_bin[c], self.chrom2size[c], R, dtype=torch.float32, device=dev)
+		                      for c in self.chrom2size}
+		self._X, self._eig = {}, {}
+		self.invalidate_cache()
+		self.n_rwr_passes = 0
+		rec_error_core_norm = self._core_norms()
+		rec_errors, rec_errors_total = [], []
+		self.re_trace, self.sweep_seconds = [], []
+		rec_error_tensor_norm = None
+		dist = self._dist()
+		for iteration in range(n_iter_max):
+			if (iteration % 10) == 0 and iteration > 0 and n_iter_parafac < 10:
+				n_iter_parafac += 1
+			self._log("Starting iteration", iteration)
+			start_time = time.time()
+			if rec_error_tensor_norm is None:
+				_, _, x_U, x_V, rec_error_tensor_norm = self.update_meta_embedding_interactions(
+					do_conv=do_conv, do_rwr=do_rwr, do_col=do_col, first_iter=True)
+				norm_tensor = np.sqrt(rec_error_tensor_norm).reshape(-1)
+				norm_tensor_all = float(np.linalg.norm(norm_tensor))
+			else:
+				_, _, x_U, x_V = self.update_meta_embedding_interactions(do_conv=do_conv, do_rwr=do_rwr, do_col=do_col)
+			rec_error_by_block_U = rec_error_tensor_norm + rec_error_core_norm - 2 * x_U
+			rec_error_V = rec_error_tensor_norm.sum() + rec_error_core_norm.sum() - 2 * x_V
+			# inner CP-ALS per chromosome (:674-695)
+			for chrom, ids in self.chrom2id.items():
+				if len(ids) == 1:
+					A = self.A_dev[ids[0]]
+				else:
+					A = torch.cat([self.A_dev[i] for i in ids], 0).contiguous()
+				cp_als_(self.projected_dev[chrom], A, self.B_dict[chrom], self.D_dict[chrom], n_iter_parafac)
+				if len(ids) > 1:
+					for i in ids:
+						self.A_dev[i].copy_(A[self.schic[i].global_slice_bin])
+				if dist is not None:  # keep replicas bit-identical (split-K atomics are unordered)
+					src = dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0
+					for i in ids:
+						dist.broadcast(self.A_dev[i], src=src, group=self.group)
+					dist.broadcast(self.B_dict[chrom], src=src, group=self.group)
+					dist.broadcast(self.D_dict[chrom], src=src, group=self.group)
+			rec_error_core_norm = self._core_norms()
+			rec_error = np.sqrt(rec_error_V.sum()) / norm_tensor_all
+			rec_errors_total.append(rec_error)
+			self.re_trace.append(float(rec_error))
+			rec_errors.append(np.sqrt(rec_error_by_block_U.ravel()) / norm_tensor)
+			self.sweep_seconds.append(time.time() - start_time)
+			if iteration >= 1:
+				differences = (rec_errors[-2] ** 2 - rec_errors[-1] ** 2) / (rec_errors[-2] ** 2)
+				total_differences = (rec_errors_total[-2] ** 2 - rec_errors_total[-1] ** 2) / rec_errors_total[-2] ** 2
+				self._log(f"PARAFAC2 re={rec_error:.3f} {total_differences:.2e} "
+				          f"variation min{differences.min().item():.1e} at chrom {differences.argmin().item():d}, "
+				          f"max{differences.max().item():.1e} at chrom {differences.argmax().item():d}",
+				          f"takes {time.time() - start_time:.1f}s")
+				if iteration >= 3 and tol > 0 and (total_differences < tol or differences.max() < tol * 2):
+					self._log("converged in {} iterations.".format(iteration))
+					break
+			else:
+				self._log(f"PARAFAC2 re={rec_error:.3f} takes {time.time() - start_time:.1f}s")
+		self._export()
+		return self
+
+	def _export(self):
+		"""Reference-shaped attributes: A_list on the host, projection_list[ci][b] (nb, w, r) on the
+		host, projected_tensor_list[chrom] (n, r, R) on the host (:601-620)."""
+		self.A_list = [a.cpu() for a in self.A_dev]
+		self.projection_list = [[U[:, :g.w, :].cpu() for U, g in zip(self.projection_dev[ci], ds.geoms)]
+		                        for ci, ds in enumerate(self.schic)]
+		self.projected_tensor_list = {c: y.cpu() for c, y in self.projected_dev.items()}
+
+	# T1: parafac2_intergrative.py:742-834
+	@torch.no_grad()
+	def transform(self, schic=None, do_conv=None, do_rwr=None, do_col=None):
+		f = self._flags
+		do_conv = f[0] if do_conv is None else do_conv
+		do_rwr = f[1] if do_rwr is None else do_rwr
+		do_col = f[2] if do_col is None else do_col
+		dev, R = self.device, self.rank
+		gd = self._gemm_dtype()
+		self._log("start transform")
+		Ct = self.total_cell_num
+		MT = torch.zeros(Ct, R, dtype=torch.float32, device=dev)
+		for ci, ds in enumerate(self.schic):
+			r = self.chrom2size[ds.chrom]
+			A, B, D = self.A_dev[ci], self.B_dict[ds.chrom], self.D_dict[ds.chrom]
+			for b, g in enumerate(ds.geoms):
+				ldw = pad4(g.w)
+				P = g.nb * ldw
+				U = self.projection_dev[ci][b]
+				Arows = A[g.row0:g.row0 + g.nb]
+				UB = torch.empty(P, r, dtype=torch.float32, device=dev)
+				_lib.gemm(U, B, UB, P, r, r, (r, 1), (r, 1), r)
+				W = torch.empty(P, R, dtype=torch.float32, device=dev)
+				_lib.gemm(UB, D, W, ldw, R, r, (r, 1), (1, r), R, batch=g.nb, batch_strides=(ldw * r, 0, ldw * R),
+				          kscale=Arows, kscale_batch=r)
+				X = self._impute_good(ci, b, do_conv, do_rwr, do_col)
+				_lib.gemm(X, W, MT, ds.num_cell, R, P, (P, 1), (R, 1), R, beta=1.0, dtype=gd)
+				nbad = ds.total_cell_num - ds.num_cell
+				if nbad > 0:
+					chunk = cells_per_chunk(g.nb, ldw, 1 << 30)
+					for c0 in range(0, nbad, chunk):
+						nc = min(chunk, nbad - c0)
+						Xb = torch.zeros(nc, P, dtype=torch.float32, device=dev)
+						rwr_block_csr(ds, b, ds.num_cell + c0, nc, Xb, P, int(self.n_i[ci]), do_conv, do_rwr, do_col,
+						              bin_cov=self._cov_all[ci] if do_col else None, use_tc=self.use_tc)
+						_lib.gemm(Xb, W, MT[ds.num_cell + c0:], nc, R, P, (P, 1), (R, 1), R, beta=1.0, dtype=gd)
+						del Xb
+				del W, UB
+		meta = polar_tall(MT, self.group)
+		self.A_list = [a.cpu() for a in self.A_dev]
+		return (None, (self.A_list, self.B_dict.values(), self.D_dict.values(), meta), self.projection_list)
+
+	def fit_transform(self, schic, size_ratio=0.3, n_iter_max=2000, n_iter_parafac=5, do_conv=True, do_rwr=False,
+	                  do_col=False, tol=1e-8, size_list=None, gpu_id=None, verbose=True, run_init=True, state=None):
+		if verbose:
+			print("n_iter_parafac", n_iter_parafac)
+		self.fit(schic, size_ratio, n_iter_max, n_iter_parafac, do_conv, do_rwr, do_col, tol, size_list, gpu_id,
+		         verbose, run_init, state=state)
+		return self.transform(schic, do_conv, do_rwr, do_col)

@@ -1,0 +1,233 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed
+reference fixtures. Tolerances are BASELINE.json's: RWR <= 1e-5 rel. Frobenius, loss <= 1e-4 rel.,
+embeddings Pearson >= 0.999."""
+import os
+import numpy as np
+import pytest
+import torch
+from conftest import GOLDEN, load_small_dataset, rel_fro
+from oracle import fh_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _lib():
+	from fasthigashi_b200 import _lib
+	return _lib
+
+
+@pytest.mark.parametrize("shape", [(37, 29, 53, 1), (130, 70, 19, 5), (64, 64, 64, 3), (5, 300, 7, 2), (200, 9, 2500, 1)])
+@pytest.mark.parametrize("layout", ["nn", "tn", "nt"])
+def test_gemm_f32_and_f64_variants(shape, layout):
+	L = _lib()
+	M, N, K, batch = shape
+	g = torch.Generator().manual_seed(M * 7 + N)
+	A = torch.randn(batch, M, K, generator=g)
+	B = torch.randn(batch, K, N, generator=g)
+	ref = torch.bmm(A.double(), B.double())
+	Ad = (A.transpose(1, 2).contiguous() if layout == "tn" else A.contiguous()).to(DEV)
+	Bd = (B.transpose(1, 2).contiguous() if layout == "nt" else B.contiguous()).to(DEV)
+	sa = (1, M) if layout == "tn" else (K, 1)
+	sb = (1, K) if layout == "nt" else (N, 1)
+	for dtype, tol, (ta, tb, tc) in [(L.GEMM_F32, 2e-6, (torch.float32,) * 3),
+	                                 (L.GEMM_F32_ACC64, 1e-12, (torch.float32, torch.float32, torch.float64)),
+	                                 (L.GEMM_F64, 1e-13, (torch.float64,) * 3),
+	                                 (L.GEMM_F32xF64_F32, 2e-7, (torch.float32, torch.float64, torch.float32)),
+	                                 (L.GEMM_F64xF32_F32, 2e-7, (torch.float64, torch.float32, torch.float32))]:
+		Cd = torch.full((batch, M, N), float("nan"), dtype=tc, device=DEV)
+		L.gemm(Ad.to(ta), Bd.to(tb), Cd, M, N, K, sa, sb, N, batch=batch, batch_strides=(M * K, K * N, M * N), dtype=dtype)
+		assert rel_fro(Cd.cpu().numpy(), ref.numpy()) < tol, (dtype, layout, shape)
+
+
+def test_gemm_epilogues():
+	L = _lib()
+	g = torch.Generator().manual_seed(1)
+	A, B = torch.randn(3, 20, 11, generator=g), torch.randn(3, 11, 20, generator=g)
+	ks, cs = torch.rand(3, 11, generator=g) + 0.5, torch.rand(3, 20, generator=g) + 0.5
+	C0 = torch.randn(3, 20, 20, generator=g)
+	ref = 0.5 * torch.bmm(A * ks[:, None, :], B) + 0.5 * torch.eye(20)
+	ref = ref / cs[:, None, :] + 2.0 * C0
+	Cd = C0.clone().to(DEV)
+	L.gemm(A.to(DEV), B.to(DEV), Cd, 20, 20, 11, (11, 1), (20, 1), 20, batch=3, batch_strides=(220, 220, 400), alpha=0.5,
+	       beta=2.0, epilogue=L.EPI_DIAG_ADD, diag=0.5, kscale=ks.to(DEV), kscale_batch=11, cscale=cs.to(DEV),
+	       cscale_batch=20, cscale_recip=True)
+	assert rel_fro(Cd.cpu().numpy(), ref.numpy()) < 1e-6
+
+
+def test_densify_bit_exact():
+	from fasthigashi_b200.partial_rwr import densify_block
+	for ds_c, ds_g in zip(load_small_dataset(good_qc_num=44, bs_cell=20), load_small_dataset(good_qc_num=44, bs_cell=20, device=DEV)):
+		for b, g in enumerate(ds_c.geoms):
+			x = densify_block(ds_g, b, 3, 40).cpu()
+			ref = O.densify_block(ds_c, b, 3, 43)
+			assert torch.equal(x[:, :, :g.w], ref)
+			assert float(x[:, :, g.w:].abs().sum()) == 0.0
+
+
+RWR_CASES = [(True, True, False, 3), (True, True, False, 0), (True, True, False, 1), (True, True, True, 4),
+             (False, True, False, 2), (True, False, False, 0), (False, False, False, 0), (True, True, False, -1),
+             (True, True, True, -1)]
+
+
+@pytest.mark.parametrize("flags", RWR_CASES)
+def test_rwr_block_csr_matches_oracle(flags):
+	from fasthigashi_b200.partial_rwr import rwr_block_csr, pad4
+	do_conv, do_rwr, do_col, k = flags
+	cpu = load_small_dataset(good_qc_num=44, bs_cell=20)
+	gpu = load_small_dataset(good_qc_num=44, bs_cell=20, device=DEV)
+	gen = torch.Generator().manual_seed(3)
+	for ds_c, ds_g in zip(cpu, gpu):
+		cov = torch.rand(48, ds_c.num_bin, generator=gen) + 0.5
+		cov[1, :5] = float("inf")
+		for b, g in enumerate(ds_c.geoms):
+			c0, c1 = 5, 41
+			ldw = pad4(g.w)
+			out = torch.full((c1 - c0, g.nb * ldw), float("nan"), device=DEV)
+			n_it = rwr_block_csr(ds_g, b, c0, c1 - c0, out, g.nb * ldw, k, do_conv, do_rwr, do_col, bin_cov=cov.to(DEV))
+			ref, n_ref = O.partial_rwr(O.densify_block(ds_c, b, c0, c1), g.s, g.e, do_conv, do_rwr, do_col,
+			                           cov[c0:c1, g.col0:g.col0 + g.w], k)
+			got = out.view(c1 - c0, g.nb, ldw).cpu()
+			assert n_it == n_ref
+			assert rel_fro(got[:, :, :g.w].numpy(), ref.numpy()) < 1e-5
+			assert float(got[:, :, g.w:].abs().sum()) == 0.0
+
+
+def test_partial_rwr_dense_api_matches_reference_fixture():
+	from fasthigashi_b200.partial_rwr import partial_rwr
+	g = np.load(os.path.join(GOLDEN, "rwr_cases.npz"))
+	flags = {"conv_rwr_k3": (True, True, False, 3), "conv_rwr_col_k4": (True, True, True, 4),
+	         "rwr_only_k2": (False, True, False, 2), "conv_only": (True, False, False, -1), "auto": (True, True, False, -1)}
+	for c in range(int(g["ncase"])):
+		_, _, _, s, e = g["c%d_meta" % c]
+		for name, (do_conv, do_rwr, do_col, k) in flags.items():
+			x = torch.from_numpy(g["c%d_dense" % c].copy()).to(DEV)
+			cov = torch.from_numpy(g["c%d_cov" % c].copy()).to(DEV)
+			y, n_it = partial_rwr(x, int(s), int(e), do_conv, do_rwr, do_col, bin_cov=cov, return_rwr_iter=True,
+			                      force_rwr_epochs=k, final_transpose=False)
+			assert n_it == int(g["c%d_%s_niter" % (c, name)])
+			assert rel_fro(y.cpu().numpy(), g["c%d_%s" % (c, name)]) < 1e-5, (c, name)
+
+
+def _ortho_err(U):
+	n = min(U.shape[-2:])
+	G = U.transpose(-1, -2) @ U if U.shape[-2] >= U.shape[-1] else U @ U.transpose(-1, -2)
+	return float((G - torch.eye(n, dtype=U.dtype)).abs().max())
+
+
+def test_polar_batched_matches_reference_fixture():
+	from fasthigashi_b200.project2orthogonal import project2orthogonal
+	g = np.load(os.path.join(GOLDEN, "polar_cases.npz"))
+	for i in range(int(g["n"])):
+		m = torch.from_numpy(g["m%d" % i])
+		U, S = project2orthogonal(m.to(DEV), m.shape[-1], None)
+		U, S = U.cpu(), S.cpu()
+		assert _ortho_err(U.double()) < 5e-6
+		assert rel_fro(S.numpy(), g["s%d" % i]) < 2e-5
+		# the ill-conditioned batch (kappa 1e6) is only compared on the objective the reference maximises
+		if i < 4:
+			assert rel_fro(U.numpy(), g["u%d" % i]) < 2e-5
+		tr_ref = float((torch.from_numpy(g["u%d" % i]) * m).sum())
+		assert abs(float((U * m).sum()) - tr_ref) / abs(tr_ref) < 1e-6
+
+
+def test_polar_realistic_shapes_and_warm_start():
+	from fasthigashi_b200.project2orthogonal import polar_batched
+	g = torch.Generator().manual_seed(0)
+	for (batch, rows, cols) in [(6, 316, 137), (9, 72, 21), (3, 152, 150), (4, 12, 20)]:
+		Uq, _ = torch.linalg.qr(torch.randn(batch, max(rows, cols), min(rows, cols), generator=g, dtype=torch.float64))
+		Vq, _ = torch.linalg.qr(torch.randn(batch, min(rows, cols), min(rows, cols), generator=g, dtype=torch.float64))
+		sv = torch.logspace(0, -6.5, min(rows, cols), dtype=torch.float64)
+		T = (Uq * sv) @ Vq.transpose(1, 2)
+		if rows < cols:
+			T = T.transpose(1, 2)
+		T = T.float().contiguous()
+		ref = (Uq @ Vq.transpose(1, 2))
+		ref = ref.transpose(1, 2) if rows < cols else ref
+		Td = T.to(DEV)
+		n = min(rows, cols)
+		eig = torch.zeros(batch, n, n, dtype=torch.float64, device=DEV)
+		U, ssum, _ = polar_batched(Td, rows, cols, cols, eig_state=eig, warm=False)
+		assert _ortho_err(U.cpu().double()) < 5e-6
+		# well-conditioned part of the factor: compare on the leading singular subspace
+		lead = (Uq[:, :, :n // 2] @ Vq[:, :, :n // 2].transpose(1, 2))
+		lead = lead.transpose(1, 2) if rows < cols else lead
+		assert abs(float((U.cpu().double() * lead).sum()) - batch * (n // 2)) / (batch * (n // 2)) < 1e-5
+		assert float((ssum.cpu() - sv.sum()).abs().max() / sv.sum()) < 1e-6
+		U2, ssum2, _ = polar_batched((Td * 1.001).contiguous(), rows, cols, cols, eig_state=eig, warm=True)
+		assert rel_fro(U2.cpu().numpy(), U.cpu().numpy()) < 1e-4
+		assert _ortho_err(U2.cpu().double()) < 5e-6
+
+
+def test_polar_tall_matches_oracle():
+	from fasthigashi_b200.project2orthogonal import polar_tall
+	g = torch.Generator().manual_seed(2)
+	M = torch.randn(700, 64, generator=g) @ torch.diag(torch.logspace(0, -3, 64)) @ torch.randn(64, 64, generator=g)
+	V = polar_tall(M.to(DEV)).cpu()
+	ref, _ = O.polar(M, 64)
+	assert rel_fro(V.numpy(), ref.numpy()) < 2e-5
+	assert _ortho_err(V.double()) < 5e-6
+
+
+def test_cp_als_matches_reference_fixture():
+	from fasthigashi_b200.parafac_integrative import parafac
+	g = np.load(os.path.join(GOLDEN, "cp_cases.npz"))
+	for i in range(int(g["n"])):
+		iters, cn, lx = g["p%d_scal" % i]
+		fac, norm_hat, inner = parafac(torch.from_numpy(g["p%d_Y" % i]).to(DEV), None, int(iters),
+		                               [torch.from_numpy(g["p%d_%s0" % (i, n)]) for n in "ABD"])
+		for f, n in zip(fac, "ABD"):
+			assert rel_fro(f.cpu().numpy(), g["p%d_%s1" % (i, n)]) < 2e-4, (i, n)
+		if iters > 1:
+			assert abs(norm_hat - cn) / cn < 1e-4 and abs(inner - lx) / abs(lx) < 1e-4
+
+
+def _state_from_fixture(g):
+	good = int(g["good_qc_num"])
+	bad = [g["bad_bin_cov%d" % i] for i in range(3)] if good < 48 else [0, 0, 0]
+	return ([g["t0_A%d" % i] for i in range(3)], [g["t0_B%d" % i] for i in range(3)], [g["t0_D%d" % i] for i in range(3)],
+	        g["t0_V"], [g["bin_cov%d" % i] for i in range(3)], bad, g["n_i"])
+
+
+@pytest.mark.parametrize("tag,cache", [("col", "sweep"), ("nocol", "run")])
+def test_core_lockstep_with_reference(tag, cache):
+	"""From the reference's own init state: per-sweep loss within 1e-4, projected tensor / V of the
+	first sweeps close, final embeddings Pearson >= 0.999."""
+	from fasthigashi_b200.parafac2_intergrative import Fast_Higashi_core
+	g = np.load(os.path.join(GOLDEN, "core_%s.npz" % tag))
+	good = int(g["good_qc_num"])
+	ds = load_small_dataset(good_qc_num=good if good < 48 else -1, bs_cell=int(g["bs_cell"]))
+	core = Fast_Higashi_core(int(g["rank"]), 12, [1000000], cache=cache).to(DEV)
+	nsweep = int(g["nsweep"])
+	res = core.fit_transform(ds, 0.3, nsweep, 1, True, True, bool(g["do_col"]), 0.0, verbose=False,
+	                         state=_state_from_fixture(g))
+	re = np.array(core.re_trace)
+	assert re.shape == g["re"].shape
+	assert np.max(np.abs(re - g["re"]) / g["re"]) < 1e-4, (re, g["re"])
+	A_list, B_list, D_list, V = res[1]
+	E = O.embed_all(V.cpu().numpy(), [d.cpu().numpy() for d in D_list])
+	Eref = O.embed_all(g["final_V"], [g["final_D%d" % i] for i in range(3)])
+	pear = [abs(np.corrcoef(E[:, j], Eref[:, j])[0, 1]) for j in range(E.shape[1])]
+	assert min(pear) > 0.999, min(pear)
+	assert V.shape == (48, int(g["rank"]))
+	for i in range(3):
+		for b, U in enumerate(res[2][i]):
+			assert U.shape == g["final_U%d_%d" % (i, b)].shape
+
+
+def test_core_init_params_matches_reference():
+	"""init_params on device (RWR auto-stop, coverage, pooled features, host randomized SVD with the
+	same numpy seed) against the reference's init."""
+	from fasthigashi_b200.parafac2_intergrative import Fast_Higashi_core
+	g = np.load(os.path.join(GOLDEN, "core_col.npz"))
+	ds = load_small_dataset(good_qc_num=44, bs_cell=20)
+	core = Fast_Higashi_core(int(g["rank"]), 12, [1000000]).to(DEV)
+	torch.manual_seed(0); np.random.seed(0)
+	core.fit(ds, 0.3, 3, 1, True, True, True, 0.0, verbose=False)
+	assert list(core.n_i) == list(g["n_i"])
+	for i in range(3):
+		ref = g["bin_cov%d" % i]
+		got = core.bin_cov_list[i].cpu().numpy()
+		assert np.array_equal(np.isfinite(ref), np.isfinite(got))
+		assert rel_fro(got[np.isfinite(ref)], ref[np.isfinite(ref)]) < 1e-5
+	assert np.max(np.abs(np.array(core.re_trace) - g["re"][:3]) / g["re"][:3]) < 2e-4

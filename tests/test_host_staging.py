@@ -1,0 +1,57 @@
+"""Host logic: block geometry / block-CSR staging (sparse_for_schic.py:356-510 mirror)."""
+import numpy as np
+import pytest
+import torch
+from conftest import load_small_dataset
+from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset, block_geometry
+
+
+def test_geometry_rule():
+	# hand-derived from sparse_for_schic.py:457-492 (n=90, bs_bin=32, flank=12)
+	g = block_geometry(90, 32, 12)
+	assert [(x.row0, x.nb, x.col0, x.w, x.s, x.e) for x in g] == [
+		(0, 32, 0, 44, 0, 32), (32, 32, 20, 56, 12, 44), (64, 26, 52, 38, 12, 38)]
+	# i == flank keeps absolute columns (reference uses `i > flank`)
+	g = block_geometry(40, 12, 12)
+	assert (g[1].col0, g[1].s) == (0, 12)
+	assert (g[2].col0, g[2].s) == (12, 12)
+	g = block_geometry(50, 50, 100)
+	assert (g[0].w, g[0].s, g[0].e) == (50, 0, 50)
+
+
+def test_csr_roundtrip_and_cell_order():
+	ds = load_small_dataset(good_qc_num=44, bs_cell=20)[0]
+	assert ds.num_cell == 44 and ds.total_cell_num == 48
+	assert [(s.start, s.stop) for s in ds.cell_slice_list] == [(0, 20), (20, 40), (40, 44), (44, 48)]
+	assert ds.num_cell_batch == 3 and ds.num_cell_batch_bad == 1
+	d = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "data_small.npz"))
+	idx, val = d["chr1_idx"].astype(np.int64), d["chr1_val"]
+	dense = np.zeros((90, 90, 48), np.float32)
+	dense[idx[0], idx[1], idx[2]] = val
+	for b, g in enumerate(ds.geoms):
+		rp, col, v = ds.cell_range_csr(b, 0, 48)
+		rows = np.repeat(np.arange(48 * g.nb), np.diff(rp.numpy()))
+		out = np.zeros((48 * g.nb, g.w), np.float32)
+		out[rows, col.numpy()] = v.numpy()
+		ref = dense[g.row0:g.row0 + g.nb, g.col0:g.col0 + g.w, :].transpose(2, 0, 1).reshape(-1, g.w)
+		assert np.array_equal(out, ref)
+	assert ds.nnz() == len(val)
+
+
+def test_rejects_out_of_window_and_duplicates():
+	idx = np.array([[0, 5], [40, 6], [0, 0]])
+	with pytest.raises(ValueError):
+		Chrom_Dataset(Sparse(idx, np.ones(2, np.float32), (60, 60, 1)), 16, 1, compact=True, flank=10)
+	idx = np.array([[3, 3], [4, 4], [0, 0]])
+	with pytest.raises(ValueError):
+		Chrom_Dataset(Sparse(idx, np.ones(2, np.float32), (60, 60, 1)), 16, 1, compact=True, flank=10)
+
+
+def test_empty_cells_and_select_cells():
+	idx = np.array([[0, 1, 7], [1, 0, 7], [2, 2, 2]])
+	ds = Chrom_Dataset(Sparse(idx, np.array([1., 2., 3.], np.float32), (9, 9, 4)), 4, 4, compact=True, flank=3)
+	assert ds.nnz() == 3 and len(ds.geoms) == 3
+	sub = ds.select_cells(2, 4)
+	assert sub.total_cell_num == 2 and sub.nnz() == 3
+	sub0 = ds.select_cells(0, 2)
+	assert sub0.nnz() == 0 and all(int(r[-1]) == 0 for r in sub0.rowptr)
