@@ -1,0 +1,382 @@
+"""bench.py - cells/s per PARAFAC2 ALS sweep (incl. RWR) on B200, with the reference's CPU path
+timed beside it (BASELINE.json metric; contract in the task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--cells C]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one full ALS sweep of the hot path over the whole resident workload: RWR imputation of
+every (cell, chromosome) from the block-CSR, the P1/P3/P5 contractions, the per-bin and cell-mode
+polar factors, the inner CP-ALS of every chromosome and the loss terms.
+Workload at N=1: BASELINE.json configs[1] (PFC-shaped: 4,238 cells, 22 autosomes at 500 kb, 5,432
+bins, rank 256, off_diag 100, dim1 0.6, do_conv=do_rwr=True, do_col=False as the wrapper decides at
+density 0.05). N>1: the same per-GPU slab on every rank (weak scaling), cells sharded.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RES, OFF_DIAG, RANK, DIM1, DENSITY = 500000, 100, 256, 0.6, 0.05
+
+
+def bs_bin_rule(n, res):
+	rec = min(max(int(15000000 / res), 128), 256)  # FastHigashi_Wrapper.py:501
+	return math.ceil(n / max(math.ceil(n / rec), 1))  # :507,512
+
+
+def make_datasets(ncell, seed, device, bins):
+	import fasthigashi_b200  # noqa: F401
+	from fasthigashi_b200 import synth
+	from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset
+	rng = np.random.default_rng(seed)
+	cluster = rng.integers(0, 8, size=ncell)
+	out = []
+	for ci, n in enumerate(bins):
+		idx, val = synth.synth_chrom(n, ncell, DENSITY, OFF_DIAG, seed * 1000 + ci, cluster, 8, device=device, cell_chunk=256)
+		sp = Sparse.__new__(Sparse)
+		sp.indices, sp.values, sp.shape, sp.ndim, sp.indptr = idx, val, np.array([n, n, ncell]), 3, None
+		out.append(Chrom_Dataset(sp, bs_bin=bs_bin_rule(n, RES), bs_cell=ncell, compact=True, flank=OFF_DIAG,
+		                         chrom="chr%d" % (ci + 1), resolution=RES, device=device))
+		del idx, val, sp
+	return out
+
+
+def random_state(datasets, rank_R, seed, device="cpu", n_i=None):
+	"""Random-init factors of the right shapes (the timed sweep does not depend on their values)."""
+	g = torch.Generator().manual_seed(seed)
+	sizes = [min(int(ds.num_bin * DIM1 * ds.resolution / 1000000), rank_R) for ds in datasets]
+	ncell = datasets[0].num_cell
+	A = [torch.randn(ds.num_bin, r, generator=g) * 1e-2 + 1 for ds, r in zip(datasets, sizes)]
+	B = [torch.eye(r) + 1e-2 * torch.randn(r, generator=g) for r in sizes]
+	D = [torch.randn(rank_R, r, generator=g) * 0.05 for r in sizes]
+	V = torch.randn(ncell, rank_R, generator=g)
+	V = torch.linalg.qr(V)[0] if ncell >= rank_R else torch.linalg.qr(V.T)[0].T
+	cov = [torch.ones(ds.total_cell_num, ds.num_bin) for ds in datasets]
+	return (A, B, D, V.contiguous(), cov, [0] * len(datasets), n_i if n_i is not None else [4] * len(datasets))
+
+
+def probe_rwr_steps(datasets, ncell_probe=128):
+	"""The auto-stop step count of init_params (parafac2_intergrative.py:131-140,265) on a cell
+	sample: every timed sweep then runs exactly that many RWR steps, as the reference does."""
+	from fasthigashi_b200.partial_rwr import rwr_block_csr, pad4
+	n_i = []
+	for ds in datasets:
+		worst = 0
+		nc = min(ncell_probe, ds.num_cell)
+		for b, g in enumerate(ds.geoms):
+			ldw = pad4(g.w)
+			x = torch.empty(nc, g.nb * ldw, dtype=torch.float32, device=ds.val[b].device)
+			worst = max(worst, rwr_block_csr(ds, b, 0, nc, x, g.nb * ldw, -1, True, True, False))
+		n_i.append(worst)
+	return n_i
+
+
+class ClockSampler:
+	Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+	     "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+	def __init__(self, gpu_index):
+		self.rows, self.proc, self.gpu = [], None, gpu_index
+
+	def start(self):
+		try:
+			self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+			                              "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+			self.t = threading.Thread(target=self._read, daemon=True)
+			self.t.start()
+		except Exception:
+			self.proc = None
+
+	def _read(self):
+		for line in self.proc.stdout:
+			self.rows.append([x.strip() for x in line.split(",")])
+
+	def stop(self):
+		if self.proc is None:
+			return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+		self.proc.terminate()
+		try:
+			self.proc.wait(timeout=2)
+		except Exception:
+			pass
+		sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+		mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+		reasons = set()
+		for r in self.rows:
+			if len(r) >= 9:
+				for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+					if v.lower().startswith("active"):
+						reasons.add(name)
+		return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+		        "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+	p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+	if os.path.exists(p):
+		d = json.load(open(p))
+		return dict(hbm=d["hbm_gbs"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+	return dict(hbm=6650.0, tensor=1400.0, src="fallback")
+
+
+def algorithmic_work(datasets, rank_R):
+	"""SURVEY.md 8d formulas, summed over (cell, bin-block) for one sweep."""
+	rwr_bytes = contraction_flops = polar_flops = 0.0
+	problems = 0
+	for ds in datasets:
+		r = min(int(ds.num_bin * DIM1 * ds.resolution / 1000000), rank_R)
+		C = ds.num_cell
+		for b, g in enumerate(ds.geoms):
+			nnz = ds.val[b].numel() * (C / ds.total_cell_num)
+			rwr_bytes += nnz * 6 + C * ((g.nb + 1) * 4 + 4 * g.nb * g.w)
+			contraction_flops += C * (6.0 * g.nb * g.w * r + 4.0 * g.nb * r * rank_R)
+			polar_flops += g.nb * (4.0 * g.w * r * r + 10.0 * r ** 3)
+			problems += g.nb
+	return dict(rwr_bytes=rwr_bytes, contraction_flops=contraction_flops, polar_flops=polar_flops, polar_problems=problems)
+
+
+# --------------------------------------------------------------------------------------------
+def time_oracle(datasets_dev, rank_R, n_i, sample_cells, steps, warmup):
+	"""The reference algorithm on the host cores (oracle/fh_oracle.py = CPU restatement pinned to the
+	reference's outputs; the reference itself is not on the GPU box) on a cell sample of the same
+	geometry. Returns per-step seconds split into the part linear in cells and the fixed part."""
+	from oracle import fh_oracle as O
+	ncpu = os.cpu_count() or 1
+	torch.set_num_threads(ncpu)
+	cpu_ds = [ds.select_cells(0, sample_cells).to("cpu") for ds in datasets_dev]
+	core = O.OracleCore(rank_R, OFF_DIAG, [RES])
+	state = random_state(cpu_ds, rank_R, 7, n_i=n_i)
+	core.set_sizes(cpu_ds, DIM1)
+	core.load_state(*state)
+	fixed = [0.0]
+	orig_polar, orig_cp = O.polar, O.cp_als
+
+	def timed(fn):
+		def w(*a, **k):
+			t = time.perf_counter()
+			r = fn(*a, **k)
+			fixed[0] += time.perf_counter() - t
+			return r
+		return w
+	O.polar, O.cp_als = timed(orig_polar), timed(orig_cp)
+	rec = []
+	try:
+		for it in range(warmup + steps):
+			fixed[0] = 0.0
+			t = time.perf_counter()
+			core.sweep(cpu_ds, True, True, False, want_norm=(it == 0))
+			for ci, ds in enumerate(cpu_ds):
+				fac, _, _ = O.cp_als(core.projected[ds.chrom], [core.A_list[ci], core.B_dict[ds.chrom], core.D_dict[ds.chrom]], 1)
+				core.A_list[ci], core.B_dict[ds.chrom], core.D_dict[ds.chrom] = fac
+			core.core_norms(cpu_ds)
+			total = time.perf_counter() - t
+			if it >= warmup:
+				rec.append((total, fixed[0]))
+	finally:
+		O.polar, O.cp_als = orig_polar, orig_cp
+	total = float(np.median([r[0] for r in rec]))
+	fx = float(np.median([r[1] for r in rec]))
+	return dict(total=total, fixed=fx, per_cell=(total - fx) / sample_cells, cores=ncpu, sample_cells=sample_cells)
+
+
+def main():
+	ap = argparse.ArgumentParser()
+	ap.add_argument("--gpus", type=int, default=1)
+	ap.add_argument("--steps", type=int, default=5)
+	ap.add_argument("--warmup", type=int, default=3)
+	ap.add_argument("--impl", default="b200")
+	ap.add_argument("--cells", type=int, default=4238)
+	ap.add_argument("--geometry", default="pfc", help="pfc (configs[1]) | hg19")
+	ap.add_argument("--cache", default="sweep", help="sweep: RWR recomputed every sweep (metric); run: once per run")
+	ap.add_argument("--cpu-sample-cells", type=int, default=32)
+	ap.add_argument("--no-cpu-baseline", action="store_true")
+	ap.add_argument("--no-e2e", action="store_true")
+	ap.add_argument("--tc", type=int, default=-1, help="1: tcgen05 3xTF32 GEMMs, 0: CUDA-core fp32 (default: library default)")
+	args = ap.parse_args()
+
+	world = int(os.environ.get("WORLD_SIZE", "1"))
+	rank = int(os.environ.get("RANK", "0"))
+	local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+	import fasthigashi_b200  # noqa: F401
+	from fasthigashi_b200 import synth
+	bins = synth.chrom_bins("pfc", RES) if args.geometry == "pfc" else synth.chrom_bins("hg19", RES)
+	workload = "%s-shaped synthetic scHi-C: %d cells/GPU, 22 autosomes @500kb (%d bins), rank %d, off_diag %d, dim1 %.1f, density %.2f" % (
+		"PFC" if args.geometry == "pfc" else "hg19", args.cells, sum(bins), RANK, OFF_DIAG, DIM1, DENSITY)
+	config = {"workload": workload, "cells_per_gpu": args.cells, "rwr": "recomputed once per sweep" if args.cache == "sweep" else "cached per run",
+	          "l2": "inputs (>= 20 GB imputed tensor per sweep) far exceed the 126 MB L2", "init": "random factors (timing does not depend on values)",
+	          "sharding": "cells x%d" % world}
+
+	if args.impl == "reference":
+		# the reference's own CPU implementation of the path, host cores only; rank 0 alone
+		if rank != 0:
+			return
+		if not torch.cuda.is_available():
+			ds = make_datasets(args.cpu_sample_cells, 1000, "cpu", bins)
+			n_i = [4] * len(ds)
+		else:
+			torch.cuda.set_device(local_rank)
+			ds = make_datasets(max(args.cpu_sample_cells, 128), 1000, "cuda", bins)
+			import __graft_entry__ as ge
+			ge.build()
+			n_i = probe_rwr_steps(ds)
+		w_eff = min(args.warmup, 1)
+		t = time_oracle(ds, RANK, n_i, args.cpu_sample_cells, args.steps, w_eff)
+		sec = t["fixed"] + args.cells * t["per_cell"]
+		val = args.cells / sec
+		cb = {"value": val, "unit": "cells/s", "cores": t["cores"], "kind": "port",
+		      "sample": "%d-cell sample of the same geometry per step; per-sweep cost = fixed (polar+CP-ALS, %.2fs) + cells x %.4fs, "
+		                "extrapolated to %d cells" % (t["sample_cells"], t["fixed"], t["per_cell"], args.cells)}
+		print(json.dumps({"impl": "reference", "metric": "cells/s per PARAFAC2 ALS sweep (incl. RWR)", "value": val, "unit": "cells/s",
+		                  "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "warmup_effective": w_eff,
+		                  "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+		                  "data": "synthetic", "config": config, "cpu_baseline": cb,
+		                  "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+		return
+
+	# ---------------------------------------------------------------------------- b200 arm
+	import __graft_entry__ as ge
+	if rank == 0:
+		ge.build()
+	assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
+	torch.cuda.set_device(local_rank)
+	dev = torch.device("cuda", local_rank)
+	group = None
+	if world > 1:
+		import torch.distributed as dist
+		dist.init_process_group("nccl", device_id=dev)
+		group = dist.group.WORLD
+		dist.barrier()
+	from fasthigashi_b200 import _lib
+	from fasthigashi_b200.parafac2_intergrative import Fast_Higashi_core
+	_lib.lib()
+	datasets = make_datasets(args.cells, 1000 + rank, dev, bins)
+	n_i = probe_rwr_steps(datasets)
+	if world > 1:
+		t = torch.tensor(n_i, device=dev)
+		dist.all_reduce(t, op=dist.ReduceOp.MAX)
+		n_i = t.tolist()
+	state = random_state(datasets, RANK, 7, n_i=n_i)
+	if world > 1:  # identical replicated factors, rank-local V rows
+		g = torch.Generator().manual_seed(100 + rank)
+		state = state[:3] + (torch.linalg.qr(torch.randn(args.cells, RANK, generator=g))[0].contiguous(),) + state[4:]
+	core = Fast_Higashi_core(RANK, OFF_DIAG, [RES], cache=args.cache, group=group,
+	                         use_tc=None if args.tc < 0 else bool(args.tc)).to(dev)
+	core.verbose = False
+	core.prepare(datasets, DIM1, True, True, False, state=state)
+	work = algorithmic_work(datasets, RANK)
+
+	def sync_all():
+		if world > 1:
+			dist.barrier()
+		torch.cuda.synchronize()
+
+	for _ in range(args.warmup):
+		core.sweep_once(1)
+	sync_all()
+	core.enable_timers(True)
+	sampler = ClockSampler(local_rank)
+	sampler.start()
+	l0 = _lib.launch_count()
+	e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	sync_all()
+	e0.record()
+	for _ in range(args.steps):
+		core.sweep_once(1)
+	e1.record()
+	sync_all()
+	ms = e0.elapsed_time(e1)
+	launches = _lib.launch_count() - l0
+	clocks = sampler.stop()
+	stages = core.collect_timers()
+	core.enable_timers(False)
+	if world > 1:
+		t = torch.tensor([ms], device=dev, dtype=torch.float64)
+		dist.all_reduce(t, op=dist.ReduceOp.MAX)
+		ms = float(t.item())
+	ms_per_step = ms / args.steps
+	total_cells = args.cells * world
+	value = total_cells / (ms_per_step / 1e3)
+
+	# ---- end-to-end: block-CSR in pinned host memory -> H2D -> sweep -> loss D2H, every step
+	e2e = None
+	if not args.no_e2e:
+		host, h2d = [], 0
+		for ds in datasets:
+			hs = []
+			for arrs in (ds.rowptr, ds.col, ds.val):
+				hs.append([a.cpu().pin_memory() for a in arrs])
+				h2d += sum(a.numel() * a.element_size() for a in arrs)
+			host.append(hs)
+		n_e2e = max(2, min(args.steps, 3))
+		sync_all()
+		e0.record()
+		for _ in range(n_e2e):
+			for ds, hs in zip(datasets, host):
+				for dst, src in zip((ds.rowptr, ds.col, ds.val), hs):
+					for d, s in zip(dst, src):
+						d.copy_(s, non_blocking=True)
+			core.sweep_once(1)  # ends with the D2H read of the loss terms
+		e1.record()
+		sync_all()
+		ms_e = e0.elapsed_time(e1) / n_e2e
+		if world > 1:
+			t = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+			dist.all_reduce(t, op=dist.ReduceOp.MAX)
+			ms_e = float(t.item())
+		e2e = {"value": total_cells / (ms_e / 1e3), "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
+		       "d2h_bytes_per_step": int((2 * len(datasets) + 1) * 8 + len(datasets) * 8), "ms_per_step": ms_e, "steps": n_e2e}
+		del host
+
+	if rank != 0:
+		return
+	pk = peaks()
+	per = {k: v / args.steps for k, v in stages.items()}
+	top = max(per, key=per.get) if per else None
+	roof_all = {}
+	if "rwr" in per:
+		a = work["rwr_bytes"] / (per["rwr"] / 1e3) / 1e9
+		roof_all["rwr"] = {"bound": "hbm", "achieved": a, "peak": pk["hbm"], "unit": "GB/s", "frac": a / pk["hbm"]}
+	gem = sum(per.get(k, 0.0) for k in ("p1_mttkrp", "p3_project", "p5_tensor"))
+	if gem > 0:
+		a = work["contraction_flops"] / (gem / 1e3) / 1e12
+		roof_all["contractions"] = {"bound": "tensor", "achieved": a, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": a / pk["tensor"],
+		                            "note": "fp32-parity maths: 3xTF32 ceiling is ~peak_tf32/3 = ~peak_bf16/6"}
+	if "polar_bins" in per:
+		a = work["polar_flops"] / (per["polar_bins"] / 1e3) / 1e12
+		roof_all["polar_bins"] = {"bound": "fp64 CUDA cores (no tensor path at fp64)", "achieved": a, "unit": "TFLOP/s fp64",
+		                          "problems_per_s": work["polar_problems"] / (per["polar_bins"] / 1e3)}
+	group_of = {"rwr": "rwr", "p1_mttkrp": "contractions", "p3_project": "contractions", "p5_tensor": "contractions",
+	            "polar_bins": "polar_bins"}
+	dom = group_of.get(top, "contractions")
+	roofline = dict(roof_all.get(dom, {}))
+	roofline.setdefault("bound", "tensor")
+	roofline["kernel_stage"] = dom
+	roofline["traffic"] = None
+	roofline["peak_source"] = pk["src"]
+	out = {"metric": "cells/s per PARAFAC2 ALS sweep (incl. RWR)", "value": value, "unit": "cells/s", "n_gpus": world,
+	       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+	       "vs_baseline": None, "dtype": "f32 (fp64 inside the polar step)", "data": "synthetic", "config": config,
+	       "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
+	       "stages_ms_per_sweep": per, "roofline_all": roof_all, "rwr_steps": n_i, "re_trace_tail": core.re_trace[-3:]}
+	if not args.no_cpu_baseline and world == 1:
+		t = time_oracle(datasets, RANK, n_i, args.cpu_sample_cells, 1, 0)
+		sec = t["fixed"] + args.cells * t["per_cell"]
+		out["cpu_baseline"] = {"value": args.cells / sec, "unit": "cells/s", "cores": t["cores"], "kind": "port",
+		                       "sample": "one oracle sweep on a %d-cell sample of the same geometry: fixed part (polar+CP-ALS) %.2fs + "
+		                                 "cells x %.4fs, extrapolated to %d cells (%.1fs per sweep)" % (
+			                       t["sample_cells"], t["fixed"], t["per_cell"], args.cells, sec)}
+	print(json.dumps(out))
+
+
+if __name__ == "__main__":
+	main()

@@ -226,7 +226,7 @@ PolarWs carve(int batch, int n, int max_sweeps, void* ws) {
 	return p;
 }
 
-constexpr int kMaxSweeps = 16;
+constexpr int kMaxSweeps = 32;
 
 }  // namespace
 

@@ -59,8 +59,8 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 		const int nrow = rb - ra;
 		const long long start = (long long)lo & ~7LL;
 		for (long long u = start + 8LL * tid; u < hi; u += 8LL * blockDim.x) {
-			short c8[8];
-			float v8[8];
+			__align__(16) short c8[8];
+			__align__(16) float v8[8];
 			if (u + 8 <= nnz_total) {
 				*reinterpret_cast<int4*>(c8) = __ldg(reinterpret_cast<const int4*>(col + u));
 				*reinterpret_cast<float4*>(v8) = __ldg(reinterpret_cast<const float4*>(val + u));

@@ -227,7 +227,6 @@ class Fast_Higashi_core:
 			off = sum(sizes_all[:dist.get_rank(self.group)])
 			meta = meta_all[off:off + self.num_cell].contiguous()
 			# A, B must be identical on every rank
-			for a in A_list: pass
 		else:
 			meta = meta_all
 		self.A_dev = [a.to(dev) for a in A_list]
@@ -303,11 +302,14 @@ class Fast_Higashi_core:
 			for b, g in enumerate(ds.geoms):
 				ldw = pad4(g.w)
 				P = g.nb * ldw
+				t = self._tic()
 				X = self._impute_good(ci, b, do_conv, do_rwr, do_col)
+				self._toc("rwr", t)
 				if first_iter:
 					_lib.check(_lib.lib().fh_sqnorm_accum(X.data_ptr(), 1, Cn * P, Cn * P, stats[nch + ci:].data_ptr(),
 					                                      _lib.stream_ptr()))
 				# P1: T1 = X^T C ; temp_i = (T1_i diag(A_i)) B^T
+				t = self._tic()
 				T1 = torch.empty(P, r, dtype=torch.float32, device=dev)
 				_lib.gemm(X, Cc, T1, P, r, Cn, (1, P), (r, 1), r, dtype=gd)
 				self._allreduce(T1)
@@ -315,7 +317,9 @@ class Fast_Higashi_core:
 				Arows = A[g.row0:g.row0 + g.nb]
 				_lib.gemm(T1, B, temp, ldw, r, r, (r, 1), (1, r), r, batch=g.nb, batch_strides=(ldw * r, 0, ldw * r),
 				          kscale=Arows, kscale_batch=r)
+				self._toc("p1_mttkrp", t)
 				# P2: U_i = polar(temp_i)
+				t = self._tic()
 				key = (ci, b)
 				eig = self._eig.get(key)
 				warm = eig is not None and self.warm_polar
@@ -325,6 +329,8 @@ class Fast_Higashi_core:
 				U = self.projection_dev[ci][b]
 				_, ssum, _ = polar_batched(temp, ldw, r, r, out=U, eig_state=eig, warm=warm)
 				stats[ci] += ssum.sum()
+				self._toc("polar_bins", t)
+				t = self._tic()
 				# P3: W_i = ((U_i B) diag(A_i)) D^T ; M += X W
 				UB = T1  # reuse
 				_lib.gemm(U, B, UB, P, r, r, (r, 1), (r, 1), r)
@@ -332,12 +338,15 @@ class Fast_Higashi_core:
 				_lib.gemm(UB, D, W, ldw, R, r, (r, 1), (1, r), R, batch=g.nb, batch_strides=(ldw * r, 0, ldw * R),
 				          kscale=Arows, kscale_batch=r)
 				_lib.gemm(X, W, MT, Cn, R, P, (P, 1), (R, 1), R, beta=1.0, dtype=gd)
+				self._toc("p3_project", t)
 				del W, T1, temp
 		# P4: V = polar(SVD_term^T) (:483-486)
 		self.last_svd_term_T = MT
+		t = self._tic()
 		Vn = polar_tall(MT, self.group)
 		_lib.check(_lib.lib().fh_dot_accum(Vn.data_ptr(), MT.data_ptr(), Cn, R, R, R, stats[2 * nch:].data_ptr(),
 		                                   _lib.stream_ptr()))
+		self._toc("polar_cells", t)
 		self.meta_embedding = Vn
 		# P5: Y_i = U_i^T X_i V (:488-529)
 		for ci, ds in enumerate(self.schic):
@@ -347,11 +356,13 @@ class Fast_Higashi_core:
 				ldw = pad4(g.w)
 				P = g.nb * ldw
 				X = self._impute_good(ci, b, do_conv, do_rwr, do_col)
+				t = self._tic()
 				Z = torch.empty(P, R, dtype=torch.float32, device=dev)
 				_lib.gemm(X, Vn, Z, P, R, Cn, (1, P), (R, 1), R, dtype=gd)
 				U = self.projection_dev[ci][b]
 				Yb = Y[ds.global_slice_bin.start + g.row0: ds.global_slice_bin.start + g.row0 + g.nb]
 				_lib.gemm(U, Z, Yb, r, R, ldw, (1, r), (R, 1), R, batch=g.nb, batch_strides=(ldw * r, ldw * R, r * R))
+				self._toc("p5_tensor", t)
 				del Z
 		for chrom in self.chrom2size:
 			self._allreduce(self.projected_dev[chrom])
@@ -375,10 +386,9 @@ class Fast_Higashi_core:
 
 	# ------------------------------------------------------------------------------------------
 	# parafac2_intergrative.py:544-740
-	def fit(self, schic, size_ratio=0.3, n_iter_max=2000, n_iter_parafac=5, do_conv=True, do_rwr=False,
-	        do_col=False, tol=1e-8, size_list=None, gpu_id=None, verbose=True, run_init=True, state=None):
-		self.gpu_id = gpu_id
-		self.verbose = verbose
+	def prepare(self, schic, size_ratio=0.3, do_conv=True, do_rwr=False, do_col=False, size_list=None,
+	            run_init=True, state=None):
+		"""Everything `fit` does before its sweep loop (:551-632)."""
 		dev, R = self.device, self.rank
 		if self.device.type != "cuda":
 			raise _lib.FHError("call .to('cuda') first; fasthigashi_b200 has no CPU path")
@@ -396,61 +406,105 @@ class Fast_Higashi_core:
 		self._X, self._eig = {}, {}
 		self.invalidate_cache()
 		self.n_rwr_passes = 0
-		rec_error_core_norm = self._core_norms()
-		rec_errors, rec_errors_total = [], []
-		self.re_trace, self.sweep_seconds = [], []
-		rec_error_tensor_norm = None
+		self._core_norm = self._core_norms()
+		self._xnorm = None
+		self.re_trace, self.sweep_seconds, self.loss_terms = [], [], []
+		self._rec_errors = []
+
+	def sweep_once(self, n_iter_parafac=1):
+		"""One iteration of the reference's outer loop (:635-737): projections + V update + projected
+		tensor, inner CP-ALS per chromosome, loss bookkeeping. Returns (re, per-chromosome re)."""
+		do_conv, do_rwr, do_col = self._flags
 		dist = self._dist()
+		start_time = time.time()
+		if self._xnorm is None:
+			_, _, x_U, x_V, self._xnorm = self.update_meta_embedding_interactions(
+				do_conv=do_conv, do_rwr=do_rwr, do_col=do_col, first_iter=True)
+		else:
+			_, _, x_U, x_V = self.update_meta_embedding_interactions(do_conv=do_conv, do_rwr=do_rwr, do_col=do_col)
+		xnorm, core = self._xnorm, self._core_norm
+		self.loss_terms.append(dict(xnorm=xnorm.ravel().copy(), core=core.ravel().copy(), x_U=x_U.ravel().copy(), x_V=x_V))
+		err_U = xnorm + core - 2 * x_U
+		err_V = xnorm.sum() + core.sum() - 2 * x_V
+		# inner CP-ALS per chromosome (:674-695)
+		t = self._tic()
+		for chrom, ids in self.chrom2id.items():
+			if len(ids) == 1:
+				A = self.A_dev[ids[0]]
+			else:
+				A = torch.cat([self.A_dev[i] for i in ids], 0).contiguous()
+			cp_als_(self.projected_dev[chrom], A, self.B_dict[chrom], self.D_dict[chrom], n_iter_parafac)
+			if len(ids) > 1:
+				for i in ids:
+					self.A_dev[i].copy_(A[self.schic[i].global_slice_bin])
+			if dist is not None:  # keep replicas bit-identical (split-K atomics are unordered)
+				src = dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0
+				for i in ids:
+					dist.broadcast(self.A_dev[i], src=src, group=self.group)
+				dist.broadcast(self.B_dict[chrom], src=src, group=self.group)
+				dist.broadcast(self.D_dict[chrom], src=src, group=self.group)
+		self._core_norm = self._core_norms()
+		self._toc("cp_als", t)
+		rec_error = float(np.sqrt(err_V) / np.sqrt(xnorm.sum()))
+		self.re_trace.append(rec_error)
+		self._rec_errors.append(np.sqrt(err_U.ravel()) / np.sqrt(xnorm.ravel()))
+		self.sweep_seconds.append(time.time() - start_time)
+		return rec_error, self._rec_errors[-1]
+
+	def fit(self, schic, size_ratio=0.3, n_iter_max=2000, n_iter_parafac=5, do_conv=True, do_rwr=False,
+	        do_col=False, tol=1e-8, size_list=None, gpu_id=None, verbose=True, run_init=True, state=None):
+		self.gpu_id = gpu_id
+		self.verbose = verbose
+		self.prepare(schic, size_ratio, do_conv, do_rwr, do_col, size_list, run_init, state)
 		for iteration in range(n_iter_max):
 			if (iteration % 10) == 0 and iteration > 0 and n_iter_parafac < 10:
 				n_iter_parafac += 1
 			self._log("Starting iteration", iteration)
-			start_time = time.time()
-			if rec_error_tensor_norm is None:
-				_, _, x_U, x_V, rec_error_tensor_norm = self.update_meta_embedding_interactions(
-					do_conv=do_conv, do_rwr=do_rwr, do_col=do_col, first_iter=True)
-				norm_tensor = np.sqrt(rec_error_tensor_norm).reshape(-1)
-				norm_tensor_all = float(np.linalg.norm(norm_tensor))
-			else:
-				_, _, x_U, x_V = self.update_meta_embedding_interactions(do_conv=do_conv, do_rwr=do_rwr, do_col=do_col)
-			rec_error_by_block_U = rec_error_tensor_norm + rec_error_core_norm - 2 * x_U
-			rec_error_V = rec_error_tensor_norm.sum() + rec_error_core_norm.sum() - 2 * x_V
-			# inner CP-ALS per chromosome (:674-695)
-			for chrom, ids in self.chrom2id.items():
-				if len(ids) == 1:
-					A = self.A_dev[ids[0]]
-				else:
-					A = torch.cat([self.A_dev[i] for i in ids], 0).contiguous()
-				cp_als_(self.projected_dev[chrom], A, self.B_dict[chrom], self.D_dict[chrom], n_iter_parafac)
-				if len(ids) > 1:
-					for i in ids:
-						self.A_dev[i].copy_(A[self.schic[i].global_slice_bin])
-				if dist is not None:  # keep replicas bit-identical (split-K atomics are unordered)
-					src = dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0
-					for i in ids:
-						dist.broadcast(self.A_dev[i], src=src, group=self.group)
-					dist.broadcast(self.B_dict[chrom], src=src, group=self.group)
-					dist.broadcast(self.D_dict[chrom], src=src, group=self.group)
-			rec_error_core_norm = self._core_norms()
-			rec_error = np.sqrt(rec_error_V.sum()) / norm_tensor_all
-			rec_errors_total.append(rec_error)
-			self.re_trace.append(float(rec_error))
-			rec_errors.append(np.sqrt(rec_error_by_block_U.ravel()) / norm_tensor)
-			self.sweep_seconds.append(time.time() - start_time)
+			rec_error, _ = self.sweep_once(n_iter_parafac)
+			took = self.sweep_seconds[-1]
 			if iteration >= 1:
-				differences = (rec_errors[-2] ** 2 - rec_errors[-1] ** 2) / (rec_errors[-2] ** 2)
-				total_differences = (rec_errors_total[-2] ** 2 - rec_errors_total[-1] ** 2) / rec_errors_total[-2] ** 2
+				e, t = self._rec_errors, self.re_trace
+				differences = (e[-2] ** 2 - e[-1] ** 2) / (e[-2] ** 2)
+				total_differences = (t[-2] ** 2 - t[-1] ** 2) / t[-2] ** 2
 				self._log(f"PARAFAC2 re={rec_error:.3f} {total_differences:.2e} "
 				          f"variation min{differences.min().item():.1e} at chrom {differences.argmin().item():d}, "
 				          f"max{differences.max().item():.1e} at chrom {differences.argmax().item():d}",
-				          f"takes {time.time() - start_time:.1f}s")
+				          f"takes {took:.1f}s")
 				if iteration >= 3 and tol > 0 and (total_differences < tol or differences.max() < tol * 2):
 					self._log("converged in {} iterations.".format(iteration))
 					break
 			else:
-				self._log(f"PARAFAC2 re={rec_error:.3f} takes {time.time() - start_time:.1f}s")
+				self._log(f"PARAFAC2 re={rec_error:.3f} takes {took:.1f}s")
 		self._export()
 		return self
+
+	# optional per-stage device timers (bench.py): CUDA events on the current stream
+	def enable_timers(self, on=True):
+		self.timers = {} if on else None
+		self._pending = []
+
+	def _tic(self):
+		if getattr(self, "timers", None) is None:
+			return None
+		e = torch.cuda.Event(enable_timing=True)
+		e.record()
+		return e
+
+	def _toc(self, name, start):
+		if start is None:
+			return
+		e = torch.cuda.Event(enable_timing=True)
+		e.record()
+		self._pending.append((name, start, e))
+
+	def collect_timers(self):
+		"""ms per stage since the last call (synchronises)."""
+		torch.cuda.synchronize()
+		out = {}
+		for name, a, b in getattr(self, "_pending", []):
+			out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+		self._pending = []
+		return out
 
 	def _export(self):
 		"""Reference-shaped attributes: A_list on the host, projection_list[ci][b] (nb, w, r) on the

@@ -8,6 +8,7 @@
     ranks when cell-sharded, inverse square root by coupled Newton-Schulz (`fh_inv_sqrt_spd`).
 """
 import ctypes as C
+import os
 import torch
 from . import _lib
 
@@ -27,7 +28,7 @@ def polar_batched(T, rows, cols, ld, out=None, eig_state=None, warm=False, want_
 	ws = _lib.workspace(lib.fh_polar_workspace_bytes(batch, rows, cols), dev, "polar")
 	_lib.check(lib.fh_polar_batched(T.data_ptr(), U.data_ptr(), batch, rows, cols, ld, T.stride(0), ssum.data_ptr(),
 	                                None if sig is None else sig.data_ptr(),
-	                                None if eig_state is None else eig_state.data_ptr(), int(bool(warm)), 0,
+	                                None if eig_state is None else eig_state.data_ptr(), int(bool(warm)), int(os.environ.get("FH_POLAR_SWEEPS", "0")),
 	                                ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
 	return U, ssum, sig
 

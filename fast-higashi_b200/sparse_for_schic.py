@@ -167,7 +167,7 @@ class Chrom_Dataset:
 				raise ValueError("block nnz exceeds int32")
 			self.rowptr.append(rp.int())
 			self.col.append(lcol[lo:hi].short())
-			self.val.append(val[lo:hi].contiguous())
+			self.val.append(val[lo:hi].clone())  # own allocation: the kernels need 16-byte aligned bases
 		self.device = dev
 
 	@classmethod
@@ -231,7 +231,7 @@ class Chrom_Dataset:
 		new.rowptr, new.col, new.val = [], [], []
 		for b in range(len(self.geoms)):
 			rp, c, v = self.cell_range_csr(b, cell_start, cell_stop)
-			new.rowptr.append(rp.contiguous()); new.col.append(c.contiguous()); new.val.append(v.contiguous())
+			new.rowptr.append(rp.clone()); new.col.append(c.clone()); new.val.append(v.clone())
 		good = [slice(c, min(c + new.bs_cell, new.num_cell)) for c in range(0, new.num_cell, new.bs_cell)]
 		bad = [slice(c, min(c + new.bs_cell, n)) for c in range(new.num_cell, n, new.bs_cell)]
 		new.cell_slice_list = good + bad

@@ -337,7 +337,7 @@ class OracleCore:
 		elif run_init:
 			self.init_params(schic, do_conv, do_rwr, do_col)
 		core = self.core_norms(schic)
-		self.re_trace, per_chrom = [], []
+		self.re_trace, per_chrom, self.loss_terms = [], [], []
 		xnorm = None
 		for it in range(n_iter_max):
 			if it % 10 == 0 and it > 0 and n_iter_parafac < 10:
@@ -345,6 +345,7 @@ class OracleCore:
 			x_U, x_V, xn = self.sweep(schic, do_conv, do_rwr, do_col, want_norm=xnorm is None)
 			if xnorm is None:
 				xnorm = xn
+			self.loss_terms.append(dict(xnorm=xnorm.copy(), core=core.copy(), x_U=x_U.copy(), x_V=x_V))
 			err_U = xnorm + core - 2 * x_U
 			err_V = xnorm.sum() + core.sum() - 2 * x_V
 			for ci, ds in enumerate(schic):
