@@ -30,7 +30,7 @@ class RwrDesc(C.Structure):
 	            ("ncell", C.c_int), ("use_tensor_cores", C.c_int), ("nnz", C.c_longlong)]
 
 
-EXPORTS = ["fh_last_error", "fh_version", "fh_launch_count", "fh_gemm_batched", "fh_rwr_workspace_bytes",
+EXPORTS = ["fh_last_error", "fh_version", "fh_launch_count", "fh_tc_fallback_count", "fh_gemm_batched", "fh_rwr_workspace_bytes",
            "fh_rwr_batched", "fh_densify", "fh_rwr_dense", "fh_colsum_accum", "fh_avgpool", "fh_sqnorm_accum",
            "fh_dot_accum", "fh_polar_workspace_bytes", "fh_polar_batched", "fh_inv_sqrt_spd",
            "fh_cp_als_workspace_bytes", "fh_cp_als", "fh_cp_core_sqnorm"]
@@ -51,6 +51,7 @@ def lib():
 		L = C.CDLL(LIB_PATH)
 		L.fh_last_error.restype = C.c_char_p
 		L.fh_launch_count.restype = C.c_longlong
+		L.fh_tc_fallback_count.restype = C.c_longlong
 		for n in ["fh_rwr_workspace_bytes", "fh_polar_workspace_bytes", "fh_cp_als_workspace_bytes"]:
 			getattr(L, n).restype = C.c_size_t
 		L.fh_rwr_workspace_bytes.argtypes = [C.POINTER(RwrDesc)]
@@ -65,7 +66,7 @@ def lib():
 		L.fh_avgpool.argtypes = [vp, ci, ci, ci, ci, ll, ci, vp, ll, vp]
 		L.fh_sqnorm_accum.argtypes = [vp, ll, ll, ll, vp, vp]
 		L.fh_dot_accum.argtypes = [vp, vp, ll, ll, ll, ll, vp, vp]
-		L.fh_polar_batched.argtypes = [vp, vp, ci, ci, ci, ll, ll, vp, vp, vp, ci, ci, vp, sz, vp]
+		L.fh_polar_batched.argtypes = [vp, vp, ci, ci, ci, ll, ll, vp, vp, ci, vp, sz, C.POINTER(ci), vp]
 		L.fh_inv_sqrt_spd.argtypes = [vp, vp, ci, vp, sz, C.POINTER(ci), vp]
 		L.fh_cp_als.argtypes = [vp, ci, ci, ci, vp, vp, vp, ci, vp, sz, C.POINTER(C.c_double), vp]
 		L.fh_cp_core_sqnorm.argtypes = [vp, ci, vp, vp, ci, ci, vp, vp, vp]

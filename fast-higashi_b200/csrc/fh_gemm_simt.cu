@@ -145,6 +145,7 @@ int launch(GemmP p, const void* A, const void* B, void* C, cudaStream_t st) {
 }  // namespace
 
 int fh_gemm_tc(const fh_gemm_desc* d, const float* A, const float* B, float* C, void* stream);
+extern "C" void fh_count_tc_fallback(void);
 
 extern "C" int fh_gemm_batched(const fh_gemm_desc* d, const void* A, const void* B, void* C, void* stream) {
 	FH_CHECK_ARG(d != nullptr, "fh_gemm_batched: null descriptor");
@@ -166,7 +167,14 @@ extern "C" int fh_gemm_batched(const fh_gemm_desc* d, const void* A, const void*
 		case FH_GEMM_F64: return launch<double, double, double, double>(p, A, B, C, st);
 		case FH_GEMM_F32xF64_F32: return launch<float, double, float, double>(p, A, B, C, st);
 		case FH_GEMM_F64xF32_F32: return launch<double, float, float, double>(p, A, B, C, st);
-		case FH_GEMM_TF32X3: return fh_gemm_tc(d, (const float*)A, (const float*)B, (float*)C, stream);
+		case FH_GEMM_TF32X3: {
+			// tensor-core path; operands TMA cannot describe (odd strides, k-scaling) run on the CUDA-core
+			// fp32 kernel instead - still on the GPU, still exact fp32, counted in fh_tc_fallback_count()
+			int rc = fh_gemm_tc(d, (const float*)A, (const float*)B, (float*)C, stream);
+			if (rc != FH_ERR_UNSUPPORTED) return rc;
+			fh_count_tc_fallback();
+			return launch<float, float, float, float>(p, A, B, C, st);
+		}
 		default: break;
 	}
 	fh_set_error("fh_gemm_batched: unknown dtype %d", d->dtype);

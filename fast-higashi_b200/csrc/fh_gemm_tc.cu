@@ -1,7 +1,377 @@
-// tcgen05 3xTF32 GEMM (placeholder until the tensor-core kernel lands; never silently falls back).
+// fp32-in / fp32-out batched GEMM on the 5th-generation tensor cores (tcgen05, sm_100a) with the
+// 3xTF32 split:  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi,  a_hi = tf32(a), a_lo = tf32(a - a_hi),
+// fp32 accumulation in TMEM. Used for every large contraction of the hot path (RWR: A A^T, Q P, Q A;
+// sweep: X^T C, X W, X^T V) - the reference's torch.bmm / matmul call sites
+// (partial_rwr.py:85,116,138; parafac2_intergrative.py:381-383,429-430,522-524).
+//
+// One CTA computes one 128 x 128 output tile of one batch item:
+//   warp 0      TMA producer: raw fp32 operand tiles (K-major or MN-major, 128-byte swizzle) from
+//               HBM/L2 into a 3-stage shared-memory ring (cp.async.bulk.tensor, mbarrier tx-count)
+//   warps 4-7   splitters: turn each landed tile into its hi / lo TF32 halves in place (+ a second
+//               buffer), fence to the async proxy, hand the stage to the MMA warp
+//   warp 1      MMA issuer: one thread issues 3 x 4 tcgen05.mma.kind::tf32 (M=128, N=128, K=8) per
+//               stage; tcgen05.commit releases the stage / publishes the accumulator
+//   warps 8-15  drain + epilogue. The tensor core accumulates with truncation, so a long K run drifts
+//               by ~7e-9*K (measured). The accumulator is therefore double-buffered in TMEM and
+//               drained every CHUNK_KB k-blocks (K=128) into fp32 registers with round-to-nearest adds
+//               (tcgen05.ld), which keeps the error at the fp32 level for any K; the final sum goes
+//               through alpha/beta/diag/column-scale and coalesced stores
+//   warp 2      TMEM allocation (256 columns: two 128-column accumulators)
+#include <cuda.h>
 #include "fh_common.cuh"
 #include "../../include/fh_b200.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;       // tile (BK fp32 = one 128-byte swizzle row)
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;          // 16 KB per operand tile
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NTHREADS = 512;
+constexpr int CHUNK_KB = 4;                      // k-blocks accumulated in TMEM before a drain (K = 128)
+
+struct TcP {
+	int M, N, K, batch;
+	long long ldc, batch_c;
+	float alpha, beta, diag;
+	int epilogue;
+	const float* cscale; long long cscale_batch; int cscale_recip;
+	int a_bcast, b_bcast;  // operand shared by all batch items (batch stride 0)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"LAB_WAIT:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra LAB_DONE;\n"
+		"bra LAB_WAIT;\n"
+		"LAB_DONE:\n"
+		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+	asm volatile(
+		"cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+			smem_u32(dst)),
+		"l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+		: "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+	// cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
+	// layout type [61,64): SWIZZLE_128B = 2 (K-major), SWIZZLE_128B_BASE32B = 1 (the only MN-major
+	// layout tf32 operands have: 32-byte chunks swizzled inside 128-byte rows, 4-row atoms)
+	uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+	d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+	d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+	d |= 1ull << 46;
+	d |= (uint64_t)layout_type << 61;
+	return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"setp.ne.b32 p, %4, 0;\n"
+		"tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+		"}\n" ::"r"(tmem_d),
+		"l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+		: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+	uint32_t r;
+	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+	return r;
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcP p,
+               float* __restrict__ C) {
+	extern __shared__ uint8_t smem_raw[];
+	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+	uint64_t* raw_full = bars;                 // TMA landed            (count 1 + tx)
+	uint64_t* split_full = bars + STAGES;      // hi/lo written         (count 4: one per splitter warp)
+	uint64_t* empty = bars + 2 * STAGES;       // MMAs of the stage done (count 1, tcgen05.commit)
+	uint64_t* acc_full = bars + 3 * STAGES;    // [2] accumulator chunk complete (count 1, tcgen05.commit)
+	uint64_t* acc_empty = bars + 3 * STAGES + 2;  // [2] accumulator drained   (count 8: one per drain warp)
+	uint32_t* tmem_holder = (uint32_t*)(bars + 3 * STAGES + 4);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, bz = blockIdx.z;
+	const int nkb = (p.K + BK - 1) / BK;
+
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < STAGES; ++s) {
+			mbar_init(&raw_full[s], 1);
+			mbar_init(&split_full[s], 4);
+			mbar_init(&empty[s], 1);
+		}
+		mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+		mbar_init(&acc_empty[0], 8); mbar_init(&acc_empty[1], 8);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 0 && lane == 0) {
+		asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+		asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+	}
+	if (warp == 2) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(2 * BN) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t tmem_acc = *tmem_holder;
+
+	if (warp == 0) {
+		// ------------------------------------------------------------------ TMA producer
+		if (lane == 0) {
+			const int za = p.a_bcast ? 0 : bz, zb = p.b_bcast ? 0 : bz;
+			for (int kb = 0; kb < nkb; ++kb) {
+				const int s = kb % STAGES;
+				const uint32_t ph = (kb / STAGES) & 1;
+				mbar_wait(&empty[s], ph ^ 1);
+				uint8_t* st = smem + s * STAGE_BYTES;
+				mbar_expect_tx(&raw_full[s], 2 * TILE_BYTES);
+				const int k0 = kb * BK;
+				if (A_MN) {  // global (K rows x M contiguous): four 32-wide boxes of BK rows
+#pragma unroll
+					for (int j = 0; j < BM / 32; ++j) tma_load_3d(st + j * (BK * 128), &tmA, &raw_full[s], m0 + 32 * j, k0, za);
+				} else {     // global (M rows x K contiguous): one box of 32 x 128
+					tma_load_3d(st, &tmA, &raw_full[s], k0, m0, za);
+				}
+				uint8_t* sb = st + 2 * TILE_BYTES;
+				if (B_MN) {
+#pragma unroll
+					for (int j = 0; j < BN / 32; ++j) tma_load_3d(sb + j * (BK * 128), &tmB, &raw_full[s], n0 + 32 * j, k0, zb);
+				} else {
+					tma_load_3d(sb, &tmB, &raw_full[s], k0, n0, zb);
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ------------------------------------------------------------------ MMA issuer
+		if (lane == 0) {
+			// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b_format TF32 [7,10)/[10,13)=2,
+			// a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+			const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+			                       ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+			// K-major tile (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO); a K=8 step = +32 B.
+			// MN-major tile (SWIZZLE_128B_BASE32B): k rows of 128 B (32 MN elements), 4-row atoms 512 B apart
+			// (SBO), 32-element MN groups BK*128 B apart (LBO); a K=8 step = 8 rows = +1024 B.
+			const uint32_t a_lbo = A_MN ? BK * 128 : 16, a_sbo = A_MN ? 512 : 1024, a_step = A_MN ? 1024 : 32, a_lt = A_MN ? 1 : 2;
+			const uint32_t b_lbo = B_MN ? BK * 128 : 16, b_sbo = B_MN ? 512 : 1024, b_step = B_MN ? 1024 : 32, b_lt = B_MN ? 1 : 2;
+			for (int kb = 0; kb < nkb; ++kb) {
+				const int s = kb % STAGES;
+				const uint32_t ph = (kb / STAGES) & 1;
+				const int chunk = kb / CHUNK_KB, cb = chunk & 1;
+				if (kb % CHUNK_KB == 0) {  // new chunk: its accumulator must have been drained
+					mbar_wait(&acc_empty[cb], ((chunk >> 1) & 1) ^ 1);
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				}
+				const uint32_t acc = tmem_acc + (uint32_t)(cb * BN);
+				mbar_wait(&split_full[s], ph);
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES;
+				const uint32_t b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
+#pragma unroll
+				for (int k = 0; k < BK / 8; ++k) {
+					const uint64_t dah = make_desc(a_hi + k * a_step, a_lbo, a_sbo, a_lt), dal = make_desc(a_lo + k * a_step, a_lbo, a_sbo, a_lt);
+					const uint64_t dbh = make_desc(b_hi + k * b_step, b_lbo, b_sbo, b_lt), dbl = make_desc(b_lo + k * b_step, b_lbo, b_sbo, b_lt);
+					umma_tf32(acc, dal, dbh, idesc, ((kb % CHUNK_KB) | k) ? 1u : 0u);  // small terms first
+					umma_tf32(acc, dah, dbl, idesc, 1u);
+					umma_tf32(acc, dah, dbh, idesc, 1u);
+				}
+				umma_commit(&empty[s]);
+				if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(&acc_full[cb]);
+			}
+		}
+	} else if (warp >= 4 && warp < 8) {
+		// ------------------------------------------------------------------ splitters
+		const int t = threadIdx.x - 128;  // 0..127
+		for (int kb = 0; kb < nkb; ++kb) {
+			const int s = kb % STAGES;
+			const uint32_t ph = (kb / STAGES) & 1;
+			mbar_wait(&raw_full[s], ph);
+			uint8_t* st = smem + s * STAGE_BYTES;
+#pragma unroll
+			for (int op = 0; op < 2; ++op) {
+				float4* hi = (float4*)(st + op * 2 * TILE_BYTES);
+				float4* lo = (float4*)(st + op * 2 * TILE_BYTES + TILE_BYTES);
+#pragma unroll
+				for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+					float4 v = hi[t + 128 * i];
+					uint4 h, l;
+					h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+					l.x = to_tf32(v.x - __uint_as_float(h.x)); l.y = to_tf32(v.y - __uint_as_float(h.y));
+					l.z = to_tf32(v.z - __uint_as_float(h.z)); l.w = to_tf32(v.w - __uint_as_float(h.w));
+					((uint4*)hi)[t + 128 * i] = h;
+					((uint4*)lo)[t + 128 * i] = l;
+				}
+			}
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&split_full[s]);
+		}
+	} else if (warp >= 8) {
+		// ------------------------------------------------------------------ drain + epilogue
+		const int q = warp & 3;             // TMEM lane quarter of this warp (rows 32q .. 32q+31)
+		const int h = (warp - 8) >> 2;      // column half (64 columns)
+		float sum[64];
+#pragma unroll
+		for (int j = 0; j < 64; ++j) sum[j] = 0.f;
+		const int nchunk = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+		for (int chunk = 0; chunk < nchunk; ++chunk) {
+			const int cb = chunk & 1;
+			mbar_wait(&acc_full[cb], (chunk >> 1) & 1);
+			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+			for (int c = 0; c < 2; ++c) {
+				uint32_t v[32];
+				const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * BN + h * 64 + c * 32);
+				asm volatile(
+					"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+					"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+					"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+					: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+					  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+					  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+					  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+					: "r"(taddr));
+				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+				for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(v[j]);
+			}
+			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&acc_empty[cb]);
+		}
+		// all MMAs, TMA loads and splits are complete here: the stage ring is free for the transposes
+		float* Cb = C + (long long)bz * p.batch_c;
+		const float* cs = p.cscale ? p.cscale + (long long)bz * p.cscale_batch : nullptr;
+		float* tile = (float*)(smem + (warp - 8) * (32 * 33 * 4));
+#pragma unroll
+		for (int c = 0; c < 2; ++c) {
+			__syncwarp();
+#pragma unroll
+			for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = sum[c * 32 + j];
+			__syncwarp();
+			const int n = n0 + h * 64 + c * 32 + lane;
+			const bool ncol = n < p.N;
+			float csv = 1.f;
+			if (cs && ncol) csv = cs[n];
+#pragma unroll 4
+			for (int rr = 0; rr < 32; ++rr) {
+				const int r = m0 + q * 32 + rr;
+				if (r < p.M && ncol) {
+					float x = p.alpha * tile[rr * 33 + lane];
+					if (p.epilogue == FH_EPI_DIAG_ADD && r == n) x += p.diag;
+					if (cs) x = p.cscale_recip ? x / csv : x * csv;
+					float* cp = Cb + (long long)r * p.ldc + n;
+					if (p.beta != 0.f) x += p.beta * *cp;
+					*cp = x;
+				}
+			}
+		}
+	}
+	__syncthreads();
+	if (warp == 2) {
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(2 * BN) : "memory");
+	}
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode() {
+	static EncodeFn fn = nullptr;
+	if (!fn) {
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+			fn = (EncodeFn)p;
+	}
+	return fn;
+}
+
+// operand viewed as (rows x contiguous) with an optional batch dimension
+bool make_map(CUtensorMap* m, const float* base, long long contig_extent, long long rows, long long row_stride,
+              int batch, long long batch_stride, int box_contig, int box_rows, bool mn_major) {
+	EncodeFn enc = get_encode();
+	if (!enc) return false;
+	cuuint64_t dims[3] = {(cuuint64_t)contig_extent, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
+	long long bs = batch_stride > 0 ? batch_stride : row_stride * rows;
+	cuuint64_t strides[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)bs * 4};
+	cuuint32_t box[3] = {(cuuint32_t)box_contig, (cuuint32_t)box_rows, 1};
+	cuuint32_t es[3] = {1, 1, 1};
+	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                 mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return r == CUDA_SUCCESS;
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+
+// returns FH_OK, or FH_ERR_UNSUPPORTED when the operands cannot be described to TMA (caller decides)
 int fh_gemm_tc(const fh_gemm_desc* d, const float* A, const float* B, float* C, void* stream) {
-	fh_set_error("FH_GEMM_TF32X3 not built into this library");
-	return FH_ERR_UNSUPPORTED;
+	if (d->M <= 0 || d->N <= 0 || d->batch <= 0) return FH_OK;
+	const bool a_mn = d->sa_m == 1 && d->sa_k != 1, b_mn = d->sb_n == 1 && d->sb_k != 1;
+	const long long a_row = a_mn ? d->sa_k : d->sa_m, b_row = b_mn ? d->sb_k : d->sb_n;
+	const bool a_bc = d->batch > 1 && d->batch_a == 0, b_bc = d->batch > 1 && d->batch_b == 0;
+	if (d->kscale || d->K <= 0 || (a_row & 3) || (b_row & 3) || !aligned16(A) || !aligned16(B) ||
+	    (d->batch > 1 && !a_bc && (d->batch_a & 3)) || (d->batch > 1 && !b_bc && (d->batch_b & 3)) ||
+	    (d->sa_m == 1 && d->sa_k == 1) || (d->sb_k == 1 && d->sb_n == 1) || d->batch > 65535) {
+		fh_set_error("fh_gemm_tc: operands not TMA-describable (strides must be multiples of 4 floats, bases 16-byte aligned)");
+		return FH_ERR_UNSUPPORTED;
+	}
+	CUtensorMap ta, tb;
+	bool ok;
+	if (a_mn) ok = make_map(&ta, A, d->M, d->K, a_row, a_bc ? 1 : d->batch, d->batch_a, 32, BK, true);
+	else ok = make_map(&ta, A, d->K, d->M, a_row, a_bc ? 1 : d->batch, d->batch_a, BK, BM, false);
+	if (ok) {
+		if (b_mn) ok = make_map(&tb, B, d->N, d->K, b_row, b_bc ? 1 : d->batch, d->batch_b, 32, BK, true);
+		else ok = make_map(&tb, B, d->K, d->N, b_row, b_bc ? 1 : d->batch, d->batch_b, BK, BN, false);
+	}
+	if (!ok) {
+		fh_set_error("fh_gemm_tc: cuTensorMapEncodeTiled failed");
+		return FH_ERR_UNSUPPORTED;
+	}
+	TcP p;
+	p.M = d->M; p.N = d->N; p.K = d->K; p.batch = d->batch;
+	p.ldc = d->ldc; p.batch_c = d->batch_c;
+	p.alpha = (float)d->alpha; p.beta = (float)d->beta; p.diag = (float)d->diag; p.epilogue = d->epilogue;
+	p.cscale = d->cscale; p.cscale_batch = d->cscale_batch; p.cscale_recip = d->cscale_recip;
+	p.a_bcast = a_bc; p.b_bcast = b_bc;
+	dim3 grid(fh_cdiv(d->N, BN), fh_cdiv(d->M, BM), d->batch);
+	cudaStream_t st = (cudaStream_t)stream;
+#define FH_TC_LAUNCH(AM, BMN)                                                                                         \
+	do {                                                                                                              \
+		FH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+		gemm_tc_kernel<AM, BMN><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, p, C);                                    \
+	} while (0)
+	if (a_mn && b_mn) FH_TC_LAUNCH(true, true);
+	else if (a_mn) FH_TC_LAUNCH(true, false);
+	else if (b_mn) FH_TC_LAUNCH(false, true);
+	else FH_TC_LAUNCH(false, false);
+#undef FH_TC_LAUNCH
+	FH_LAUNCH_CHECK();
+	return FH_OK;
 }

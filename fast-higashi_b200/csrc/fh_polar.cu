@@ -3,14 +3,16 @@
 //
 // U = T (T^T T)^{-1/2}. The per-bin matrices have condition numbers 1e4..2e7, so the
 // Gram route only reaches parity in fp64 (measured: fp32 Gram -> 15 % loss error, fp64 Gram -> 3e-6;
-// DESIGN.md "polar"). Pipeline, all batched over the bins of one block:
-//   G = T^T T                     fp64 accumulate           (fh_gemm_batched, FH_GEMM_F32_ACC64)
-//   [warm start: G <- V0^T G V0]  fp64                      (FH_GEMM_F64)
-//   G -> diag(lambda), rotation log   two-sided cyclic Jacobi, G resident in shared memory,
-//                                     parallel (round-robin) ordering, fused 2x2-block updates
-//   V = V0 * rotations            row slabs of V in shared memory, embarrassingly parallel
-//   M = V lambda^{-1/2} V^T       fp64
-//   U = T M                       fp64 accumulate, fp32 out
+// DESIGN.md "polar"). Pipeline, batched over the bins of one block, all fp64:
+//   G = T^T T                          fp64 accumulate      (fh_gemm_batched, FH_GEMM_F32_ACC64)
+//   G = P L L^T P^T                    diagonally pivoted Cholesky, G resident in shared memory
+//   L V = W, columns of W orthogonal   one-sided (Hestenes) Jacobi on the columns of L, parallel
+//                                      round-robin ordering, column pairs held in registers.
+//                                      (Veselic-Hari: L^T L is far closer to diagonal than L L^T, so
+//                                      the strongly graded spectra converge in ~5 sweeps where Jacobi
+//                                      on G itself needed 14-24, measured.) lambda_j = |w_j|^2.
+//   M = sum_j w_j w_j^T lambda_j^{-3/2}  = G^{-1/2}          (FH_GEMM_F64)
+//   U = T M                            fp64 accumulate, fp32 out
 #include "fh_common.cuh"
 #include "../../include/fh_b200.h"
 #include <math.h>
@@ -31,163 +33,166 @@ __device__ __forceinline__ void rr_pair(int m, int s, int t, int& p, int& q) {
 	}
 }
 
-// One CTA per matrix. G (n x n, fp64, symmetric) is copied to shared memory (m x ldg, zero
-// padded to even m), swept until no rotation exceeds the threshold, and written back
-// diagonalised. Every rotation (c, s) is logged: rot[((sweep*(m-1) + step)*(m/2) + t)].
-__global__ void __launch_bounds__(512)
-jacobi_kernel(double* __restrict__ Gall, int n, int max_sweeps, double2* __restrict__ rot_all,
-              int* __restrict__ nsweep_out, double* __restrict__ lam_all) {
+constexpr int JT = 512;       // threads per CTA
+constexpr int MAXPL = 6;      // column elements per lane: n <= 32 * MAXPL = 192 (smem caps n at ~166 anyway)
+
+// One CTA per matrix. Shared memory holds R (n x ld, row-major): first the symmetric G, then its
+// pivoted Cholesky factor as the UPPER triangle R = L^T (row j of R = column j of L), then the rows
+// are orthogonalised in place. Output WT (n x n): row j = w_j * lambda_j^{-3/4} in the ORIGINAL index
+// order, sigma[j] = sqrt(lambda_j), sigma_sum = sum_j sigma_j.
+__global__ void __launch_bounds__(JT)
+chol_jacobi_kernel(const double* __restrict__ Gall, int n, int max_sweeps, double* __restrict__ WTall,
+                   double* __restrict__ sigma_all, double* __restrict__ sigma_sum, int* __restrict__ nsweep_out) {
 	extern __shared__ double sm[];
-	const int m = even_up(n), half = m >> 1;
-	const int ldg = m | 1;
-	double* G = sm;                       // m x ldg
-	double* cs_c = G + (size_t)m * ldg;   // half
-	double* cs_s = cs_c + half;           // half
-	int* pq = (int*)(cs_s + half);        // 2*half
-	__shared__ int s_rotated;
-	const int b = blockIdx.x;
-	double* Gg = Gall + (size_t)b * n * n;
-	double2* rot = rot_all + (size_t)b * max_sweeps * (m - 1) * half;
-	const int tid = threadIdx.x, nt = blockDim.x;
-	for (int i = tid; i < m * ldg; i += nt) {
-		int r = i / ldg, c = i - r * ldg;
-		G[i] = (r < n && c < n) ? Gg[(size_t)r * n + c] : 0.0;
+	const int ld = n | 1;
+	double* R = sm;                          // n x ld
+	double* red = R + (size_t)n * ld;        // 64 doubles scratch
+	int* perm = (int*)(red + 64);            // n
+	__shared__ int s_piv, s_rot;
+	__shared__ double s_val;
+	const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = JT / 32;
+	const double* Gg = Gall + (size_t)b * n * n;
+	for (int i = tid; i < n * n; i += JT) R[(i / n) * ld + (i % n)] = Gg[i];
+	for (int i = tid; i < n; i += JT) perm[i] = i;
+	__syncthreads();
+	// ---------------- diagonally pivoted Cholesky, upper factor in place ----------------
+	double dmax0 = 0.0;
+	for (int k = 0; k < n; ++k) {
+		if (warp == 0) {  // pivot = largest remaining diagonal
+			double best = -1.0; int bi = k;
+			for (int i = k + lane; i < n; i += 32) {
+				double v = R[i * ld + i];
+				if (v > best) { best = v; bi = i; }
+			}
+			for (int o = 16; o > 0; o >>= 1) {
+				double ov = __shfl_xor_sync(0xffffffffu, best, o);
+				int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+				if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+			}
+			if (lane == 0) { s_piv = bi; s_val = best; }
+		}
+		__syncthreads();
+		const int pv = s_piv;
+		if (k == 0) dmax0 = s_val;
+		// rank-revealing stop: once the largest remaining diagonal is below the rounding level of the
+		// fp64 Gram (~n eps lambda_max) the trailing block is noise. It is replaced by thr * I, i.e.
+		// singular values ~1e-7 sigma_max in directions T has no resolvable energy in.
+		if (s_val <= dmax0 * 1e-14 || !(s_val > 0.0)) {
+			const double rt = sqrt(fmax(dmax0 * 1e-14, 1e-300));
+			const int rem0 = n - k;
+			__syncthreads();
+			for (int t = tid; t < rem0 * rem0; t += JT) {
+				int i = k + t / rem0, j = k + t % rem0;
+				R[i * ld + j] = (i == j) ? rt : 0.0;
+			}
+			__syncthreads();
+			break;
+		}
+		if (pv != k) {  // symmetric swap k <-> pv: rows, then columns (earlier factor rows included)
+			for (int j = tid; j < n; j += JT) { double t = R[k * ld + j]; R[k * ld + j] = R[pv * ld + j]; R[pv * ld + j] = t; }
+			__syncthreads();
+			for (int i = tid; i < n; i += JT) { double t = R[i * ld + k]; R[i * ld + k] = R[i * ld + pv]; R[i * ld + pv] = t; }
+			if (tid == 0) { int t = perm[k]; perm[k] = perm[pv]; perm[pv] = t; }
+			__syncthreads();
+		}
+		// a non-positive pivot only appears below the rounding level of G: clamp (noise directions)
+		const double d = fmax(R[k * ld + k], dmax0 * 1e-32 + 1e-300);
+		const double rkk = sqrt(d);
+		__syncthreads();
+		for (int j = k + tid; j < n; j += JT) R[k * ld + j] = (j == k) ? rkk : R[k * ld + j] / rkk;
+		__syncthreads();
+		// trailing update (full square keeps the swaps simple): G[i][j] -= R[k][i] R[k][j]
+		const int rem = n - k - 1;
+		for (int t = tid; t < rem * rem; t += JT) {
+			int i = k + 1 + t / rem, j = k + 1 + t % rem;
+			R[i * ld + j] -= R[k * ld + i] * R[k * ld + j];
+		}
+		__syncthreads();
+	}
+	for (int t = tid; t < n * n; t += JT) {  // strict lower triangle of R is not part of the factor
+		int i = t / n, j = t % n;
+		if (j < i) R[i * ld + j] = 0.0;
 	}
 	__syncthreads();
+	// ---------------- one-sided Jacobi on the rows of R (columns of L) ----------------
+	const int m = even_up(n), half = m >> 1;
+	const double tol = 1e-15 * sqrt((double)n);
 	int sweep = 0;
 	for (; sweep < max_sweeps; ++sweep) {
-		if (tid == 0) s_rotated = 0;
+		if (tid == 0) s_rot = 0;
 		__syncthreads();
+		int rotated = 0;
 		for (int step = 0; step < m - 1; ++step) {
-			if (tid < half) {
-				int p, q;
-				rr_pair(m, step, tid, p, q);
-				double c = 1.0, s = 0.0;
-				if (p < n && q < n) {
-					double a = G[p * ldg + p], bb = G[q * ldg + q], g = G[p * ldg + q];
-					if (fabs(g) > 1e-15 * sqrt(fabs(a * bb)) && g != 0.0) {
-						double theta = (bb - a) / (2.0 * g);
-						double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-						c = 1.0 / sqrt(t * t + 1.0);
-						s = t * c;
-						s_rotated = 1;
-					}
-				}
-				cs_c[tid] = c; cs_s[tid] = s;
-				pq[2 * tid] = p; pq[2 * tid + 1] = q;
-				rot[((size_t)sweep * (m - 1) + step) * half + tid] = make_double2(c, s);
-			}
-			__syncthreads();
-			// G <- J^T G J, one thread per 2x2 block (row pair a, column pair bcol)
-			for (int i = tid; i < half * half; i += nt) {
-				int a = i / half, bc = i - a * half;
-				int pa = pq[2 * a], qa = pq[2 * a + 1], pb = pq[2 * bc], qb = pq[2 * bc + 1];
-				double ca = cs_c[a], sa = cs_s[a], cb = cs_c[bc], sb = cs_s[bc];
-				double g00 = G[pa * ldg + pb], g01 = G[pa * ldg + qb];
-				double g10 = G[qa * ldg + pb], g11 = G[qa * ldg + qb];
-				// columns: col_p' = c col_p - s col_q ; col_q' = s col_p + c col_q
-				double h00 = cb * g00 - sb * g01, h01 = sb * g00 + cb * g01;
-				double h10 = cb * g10 - sb * g11, h11 = sb * g10 + cb * g11;
-				// rows, same form
-				G[pa * ldg + pb] = ca * h00 - sa * h10;
-				G[pa * ldg + qb] = ca * h01 - sa * h11;
-				G[qa * ldg + pb] = sa * h00 + ca * h10;
-				G[qa * ldg + qb] = sa * h01 + ca * h11;
-			}
-			__syncthreads();
-		}
-		if (!s_rotated) break;  // block-uniform: read after the barrier above
-		__syncthreads();
-	}
-	const int done = sweep;  // sweeps [0, done) contain rotations; a rotation-free sweep ends the loop
-	if (tid == 0) nsweep_out[b] = done;
-	for (int i = tid; i < n * n; i += nt) {
-		int r = i / n, c = i - r * n;
-		Gg[i] = G[r * ldg + c];
-	}
-	for (int i = tid; i < n; i += nt) lam_all[(size_t)b * n + i] = G[i * ldg + i];
-}
-
-// V <- V0 * (logged rotations). grid (slabs, batch); RS rows of V per CTA in shared memory.
-constexpr int RS = 32;
-__global__ void __launch_bounds__(256)
-vapply_kernel(const double* __restrict__ V0, double* __restrict__ Vout, int n, int max_sweeps,
-              const double2* __restrict__ rot_all, const int* __restrict__ nsweep) {
-	extern __shared__ double sm[];
-	const int m = even_up(n), half = m >> 1;
-	const int ldv = m | 1;
-	double* V = sm;  // RS x ldv
-	double2* cs = (double2*)(V + (size_t)RS * ldv);
-	const int b = blockIdx.y, r0 = blockIdx.x * RS;
-	const int rows = min(RS, n - r0);
-	const int tid = threadIdx.x, nt = blockDim.x;
-	for (int i = tid; i < RS * ldv; i += nt) {
-		int r = i / ldv, c = i - r * ldv;
-		double v = 0.0;
-		if (r < rows && c < n) v = V0 ? V0[((size_t)b * n + r0 + r) * n + c] : ((r0 + r) == c ? 1.0 : 0.0);
-		V[i] = v;
-	}
-	const double2* rot = rot_all + (size_t)b * max_sweeps * (m - 1) * half;
-	const int ns = nsweep[b];
-	__syncthreads();
-	for (int sw = 0; sw < ns; ++sw) {
-		for (int step = 0; step < m - 1; ++step) {
-			for (int i = tid; i < half; i += nt) cs[i] = rot[((size_t)sw * (m - 1) + step) * half + i];
-			__syncthreads();
-			for (int i = tid; i < rows * half; i += nt) {
-				int r = i / half, t = i - r * half;
-				double2 c_s = cs[t];
-				if (c_s.y == 0.0) continue;
+			for (int t = warp; t < half; t += nw) {
 				int p, q;
 				rr_pair(m, step, t, p, q);
-				double vp = V[r * ldv + p], vq = V[r * ldv + q];
-				V[r * ldv + p] = c_s.x * vp - c_s.y * vq;
-				V[r * ldv + q] = c_s.y * vp + c_s.x * vq;
+				if (p >= n || q >= n) continue;  // the padding player of an odd n
+				if (p > q) { int x = p; p = q; q = x; }
+				double* rp = R + p * ld;
+				double* rq = R + q * ld;
+				double a[MAXPL], c[MAXPL];
+				double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+				for (int e = 0; e < MAXPL; ++e) {
+					int i = lane + 32 * e;
+					a[e] = (i < n) ? rp[i] : 0.0;
+					c[e] = (i < n) ? rq[i] : 0.0;
+					al += a[e] * a[e]; be += c[e] * c[e]; ga += a[e] * c[e];
+				}
+				al = fh_warp_sum(al); be = fh_warp_sum(be); ga = fh_warp_sum(ga);
+				if (fabs(ga) > tol * sqrt(al * be) && ga != 0.0) {
+					double theta = (be - al) / (2.0 * ga);
+					double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+					double cs = 1.0 / sqrt(tt * tt + 1.0), sn = tt * cs;
+#pragma unroll
+					for (int e = 0; e < MAXPL; ++e) {
+						int i = lane + 32 * e;
+						if (i < n) {
+							rp[i] = cs * a[e] - sn * c[e];
+							rq[i] = sn * a[e] + cs * c[e];
+						}
+					}
+					rotated = 1;
+				}
 			}
 			__syncthreads();
 		}
+		if (rotated && lane == 0) s_rot = 1;
+		__syncthreads();
+		const int any = s_rot;
+		__syncthreads();
+		if (!any) break;
 	}
-	for (int i = tid; i < rows * n; i += nt) {
-		int r = i / n, c = i - r * n;
-		Vout[((size_t)b * n + r0 + r) * n + c] = V[r * ldv + c];
-	}
-}
+	if (tid == 0 && nsweep_out) nsweep_out[b] = sweep;
+	// ---------------- lambda_j = |w_j|^2, outputs ----------------
 
-// W = V * diag(lambda_clamped^{-1/4});  sigma_sum[b] = sum sqrt(max(lambda, 0))
-__global__ void __launch_bounds__(256)
-scale_cols_kernel(const double* __restrict__ V, const double* __restrict__ lam, int n,
-                  double* __restrict__ W, double* __restrict__ sigma_sum, double* __restrict__ sigma) {
-	__shared__ double red[32];
-	__shared__ double s_max;
-	const int b = blockIdx.x;
-	const double* l = lam + (size_t)b * n;
-	double mx = 0.0, ss = 0.0;
-	for (int i = threadIdx.x; i < n; i += blockDim.x) {
-		mx = fmax(mx, l[i]);
-		double sv = sqrt(fmax(l[i], 0.0));
-		ss += sv;
-		if (sigma) sigma[(size_t)b * n + i] = sv;
-	}
-	ss = fh_block_sum(ss, red);
-	// block max via the same scratch
-	for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	__shared__ double s_lmax, s_ssum;
+	if (tid == 0) { s_lmax = 0.0; s_ssum = 0.0; }
 	__syncthreads();
-	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		double v = 0.0;
-		for (int i = 0; i < (blockDim.x + 31) / 32; ++i) v = fmax(v, red[i]);
-		s_max = v;
-		if (sigma_sum) sigma_sum[b] = ss;
+	double* lamv = sigma_all ? sigma_all + (size_t)b * n : nullptr;
+	// per-row squared norms (warp per row), kept in registers of lane 0 via shared perm-sized scratch
+	// stored into the pad column R[j*ld + n] when ld > n, else recomputed
+	for (int j = warp; j < n; j += nw) {
+		double s2 = 0.0;
+		for (int i = lane; i < n; i += 32) { double v = R[j * ld + i]; s2 += v * v; }
+		s2 = fh_warp_sum(s2);
+		if (lane == 0) {
+			atomicMax((unsigned long long*)&s_lmax, (unsigned long long)__double_as_longlong(s2));  // s2 >= 0: order preserved
+			atomicAdd(&s_ssum, sqrt(s2));
+			if (lamv) lamv[j] = sqrt(s2);
+		}
 	}
 	__syncthreads();
-	const double floor_l = fmax(s_max * 1e-17, 1e-300);
-	const double* v = V + (size_t)b * n * n;
-	double* w = W + (size_t)b * n * n;
-	for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
-		int c = i % n;
-		double lc = fmax(l[c], floor_l);
-		w[i] = v[i] * rsqrt(sqrt(lc));
+
+	const double floor_l = fmax(s_lmax * 1e-17, 1e-300);
+	if (tid == 0 && sigma_sum) sigma_sum[b] = s_ssum;
+	double* WT = WTall + (size_t)b * n * n;
+	for (int j = warp; j < n; j += nw) {
+		double s2 = 0.0;
+		for (int i = lane; i < n; i += 32) { double v = R[j * ld + i]; s2 += v * v; }
+		s2 = fh_warp_sum(s2);
+		const double f = rsqrt(sqrt(fmax(s2, floor_l))) / sqrt(fmax(s2, floor_l));  // lambda^{-3/4}
+		for (int i = lane; i < n; i += 32) WT[(size_t)j * n + perm[i]] = R[j * ld + i] * f;
 	}
 }
 
@@ -206,51 +211,48 @@ int gemm(int dtype, int M, int N, int K, int batch, const void* A, long long sa_
 size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 struct PolarWs {
-	double *G, *V, *W, *lam;
-	double2* rot;
+	double *G, *WT;
 	int* nsweep;
 	size_t bytes;
 };
-PolarWs carve(int batch, int n, int max_sweeps, void* ws) {
+PolarWs carve(int batch, int n, void* ws) {
 	PolarWs p;
-	const int m = even_up(n);
 	char* b = (char*)ws;
 	size_t nn = al((size_t)batch * n * n * 8);
 	p.G = (double*)b; b += nn;
-	p.V = (double*)b; b += nn;
-	p.W = (double*)b; b += nn;
-	p.lam = (double*)b; b += al((size_t)batch * n * 8);
-	p.rot = (double2*)b; b += al((size_t)batch * max_sweeps * (m - 1) * (m / 2) * 16);
+	p.WT = (double*)b; b += nn;
 	p.nsweep = (int*)b; b += al((size_t)batch * 4);
 	p.bytes = (size_t)(b - (char*)ws);
 	return p;
 }
 
-constexpr int kMaxSweeps = 32;
+constexpr int kMaxSweeps = 30;
+
+size_t jacobi_smem(int n) { return ((size_t)n * (n | 1) + 64) * 8 + (size_t)n * 4 + 16; }
 
 }  // namespace
 
 extern "C" size_t fh_polar_workspace_bytes(int batch, int rows, int cols) {
 	int n = rows < cols ? rows : cols;
 	if (batch <= 0 || n <= 0) return 0;
-	return carve(batch, n, kMaxSweeps, nullptr).bytes;
+	return carve(batch, n, nullptr).bytes;
 }
 
 extern "C" int fh_polar_batched(const float* T, float* U, int batch, int rows, int cols, long long ld,
-                                long long batch_stride, double* sigma_sum, double* sigma, double* eigvec_state,
-                                int warm, int max_sweeps, void* workspace, size_t workspace_bytes, void* stream) {
+                                long long batch_stride, double* sigma_sum, double* sigma, int max_sweeps,
+                                void* workspace, size_t workspace_bytes, int* host_max_sweeps, void* stream) {
 	FH_CHECK_ARG(batch >= 0 && rows > 0 && cols > 0 && ld >= cols, "fh_polar_batched: bad shape");
+	if (host_max_sweeps) *host_max_sweeps = 0;
 	if (batch == 0) return FH_OK;
-	FH_CHECK_ARG(batch <= 65535, "fh_polar_batched: batch > 65535");
+	FH_CHECK_ARG(batch <= 32768, "fh_polar_batched: batch > 32768");
 	if (max_sweeps <= 0 || max_sweeps > kMaxSweeps) max_sweeps = kMaxSweeps;
 	const bool tall = rows >= cols;
 	const int n = tall ? cols : rows;
-	const int m = even_up(n), half = m / 2, ldg = m | 1;
-	size_t smem = ((size_t)m * ldg + 2 * half) * 8 + (size_t)2 * half * 4;
-	FH_CHECK_ARG(smem <= 227 * 1024, "fh_polar_batched: Gram side %d does not fit shared memory (max ~166)", n);
+	const size_t smem = jacobi_smem(n);
+	FH_CHECK_ARG(smem <= 227 * 1024 && n <= 32 * MAXPL, "fh_polar_batched: Gram side %d does not fit shared memory (max ~166)", n);
 	FH_CHECK_ARG(workspace && workspace_bytes >= fh_polar_workspace_bytes(batch, rows, cols),
 	             "fh_polar_batched: workspace too small");
-	PolarWs ws = carve(batch, n, kMaxSweeps, workspace);
+	PolarWs ws = carve(batch, n, workspace);
 	cudaStream_t st = (cudaStream_t)stream;
 	const long long nn = (long long)n * n;
 	int rc;
@@ -258,30 +260,22 @@ extern "C" int fh_polar_batched(const float* T, float* U, int batch, int rows, i
 	if (tall) rc = gemm(FH_GEMM_F32_ACC64, n, n, rows, batch, T, 1, ld, batch_stride, T, ld, 1, batch_stride, ws.G, n, nn, stream);
 	else rc = gemm(FH_GEMM_F32_ACC64, n, n, cols, batch, T, ld, 1, batch_stride, T, 1, ld, batch_stride, ws.G, n, nn, stream);
 	if (rc) return rc;
-	const double* V0 = nullptr;
-	if (warm && eigvec_state) {
-		// G <- V0^T G V0 : nearly diagonal when the factors moved little since the last sweep
-		rc = gemm(FH_GEMM_F64, n, n, n, batch, ws.G, n, 1, nn, eigvec_state, n, 1, nn, ws.W, n, nn, stream);
-		if (rc) return rc;
-		rc = gemm(FH_GEMM_F64, n, n, n, batch, eigvec_state, 1, n, nn, ws.W, n, 1, nn, ws.G, n, nn, stream);
-		if (rc) return rc;
-		V0 = eigvec_state;
+	FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	chol_jacobi_kernel<<<batch, JT, smem, st>>>(ws.G, n, max_sweeps, ws.WT, sigma, sigma_sum, ws.nsweep);
+	FH_LAUNCH_CHECK();
+	if (host_max_sweeps) {  // diagnostics only: synchronises
+		int* h = (int*)malloc(sizeof(int) * batch);
+		if (h) {
+			FH_CUDA(cudaMemcpyAsync(h, ws.nsweep, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+			FH_CUDA(cudaStreamSynchronize(st));
+			int mx = 0;
+			for (int i = 0; i < batch; ++i) mx = h[i] > mx ? h[i] : mx;
+			*host_max_sweeps = mx;
+			free(h);
+		}
 	}
-	int threads = half * half;
-	threads = threads < 64 ? 64 : (threads > 512 ? 512 : (threads + 31) / 32 * 32);
-	FH_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	jacobi_kernel<<<batch, threads, smem, st>>>(ws.G, n, max_sweeps, ws.rot, ws.nsweep, ws.lam);
-	FH_LAUNCH_CHECK();
-	size_t smem_v = ((size_t)RS * (m | 1)) * 8 + (size_t)half * 16;
-	FH_CUDA(cudaFuncSetAttribute(vapply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
-	dim3 gv(fh_cdiv(n, RS), batch);
-	vapply_kernel<<<gv, 256, smem_v, st>>>(V0, ws.V, n, max_sweeps, ws.rot, ws.nsweep);
-	FH_LAUNCH_CHECK();
-	if (eigvec_state) FH_CUDA(cudaMemcpyAsync(eigvec_state, ws.V, (size_t)batch * nn * 8, cudaMemcpyDeviceToDevice, st));
-	scale_cols_kernel<<<batch, 256, 0, st>>>(ws.V, ws.lam, n, ws.W, sigma_sum, sigma);
-	FH_LAUNCH_CHECK();
-	// M = W W^T (into G), U = T M or M T
-	rc = gemm(FH_GEMM_F64, n, n, n, batch, ws.W, n, 1, nn, ws.W, 1, n, nn, ws.G, n, nn, stream);
+	// M = WT^T WT (into G):  M[a][b] = sum_j WT[j][a] WT[j][b]
+	rc = gemm(FH_GEMM_F64, n, n, n, batch, ws.WT, 1, n, nn, ws.WT, n, 1, nn, ws.G, n, nn, stream);
 	if (rc) return rc;
 	if (tall) rc = gemm(FH_GEMM_F32xF64_F32, rows, n, n, batch, T, ld, 1, batch_stride, ws.G, n, 1, nn, U, ld, batch_stride, stream);
 	else rc = gemm(FH_GEMM_F64xF32_F32, n, cols, n, batch, ws.G, n, 1, nn, T, ld, 1, batch_stride, U, ld, batch_stride, stream);

@@ -124,33 +124,53 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 __global__ void __launch_bounds__(256)
 transition_kernel(const float* __restrict__ A, long long a_cell_stride, int ldw, int s,
                   float* __restrict__ SP, int nb, int ldp) {
+	// 256 threads = 8 row groups x 32 columns; a column tile of 32 is reduced over the 8 groups in smem
+	__shared__ float red[3][8][33];
 	const int cell = blockIdx.x;
 	const float* a = A + (long long)cell * a_cell_stride + s;
 	float* p = SP + (long long)cell * nb * ldp;
-	for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+	const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+	for (int j0 = 0; j0 < nb; j0 += 32) {
+		const int j = j0 + cx;
+		const bool ok = j < nb;
 		float cs1 = 0.f, cs2 = 0.f;
-		for (int i = 0; i < nb; ++i) {
-			cs1 += a[(long long)i * ldw + j];
-			if (i != j) cs2 += p[i * ldp + j];
-		}
+		if (ok)
+			for (int i = g; i < nb; i += 8) {
+				cs1 += a[(long long)i * ldw + j];
+				if (i != j) cs2 += p[i * ldp + j];
+			}
+		red[0][g][cx] = cs1; red[1][g][cx] = cs2;
+		__syncthreads();
+		cs1 = 0.f; cs2 = 0.f;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) { cs1 += red[0][k][cx]; cs2 += red[1][k][cx]; }
 		cs1 += FH_EPS; cs2 += FH_EPS;
 		float csl = 0.f;
-		for (int i = 0; i < nb; ++i) {
-			float f = (a[(long long)i * ldw + j] / cs1) * 0.75f;
-			float g = (i != j) ? (p[i * ldp + j] / cs2) * 0.25f : 0.f;
-			float l = f + g;
-			p[i * ldp + j] = l;
-			csl += l;
-		}
-		if (csl == 0.f) {  // unreachable after the 1e-8 floor, kept for parity (partial_rwr.py:96-97)
-			p[j * ldp + j] += 1.f;
-			csl += 1.f;
-		}
+		if (ok)
+			for (int i = g; i < nb; i += 8) {
+				float f = (a[(long long)i * ldw + j] / cs1) * 0.75f;
+				float gg = (i != j) ? (p[i * ldp + j] / cs2) * 0.25f : 0.f;
+				float l = f + gg;
+				p[i * ldp + j] = l;
+				csl += l;
+			}
+		red[2][g][cx] = csl;
+		__syncthreads();
+		csl = 0.f;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) csl += red[2][k][cx];
+		// a zero column is unreachable after the 1e-8 floor; kept for parity (partial_rwr.py:96-97)
+		const bool empty = (csl == 0.f);
+		if (empty) csl += 1.f;
 		csl += FH_EPS;
-		for (int i = 0; i < nb; ++i) p[i * ldp + j] = p[i * ldp + j] / csl;
+		if (ok)
+			for (int i = g; i < nb; i += 8) {
+				float l = p[i * ldp + j];
+				if (empty && i == j) l += 1.f;
+				p[i * ldp + j] = l / csl;
+			}
+		__syncthreads();
 	}
-	// pad columns [nb, ldp) must stay zero for the GEMMs that read P/Q with K = nb only: they are
-	// never read, nothing to do.
 }
 
 // Q = 0.5 * P + 0.5 * I  (first RWR step: Q0 = I so bmm(Q0, P) = P exactly)

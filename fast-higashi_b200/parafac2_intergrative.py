@@ -59,7 +59,7 @@ class Fast_Higashi_core:
 			raise _lib.FHError("fasthigashi_b200 runs on CUDA devices only; there is no CPU path")
 		_lib.lib()
 		if self.use_tc is None:
-			self.use_tc = False
+			self.use_tc = True  # tcgen05 3xTF32 for the large contractions (csrc/fh_gemm_tc.cu)
 		return self
 
 	# ------------------------------------------------------------------------------------------
@@ -297,8 +297,9 @@ class Fast_Higashi_core:
 		for ci, ds in enumerate(self.schic):
 			r = self.chrom2size[ds.chrom]
 			A, B, D = self.A_dev[ci], self.B_dict[ds.chrom], self.D_dict[ds.chrom]
-			Cc = torch.empty(Cn, r, dtype=torch.float32, device=dev)
-			_lib.gemm(V, D, Cc, Cn, r, R, (R, 1), (r, 1), r, dtype=gd)  # C = V D  (:336)
+			rp = pad4(r)  # row pitch of the r-wide operands (TMA needs 16-byte multiples)
+			Cc = torch.zeros(Cn, rp, dtype=torch.float32, device=dev)
+			_lib.gemm(V, D, Cc, Cn, r, R, (R, 1), (r, 1), rp, dtype=gd)  # C = V D  (:336)
 			for b, g in enumerate(ds.geoms):
 				ldw = pad4(g.w)
 				P = g.nb * ldw
@@ -310,36 +311,30 @@ class Fast_Higashi_core:
 					                                      _lib.stream_ptr()))
 				# P1: T1 = X^T C ; temp_i = (T1_i diag(A_i)) B^T
 				t = self._tic()
-				T1 = torch.empty(P, r, dtype=torch.float32, device=dev)
-				_lib.gemm(X, Cc, T1, P, r, Cn, (1, P), (r, 1), r, dtype=gd)
+				T1 = torch.empty(P, rp, dtype=torch.float32, device=dev)
+				_lib.gemm(X, Cc, T1, P, r, Cn, (1, P), (rp, 1), rp, dtype=gd)
 				self._allreduce(T1)
 				temp = torch.empty(g.nb, ldw, r, dtype=torch.float32, device=dev)
 				Arows = A[g.row0:g.row0 + g.nb]
-				_lib.gemm(T1, B, temp, ldw, r, r, (r, 1), (1, r), r, batch=g.nb, batch_strides=(ldw * r, 0, ldw * r),
+				_lib.gemm(T1, B, temp, ldw, r, r, (rp, 1), (1, r), r, batch=g.nb, batch_strides=(ldw * rp, 0, ldw * r),
 				          kscale=Arows, kscale_batch=r)
 				self._toc("p1_mttkrp", t)
 				# P2: U_i = polar(temp_i)
 				t = self._tic()
-				key = (ci, b)
-				eig = self._eig.get(key)
-				warm = eig is not None and self.warm_polar
-				if eig is None and self.warm_polar:
-					n_side = min(ldw, r)
-					eig = self._eig[key] = torch.empty(g.nb, n_side, n_side, dtype=torch.float64, device=dev)
 				U = self.projection_dev[ci][b]
-				_, ssum, _ = polar_batched(temp, ldw, r, r, out=U, eig_state=eig, warm=warm)
+				_, ssum, _ = polar_batched(temp, ldw, r, r, out=U)
 				stats[ci] += ssum.sum()
 				self._toc("polar_bins", t)
 				t = self._tic()
 				# P3: W_i = ((U_i B) diag(A_i)) D^T ; M += X W
-				UB = T1  # reuse
+				UB = torch.empty(P, r, dtype=torch.float32, device=dev)
 				_lib.gemm(U, B, UB, P, r, r, (r, 1), (r, 1), r)
 				W = torch.empty(P, R, dtype=torch.float32, device=dev)
 				_lib.gemm(UB, D, W, ldw, R, r, (r, 1), (1, r), R, batch=g.nb, batch_strides=(ldw * r, 0, ldw * R),
 				          kscale=Arows, kscale_batch=r)
 				_lib.gemm(X, W, MT, Cn, R, P, (P, 1), (R, 1), R, beta=1.0, dtype=gd)
 				self._toc("p3_project", t)
-				del W, T1, temp
+				del W, T1, temp, UB
 		# P4: V = polar(SVD_term^T) (:483-486)
 		self.last_svd_term_T = MT
 		t = self._tic()

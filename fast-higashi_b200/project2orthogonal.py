@@ -15,9 +15,9 @@ from . import _lib
 JACOBI_MAX_SIDE = 166  # Gram side that still fits shared memory (fh_polar.cu)
 
 
-def polar_batched(T, rows, cols, ld, out=None, eig_state=None, warm=False, want_sigma=False):
+def polar_batched(T, rows, cols, ld, out=None, want_sigma=False, want_sweeps=False):
 	"""T: (batch, rows, ld) fp32 device (columns >= cols are ignored/kept). Returns (U, sigma_sum
-	(batch,) fp64 device, sigma (batch, min(rows, cols)) fp64 or None)."""
+	(batch,) fp64 device, sigma (batch, min(rows, cols)) fp64 or None[, max Jacobi sweeps])."""
 	batch = T.shape[0]
 	dev = T.device
 	U = torch.zeros_like(T) if out is None else out
@@ -26,10 +26,12 @@ def polar_batched(T, rows, cols, ld, out=None, eig_state=None, warm=False, want_
 	sig = torch.empty(batch, n, dtype=torch.float64, device=dev) if want_sigma else None
 	lib = _lib.lib()
 	ws = _lib.workspace(lib.fh_polar_workspace_bytes(batch, rows, cols), dev, "polar")
+	nsw = C.c_int(0)
 	_lib.check(lib.fh_polar_batched(T.data_ptr(), U.data_ptr(), batch, rows, cols, ld, T.stride(0), ssum.data_ptr(),
-	                                None if sig is None else sig.data_ptr(),
-	                                None if eig_state is None else eig_state.data_ptr(), int(bool(warm)), int(os.environ.get("FH_POLAR_SWEEPS", "0")),
-	                                ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+	                                None if sig is None else sig.data_ptr(), int(os.environ.get("FH_POLAR_SWEEPS", "0")),
+	                                ws.data_ptr(), ws.numel(), C.byref(nsw) if want_sweeps else None, _lib.stream_ptr()))
+	if want_sweeps:
+		return U, ssum, sig, nsw.value
 	return U, ssum, sig
 
 

@@ -23,6 +23,8 @@ const char* fh_last_error(void);
 int fh_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
 long long fh_launch_count(void);
+/* FH_GEMM_TF32X3 calls that ran on the CUDA-core fp32 kernel because TMA could not describe them */
+long long fh_tc_fallback_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Generic batched strided GEMM.  C[b](m,n) = alpha * sum_k A[b](m,k)*kscale[b][k]*B[b](k,n)
@@ -111,16 +113,16 @@ int fh_dot_accum(const float* x, const float* y, long long rows, long long cols,
 /* ---------------------------------------------------------------------------------------------
  * Batched polar factor U = T (T^T T)^{-1/2}  (= U_svd Vh_svd) and sum of singular values.
  * Replaces project2orthogonal (project2orthogonal.py:6-55) as called at
- * parafac2_intergrative.py:396. fp64 Gram + fp64 Jacobi eigensolver (DESIGN.md "polar").
+ * parafac2_intergrative.py:396. fp64 Gram + pivoted Cholesky + one-sided Jacobi (DESIGN.md "polar").
  * ------------------------------------------------------------------------------------------- */
 size_t fh_polar_workspace_bytes(int batch, int rows, int cols);
-/* T, U: (batch, rows, ld) fp32 (U may alias T); sigma_sum: NULL or [batch] doubles (sum of singular
- * values); sigma: NULL or [batch][n] doubles, the singular values (unsorted), n = min(rows, cols);
- * eigvec_state: NULL or (batch, n, n) fp64: eigenvectors of the Gram, read as warm start when
- * warm != 0 and always written back. */
+/* T, U: (batch, rows, ld) fp32; sigma_sum: NULL or [batch] doubles (sum of singular values);
+ * sigma: NULL or [batch][n] doubles, the singular values (unsorted), n = min(rows, cols);
+ * max_sweeps <= 0: default cap; host_max_sweeps: NULL, or receives the largest Jacobi sweep count
+ * of the batch (diagnostics; synchronises the stream). */
 int fh_polar_batched(const float* T, float* U, int batch, int rows, int cols, long long ld,
-                     long long batch_stride, double* sigma_sum, double* sigma, double* eigvec_state,
-                     int warm, int max_sweeps, void* workspace, size_t workspace_bytes, void* stream);
+                     long long batch_stride, double* sigma_sum, double* sigma, int max_sweeps,
+                     void* workspace, size_t workspace_bytes, int* host_max_sweeps, void* stream);
 
 /* Inverse square root of ONE symmetric positive definite n x n fp64 matrix by the coupled
  * Newton-Schulz iteration (tall cells x R polar, parafac2_intergrative.py:483,831: V = M G^{-1/2}

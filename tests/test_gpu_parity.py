@@ -132,32 +132,34 @@ def test_polar_batched_matches_reference_fixture():
 		assert abs(float((U * m).sum()) - tr_ref) / abs(tr_ref) < 1e-6
 
 
-def test_polar_realistic_shapes_and_warm_start():
+def test_polar_realistic_shapes_graded_spectra():
+	"""Block-sized problems with log-spaced spectra up to kappa = 3e6 (median 4e5-1e6 on
+	real blocks), tall, nearly square and wide; checks orthogonality, the factor against an fp64 SVD,
+	the singular values and the Jacobi sweep count of the Cholesky-preconditioned solver."""
 	from fasthigashi_b200.project2orthogonal import polar_batched
 	g = torch.Generator().manual_seed(0)
-	for (batch, rows, cols) in [(6, 316, 137), (9, 72, 21), (3, 152, 150), (4, 12, 20)]:
-		Uq, _ = torch.linalg.qr(torch.randn(batch, max(rows, cols), min(rows, cols), generator=g, dtype=torch.float64))
-		Vq, _ = torch.linalg.qr(torch.randn(batch, min(rows, cols), min(rows, cols), generator=g, dtype=torch.float64))
-		sv = torch.logspace(0, -5.5, min(rows, cols), dtype=torch.float64)  # kappa 3e5 (median on real blocks ~3e4)
-		T = (Uq * sv) @ Vq.transpose(1, 2)
-		if rows < cols:
-			T = T.transpose(1, 2)
-		T = T.float().contiguous()
-		ref = (Uq @ Vq.transpose(1, 2))
-		ref = ref.transpose(1, 2) if rows < cols else ref
-		Td = T.to(DEV)
-		n = min(rows, cols)
-		eig = torch.zeros(batch, n, n, dtype=torch.float64, device=DEV)
-		U, ssum, _ = polar_batched(Td, rows, cols, cols, eig_state=eig, warm=False)
-		assert _ortho_err(U.cpu().double()) < 1e-3  # defect ~ eps64 * kappa^2 * K
-		# well-conditioned part of the factor: compare on the leading singular subspace
-		lead = (Uq[:, :, :n // 2] @ Vq[:, :, :n // 2].transpose(1, 2))
-		lead = lead.transpose(1, 2) if rows < cols else lead
-		assert abs(float((U.cpu().double() * lead).sum()) - batch * (n // 2)) / (batch * (n // 2)) < 1e-5
-		assert float((ssum.cpu() - sv.sum()).abs().max() / sv.sum()) < 1e-6
-		U2, ssum2, _ = polar_batched((Td * 1.001).contiguous(), rows, cols, cols, eig_state=eig, warm=True)
-		assert rel_fro(U2.cpu().numpy(), U.cpu().numpy()) < 1e-3
-		assert _ortho_err(U2.cpu().double()) < 1e-3
+	for (batch, rows, cols) in [(6, 316, 137), (9, 72, 21), (3, 152, 150), (4, 12, 20), (2, 1, 1)]:
+		for logk in [2.0, 5.5, 6.5]:
+			n = min(rows, cols)
+			Uq, _ = torch.linalg.qr(torch.randn(batch, max(rows, cols), n, generator=g, dtype=torch.float64))
+			Vq, _ = torch.linalg.qr(torch.randn(batch, n, n, generator=g, dtype=torch.float64))
+			sv = torch.logspace(0, -logk, n, dtype=torch.float64)
+			T = (Uq * sv) @ Vq.transpose(1, 2)
+			if rows < cols:
+				T = T.transpose(1, 2)
+			T = T.float().contiguous()
+			Ud, Sd, Vhd = torch.linalg.svd(T.double(), full_matrices=False)
+			truth = Ud @ Vhd
+			U, ssum, sig, nsw = polar_batched(T.to(DEV), rows, cols, cols, want_sigma=True, want_sweeps=True)
+			U = U.cpu().double()
+			# fp64 Gram: errors ~ eps64 * kappa^2 in the weakest direction
+			lim = 2e-6 if logk <= 5.5 else 1e-3
+			assert _ortho_err(U) < lim, (rows, cols, logk, _ortho_err(U))
+			assert rel_fro(U.numpy(), truth.numpy()) < lim
+			assert float((ssum.cpu() - Sd.sum(1)).abs().max() / Sd.sum(1).max()) < 1e-9
+			sg = torch.sort(sig.cpu(), dim=1, descending=True).values
+			assert float(((sg - Sd).abs() / Sd[:, :1]).max()) < 1e-9
+			assert nsw <= 12, nsw
 
 
 def test_polar_tall_matches_oracle():
@@ -286,3 +288,52 @@ def test_core_init_params_matches_reference():
 		assert np.array_equal(np.isfinite(ref), np.isfinite(got))
 		assert rel_fro(got[np.isfinite(ref)], ref[np.isfinite(ref)]) < 1e-5
 	assert np.max(np.abs(np.array(core.re_trace) - g["re"][:3]) / g["re"][:3]) < 2e-4
+
+
+@pytest.mark.parametrize("layout", ["nn", "tn", "nt", "tt"])
+@pytest.mark.parametrize("shape", [(128, 128, 32, 1), (115, 115, 316, 7), (300, 137, 1000, 2), (64, 260, 40, 3), (129, 1, 33, 1)])
+def test_gemm_tcgen05_3xtf32(shape, layout):
+	"""tcgen05 3xTF32 kernel vs an fp64 reference, all operand majors, ragged edges, batches."""
+	L = _lib()
+	M, N, K, batch = shape
+	g = torch.Generator().manual_seed(M + 3 * N + 5 * K)
+	lda = (K + 3) // 4 * 4 if layout[0] == "n" else (M + 3) // 4 * 4
+	ldb = (N + 3) // 4 * 4 if layout[1] == "n" else (K + 3) // 4 * 4
+	A = torch.randn(batch, M, K, generator=g) * torch.exp(torch.randn(batch, M, 1, generator=g))
+	B = torch.randn(batch, K, N, generator=g)
+	ref = torch.bmm(A.double(), B.double())
+	if layout[0] == "n":
+		Ad = torch.zeros(batch, M, lda); Ad[:, :, :K] = A; sa = (lda, 1); ba = M * lda
+	else:
+		Ad = torch.zeros(batch, K, lda); Ad[:, :, :M] = A.transpose(1, 2); sa = (1, lda); ba = K * lda
+	if layout[1] == "n":
+		Bd = torch.zeros(batch, K, ldb); Bd[:, :, :N] = B; sb = (ldb, 1); bb = K * ldb
+	else:
+		Bd = torch.zeros(batch, N, ldb); Bd[:, :, :K] = B.transpose(1, 2); sb = (1, ldb); bb = N * ldb
+	Cd = torch.full((batch, M, N), float("nan"), device=DEV)
+	f0 = L.lib().fh_tc_fallback_count()
+	L.gemm(Ad.to(DEV), Bd.to(DEV), Cd, M, N, K, sa, sb, N, batch=batch, batch_strides=(ba, bb, M * N), dtype=L.GEMM_TF32X3)
+	assert L.lib().fh_tc_fallback_count() == f0, "expected the tensor-core path"
+	assert rel_fro(Cd.cpu().numpy(), ref.numpy()) < 2e-6, (shape, layout)
+
+
+def test_gemm_tcgen05_epilogues_and_broadcast():
+	L = _lib()
+	g = torch.Generator().manual_seed(5)
+	batch, M, N, K = 5, 115, 216, 115
+	A, B = torch.randn(batch, M, K + 1, generator=g), torch.randn(K, N, generator=g)
+	cs, C0 = torch.rand(batch, N, generator=g) + 0.5, torch.randn(batch, M, N, generator=g)
+	ref = 0.5 * torch.matmul(A[:, :, :K].double(), B.double())
+	ref[:, torch.arange(M), torch.arange(M)] += 0.5
+	ref = ref / cs[:, None, :].double() + 2.0 * C0.double()
+	Cd = C0.clone().to(DEV)
+	L.gemm(A.to(DEV), B.to(DEV), Cd, M, N, K, (K + 1, 1), (N, 1), N, batch=batch, batch_strides=(M * (K + 1), 0, M * N), alpha=0.5,
+	       beta=2.0, epilogue=L.EPI_DIAG_ADD, diag=0.5, cscale=cs.to(DEV), cscale_batch=N, cscale_recip=True, dtype=L.GEMM_TF32X3)
+	assert rel_fro(Cd.cpu().numpy(), ref.numpy()) < 2e-6
+	# odd strides are not TMA-describable: the call must still be exact (CUDA-core kernel) and be counted
+	f0 = L.lib().fh_tc_fallback_count()
+	A2 = torch.randn(33, 35, generator=g); B2 = torch.randn(35, 37, generator=g)
+	C2 = torch.empty(33, 37, device=DEV)
+	L.gemm(A2.to(DEV), B2.to(DEV), C2, 33, 37, 35, (35, 1), (37, 1), 37, dtype=L.GEMM_TF32X3)
+	assert L.lib().fh_tc_fallback_count() == f0 + 1
+	assert rel_fro(C2.cpu().numpy(), (A2.double() @ B2.double()).numpy()) < 2e-6
