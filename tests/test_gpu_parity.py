@@ -337,3 +337,43 @@ def test_gemm_tcgen05_epilogues_and_broadcast():
 	L.gemm(A2.to(DEV), B2.to(DEV), C2, 33, 37, 35, (35, 1), (37, 1), 37, dtype=L.GEMM_TF32X3)
 	assert L.lib().fh_tc_fallback_count() == f0 + 1
 	assert rel_fro(C2.cpu().numpy(), (A2.double() @ B2.double()).numpy()) < 2e-6
+
+
+def test_fasthigashi_wrapper_end_to_end(tmp_path):
+	"""FastHigashi API shell (prep_dataset from in-memory tensors -> run_model -> fetch_cell_embedding)
+	against the oracle driven with the same datasets, flags and seeds."""
+	import json
+	from fasthigashi_b200.FastHigashi_Wrapper import FastHigashi
+	from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset
+	d = np.load(os.path.join(GOLDEN, "data_small.npz"))
+	ncell, off, res = int(d["ncell"]), int(d["off_diag"]), int(d["res"])
+	chroms = ["chr1", "chr2", "chr3"]
+	cfg = dict(chrom_list=chroms, temp_dir=str(tmp_path), data_dir=str(tmp_path), resolution=res, resolution_fh=[res])
+	json.dump(cfg, open(tmp_path / "config.JSON", "w"))
+	tensors = {res: [(d[c + "_idx"].astype(np.int64), d[c + "_val"], (int(n), int(n), ncell)) for c, n in zip(chroms, d["bins"])]}
+	qc = np.ones(ncell); qc[[5, 17]] = 0
+	w = FastHigashi(str(tmp_path / "config.JSON"), None, None, off, True, True, True, False, False)
+	w.set_tensors(tensors, qc=qc, readcount=np.linspace(8, 10, ncell))
+	w.prep_dataset()
+	assert w.good_qc_num == ncell - 2 and len(w.all_matrix) == 3
+	torch.manual_seed(0); np.random.seed(0)
+	w.run_model(dim1=0.3, rank=16, n_iter_parafac=1, n_iter_max=4, tol=0.0)
+	emb = w.fetch_cell_embedding(final_dim=8)
+	for k in ["embed_all", "embed_raw", "embed_l2_norm", "restore_order", "embed_correct_coverage_fh", "embed_l2_norm_correct_coverage_fh"]:
+		assert k in emb
+	assert os.path.exists(tmp_path / ("results_all%s.pkl" % w.save_str)) and os.path.exists(tmp_path / ("results%s.pkl" % w.save_str))
+	# oracle with the same (reordered) datasets
+	reorder = w.reorder
+	inv = np.empty(ncell, dtype=np.int64); inv[reorder] = np.arange(ncell)
+	ods = []
+	for ds, (idx, val, shape) in zip(w.all_matrix, tensors[res]):
+		idx = idx.copy(); idx[2] = inv[idx[2]]
+		ods.append(Chrom_Dataset(Sparse(idx, val, shape), bs_bin=ds.bs_bin, bs_cell=ds.bs_cell, good_qc_num=ds.num_cell,
+		                         compact=True, flank=off, chrom=ds.chrom, resolution=res))
+	oc = O.OracleCore(16, off, [res])
+	torch.manual_seed(0); np.random.seed(0)
+	oc.fit(ods, 0.3, 4, 1, True, True, w.final_do_col, 0.0)
+	Vo = oc.transform(ods, True, True, w.final_do_col)
+	Eo = O.embed_all(Vo.numpy(), [x.numpy() for x in oc.D_dict.values()])
+	pear = [abs(np.corrcoef(emb["embed_all"][:, j], Eo[:, j])[0, 1]) for j in range(Eo.shape[1])]
+	assert min(pear) > 0.999, min(pear)
