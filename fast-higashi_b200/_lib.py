@@ -32,7 +32,7 @@ class RwrDesc(C.Structure):
 
 EXPORTS = ["fh_last_error", "fh_version", "fh_launch_count", "fh_tc_fallback_count", "fh_gemm_batched", "fh_rwr_workspace_bytes",
            "fh_rwr_batched", "fh_densify", "fh_rwr_dense", "fh_colsum_accum", "fh_avgpool", "fh_sqnorm_accum",
-           "fh_dot_accum", "fh_polar_workspace_bytes", "fh_polar_batched", "fh_inv_sqrt_spd",
+           "fh_dot_accum", "fh_polar_workspace_bytes", "fh_polar_batched", "fh_polar_isqrt_multi", "fh_inv_sqrt_spd",
            "fh_cp_als_workspace_bytes", "fh_cp_als", "fh_cp_core_sqnorm"]
 
 _lib = None
@@ -67,6 +67,7 @@ def lib():
 		L.fh_sqnorm_accum.argtypes = [vp, ll, ll, ll, vp, vp]
 		L.fh_dot_accum.argtypes = [vp, vp, ll, ll, ll, ll, vp, vp]
 		L.fh_polar_batched.argtypes = [vp, vp, ci, ci, ci, ll, ll, vp, vp, ci, vp, sz, C.POINTER(ci), vp]
+		L.fh_polar_isqrt_multi.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp, ci, vp, vp]
 		L.fh_inv_sqrt_spd.argtypes = [vp, vp, ci, vp, sz, C.POINTER(ci), vp]
 		L.fh_cp_als.argtypes = [vp, ci, ci, ci, vp, vp, vp, ci, vp, sz, C.POINTER(C.c_double), vp]
 		L.fh_cp_core_sqnorm.argtypes = [vp, ci, vp, vp, ci, ci, vp, vp, vp]

@@ -33,25 +33,33 @@ __device__ __forceinline__ void rr_pair(int m, int s, int t, int& p, int& q) {
 	}
 }
 
-constexpr int JT = 512;       // threads per CTA
 constexpr int MAXPL = 6;      // column elements per lane: n <= 32 * MAXPL = 192 (smem caps n at ~166 anyway)
 
-// One CTA per matrix. Shared memory holds R (n x ld, row-major): first the symmetric G, then its
-// pivoted Cholesky factor as the UPPER triangle R = L^T (row j of R = column j of L), then the rows
-// are orthogonalised in place. Output WT (n x n): row j = w_j * lambda_j^{-3/4} in the ORIGINAL index
-// order, sigma[j] = sqrt(lambda_j), sigma_sum = sum_j sigma_j.
-__global__ void __launch_bounds__(JT)
-chol_jacobi_kernel(const double* __restrict__ Gall, int n, int max_sweeps, double* __restrict__ WTall,
-                   double* __restrict__ sigma_all, double* __restrict__ sigma_sum, int* __restrict__ nsweep_out) {
+// One CTA per matrix (problem b: size prob_n[b], data at prob_off[b] doubles into Gall / WTall).
+// Shared memory holds R (n x ld, row-major): first the symmetric G, then its pivoted Cholesky factor
+// as the UPPER triangle R = L^T (row j of R = column j of L), then the rows are orthogonalised in
+// place. Output WT (n x n): row j = w_j * lambda_j^{-3/4} in the ORIGINAL index order;
+// sigma[prob_sig[b] + j] = sqrt(lambda_j); sigma_sum[prob_slot[b]] = sum_j sqrt(lambda_j).
+__global__ void __launch_bounds__(1024)
+chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob_n, const long long* __restrict__ prob_off,
+                   const int* __restrict__ prob_slot, const long long* __restrict__ prob_sig, int uniform_n,
+                   int max_sweeps, double* __restrict__ WTall, double* __restrict__ sigma_all,
+                   double* __restrict__ sigma_sum, int* __restrict__ nsweep_out) {
 	extern __shared__ double sm[];
+	const int b = blockIdx.x;
+	const int n = prob_n ? prob_n[b] : uniform_n;
+	const long long off = prob_off ? prob_off[b] : (long long)b * n * n;
+	const int slot = prob_slot ? prob_slot[b] : b;
+	const long long sig_off = prob_sig ? prob_sig[b] : (long long)b * n;
 	const int ld = n | 1;
 	double* R = sm;                          // n x ld
 	double* red = R + (size_t)n * ld;        // 64 doubles scratch
 	int* perm = (int*)(red + 64);            // n
-	__shared__ int s_piv, s_rot;
+	__shared__ int s_piv;
 	__shared__ double s_val;
-	const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = JT / 32;
-	const double* Gg = Gall + (size_t)b * n * n;
+	const int JT = blockDim.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = JT >> 5;
+	const double* Gg = Gall + off;
 	for (int i = tid; i < n * n; i += JT) R[(i / n) * ld + (i % n)] = Gg[i];
 	for (int i = tid; i < n; i += JT) perm[i] = i;
 	__syncthreads();
@@ -95,11 +103,10 @@ chol_jacobi_kernel(const double* __restrict__ Gall, int n, int max_sweeps, doubl
 			if (tid == 0) { int t = perm[k]; perm[k] = perm[pv]; perm[pv] = t; }
 			__syncthreads();
 		}
-		// a non-positive pivot only appears below the rounding level of G: clamp (noise directions)
-		const double d = fmax(R[k * ld + k], dmax0 * 1e-32 + 1e-300);
-		const double rkk = sqrt(d);
+		const double rkk = sqrt(R[k * ld + k]);
+		const double rinv = 1.0 / rkk;
 		__syncthreads();
-		for (int j = k + tid; j < n; j += JT) R[k * ld + j] = (j == k) ? rkk : R[k * ld + j] / rkk;
+		for (int j = k + tid; j < n; j += JT) R[k * ld + j] = (j == k) ? rkk : R[k * ld + j] * rinv;
 		__syncthreads();
 		// trailing update (full square keeps the swaps simple): G[i][j] -= R[k][i] R[k][j]
 		const int rem = n - k - 1;
@@ -116,17 +123,15 @@ chol_jacobi_kernel(const double* __restrict__ Gall, int n, int max_sweeps, doubl
 	__syncthreads();
 	// ---------------- one-sided Jacobi on the rows of R (columns of L) ----------------
 	const int m = even_up(n), half = m >> 1;
-	const double tol = 1e-15 * sqrt((double)n);
+	const double tol2 = 1e-30 * (double)n;       // (1e-15 sqrt(n))^2 on gamma^2 / (alpha beta)
 	int sweep = 0;
 	for (; sweep < max_sweeps; ++sweep) {
-		if (tid == 0) s_rot = 0;
-		__syncthreads();
-		int rotated = 0;
+		double worst = 0.0;                        // largest gamma^2/(alpha beta) met in this sweep
 		for (int step = 0; step < m - 1; ++step) {
 			for (int t = warp; t < half; t += nw) {
 				int p, q;
 				rr_pair(m, step, t, p, q);
-				if (p >= n || q >= n) continue;  // the padding player of an odd n
+				if (p >= n || q >= n) continue;      // the padding player of an odd n
 				if (p > q) { int x = p; p = q; q = x; }
 				double* rp = R + p * ld;
 				double* rq = R + q * ld;
@@ -140,10 +145,13 @@ chol_jacobi_kernel(const double* __restrict__ Gall, int n, int max_sweeps, doubl
 					al += a[e] * a[e]; be += c[e] * c[e]; ga += a[e] * c[e];
 				}
 				al = fh_warp_sum(al); be = fh_warp_sum(be); ga = fh_warp_sum(ga);
-				if (fabs(ga) > tol * sqrt(al * be) && ga != 0.0) {
-					double theta = (be - al) / (2.0 * ga);
-					double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-					double cs = 1.0 / sqrt(tt * tt + 1.0), sn = tt * cs;
+				const double g2 = ga * ga, ab = al * be;
+				if (g2 > tol2 * ab && ga != 0.0) {
+					worst = fmax(worst, g2 / ab);
+					// t = sign(d) 2 gamma / (|d| + sqrt(d^2 + 4 gamma^2)), d = beta - alpha (smaller root)
+					const double d = be - al;
+					const double tt = (d >= 0.0 ? 2.0 : -2.0) * ga / (fabs(d) + sqrt(d * d + 4.0 * g2));
+					const double cs = rsqrt(tt * tt + 1.0), sn = tt * cs;
 #pragma unroll
 					for (int e = 0; e < MAXPL; ++e) {
 						int i = lane + 32 * e;
@@ -152,26 +160,26 @@ chol_jacobi_kernel(const double* __restrict__ Gall, int n, int max_sweeps, doubl
 							rq[i] = sn * a[e] + cs * c[e];
 						}
 					}
-					rotated = 1;
 				}
 			}
 			__syncthreads();
 		}
-		if (rotated && lane == 0) s_rot = 1;
+		// block max of `worst`
+		if (lane == 0) red[warp] = worst;
 		__syncthreads();
-		const int any = s_rot;
+		double wmax = 0.0;
+		for (int i = 0; i < nw; ++i) wmax = fmax(wmax, red[i]);
 		__syncthreads();
-		if (!any) break;
+		// quadratic convergence: rotations of a sweep whose largest scaled off-diagonal was <= 1e-7
+		// leave ~1e-14 behind - no confirming sweep needed
+		if (wmax <= 1e-14) { ++sweep; break; }
 	}
-	if (tid == 0 && nsweep_out) nsweep_out[b] = sweep;
+	if (tid == 0 && nsweep_out) nsweep_out[slot] = sweep;
 	// ---------------- lambda_j = |w_j|^2, outputs ----------------
-
 	__shared__ double s_lmax, s_ssum;
 	if (tid == 0) { s_lmax = 0.0; s_ssum = 0.0; }
 	__syncthreads();
-	double* lamv = sigma_all ? sigma_all + (size_t)b * n : nullptr;
-	// per-row squared norms (warp per row), kept in registers of lane 0 via shared perm-sized scratch
-	// stored into the pad column R[j*ld + n] when ld > n, else recomputed
+	double* lamv = sigma_all ? sigma_all + sig_off : nullptr;
 	for (int j = warp; j < n; j += nw) {
 		double s2 = 0.0;
 		for (int i = lane; i < n; i += 32) { double v = R[j * ld + i]; s2 += v * v; }
@@ -183,15 +191,15 @@ chol_jacobi_kernel(const double* __restrict__ Gall, int n, int max_sweeps, doubl
 		}
 	}
 	__syncthreads();
-
 	const double floor_l = fmax(s_lmax * 1e-17, 1e-300);
-	if (tid == 0 && sigma_sum) sigma_sum[b] = s_ssum;
-	double* WT = WTall + (size_t)b * n * n;
+	if (tid == 0 && sigma_sum) sigma_sum[slot] = s_ssum;
+	double* WT = WTall + off;
 	for (int j = warp; j < n; j += nw) {
 		double s2 = 0.0;
 		for (int i = lane; i < n; i += 32) { double v = R[j * ld + i]; s2 += v * v; }
 		s2 = fh_warp_sum(s2);
-		const double f = rsqrt(sqrt(fmax(s2, floor_l))) / sqrt(fmax(s2, floor_l));  // lambda^{-3/4}
+		const double l = fmax(s2, floor_l);
+		const double f = rsqrt(l) * rsqrt(sqrt(l));  // lambda^{-3/4}
 		for (int i = lane; i < n; i += 32) WT[(size_t)j * n + perm[i]] = R[j * ld + i] * f;
 	}
 }
@@ -228,6 +236,8 @@ PolarWs carve(int batch, int n, void* ws) {
 
 constexpr int kMaxSweeps = 30;
 
+int jacobi_threads(int n) { return n > 83 ? 1024 : (n > 58 ? 512 : 256); }
+
 size_t jacobi_smem(int n) { return ((size_t)n * (n | 1) + 64) * 8 + (size_t)n * 4 + 16; }
 
 }  // namespace
@@ -261,7 +271,8 @@ extern "C" int fh_polar_batched(const float* T, float* U, int batch, int rows, i
 	else rc = gemm(FH_GEMM_F32_ACC64, n, n, cols, batch, T, ld, 1, batch_stride, T, 1, ld, batch_stride, ws.G, n, nn, stream);
 	if (rc) return rc;
 	FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	chol_jacobi_kernel<<<batch, JT, smem, st>>>(ws.G, n, max_sweeps, ws.WT, sigma, sigma_sum, ws.nsweep);
+	chol_jacobi_kernel<<<batch, jacobi_threads(n), smem, st>>>(ws.G, nullptr, nullptr, nullptr, nullptr, n, max_sweeps, ws.WT, sigma,
+	                                                             sigma_sum, ws.nsweep);
 	FH_LAUNCH_CHECK();
 	if (host_max_sweeps) {  // diagnostics only: synchronises
 		int* h = (int*)malloc(sizeof(int) * batch);
@@ -280,6 +291,40 @@ extern "C" int fh_polar_batched(const float* T, float* U, int batch, int rows, i
 	if (tall) rc = gemm(FH_GEMM_F32xF64_F32, rows, n, n, batch, T, ld, 1, batch_stride, ws.G, n, 1, nn, U, ld, batch_stride, stream);
 	else rc = gemm(FH_GEMM_F64xF32_F32, n, cols, n, batch, ws.G, n, 1, nn, T, ld, 1, batch_stride, U, ld, batch_stride, stream);
 	return rc;
+}
+
+// Many Gram matrices of different sizes in one go (all bins of all chromosomes of a sweep): the
+// device tables are sorted by decreasing n (longest problems first); one launch per size class so
+// that small problems share an SM (8 / 4 / 2 / 1 CTAs per SM).
+extern "C" int fh_polar_isqrt_multi(const double* G_all, double* WT_all, const int* dev_prob_n,
+                                    const long long* dev_prob_off, const int* dev_prob_slot, const int* host_prob_n,
+                                    int count, double* sigma_sum, int max_sweeps, int* dev_nsweep, void* stream) {
+	FH_CHECK_ARG(count >= 0 && G_all && WT_all && dev_prob_n && dev_prob_off && dev_prob_slot && host_prob_n,
+	             "fh_polar_isqrt_multi: null argument");
+	if (max_sweeps <= 0 || max_sweeps > kMaxSweeps) max_sweeps = kMaxSweeps;
+	cudaStream_t st = (cudaStream_t)stream;
+	const int bounds[4] = {117, 83, 58, 0};  // class lower bounds (exclusive): (117,166], (83,117], (58,83], (0,58]
+	int i = 0;
+	while (i < count) {
+		const int nmax = host_prob_n[i];
+		FH_CHECK_ARG(nmax > 0 && jacobi_smem(nmax) <= 227 * 1024 && nmax <= 32 * MAXPL,
+		             "fh_polar_isqrt_multi: Gram side %d does not fit shared memory (max ~166)", nmax);
+		int lb = 0;
+		for (int c = 0; c < 4; ++c)
+			if (nmax > bounds[c]) { lb = bounds[c]; break; }
+		int j = i;
+		while (j < count && host_prob_n[j] > lb) {
+			FH_CHECK_ARG(host_prob_n[j] <= nmax, "fh_polar_isqrt_multi: table not sorted by decreasing n");
+			++j;
+		}
+		const size_t smem = jacobi_smem(nmax);
+		FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		chol_jacobi_kernel<<<j - i, jacobi_threads(nmax), smem, st>>>(G_all, dev_prob_n + i, dev_prob_off + i, dev_prob_slot + i,
+		                                                            nullptr, 0, max_sweeps, WT_all, nullptr, sigma_sum, dev_nsweep);
+		FH_LAUNCH_CHECK();
+		i = j;
+	}
+	return FH_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -277,6 +277,36 @@ class Fast_Higashi_core:
 			self._X_valid.add(key)
 		return X
 
+	def _polar_table(self):
+		"""Problem table of the per-bin polar step (one Gram matrix per bin, all chromosomes): offsets
+		into one fp64 buffer, sorted by decreasing size for fh_polar_isqrt_multi. Built once."""
+		if getattr(self, "_ptab", None) is not None:
+			return self._ptab
+		dev = self.device
+		block, n_list, off_list, lengths = {}, [], [], []
+		off = 0
+		for ci, ds in enumerate(self.schic):
+			r = self.chrom2size[ds.chrom]
+			cnt = 0
+			for b, g in enumerate(ds.geoms):
+				ns = min(pad4(g.w), r)
+				block[(ci, b)] = (off, ns)
+				for i in range(g.nb):
+					n_list.append(ns); off_list.append(off + i * ns * ns)
+				off += g.nb * ns * ns
+				cnt += g.nb
+			lengths.append(cnt)
+		n_arr = np.asarray(n_list, dtype=np.int32)
+		order = np.argsort(-n_arr, kind="stable")
+		self._ptab = dict(block=block, count=len(n_list), n_host=np.ascontiguousarray(n_arr[order]),
+		                  n_dev=torch.from_numpy(np.ascontiguousarray(n_arr[order])).to(dev),
+		                  off_dev=torch.from_numpy(np.asarray(off_list, dtype=np.int64)[order].copy()).to(dev),
+		                  slot_dev=torch.from_numpy(order.astype(np.int32)).to(dev),
+		                  ssum=torch.zeros(len(n_list), dtype=torch.float64, device=dev),
+		                  chrom_lengths=torch.tensor(lengths, device=dev),
+		                  G=torch.empty(off, dtype=torch.float64, device=dev), WT=torch.empty(off, dtype=torch.float64, device=dev))
+		return self._ptab
+
 	def invalidate_cache(self):
 		self._X_valid = set()
 
@@ -294,6 +324,10 @@ class Fast_Higashi_core:
 			self.n_rwr_passes += 1
 		MT = torch.zeros(Cn, R, dtype=torch.float32, device=dev)  # SVD_term^T
 		stats = torch.zeros(2 * nch + 1, dtype=torch.float64, device=dev)  # x_U | ||X||^2 | x_V
+		tab = self._polar_table()
+		G_all, WT_all = tab["G"], tab["WT"]
+		temps = {}
+		# ---- phase A: impute, P1, Gram of every temp_i
 		for ci, ds in enumerate(self.schic):
 			r = self.chrom2size[ds.chrom]
 			A, B, D = self.A_dev[ci], self.B_dict[ds.chrom], self.D_dict[ds.chrom]
@@ -318,12 +352,50 @@ class Fast_Higashi_core:
 				Arows = A[g.row0:g.row0 + g.nb]
 				_lib.gemm(T1, B, temp, ldw, r, r, (rp, 1), (1, r), r, batch=g.nb, batch_strides=(ldw * rp, 0, ldw * r),
 				          kscale=Arows, kscale_batch=r)
+				temps[(ci, b)] = temp
 				self._toc("p1_mttkrp", t)
-				# P2: U_i = polar(temp_i)
+				# P2a: Gram of every temp_i in fp64 (tall: T^T T, wide: T T^T)
 				t = self._tic()
+				off, ns = tab["block"][(ci, b)]
+				Gb = G_all[off:off + g.nb * ns * ns]
+				if ldw >= r:
+					_lib.gemm(temp, temp, Gb, ns, ns, ldw, (1, r), (r, 1), ns, batch=g.nb, batch_strides=(ldw * r, ldw * r, ns * ns),
+					          dtype=_lib.GEMM_F32_ACC64)
+				else:
+					_lib.gemm(temp, temp, Gb, ns, ns, r, (r, 1), (1, r), ns, batch=g.nb, batch_strides=(ldw * r, ldw * r, ns * ns),
+					          dtype=_lib.GEMM_F32_ACC64)
+				self._toc("polar_bins", t)
+				del T1
+		# ---- phase B: G^{-1/2} of all bins of all chromosomes at once (P2b)
+		t = self._tic()
+		_lib.check(_lib.lib().fh_polar_isqrt_multi(G_all.data_ptr(), WT_all.data_ptr(), tab["n_dev"].data_ptr(),
+		                                           tab["off_dev"].data_ptr(), tab["slot_dev"].data_ptr(),
+		                                           tab["n_host"].ctypes.data, tab["count"], tab["ssum"].data_ptr(), 0, None,
+		                                           _lib.stream_ptr()))
+		stats[:nch] = torch.segment_reduce(tab["ssum"], "sum", lengths=tab["chrom_lengths"])
+		self._toc("polar_bins", t)
+		# ---- phase C: U_i = temp_i M_i, P3
+		for ci, ds in enumerate(self.schic):
+			r = self.chrom2size[ds.chrom]
+			A, B, D = self.A_dev[ci], self.B_dict[ds.chrom], self.D_dict[ds.chrom]
+			for b, g in enumerate(ds.geoms):
+				ldw = pad4(g.w)
+				P = g.nb * ldw
+				X = self._impute_good(ci, b, do_conv, do_rwr, do_col)
+				temp = temps.pop((ci, b))
+				Arows = A[g.row0:g.row0 + g.nb]
+				t = self._tic()
+				off, ns = tab["block"][(ci, b)]
+				nn = ns * ns
+				WTb, Mb = WT_all[off:off + g.nb * nn], G_all[off:off + g.nb * nn]
+				_lib.gemm(WTb, WTb, Mb, ns, ns, ns, (1, ns), (ns, 1), ns, batch=g.nb, batch_strides=(nn, nn, nn), dtype=_lib.GEMM_F64)
 				U = self.projection_dev[ci][b]
-				_, ssum, _ = polar_batched(temp, ldw, r, r, out=U)
-				stats[ci] += ssum.sum()
+				if ldw >= r:
+					_lib.gemm(temp, Mb, U, ldw, r, r, (r, 1), (r, 1), r, batch=g.nb, batch_strides=(ldw * r, nn, ldw * r),
+					          dtype=_lib.GEMM_F32xF64_F32)
+				else:
+					_lib.gemm(Mb, temp, U, ldw, r, ldw, (ns, 1), (r, 1), r, batch=g.nb, batch_strides=(nn, ldw * r, ldw * r),
+					          dtype=_lib.GEMM_F64xF32_F32)
 				self._toc("polar_bins", t)
 				t = self._tic()
 				# P3: W_i = ((U_i B) diag(A_i)) D^T ; M += X W
@@ -334,7 +406,7 @@ class Fast_Higashi_core:
 				          kscale=Arows, kscale_batch=r)
 				_lib.gemm(X, W, MT, Cn, R, P, (P, 1), (R, 1), R, beta=1.0, dtype=gd)
 				self._toc("p3_project", t)
-				del W, T1, temp, UB
+				del W, temp, UB
 		# P4: V = polar(SVD_term^T) (:483-486)
 		self.last_svd_term_T = MT
 		t = self._tic()
@@ -398,7 +470,7 @@ class Fast_Higashi_core:
 		                        for g in ds.geoms] for ds in self.schic]
 		self.projected_dev = {c: torch.zeros(self.chrom2num_bin[c], self.chrom2size[c], R, dtype=torch.float32, device=dev)
 		                      for c in self.chrom2size}
-		self._X, self._eig = {}, {}
+		self._X, self._eig, self._ptab = {}, {}, None
 		self.invalidate_cache()
 		self.n_rwr_passes = 0
 		self._core_norm = self._core_norms()

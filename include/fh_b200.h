@@ -124,6 +124,16 @@ int fh_polar_batched(const float* T, float* U, int batch, int rows, int cols, lo
                      long long batch_stride, double* sigma_sum, double* sigma, int max_sweeps,
                      void* workspace, size_t workspace_bytes, int* host_max_sweeps, void* stream);
 
+/* The eigen step of the polar factor for MANY Gram matrices of different sizes at once (all bins of
+ * all chromosomes of one sweep). G_all / WT_all: concatenated n_i x n_i fp64 matrices; problem i
+ * (device tables, sorted by DEcreasing n; host_prob_n is the same n table on the host) reads G at
+ * dev_prob_off[i] doubles and writes WT there: row j = w_j lambda_j^{-3/4}, so that
+ * G^{-1/2} = WT^T WT; sigma_sum[dev_prob_slot[i]] = sum of sqrt(eigenvalues). dev_nsweep: NULL or
+ * [count] ints (by slot). */
+int fh_polar_isqrt_multi(const double* G_all, double* WT_all, const int* dev_prob_n,
+                         const long long* dev_prob_off, const int* dev_prob_slot, const int* host_prob_n,
+                         int count, double* sigma_sum, int max_sweeps, int* dev_nsweep, void* stream);
+
 /* Inverse square root of ONE symmetric positive definite n x n fp64 matrix by the coupled
  * Newton-Schulz iteration (tall cells x R polar, parafac2_intergrative.py:483,831: V = M G^{-1/2}
  * with G = M^T M all-reduced across ranks). Synchronises the stream to test convergence.
