@@ -4,7 +4,9 @@
 // sweep: X^T C, X W, X^T V) - the reference's torch.bmm / matmul call sites
 // (partial_rwr.py:85,116,138; parafac2_intergrative.py:381-383,429-430,522-524).
 //
-// One CTA computes one 128 x 128 output tile of one batch item:
+// Persistent: one CTA per SM loops over 128 x 128 output tiles (tile t, t + #SMs, ...); the shared-memory
+// ring and the two TMEM accumulators keep rolling across tiles, so the epilogue of one tile overlaps
+// the loads / MMAs of the next. Roles inside a CTA:
 //   warp 0      TMA producer: raw fp32 operand tiles (K-major or MN-major, 128-byte swizzle) from
 //               HBM/L2 into a 3-stage shared-memory ring (cp.async.bulk.tensor, mbarrier tx-count)
 //   warps 4-7   splitters: turn each landed tile into its hi / lo TF32 halves in place (+ a second
@@ -27,7 +29,8 @@ constexpr int BM = 128, BN = 128, BK = 32;       // tile (BK fp32 = one 128-byte
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;          // 16 KB per operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_BYTES = 8 * 32 * 33 * 4;         // epilogue transposes: 8 drain warps x 32 rows x 33 floats
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NTHREADS = 512;
 constexpr int CHUNK_KB = 4;                      // k-blocks accumulated in TMEM before a drain (K = 128)
 
@@ -38,6 +41,7 @@ struct TcP {
 	int epilogue;
 	const float* cscale; long long cscale_batch; int cscale_recip;
 	int a_bcast, b_bcast;  // operand shared by all batch items (batch stride 0)
+	int vec_ok;            // C rows are 16-byte aligned: 128-bit epilogue accesses allowed
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -93,6 +97,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ uint32_t tf32_rn(uint32_t bits) { return (bits + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ uint32_t to_tf32(float x) {
 	uint32_t r;
 	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -105,7 +110,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                float* __restrict__ C) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-	uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+	uint8_t* stagebuf = smem + STAGES * STAGE_BYTES;           // 8 warps x 16 x 33 floats (epilogue transposes)
+	uint64_t* bars = (uint64_t*)(stagebuf + EPI_BYTES);
 	uint64_t* raw_full = bars;                 // TMA landed            (count 1 + tx)
 	uint64_t* split_full = bars + STAGES;      // hi/lo written         (count 4: one per splitter warp)
 	uint64_t* empty = bars + 2 * STAGES;       // MMAs of the stage done (count 1, tcgen05.commit)
@@ -114,8 +120,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 	uint32_t* tmem_holder = (uint32_t*)(bars + 3 * STAGES + 4);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, bz = blockIdx.z;
 	const int nkb = (p.K + BK - 1) / BK;
+	const int nchunk = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+	// persistent: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, then m, then batch)
+	const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + BM - 1) / BM;
+	const long long total_tiles = (long long)tiles_n * tiles_m * p.batch;
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < STAGES; ++s) {
@@ -143,26 +152,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 	if (warp == 0) {
 		// ------------------------------------------------------------------ TMA producer
 		if (lane == 0) {
-			const int za = p.a_bcast ? 0 : bz, zb = p.b_bcast ? 0 : bz;
-			for (int kb = 0; kb < nkb; ++kb) {
-				const int s = kb % STAGES;
-				const uint32_t ph = (kb / STAGES) & 1;
-				mbar_wait(&empty[s], ph ^ 1);
-				uint8_t* st = smem + s * STAGE_BYTES;
-				mbar_expect_tx(&raw_full[s], 2 * TILE_BYTES);
-				const int k0 = kb * BK;
-				if (A_MN) {  // global (K rows x M contiguous): four 32-wide boxes of BK rows
+			long long it = 0;  // k-blocks issued by this CTA so far (ring position continues across tiles)
+			for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+				const int bz = (int)(tile / ((long long)tiles_n * tiles_m));
+				const int rem = (int)(tile - (long long)bz * tiles_n * tiles_m);
+				const int m0 = (rem / tiles_n) * BM, n0 = (rem % tiles_n) * BN;
+				const int za = p.a_bcast ? 0 : bz, zb = p.b_bcast ? 0 : bz;
+				for (int kb = 0; kb < nkb; ++kb, ++it) {
+					const int s = (int)(it % STAGES);
+					const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+					mbar_wait(&empty[s], ph ^ 1);
+					uint8_t* st = smem + s * STAGE_BYTES;
+					mbar_expect_tx(&raw_full[s], 2 * TILE_BYTES);
+					const int k0 = kb * BK;
+					if (A_MN) {  // global (K rows x M contiguous): four 32-wide boxes of BK rows
 #pragma unroll
-					for (int j = 0; j < BM / 32; ++j) tma_load_3d(st + j * (BK * 128), &tmA, &raw_full[s], m0 + 32 * j, k0, za);
-				} else {     // global (M rows x K contiguous): one box of 32 x 128
-					tma_load_3d(st, &tmA, &raw_full[s], k0, m0, za);
-				}
-				uint8_t* sb = st + 2 * TILE_BYTES;
-				if (B_MN) {
+						for (int j = 0; j < BM / 32; ++j) tma_load_3d(st + j * (BK * 128), &tmA, &raw_full[s], m0 + 32 * j, k0, za);
+					} else {     // global (M rows x K contiguous): one box of 32 x 128
+						tma_load_3d(st, &tmA, &raw_full[s], k0, m0, za);
+					}
+					uint8_t* sb = st + 2 * TILE_BYTES;
+					if (B_MN) {
 #pragma unroll
-					for (int j = 0; j < BN / 32; ++j) tma_load_3d(sb + j * (BK * 128), &tmB, &raw_full[s], n0 + 32 * j, k0, zb);
-				} else {
-					tma_load_3d(sb, &tmB, &raw_full[s], k0, n0, zb);
+						for (int j = 0; j < BN / 32; ++j) tma_load_3d(sb + j * (BK * 128), &tmB, &raw_full[s], n0 + 32 * j, k0, zb);
+					} else {
+						tma_load_3d(sb, &tmB, &raw_full[s], k0, n0, zb);
+					}
 				}
 			}
 		}
@@ -178,119 +193,162 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 			// (SBO), 32-element MN groups BK*128 B apart (LBO); a K=8 step = 8 rows = +1024 B.
 			const uint32_t a_lbo = A_MN ? BK * 128 : 16, a_sbo = A_MN ? 512 : 1024, a_step = A_MN ? 1024 : 32, a_lt = A_MN ? 1 : 2;
 			const uint32_t b_lbo = B_MN ? BK * 128 : 16, b_sbo = B_MN ? 512 : 1024, b_step = B_MN ? 1024 : 32, b_lt = B_MN ? 1 : 2;
-			for (int kb = 0; kb < nkb; ++kb) {
-				const int s = kb % STAGES;
-				const uint32_t ph = (kb / STAGES) & 1;
-				const int chunk = kb / CHUNK_KB, cb = chunk & 1;
-				if (kb % CHUNK_KB == 0) {  // new chunk: its accumulator must have been drained
-					mbar_wait(&acc_empty[cb], ((chunk >> 1) & 1) ^ 1);
+			long long it = 0, ch = 0;  // k-blocks / accumulator chunks consumed by this CTA so far
+			for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+				for (int kb = 0; kb < nkb; ++kb, ++it) {
+					const int s = (int)(it % STAGES);
+					const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+					const int cb = (int)(ch & 1);
+					if (kb % CHUNK_KB == 0) {  // new chunk: its accumulator must have been drained
+						mbar_wait(&acc_empty[cb], (uint32_t)(((ch >> 1) & 1) ^ 1));
+						asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					}
+					const uint32_t acc = tmem_acc + (uint32_t)(cb * BN);
+					mbar_wait(&split_full[s], ph);
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-				}
-				const uint32_t acc = tmem_acc + (uint32_t)(cb * BN);
-				mbar_wait(&split_full[s], ph);
-				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-				const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES;
-				const uint32_t b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
+					const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES;
+					const uint32_t b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
 #pragma unroll
-				for (int k = 0; k < BK / 8; ++k) {
-					const uint64_t dah = make_desc(a_hi + k * a_step, a_lbo, a_sbo, a_lt), dal = make_desc(a_lo + k * a_step, a_lbo, a_sbo, a_lt);
-					const uint64_t dbh = make_desc(b_hi + k * b_step, b_lbo, b_sbo, b_lt), dbl = make_desc(b_lo + k * b_step, b_lbo, b_sbo, b_lt);
-					umma_tf32(acc, dal, dbh, idesc, ((kb % CHUNK_KB) | k) ? 1u : 0u);  // small terms first
-					umma_tf32(acc, dah, dbl, idesc, 1u);
-					umma_tf32(acc, dah, dbh, idesc, 1u);
+					for (int k = 0; k < BK / 8; ++k) {
+						const uint64_t dah = make_desc(a_hi + k * a_step, a_lbo, a_sbo, a_lt), dal = make_desc(a_lo + k * a_step, a_lbo, a_sbo, a_lt);
+						const uint64_t dbh = make_desc(b_hi + k * b_step, b_lbo, b_sbo, b_lt), dbl = make_desc(b_lo + k * b_step, b_lbo, b_sbo, b_lt);
+						umma_tf32(acc, dal, dbh, idesc, ((kb % CHUNK_KB) | k) ? 1u : 0u);  // small terms first
+						umma_tf32(acc, dah, dbl, idesc, 1u);
+						umma_tf32(acc, dah, dbh, idesc, 1u);
+					}
+					umma_commit(&empty[s]);
+					if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) {
+						umma_commit(&acc_full[cb]);
+						++ch;
+					}
 				}
-				umma_commit(&empty[s]);
-				if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(&acc_full[cb]);
 			}
 		}
 	} else if (warp >= 4 && warp < 8) {
 		// ------------------------------------------------------------------ splitters
 		const int t = threadIdx.x - 128;  // 0..127
-		for (int kb = 0; kb < nkb; ++kb) {
-			const int s = kb % STAGES;
-			const uint32_t ph = (kb / STAGES) & 1;
-			mbar_wait(&raw_full[s], ph);
-			uint8_t* st = smem + s * STAGE_BYTES;
+		long long it = 0;
+		for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+			for (int kb = 0; kb < nkb; ++kb, ++it) {
+				const int s = (int)(it % STAGES);
+				const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+				mbar_wait(&raw_full[s], ph);
+				uint8_t* st = smem + s * STAGE_BYTES;
 #pragma unroll
-			for (int op = 0; op < 2; ++op) {
-				float4* hi = (float4*)(st + op * 2 * TILE_BYTES);
-				float4* lo = (float4*)(st + op * 2 * TILE_BYTES + TILE_BYTES);
+				for (int op = 0; op < 2; ++op) {
+					float4* hi = (float4*)(st + op * 2 * TILE_BYTES);
+					float4* lo = (float4*)(st + op * 2 * TILE_BYTES + TILE_BYTES);
 #pragma unroll
-				for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
-					float4 v = hi[t + 128 * i];
-					uint4 h, l;
-					h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-					l.x = to_tf32(v.x - __uint_as_float(h.x)); l.y = to_tf32(v.y - __uint_as_float(h.y));
-					l.z = to_tf32(v.z - __uint_as_float(h.z)); l.w = to_tf32(v.w - __uint_as_float(h.w));
-					((uint4*)hi)[t + 128 * i] = h;
-					((uint4*)lo)[t + 128 * i] = l;
+					for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+						float4 v = hi[t + 128 * i];
+						uint4 h, l;
+						// tf32 round-to-nearest (ties away, = cvt.rna.tf32.f32) with two integer ops; ptxas expands
+						// the cvt itself to ~10 instructions and the splitters were the busiest warps (ncu)
+						h.x = tf32_rn(__float_as_uint(v.x)); h.y = tf32_rn(__float_as_uint(v.y));
+						h.z = tf32_rn(__float_as_uint(v.z)); h.w = tf32_rn(__float_as_uint(v.w));
+						l.x = tf32_rn(__float_as_uint(v.x - __uint_as_float(h.x))); l.y = tf32_rn(__float_as_uint(v.y - __uint_as_float(h.y)));
+						l.z = tf32_rn(__float_as_uint(v.z - __uint_as_float(h.z))); l.w = tf32_rn(__float_as_uint(v.w - __uint_as_float(h.w)));
+						((uint4*)hi)[t + 128 * i] = h;
+						((uint4*)lo)[t + 128 * i] = l;
+					}
 				}
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&split_full[s]);
 			}
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
-			__syncwarp();
-			if (lane == 0) mbar_arrive(&split_full[s]);
 		}
 	} else if (warp >= 8) {
 		// ------------------------------------------------------------------ drain + epilogue
 		const int q = warp & 3;             // TMEM lane quarter of this warp (rows 32q .. 32q+31)
 		const int h = (warp - 8) >> 2;      // column half (64 columns)
-		float sum[64];
+		float* tile_s = (float*)(stagebuf + (warp - 8) * (32 * 33 * 4));
+		long long ch = 0;
+		for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+			const int bz = (int)(tile / ((long long)tiles_n * tiles_m));
+			const int rem = (int)(tile - (long long)bz * tiles_n * tiles_m);
+			const int m0 = (rem / tiles_n) * BM, n0 = (rem % tiles_n) * BN;
+			float sum[64];
 #pragma unroll
-		for (int j = 0; j < 64; ++j) sum[j] = 0.f;
-		const int nchunk = (nkb + CHUNK_KB - 1) / CHUNK_KB;
-		for (int chunk = 0; chunk < nchunk; ++chunk) {
-			const int cb = chunk & 1;
-			mbar_wait(&acc_full[cb], (chunk >> 1) & 1);
-			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			for (int j = 0; j < 64; ++j) sum[j] = 0.f;
+			for (int chunk = 0; chunk < nchunk; ++chunk, ++ch) {
+				const int cb = (int)(ch & 1);
+				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+				for (int c = 0; c < 2; ++c) {
+					uint32_t v[32];
+					const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * BN + h * 64 + c * 32);
+					asm volatile(
+						"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+						"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+						"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+						: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+						  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+						  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+						  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+						: "r"(taddr));
+					asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+					for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(v[j]);
+				}
+				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&acc_empty[cb]);
+			}
+			// epilogue of this tile; the MMA warp is already free to start the next tile's chunks.
+			// A 32 x 32 transpose through a private staging buffer, then each lane owns 4 consecutive
+			// columns of 8 rows: 128-bit stores, every warp store instruction covers four 128-byte rows.
+			float* Cb = C + (long long)bz * p.batch_c;
+			const float* cs = p.cscale ? p.cscale + (long long)bz * p.cscale_batch : nullptr;
+			const int cg = lane & 7, ro = lane >> 3;
 #pragma unroll
 			for (int c = 0; c < 2; ++c) {
-				uint32_t v[32];
-				const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * BN + h * 64 + c * 32);
-				asm volatile(
-					"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-					"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-					"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-					: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-					  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-					  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-					  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-					: "r"(taddr));
-				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+				__syncwarp();
 #pragma unroll
-				for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(v[j]);
-			}
-			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-			__syncwarp();
-			if (lane == 0) mbar_arrive(&acc_empty[cb]);
-		}
-		// all MMAs, TMA loads and splits are complete here: the stage ring is free for the transposes
-		float* Cb = C + (long long)bz * p.batch_c;
-		const float* cs = p.cscale ? p.cscale + (long long)bz * p.cscale_batch : nullptr;
-		float* tile = (float*)(smem + (warp - 8) * (32 * 33 * 4));
+				for (int j = 0; j < 32; ++j) tile_s[lane * 33 + j] = sum[c * 32 + j];
+				__syncwarp();
+				const int n = n0 + h * 64 + c * 32 + 4 * cg;  // first of this lane's 4 columns
+				if (n < p.N) {
+					float csv[4] = {1.f, 1.f, 1.f, 1.f};
+					if (cs) {
 #pragma unroll
-		for (int c = 0; c < 2; ++c) {
-			__syncwarp();
+						for (int e = 0; e < 4; ++e)
+							if (n + e < p.N) csv[e] = cs[n + e];
+					}
+					const bool vec = p.vec_ok && (n + 3 < p.N);
 #pragma unroll
-			for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = sum[c * 32 + j];
-			__syncwarp();
-			const int n = n0 + h * 64 + c * 32 + lane;
-			const bool ncol = n < p.N;
-			float csv = 1.f;
-			if (cs && ncol) csv = cs[n];
-#pragma unroll 4
-			for (int rr = 0; rr < 32; ++rr) {
-				const int r = m0 + q * 32 + rr;
-				if (r < p.M && ncol) {
-					float x = p.alpha * tile[rr * 33 + lane];
-					if (p.epilogue == FH_EPI_DIAG_ADD && r == n) x += p.diag;
-					if (cs) x = p.cscale_recip ? x / csv : x * csv;
-					float* cp = Cb + (long long)r * p.ldc + n;
-					if (p.beta != 0.f) x += p.beta * *cp;
-					*cp = x;
+					for (int itr = 0; itr < 8; ++itr) {
+						const int rr = itr * 4 + ro;
+						const int r = m0 + q * 32 + rr;
+						if (r >= p.M) continue;
+						float x[4];
+#pragma unroll
+						for (int e = 0; e < 4; ++e) {
+							x[e] = p.alpha * tile_s[rr * 33 + 4 * cg + e];
+							if (p.epilogue == FH_EPI_DIAG_ADD && r == n + e) x[e] += p.diag;
+							if (cs) x[e] = p.cscale_recip ? x[e] / csv[e] : x[e] * csv[e];
+						}
+						float* cp = Cb + (long long)r * p.ldc + n;
+						if (vec) {
+							if (p.beta != 0.f) {
+								const float4 o = *reinterpret_cast<const float4*>(cp);
+								x[0] += p.beta * o.x; x[1] += p.beta * o.y; x[2] += p.beta * o.z; x[3] += p.beta * o.w;
+							}
+							*reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+						} else {
+#pragma unroll
+							for (int e = 0; e < 4; ++e)
+								if (n + e < p.N) {
+									if (p.beta != 0.f) x[e] += p.beta * cp[e];
+									cp[e] = x[e];
+								}
+						}
+					}
 				}
 			}
 		}
 	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 	__syncthreads();
 	if (warp == 2) {
 		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(2 * BN) : "memory");
@@ -360,7 +418,15 @@ int fh_gemm_tc(const fh_gemm_desc* d, const float* A, const float* B, float* C, 
 	p.alpha = (float)d->alpha; p.beta = (float)d->beta; p.diag = (float)d->diag; p.epilogue = d->epilogue;
 	p.cscale = d->cscale; p.cscale_batch = d->cscale_batch; p.cscale_recip = d->cscale_recip;
 	p.a_bcast = a_bc; p.b_bcast = b_bc;
-	dim3 grid(fh_cdiv(d->N, BN), fh_cdiv(d->M, BM), d->batch);
+	p.vec_ok = aligned16(C) && (d->ldc % 4 == 0) && (d->batch <= 1 || d->batch_c % 4 == 0);
+	const long long total_tiles = (long long)fh_cdiv(d->N, BN) * fh_cdiv(d->M, BM) * d->batch;
+	static int num_sms = 0;
+	if (!num_sms) {
+		int dev = 0;
+		FH_CUDA(cudaGetDevice(&dev));
+		FH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+	}
+	dim3 grid((unsigned)(total_tiles < num_sms ? total_tiles : num_sms));  // persistent: one CTA per SM
 	cudaStream_t st = (cudaStream_t)stream;
 #define FH_TC_LAUNCH(AM, BMN)                                                                                         \
 	do {                                                                                                              \
