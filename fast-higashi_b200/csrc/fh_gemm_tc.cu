@@ -316,7 +316,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 							if (n + e < p.N) csv[e] = cs[n + e];
 					}
 					const bool vec = p.vec_ok && (n + 3 < p.N);
-#pragma unroll
+					// rolled on purpose: ncu showed the drain warps stalled on instruction fetch (stall_no_inst)
+					// when this was fully unrolled - the kernel must stay inside the instruction cache
+#pragma unroll 1
 					for (int itr = 0; itr < 8; ++itr) {
 						const int rr = itr * 4 + ro;
 						const int r = m0 + q * 32 + rr;
