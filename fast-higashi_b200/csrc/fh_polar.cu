@@ -33,7 +33,8 @@ __device__ __forceinline__ void rr_pair(int m, int s, int t, int& p, int& q) {
 	}
 }
 
-constexpr int MAXPL = 6;      // column elements per lane: n <= 32 * MAXPL = 192 (smem caps n at ~166 anyway)
+constexpr int MAXPL = 6;        // n <= 32 * MAXPL = 192 (shared memory caps n at ~166 anyway)
+constexpr int MAXPL16 = 12;     // column elements per lane of a half warp
 
 // One CTA per matrix (problem b: size prob_n[b], data at prob_off[b] doubles into Gall / WTall).
 // Shared memory holds R (n x ld, row-major): first the symmetric G, then its pivoted Cholesky factor
@@ -122,56 +123,95 @@ chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob
 	}
 	__syncthreads();
 	// ---------------- one-sided Jacobi on the rows of R (columns of L) ----------------
-	const int m = even_up(n), half = m >> 1;
+	// ncu: the first version was instruction-issue bound (32 warps x ~250 instructions per pair, mostly
+	// fp64 reductions and the sqrt/div chain). Now: a HALF-warp per pair (two pairs share every
+	// instruction), squared norms tracked incrementally (one dot product per pair, norms refreshed every
+	// sweep), tan(theta) from fp32 arithmetic (cos = rsqrt(1+t^2) in fp64 keeps the rotation orthogonal to
+	// fp64 rounding; an fp32-accurate angle only leaves a 1e-7 relative residual), no integer division.
+	const int m = even_up(n), half = m >> 1, mm = m - 1;
 	const double tol2 = 1e-30 * (double)n;       // (1e-15 sqrt(n))^2 on gamma^2 / (alpha beta)
+	double* nrm = red + 64 + ((n + 1) >> 1);     // n squared norms, after perm (ints) in the scratch area
+	const int hw = lane >> 4, hl = lane & 15;
+	const unsigned hmask = hw ? 0xffff0000u : 0x0000ffffu;
+	const int nslot = nw * 2;
 	int sweep = 0;
 	for (; sweep < max_sweeps; ++sweep) {
+		for (int j = warp; j < n; j += nw) {        // refresh the tracked norms
+			double s2 = 0.0;
+			for (int i = lane; i < n; i += 32) { double v = R[j * ld + i]; s2 += v * v; }
+			s2 = fh_warp_sum(s2);
+			if (lane == 0) nrm[j] = s2;
+		}
+		__syncthreads();
 		double worst = 0.0;                        // largest gamma^2/(alpha beta) met in this sweep
-		for (int step = 0; step < m - 1; ++step) {
-			for (int t = warp; t < half; t += nw) {
+		for (int step = 0; step < mm; ++step) {
+			for (int t = warp * 2 + hw; t < half; t += nslot) {
 				int p, q;
-				rr_pair(m, step, t, p, q);
+				if (t == 0) { p = mm; q = step; }
+				else {
+					p = step + t; if (p >= mm) p -= mm;
+					q = step - t + mm; if (q >= mm) q -= mm;
+				}
 				if (p >= n || q >= n) continue;      // the padding player of an odd n
 				if (p > q) { int x = p; p = q; q = x; }
 				double* rp = R + p * ld;
 				double* rq = R + q * ld;
-				double a[MAXPL], c[MAXPL];
-				double al = 0.0, be = 0.0, ga = 0.0;
+				double a[MAXPL16];
+				double ga = 0.0;
 #pragma unroll
-				for (int e = 0; e < MAXPL; ++e) {
-					int i = lane + 32 * e;
+				for (int e = 0; e < MAXPL16; ++e) {
+					int i = hl + 16 * e;
 					a[e] = (i < n) ? rp[i] : 0.0;
-					c[e] = (i < n) ? rq[i] : 0.0;
-					al += a[e] * a[e]; be += c[e] * c[e]; ga += a[e] * c[e];
+					ga += a[e] * ((i < n) ? rq[i] : 0.0);
 				}
-				al = fh_warp_sum(al); be = fh_warp_sum(be); ga = fh_warp_sum(ga);
+#pragma unroll
+				for (int o = 8; o > 0; o >>= 1) ga += __shfl_xor_sync(hmask, ga, o);
+				const double al = nrm[p], be = nrm[q];
 				const double g2 = ga * ga, ab = al * be;
 				if (g2 > tol2 * ab && ga != 0.0) {
 					worst = fmax(worst, g2 / ab);
-					// t = sign(d) 2 gamma / (|d| + sqrt(d^2 + 4 gamma^2)), d = beta - alpha (smaller root)
+					// t = sign(d) rho / (1 + sqrt(1 + rho^2)), rho = 2 gamma / |d|, d = beta - alpha (fp32)
 					const double d = be - al;
-					const double tt = (d >= 0.0 ? 2.0 : -2.0) * ga / (fabs(d) + sqrt(d * d + 4.0 * g2));
+					// common power-of-two scale so the fp32 ratio cannot over/underflow
+					const double big = fmax(fabs(d), fabs(ga));
+					const int ex = (__double2hiint(big) >> 20) & 0x7ff;
+					const double scale = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023 - ex)
+					const float rho = (float)(2.0 * ga * scale) / fmaxf((float)(fabs(d) * scale), 1e-30f);
+					float tf;
+					if (fabsf(rho) <= 1.f) tf = rho / (1.f + sqrtf(1.f + rho * rho));
+					else {
+						const float ir = 1.f / fabsf(rho);
+						tf = copysignf(1.f / (ir + sqrtf(1.f + ir * ir)), rho);
+					}
+					if (!(fabsf(tf) <= 1.f)) tf = copysignf(1.f, rho);  // inf/nan guard: 45 degrees
+					const double tt = (d >= 0.0) ? (double)tf : -(double)tf;
 					const double cs = rsqrt(tt * tt + 1.0), sn = tt * cs;
 #pragma unroll
-					for (int e = 0; e < MAXPL; ++e) {
-						int i = lane + 32 * e;
+					for (int e = 0; e < MAXPL16; ++e) {
+						int i = hl + 16 * e;
 						if (i < n) {
-							rp[i] = cs * a[e] - sn * c[e];
-							rq[i] = sn * a[e] + cs * c[e];
+							const double c = rq[i];
+							rp[i] = cs * a[e] - sn * c;
+							rq[i] = sn * a[e] + cs * c;
 						}
+					}
+					if (hl == 0) {  // |w_p|^2, |w_q|^2 after the rotation
+						nrm[p] = fmax(al - tt * ga, 0.0);
+						nrm[q] = be + tt * ga;
 					}
 				}
 			}
 			__syncthreads();
 		}
 		// block max of `worst`
+		worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, 16));
 		if (lane == 0) red[warp] = worst;
 		__syncthreads();
 		double wmax = 0.0;
 		for (int i = 0; i < nw; ++i) wmax = fmax(wmax, red[i]);
 		__syncthreads();
-		// quadratic convergence: rotations of a sweep whose largest scaled off-diagonal was <= 1e-7
-		// leave ~1e-14 behind - no confirming sweep needed
+		// convergence: the largest scaled off-diagonal met in the sweep was <= 1e-7, its rotations leave
+		// ~1e-14 behind - no confirming sweep needed
 		if (wmax <= 1e-14) { ++sweep; break; }
 	}
 	if (tid == 0 && nsweep_out) nsweep_out[slot] = sweep;
@@ -238,7 +278,7 @@ constexpr int kMaxSweeps = 30;
 
 int jacobi_threads(int n) { return n > 83 ? 1024 : (n > 58 ? 512 : 256); }
 
-size_t jacobi_smem(int n) { return ((size_t)n * (n | 1) + 64) * 8 + (size_t)n * 4 + 16; }
+size_t jacobi_smem(int n) { return ((size_t)n * (n | 1) + 64 + (n + 1) / 2 + n) * 8 + 16; }
 
 }  // namespace
 
