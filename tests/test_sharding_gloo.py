@@ -1,0 +1,60 @@
+"""Host-side logic of the N>1 path on CPU with the gloo backend (world_size 2): slab bounds, per-rank
+block-CSR views, and the collective plumbing of the core (`_allreduce`) - no compute kernels involved."""
+import os
+import socket
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from conftest import load_small_dataset
+
+
+def _free_port():
+	s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+	os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+	dist.init_process_group("gloo", rank=rank, world_size=world)
+	from fasthigashi_b200.sharding import cell_slab, shard_datasets
+	from fasthigashi_b200.parafac2_intergrative import Fast_Higashi_core
+	full = load_small_dataset()
+	mine = shard_datasets(full, world, rank)
+	lo, hi = cell_slab(full[0].num_cell, world, rank)
+	nnz = torch.tensor([float(sum(d.nnz() for d in mine))])
+	core = Fast_Higashi_core(8, 12, [1000000], group=dist.group.WORLD)
+	core._allreduce(nnz)                                   # the core's own collective helper, SUM
+	mx = torch.tensor([hi - lo]); core._allreduce(mx, dist.ReduceOp.MAX)
+	# every (cell, row) of the slab keeps exactly its entries
+	ok = True
+	for d_full, d_mine in zip(full, mine):
+		for b, g in enumerate(d_full.geoms):
+			rp, col, val = d_full.cell_range_csr(b, lo, hi)
+			ok &= torch.equal(rp, d_mine.rowptr[b]) and torch.equal(col, d_mine.col[b]) and torch.equal(val, d_mine.val[b])
+	q.put((rank, lo, hi, float(nnz), int(mx), bool(ok), [d.num_cell for d in mine]))
+	dist.destroy_process_group()
+
+
+def test_cell_slabs_cover_everything():
+	from fasthigashi_b200.sharding import cell_slab
+	for total in [1, 7, 48, 4238, 100000]:
+		for world in [1, 2, 3, 8]:
+			slabs = [cell_slab(total, world, r) for r in range(world)]
+			assert slabs[0][0] == 0 and slabs[-1][1] == total
+			assert all(a[1] == b[0] for a, b in zip(slabs[:-1], slabs[1:]))
+			assert max(h - l for l, h in slabs) - min(h - l for l, h in slabs) <= 1
+
+
+def test_two_rank_gloo_sharding():
+	ctx = mp.get_context("spawn")
+	q = ctx.Queue()
+	port = _free_port()
+	procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+	for p in procs: p.start()
+	res = sorted(q.get(timeout=120) for _ in procs)
+	for p in procs: p.join(timeout=60)
+	total_nnz = float(sum(d.nnz() for d in load_small_dataset()))
+	assert [r[1:3] for r in res] == [(0, 24), (24, 48)]
+	assert all(r[3] == total_nnz for r in res)            # SUM all-reduce saw both slabs
+	assert all(r[4] == 24 for r in res) and all(r[5] for r in res)
+	assert all(r[6] == [24, 24, 24] for r in res)
