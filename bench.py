@@ -337,6 +337,9 @@ def main():
 		       "d2h_bytes_per_step": int((2 * len(datasets) + 1) * 8 + len(datasets) * 8), "ms_per_step": ms_e, "steps": n_e2e}
 		del host
 
+	if world > 1:
+		dist.barrier()
+		dist.destroy_process_group()
 	if rank != 0:
 		return
 	pk = peaks()

@@ -42,6 +42,7 @@ struct TcP {
 	const float* cscale; long long cscale_batch; int cscale_recip;
 	int a_bcast, b_bcast;  // operand shared by all batch items (batch stride 0)
 	int vec_ok;            // C rows are 16-byte aligned: 128-bit epilogue accesses allowed
+	int ksplit, kb_per_split;  // split-K: work item = (tile, k range); partial sums are atomically added to C
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,10 +122,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int nkb = (p.K + BK - 1) / BK;
-	const int nchunk = (nkb + CHUNK_KB - 1) / CHUNK_KB;
 	// persistent: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, then m, then batch)
 	const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + BM - 1) / BM;
-	const long long total_tiles = (long long)tiles_n * tiles_m * p.batch;
+	const long long total_tiles = (long long)tiles_n * tiles_m * p.batch * p.ksplit;  // work items
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < STAGES; ++s) {
@@ -154,11 +154,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 		if (lane == 0) {
 			long long it = 0;  // k-blocks issued by this CTA so far (ring position continues across tiles)
 			for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-				const int bz = (int)(tile / ((long long)tiles_n * tiles_m));
-				const int rem = (int)(tile - (long long)bz * tiles_n * tiles_m);
+				const long long tl = tile / p.ksplit;
+				const int ks = (int)(tile - tl * p.ksplit);
+				const int bz = (int)(tl / ((long long)tiles_n * tiles_m));
+				const int rem = (int)(tl - (long long)bz * tiles_n * tiles_m);
 				const int m0 = (rem / tiles_n) * BM, n0 = (rem % tiles_n) * BN;
 				const int za = p.a_bcast ? 0 : bz, zb = p.b_bcast ? 0 : bz;
-				for (int kb = 0; kb < nkb; ++kb, ++it) {
+				const int kb0 = ks * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+				for (int kb = kb0; kb < kb1; ++kb, ++it) {
 					const int s = (int)(it % STAGES);
 					const uint32_t ph = (uint32_t)((it / STAGES) & 1);
 					mbar_wait(&empty[s], ph ^ 1);
@@ -195,7 +198,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 			const uint32_t b_lbo = B_MN ? BK * 128 : 16, b_sbo = B_MN ? 512 : 1024, b_step = B_MN ? 1024 : 32, b_lt = B_MN ? 1 : 2;
 			long long it = 0, ch = 0;  // k-blocks / accumulator chunks consumed by this CTA so far
 			for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-				for (int kb = 0; kb < nkb; ++kb, ++it) {
+				const int ksm = (int)(tile % p.ksplit);
+				const int nkb_t = min(nkb, (ksm + 1) * p.kb_per_split) - ksm * p.kb_per_split;
+				for (int kb = 0; kb < nkb_t; ++kb, ++it) {
 					const int s = (int)(it % STAGES);
 					const uint32_t ph = (uint32_t)((it / STAGES) & 1);
 					const int cb = (int)(ch & 1);
@@ -217,7 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 						umma_tf32(acc, dah, dbh, idesc, 1u);
 					}
 					umma_commit(&empty[s]);
-					if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) {
+					if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb_t - 1) {
 						umma_commit(&acc_full[cb]);
 						++ch;
 					}
@@ -229,7 +234,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 		const int t = threadIdx.x - 128;  // 0..127
 		long long it = 0;
 		for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-			for (int kb = 0; kb < nkb; ++kb, ++it) {
+			const int ksm = (int)(tile % p.ksplit);
+			const int nkb_t = min(nkb, (ksm + 1) * p.kb_per_split) - ksm * p.kb_per_split;
+			for (int kb = 0; kb < nkb_t; ++kb, ++it) {
 				const int s = (int)(it % STAGES);
 				const uint32_t ph = (uint32_t)((it / STAGES) & 1);
 				mbar_wait(&raw_full[s], ph);
@@ -264,13 +271,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 		float* tile_s = (float*)(stagebuf + (warp - 8) * (32 * 33 * 4));
 		long long ch = 0;
 		for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-			const int bz = (int)(tile / ((long long)tiles_n * tiles_m));
-			const int rem = (int)(tile - (long long)bz * tiles_n * tiles_m);
+			const long long tl = tile / p.ksplit;
+			const int ksm = (int)(tile - tl * p.ksplit);
+			const int nkb_t = min(nkb, (ksm + 1) * p.kb_per_split) - ksm * p.kb_per_split;
+			const int nchunk_t = (nkb_t + CHUNK_KB - 1) / CHUNK_KB;
+			const int bz = (int)(tl / ((long long)tiles_n * tiles_m));
+			const int rem = (int)(tl - (long long)bz * tiles_n * tiles_m);
 			const int m0 = (rem / tiles_n) * BM, n0 = (rem % tiles_n) * BN;
 			float sum[64];
 #pragma unroll
 			for (int j = 0; j < 64; ++j) sum[j] = 0.f;
-			for (int chunk = 0; chunk < nchunk; ++chunk, ++ch) {
+			for (int chunk = 0; chunk < nchunk_t; ++chunk, ++ch) {
 				const int cb = (int)(ch & 1);
 				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -331,7 +342,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 							if (cs) x[e] = p.cscale_recip ? x[e] / csv[e] : x[e] * csv[e];
 						}
 						float* cp = Cb + (long long)r * p.ldc + n;
-						if (vec) {
+						if (p.ksplit > 1) {  // split-K partial: C already holds beta*C (host), add atomically
+#pragma unroll
+							for (int e = 0; e < 4; ++e)
+								if (n + e < p.N) atomicAdd(cp + e, x[e]);
+						} else if (vec) {
 							if (p.beta != 0.f) {
 								const float4 o = *reinterpret_cast<const float4*>(cp);
 								x[0] += p.beta * o.x; x[1] += p.beta * o.y; x[2] += p.beta * o.z; x[3] += p.beta * o.w;
@@ -428,7 +443,24 @@ int fh_gemm_tc(const fh_gemm_desc* d, const float* A, const float* B, float* C, 
 		FH_CUDA(cudaGetDevice(&dev));
 		FH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
 	}
-	dim3 grid((unsigned)(total_tiles < num_sms ? total_tiles : num_sms));  // persistent: one CTA per SM
+	// long-K problems with few output tiles (P3: cells x 256 outputs, K = nb*ldw ~ 36k): split K so every SM
+	// has work; partial sums are added with fp32 atomics (C pre-scaled by beta here)
+	const int nkb_h = fh_cdiv(d->K, BK);
+	p.ksplit = 1; p.kb_per_split = nkb_h;
+	if (total_tiles * 2 <= num_sms + 12 && nkb_h >= 64 && !d->cscale && d->epilogue == FH_EPI_NONE && (d->beta == 0.0 || d->beta == 1.0)) {
+		int ks = (int)(num_sms / total_tiles);
+		if (ks > nkb_h / 32) ks = nkb_h / 32;
+		if (ks > 1) {
+			p.kb_per_split = (fh_cdiv(nkb_h, ks) + CHUNK_KB - 1) / CHUNK_KB * CHUNK_KB;
+			p.ksplit = fh_cdiv(nkb_h, p.kb_per_split);
+			if (d->beta == 0.0)
+				for (int b = 0; b < d->batch; ++b)
+					FH_CUDA(cudaMemset2DAsync(C + (long long)b * d->batch_c, (size_t)d->ldc * 4, 0, (size_t)d->N * 4, (size_t)d->M, (cudaStream_t)stream));
+			p.beta = 0.f;
+		}
+	}
+	const long long work = total_tiles * p.ksplit;
+	dim3 grid((unsigned)(work < num_sms ? work : num_sms));  // persistent: one CTA per SM
 	cudaStream_t st = (cudaStream_t)stream;
 #define FH_TC_LAUNCH(AM, BMN)                                                                                         \
 	do {                                                                                                              \

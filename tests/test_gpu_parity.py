@@ -377,3 +377,18 @@ def test_fasthigashi_wrapper_end_to_end(tmp_path):
 	Eo = O.embed_all(Vo.numpy(), [x.numpy() for x in oc.D_dict.values()])
 	pear = [abs(np.corrcoef(emb["embed_all"][:, j], Eo[:, j])[0, 1]) for j in range(Eo.shape[1])]
 	assert min(pear) > 0.999, min(pear)
+
+
+@pytest.mark.parametrize("beta", [0.0, 1.0])
+def test_gemm_tcgen05_split_k(beta):
+	"""Long-K / few-tile shape (the P3 accumulation M += X W): split-K work items with atomic partial sums."""
+	L = _lib()
+	g = torch.Generator().manual_seed(11)
+	M, N, K = 200, 256, 4100
+	A, B, C0 = torch.randn(M, K + 0, generator=g), torch.randn(K, N, generator=g), torch.randn(M, N, generator=g)
+	lda = (K + 3) // 4 * 4
+	Ad = torch.zeros(M, lda); Ad[:, :K] = A
+	ref = A.double() @ B.double() + beta * C0.double()
+	Cd = C0.clone().to(DEV)
+	L.gemm(Ad.to(DEV), B.to(DEV), Cd, M, N, K, (lda, 1), (N, 1), N, beta=beta, dtype=L.GEMM_TF32X3)
+	assert rel_fro(Cd.cpu().numpy(), ref.numpy()) < 2e-6
