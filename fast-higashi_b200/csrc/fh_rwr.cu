@@ -121,24 +121,34 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 // K4: second-order affinity S2 = A A^T (diagonal ignored) + first-order block of A -> column
 // stochastic P, in place over S2. grid (ncell), thread per column.
 // ---------------------------------------------------------------------------------------------
+// Each thread keeps its <= 32 rows of the column in registers, so S2 and the diagonal block of A are read
+// once and P (and Q1 = 0.5 P + 0.5 I, the first RWR step, when Q1 != nullptr) are written once.
+template <int MAXR>  // rows per thread: nb <= 8 * MAXR
 __global__ void __launch_bounds__(256)
 transition_kernel(const float* __restrict__ A, long long a_cell_stride, int ldw, int s,
-                  float* __restrict__ SP, int nb, int ldp) {
+                  float* __restrict__ SP, int nb, int ldp, float* __restrict__ Q1) {
 	// 256 threads = 8 row groups x 32 columns; a column tile of 32 is reduced over the 8 groups in smem
 	__shared__ float red[3][8][33];
 	const int cell = blockIdx.x;
 	const float* a = A + (long long)cell * a_cell_stride + s;
 	float* p = SP + (long long)cell * nb * ldp;
+	float* q1 = Q1 ? Q1 + (long long)cell * nb * ldp : nullptr;
 	const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
 	for (int j0 = 0; j0 < nb; j0 += 32) {
 		const int j = j0 + cx;
 		const bool ok = j < nb;
+		float f[MAXR], h[MAXR];
 		float cs1 = 0.f, cs2 = 0.f;
-		if (ok)
-			for (int i = g; i < nb; i += 8) {
-				cs1 += a[(long long)i * ldw + j];
-				if (i != j) cs2 += p[i * ldp + j];
+#pragma unroll
+		for (int e = 0; e < MAXR; ++e) {
+			const int i = g + 8 * e;
+			f[e] = 0.f; h[e] = 0.f;
+			if (ok && i < nb) {
+				f[e] = a[(long long)i * ldw + j];
+				h[e] = (i != j) ? p[i * ldp + j] : 0.f;
 			}
+			cs1 += f[e]; cs2 += h[e];
+		}
 		red[0][g][cx] = cs1; red[1][g][cx] = cs2;
 		__syncthreads();
 		cs1 = 0.f; cs2 = 0.f;
@@ -146,14 +156,14 @@ transition_kernel(const float* __restrict__ A, long long a_cell_stride, int ldw,
 		for (int k = 0; k < 8; ++k) { cs1 += red[0][k][cx]; cs2 += red[1][k][cx]; }
 		cs1 += FH_EPS; cs2 += FH_EPS;
 		float csl = 0.f;
-		if (ok)
-			for (int i = g; i < nb; i += 8) {
-				float f = (a[(long long)i * ldw + j] / cs1) * 0.75f;
-				float gg = (i != j) ? (p[i * ldp + j] / cs2) * 0.25f : 0.f;
-				float l = f + gg;
-				p[i * ldp + j] = l;
-				csl += l;
-			}
+#pragma unroll
+		for (int e = 0; e < MAXR; ++e) {
+			const int i = g + 8 * e;
+			float l = (f[e] / cs1) * 0.75f + ((i != j) ? (h[e] / cs2) * 0.25f : 0.f);
+			if (!(ok && i < nb)) l = 0.f;
+			f[e] = l;
+			csl += l;
+		}
 		red[2][g][cx] = csl;
 		__syncthreads();
 		csl = 0.f;
@@ -163,14 +173,21 @@ transition_kernel(const float* __restrict__ A, long long a_cell_stride, int ldw,
 		const bool empty = (csl == 0.f);
 		if (empty) csl += 1.f;
 		csl += FH_EPS;
-		if (ok)
-			for (int i = g; i < nb; i += 8) {
-				float l = p[i * ldp + j];
+#pragma unroll
+		for (int e = 0; e < MAXR; ++e) {
+			const int i = g + 8 * e;
+			if (ok && i < nb) {
+				float l = f[e];
 				if (empty && i == j) l += 1.f;
-				p[i * ldp + j] = l / csl;
+				const float pv = l / csl;
+				p[i * ldp + j] = pv;
+				if (q1) q1[i * ldp + j] = 0.5f * pv + ((i == j) ? 0.5f : 0.f);
 			}
+		}
 		__syncthreads();
 	}
+	if (q1)  // pad columns of Q1
+		for (int t = threadIdx.x; t < nb * (ldp - nb); t += blockDim.x) q1[(t / (ldp - nb)) * ldp + nb + t % (ldp - nb)] = 0.f;
 }
 
 // Q = 0.5 * P + 0.5 * I  (first RWR step: Q0 = I so bmm(Q0, P) = P exactly)
@@ -333,7 +350,10 @@ int rwr_from_panel(const fh_rwr_desc* d, const RwrWs& ws, const float* bin_cov, 
 	rc = gemm_f32(tc, nb, nb, w, nc, ws.A, ldw, 1, acs, ws.A, 1, ldw, acs, ws.P, ldp, pcs, 1.0, FH_EPI_NONE, 0.0,
 	              nullptr, 0, 0, st);
 	if (rc) return rc;
-	transition_kernel<<<nc, 256, 0, st>>>(ws.A, acs, ldw, d->s, ws.P, nb, ldp);
+	FH_CHECK_ARG(nb <= 256, "fh_rwr: bin block of %d rows (max 256: recommend_bs_bin, FastHigashi_Wrapper.py:501)", nb);
+	const bool fuse_q1 = d->k >= 1;  // forced mode: Q1 comes out of the transition kernel
+	if (nb <= 128) transition_kernel<16><<<nc, 256, 0, st>>>(ws.A, acs, ldw, d->s, ws.P, nb, ldp, fuse_q1 ? ws.Q0 : nullptr);
+	else transition_kernel<32><<<nc, 256, 0, st>>>(ws.A, acs, ldw, d->s, ws.P, nb, ldp, fuse_q1 ? ws.Q0 : nullptr);
 	FH_LAUNCH_CHECK();
 	float* Q = ws.Q0;
 	float* Qn = ws.Q1;
@@ -345,8 +365,6 @@ int rwr_from_panel(const fh_rwr_desc* d, const RwrWs& ws, const float* bin_cov, 
 			identity_kernel<<<nblk, tpb, 0, st>>>(Q, nb, ldp, ptotal);
 			FH_LAUNCH_CHECK();
 		} else {
-			first_step_kernel<<<nblk, tpb, 0, st>>>(ws.P, Q, nb, ldp, ptotal);
-			FH_LAUNCH_CHECK();
 			for (int it = 1; it < d->k; ++it) {
 				rc = gemm_f32(tc, nb, nb, nb, nc, Q, ldp, 1, pcs, ws.P, ldp, 1, pcs, Qn, ldp, pcs, 0.5,
 				              FH_EPI_DIAG_ADD, 0.5, nullptr, 0, 0, st);
