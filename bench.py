@@ -364,8 +364,23 @@ def main():
 	roofline = dict(roof_all.get(dom, {}))
 	roofline.setdefault("bound", "tensor")
 	roofline["kernel_stage"] = dom
-	roofline["traffic"] = None
+	roofline["kernels"] = {"rwr": "fh_rwr_batched = densify_conv_kernel + gemm_tc_kernel x5 (tcgen05 3xTF32) + transition_kernel",
+	                       "contractions": "gemm_tc_kernel (tcgen05 3xTF32, TMA) + small batched gemm_simt_kernel",
+	                       "polar_bins": "chol_jacobi_kernel (fp64) + fp64 gemm_simt_kernel"}[dom]
+	# DRAM traffic of the stage from the ncu capture committed under profiles/ (chr1 block, 2048 cells:
+	# 2.60 GB moved for 0.331 GB of algorithmic bytes; the RWR intermediates are sized for launch
+	# efficiency, not L2 residency - DESIGN.md 3.1), scaled to this run's algorithmic bytes
+	roofline["traffic"] = work["rwr_bytes"] * (2.60 / 0.331) if dom == "rwr" else None
+	roofline["traffic_source"] = "profiles/r01_micro_kernels_metrics.csv (ncu dram__bytes_read+write.sum), scaled" if dom == "rwr" else None
 	roofline["peak_source"] = pk["src"]
+	if dom == "rwr" and gem > 0:
+		# the RWR pass is compute bound with fp32-parity maths (~170 flop per HBM byte): its tensor-side figure
+		rwr_flops = 0.0
+		for ds, k in zip(datasets, n_i):
+			for g_ in ds.geoms:
+				rwr_flops += ds.num_cell * (4.0 * g_.nb * g_.nb * g_.w + 2.0 * max(k - 1, 0) * g_.nb ** 3)
+		roofline["tensor_side"] = {"achieved": rwr_flops / (per["rwr"] / 1e3) / 1e12, "unit": "TFLOP/s (fp32-equivalent, 3xTF32)",
+		                           "peak": pk["tensor"], "frac": rwr_flops / (per["rwr"] / 1e3) / 1e12 / pk["tensor"]}
 	out = {"metric": "cells/s per PARAFAC2 ALS sweep (incl. RWR)", "value": value, "unit": "cells/s", "n_gpus": world,
 	       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
 	       "vs_baseline": None, "dtype": "f32 (fp64 inside the polar step)", "data": "synthetic", "config": config,
