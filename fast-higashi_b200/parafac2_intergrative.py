@@ -493,24 +493,45 @@ class Fast_Higashi_core:
 		self.loss_terms.append(dict(xnorm=xnorm.ravel().copy(), core=core.ravel().copy(), x_U=x_U.ravel().copy(), x_V=x_V))
 		err_U = xnorm + core - 2 * x_U
 		err_V = xnorm.sum() + core.sum() - 2 * x_V
-		# inner CP-ALS per chromosome (:674-695)
+		# inner CP-ALS per chromosome (:674-695) + the new core norms (:697-706). The chromosomes are
+		# independent and every kernel is tiny (r x r work, single-CTA solves): they are spread
+		# round-robin over a few CUDA streams so they overlap instead of running back to back.
 		t = self._tic()
-		for chrom, ids in self.chrom2id.items():
-			if len(ids) == 1:
-				A = self.A_dev[ids[0]]
-			else:
-				A = torch.cat([self.A_dev[i] for i in ids], 0).contiguous()
-			cp_als_(self.projected_dev[chrom], A, self.B_dict[chrom], self.D_dict[chrom], n_iter_parafac)
-			if len(ids) > 1:
-				for i in ids:
-					self.A_dev[i].copy_(A[self.schic[i].global_slice_bin])
-			if dist is not None:  # keep replicas bit-identical (split-K atomics are unordered)
-				src = dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0
+		nch = len(self.schic)
+		acc = torch.zeros(nch, dtype=torch.float64, device=self.device)
+		main = torch.cuda.current_stream()
+		if getattr(self, "_cp_streams", None) is None:
+			self._cp_streams = [torch.cuda.Stream(device=self.device) for _ in range(6)]
+		ready = torch.cuda.Event()
+		ready.record(main)
+		for k, (chrom, ids) in enumerate(self.chrom2id.items()):
+			st = self._cp_streams[k % len(self._cp_streams)]
+			st.wait_event(ready)
+			with torch.cuda.stream(st):
+				tag = "cp%d" % (k % len(self._cp_streams))
+				if len(ids) == 1:
+					A = self.A_dev[ids[0]]
+				else:
+					A = torch.cat([self.A_dev[i] for i in ids], 0).contiguous()
+				cp_als_(self.projected_dev[chrom], A, self.B_dict[chrom], self.D_dict[chrom], n_iter_parafac, tag=tag)
+				if len(ids) > 1:
+					for i in ids:
+						self.A_dev[i].copy_(A[self.schic[i].global_slice_bin])
+				if dist is None:
+					for i in ids:
+						core_sqnorm_accum(self.A_dev[i], self.B_dict[chrom], self.D_dict[chrom], acc[i:], tag=tag)
+		for st in self._cp_streams:
+			main.wait_stream(st)
+		if dist is not None:  # keep replicas bit-identical (split-K atomics are unordered)
+			src = dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0
+			for chrom, ids in self.chrom2id.items():
 				for i in ids:
 					dist.broadcast(self.A_dev[i], src=src, group=self.group)
 				dist.broadcast(self.B_dict[chrom], src=src, group=self.group)
 				dist.broadcast(self.D_dict[chrom], src=src, group=self.group)
-		self._core_norm = self._core_norms()
+			self._core_norm = self._core_norms()
+		else:
+			self._core_norm = acc.cpu().numpy().reshape(-1, 1)
 		self._toc("cp_als", t)
 		rec_error = float(np.sqrt(err_V) / np.sqrt(xnorm.sum()))
 		self.re_trace.append(rec_error)

@@ -4,23 +4,23 @@ import torch
 from . import _lib
 
 
-def cp_als_(Y, A, B, D, n_iter_max):
+def cp_als_(Y, A, B, D, n_iter_max, tag="cp"):
 	"""In-place device CP-ALS: Y (n, r, R) fp32 contiguous; A (n,r), B (r,r), D (R,r) fp32 contiguous.
 	Returns (||Xhat||^2, <Xhat, Y>) (zeros unless n_iter_max > 1, see include/fh_b200.h)."""
 	n, r, R = Y.shape
 	lib = _lib.lib()
-	ws = _lib.workspace(lib.fh_cp_als_workspace_bytes(n, r, R), Y.device, "cp")
+	ws = _lib.workspace(lib.fh_cp_als_workspace_bytes(n, r, R), Y.device, tag)
 	out = (C.c_double * 2)()
 	_lib.check(lib.fh_cp_als(Y.data_ptr(), n, r, R, A.data_ptr(), B.data_ptr(), D.data_ptr(), int(n_iter_max),
 	                         ws.data_ptr(), ws.numel(), out, _lib.stream_ptr()))
 	return out[0], out[1]
 
 
-def core_sqnorm_accum(A, B, D, acc):
+def core_sqnorm_accum(A, B, D, acc, tag="core"):
 	"""acc (device fp64 scalar tensor) += ||[[A,B,D]]||^2 (parafac2_intergrative.py:623-632)."""
 	n, r = A.shape
 	R = D.shape[0]
-	ws = _lib.workspace(3 * r * r * 8, A.device, "core")
+	ws = _lib.workspace(3 * r * r * 8, A.device, tag + "_core")
 	_lib.check(_lib.lib().fh_cp_core_sqnorm(A.data_ptr(), n, B.data_ptr(), D.data_ptr(), R, r, ws.data_ptr(),
 	                                        acc.data_ptr(), _lib.stream_ptr()))
 
