@@ -33,7 +33,7 @@ class RwrDesc(C.Structure):
 EXPORTS = ["fh_last_error", "fh_version", "fh_launch_count", "fh_tc_fallback_count", "fh_gemm_batched", "fh_rwr_workspace_bytes",
            "fh_rwr_batched", "fh_densify", "fh_rwr_dense", "fh_colsum_accum", "fh_avgpool", "fh_sqnorm_accum",
            "fh_dot_accum", "fh_polar_workspace_bytes", "fh_polar_batched", "fh_polar_isqrt_multi", "fh_inv_sqrt_spd",
-           "fh_cp_als_workspace_bytes", "fh_cp_als", "fh_cp_core_sqnorm"]
+           "fh_cp_als_workspace_bytes", "fh_cp_als", "fh_cp_core_sqnorm", "fh_scale_cols_batched"]
 
 _lib = None
 
@@ -70,6 +70,7 @@ def lib():
 		L.fh_polar_isqrt_multi.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp, ci, vp, vp]
 		L.fh_inv_sqrt_spd.argtypes = [vp, vp, ci, vp, sz, C.POINTER(ci), vp]
 		L.fh_cp_als.argtypes = [vp, ci, ci, ci, vp, vp, vp, ci, vp, sz, C.POINTER(C.c_double), vp]
+		L.fh_scale_cols_batched.argtypes = [vp, ci, ci, ll, vp, ci, ci, vp, vp]
 		L.fh_cp_core_sqnorm.argtypes = [vp, ci, vp, vp, ci, ci, vp, vp, vp]
 		_lib = L
 	return _lib
@@ -137,3 +138,8 @@ def rwr_desc(nb, w, ldw, s, k, do_conv, do_rwr, do_col, cell0, ncell, nnz, use_t
 	d.do_conv, d.do_rwr, d.do_col = int(bool(do_conv)), int(bool(do_rwr)), int(bool(do_col))
 	d.cell0, d.ncell, d.use_tensor_cores, d.nnz = int(cell0), int(ncell), int(bool(use_tc)), int(nnz)
 	return d
+
+
+def scale_cols_batched(F, rows, r, ldf, Arows, nb, ldo, out):
+	check(lib().fh_scale_cols_batched(_ptr(F), int(rows), int(r), int(ldf), _ptr(Arows), int(nb), int(ldo), _ptr(out), stream_ptr()))
+	return out

@@ -139,6 +139,21 @@ int gram(const float* F, int rows, int r, double* G, void* stream) {
 	return gemm(FH_GEMM_F32_ACC64, r, r, rows, F, 1, r, F, r, 1, G, r, stream);
 }
 
+// out[i][j][p] = F[j][p] * Arows[i][p]  (p < r; pad columns r..ldo-1 are 0): the per-bin scaled copies
+// B diag(A_i), D diag(A_i) that turn temp_i = T1_i diag(A_i) B^T and W_i = (U_i B) diag(A_i) D^T into plain
+// batched GEMMs for the tensor-core kernel.
+__global__ void scale_cols_batched_kernel(const float* __restrict__ F, int rows, int r, long long ldf,
+                                          const float* __restrict__ Arows, int nb, int ldo, float* __restrict__ out) {
+	const long long total = (long long)nb * rows * ldo;
+	for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+		const int p = (int)(t % ldo);
+		const long long ij = t / ldo;
+		const int j = (int)(ij % rows);
+		const long long i = ij / rows;
+		out[t] = (p < r) ? F[(long long)j * ldf + p] * Arows[i * r + p] : 0.f;
+	}
+}
+
 size_t al(size_t x) { return (x + 255) / 256 * 256; }
 struct CpWs {
 	float *Z, *M, *norms;
@@ -261,6 +276,16 @@ extern "C" int fh_cp_core_sqnorm(const float* A, int n, const float* B, const fl
 	if ((rc = gram(B, r, r, Gb, stream))) return rc;
 	if ((rc = gram(D, R, r, Gd, stream))) return rc;
 	triple_hadamard_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(Ga, Gb, Gd, r * r, acc);
+	FH_LAUNCH_CHECK();
+	return FH_OK;
+}
+
+extern "C" int fh_scale_cols_batched(const float* F, int rows, int r, long long ldf, const float* Arows, int nb, int ldo,
+                                     float* out, void* stream) {
+	FH_CHECK_ARG(rows > 0 && r > 0 && nb > 0 && ldo >= r && ldf >= r, "fh_scale_cols_batched: bad shape");
+	long long total = (long long)nb * rows * ldo;
+	int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+	scale_cols_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(F, rows, r, ldf, Arows, nb, ldo, out);
 	FH_LAUNCH_CHECK();
 	return FH_OK;
 }

@@ -307,6 +307,37 @@ class Fast_Higashi_core:
 		                  G=torch.empty(off, dtype=torch.float64, device=dev), WT=torch.empty(off, dtype=torch.float64, device=dev))
 		return self._ptab
 
+	def _padded_factors(self, chrom):
+		"""B (r x r) and D (R x r) copied to the row pitch round_up(r, 4) (zero pad columns)."""
+		B, D = self.B_dict[chrom], self.D_dict[chrom]
+		r = B.shape[0]
+		rp = pad4(r)
+		if rp == r:
+			return B, D
+		Bp = torch.zeros(r, rp, dtype=torch.float32, device=B.device); Bp[:, :r] = B
+		Dp = torch.zeros(D.shape[0], rp, dtype=torch.float32, device=B.device); Dp[:, :r] = D
+		return Bp, Dp
+
+	def _build_W(self, ci, b):
+		"""W (nb*ldw, R) with W_i = U_i B diag(A_i) D^T = (U_i B) (D diag(A_i))^T  (lhs of :422-430, transposed)."""
+		ds = self.schic[ci]
+		g = ds.geoms[b]
+		dev, R = self.device, self.rank
+		gd = self._gemm_dtype()
+		r = self.chrom2size[ds.chrom]
+		rp, ldw = pad4(r), pad4(g.w)
+		P = g.nb * ldw
+		Bp, Dp = self._padded_factors(ds.chrom)
+		U = self.projection_dev[ci][b]
+		Arows = self.A_dev[ci][g.row0:g.row0 + g.nb]
+		UB = torch.zeros(P, rp, dtype=torch.float32, device=dev)
+		_lib.gemm(U, Bp, UB, P, r, r, (rp, 1), (rp, 1), rp, dtype=gd)
+		Dsc = torch.empty(g.nb, R, rp, dtype=torch.float32, device=dev)
+		_lib.scale_cols_batched(Dp, R, r, rp, Arows, g.nb, rp, Dsc)
+		W = torch.empty(P, R, dtype=torch.float32, device=dev)
+		_lib.gemm(UB, Dsc, W, ldw, R, r, (rp, 1), (1, rp), R, batch=g.nb, batch_strides=(ldw * rp, R * rp, ldw * R), dtype=gd)
+		return W
+
 	def invalidate_cache(self):
 		self._X_valid = set()
 
@@ -327,13 +358,16 @@ class Fast_Higashi_core:
 		tab = self._polar_table()
 		G_all, WT_all = tab["G"], tab["WT"]
 		temps = {}
+		# Every r-wide operand lives at a row pitch rp = round_up(r, 4) (zero pad columns) so that TMA can
+		# describe it and all GEMMs below except the fp64 ones run on the tcgen05 kernel.
 		# ---- phase A: impute, P1, Gram of every temp_i
 		for ci, ds in enumerate(self.schic):
 			r = self.chrom2size[ds.chrom]
-			A, B, D = self.A_dev[ci], self.B_dict[ds.chrom], self.D_dict[ds.chrom]
-			rp = pad4(r)  # row pitch of the r-wide operands (TMA needs 16-byte multiples)
+			rp = pad4(r)
+			A = self.A_dev[ci]
+			Bp, Dp = self._padded_factors(ds.chrom)
 			Cc = torch.zeros(Cn, rp, dtype=torch.float32, device=dev)
-			_lib.gemm(V, D, Cc, Cn, r, R, (R, 1), (r, 1), rp, dtype=gd)  # C = V D  (:336)
+			_lib.gemm(V, Dp, Cc, Cn, r, R, (R, 1), (rp, 1), rp, dtype=gd)  # C = V D  (:336)
 			for b, g in enumerate(ds.geoms):
 				ldw = pad4(g.w)
 				P = g.nb * ldw
@@ -343,15 +377,18 @@ class Fast_Higashi_core:
 				if first_iter:
 					_lib.check(_lib.lib().fh_sqnorm_accum(X.data_ptr(), 1, Cn * P, Cn * P, stats[nch + ci:].data_ptr(),
 					                                      _lib.stream_ptr()))
-				# P1: T1 = X^T C ; temp_i = (T1_i diag(A_i)) B^T
+				# P1: T1 = X^T C ; temp_i = T1_i (B diag(A_i))^T
 				t = self._tic()
 				T1 = torch.empty(P, rp, dtype=torch.float32, device=dev)
 				_lib.gemm(X, Cc, T1, P, r, Cn, (1, P), (rp, 1), rp, dtype=gd)
+				if rp > r:
+					T1[:, r:].zero_()
 				self._allreduce(T1)
-				temp = torch.empty(g.nb, ldw, r, dtype=torch.float32, device=dev)
 				Arows = A[g.row0:g.row0 + g.nb]
-				_lib.gemm(T1, B, temp, ldw, r, r, (rp, 1), (1, r), r, batch=g.nb, batch_strides=(ldw * rp, 0, ldw * r),
-				          kscale=Arows, kscale_batch=r)
+				Bsc = torch.empty(g.nb, r, rp, dtype=torch.float32, device=dev)
+				_lib.scale_cols_batched(Bp, r, r, rp, Arows, g.nb, rp, Bsc)
+				temp = torch.zeros(g.nb, ldw, rp, dtype=torch.float32, device=dev)
+				_lib.gemm(T1, Bsc, temp, ldw, r, r, (rp, 1), (1, rp), rp, batch=g.nb, batch_strides=(ldw * rp, r * rp, ldw * rp), dtype=gd)
 				temps[(ci, b)] = temp
 				self._toc("p1_mttkrp", t)
 				# P2a: Gram of every temp_i in fp64 (tall: T^T T, wide: T T^T)
@@ -359,13 +396,13 @@ class Fast_Higashi_core:
 				off, ns = tab["block"][(ci, b)]
 				Gb = G_all[off:off + g.nb * ns * ns]
 				if ldw >= r:
-					_lib.gemm(temp, temp, Gb, ns, ns, ldw, (1, r), (r, 1), ns, batch=g.nb, batch_strides=(ldw * r, ldw * r, ns * ns),
+					_lib.gemm(temp, temp, Gb, ns, ns, ldw, (1, rp), (rp, 1), ns, batch=g.nb, batch_strides=(ldw * rp, ldw * rp, ns * ns),
 					          dtype=_lib.GEMM_F32_ACC64)
 				else:
-					_lib.gemm(temp, temp, Gb, ns, ns, r, (r, 1), (1, r), ns, batch=g.nb, batch_strides=(ldw * r, ldw * r, ns * ns),
+					_lib.gemm(temp, temp, Gb, ns, ns, r, (rp, 1), (1, rp), ns, batch=g.nb, batch_strides=(ldw * rp, ldw * rp, ns * ns),
 					          dtype=_lib.GEMM_F32_ACC64)
 				self._toc("polar_bins", t)
-				del T1
+				del T1, Bsc
 		# ---- phase B: G^{-1/2} of all bins of all chromosomes at once (P2b)
 		t = self._tic()
 		_lib.check(_lib.lib().fh_polar_isqrt_multi(G_all.data_ptr(), WT_all.data_ptr(), tab["n_dev"].data_ptr(),
@@ -377,13 +414,12 @@ class Fast_Higashi_core:
 		# ---- phase C: U_i = temp_i M_i, P3
 		for ci, ds in enumerate(self.schic):
 			r = self.chrom2size[ds.chrom]
-			A, B, D = self.A_dev[ci], self.B_dict[ds.chrom], self.D_dict[ds.chrom]
+			rp = pad4(r)
 			for b, g in enumerate(ds.geoms):
 				ldw = pad4(g.w)
 				P = g.nb * ldw
 				X = self._impute_good(ci, b, do_conv, do_rwr, do_col)
 				temp = temps.pop((ci, b))
-				Arows = A[g.row0:g.row0 + g.nb]
 				t = self._tic()
 				off, ns = tab["block"][(ci, b)]
 				nn = ns * ns
@@ -391,22 +427,18 @@ class Fast_Higashi_core:
 				_lib.gemm(WTb, WTb, Mb, ns, ns, ns, (1, ns), (ns, 1), ns, batch=g.nb, batch_strides=(nn, nn, nn), dtype=_lib.GEMM_F64)
 				U = self.projection_dev[ci][b]
 				if ldw >= r:
-					_lib.gemm(temp, Mb, U, ldw, r, r, (r, 1), (r, 1), r, batch=g.nb, batch_strides=(ldw * r, nn, ldw * r),
+					_lib.gemm(temp, Mb, U, ldw, r, r, (rp, 1), (ns, 1), rp, batch=g.nb, batch_strides=(ldw * rp, nn, ldw * rp),
 					          dtype=_lib.GEMM_F32xF64_F32)
 				else:
-					_lib.gemm(Mb, temp, U, ldw, r, ldw, (ns, 1), (r, 1), r, batch=g.nb, batch_strides=(nn, ldw * r, ldw * r),
+					_lib.gemm(Mb, temp, U, ldw, r, ldw, (ns, 1), (rp, 1), rp, batch=g.nb, batch_strides=(nn, ldw * rp, ldw * rp),
 					          dtype=_lib.GEMM_F64xF32_F32)
 				self._toc("polar_bins", t)
 				t = self._tic()
-				# P3: W_i = ((U_i B) diag(A_i)) D^T ; M += X W
-				UB = torch.empty(P, r, dtype=torch.float32, device=dev)
-				_lib.gemm(U, B, UB, P, r, r, (r, 1), (r, 1), r)
-				W = torch.empty(P, R, dtype=torch.float32, device=dev)
-				_lib.gemm(UB, D, W, ldw, R, r, (r, 1), (1, r), R, batch=g.nb, batch_strides=(ldw * r, 0, ldw * R),
-				          kscale=Arows, kscale_batch=r)
+				# P3: M += X W,  W_i = (U_i B) (D diag(A_i))^T
+				W = self._build_W(ci, b)
 				_lib.gemm(X, W, MT, Cn, R, P, (P, 1), (R, 1), R, beta=1.0, dtype=gd)
 				self._toc("p3_project", t)
-				del W, temp, UB
+				del W, temp
 		# P4: V = polar(SVD_term^T) (:483-486)
 		self.last_svd_term_T = MT
 		t = self._tic()
@@ -418,6 +450,7 @@ class Fast_Higashi_core:
 		# P5: Y_i = U_i^T X_i V (:488-529)
 		for ci, ds in enumerate(self.schic):
 			r = self.chrom2size[ds.chrom]
+			rp = pad4(r)
 			Y = self.projected_dev[ds.chrom]
 			for b, g in enumerate(ds.geoms):
 				ldw = pad4(g.w)
@@ -428,7 +461,7 @@ class Fast_Higashi_core:
 				_lib.gemm(X, Vn, Z, P, R, Cn, (1, P), (R, 1), R, dtype=gd)
 				U = self.projection_dev[ci][b]
 				Yb = Y[ds.global_slice_bin.start + g.row0: ds.global_slice_bin.start + g.row0 + g.nb]
-				_lib.gemm(U, Z, Yb, r, R, ldw, (1, r), (R, 1), R, batch=g.nb, batch_strides=(ldw * r, ldw * R, r * R))
+				_lib.gemm(U, Z, Yb, r, R, ldw, (1, rp), (R, 1), R, batch=g.nb, batch_strides=(ldw * rp, ldw * R, r * R), dtype=gd)
 				self._toc("p5_tensor", t)
 				del Z
 		for chrom in self.chrom2size:
@@ -466,7 +499,7 @@ class Fast_Higashi_core:
 		elif run_init:
 			self.init_params(schic, do_conv, do_rwr, do_col)
 		self._flags = (do_conv, do_rwr, do_col)
-		self.projection_dev = [[torch.zeros(g.nb, pad4(g.w), self.chrom2size[ds.chrom], dtype=torch.float32, device=dev)
+		self.projection_dev = [[torch.zeros(g.nb, pad4(g.w), pad4(self.chrom2size[ds.chrom]), dtype=torch.float32, device=dev)
 		                        for g in ds.geoms] for ds in self.schic]
 		self.projected_dev = {c: torch.zeros(self.chrom2num_bin[c], self.chrom2size[c], R, dtype=torch.float32, device=dev)
 		                      for c in self.chrom2size}
@@ -598,7 +631,7 @@ class Fast_Higashi_core:
 		"""Reference-shaped attributes: A_list on the host, projection_list[ci][b] (nb, w, r) on the
 		host, projected_tensor_list[chrom] (n, r, R) on the host (:601-620)."""
 		self.A_list = [a.cpu() for a in self.A_dev]
-		self.projection_list = [[U[:, :g.w, :].cpu() for U, g in zip(self.projection_dev[ci], ds.geoms)]
+		self.projection_list = [[U[:, :g.w, :self.chrom2size[ds.chrom]].cpu() for U, g in zip(self.projection_dev[ci], ds.geoms)]
 		                        for ci, ds in enumerate(self.schic)]
 		self.projected_tensor_list = {c: y.cpu() for c, y in self.projected_dev.items()}
 
@@ -615,18 +648,10 @@ class Fast_Higashi_core:
 		Ct = self.total_cell_num
 		MT = torch.zeros(Ct, R, dtype=torch.float32, device=dev)
 		for ci, ds in enumerate(self.schic):
-			r = self.chrom2size[ds.chrom]
-			A, B, D = self.A_dev[ci], self.B_dict[ds.chrom], self.D_dict[ds.chrom]
 			for b, g in enumerate(ds.geoms):
 				ldw = pad4(g.w)
 				P = g.nb * ldw
-				U = self.projection_dev[ci][b]
-				Arows = A[g.row0:g.row0 + g.nb]
-				UB = torch.empty(P, r, dtype=torch.float32, device=dev)
-				_lib.gemm(U, B, UB, P, r, r, (r, 1), (r, 1), r)
-				W = torch.empty(P, R, dtype=torch.float32, device=dev)
-				_lib.gemm(UB, D, W, ldw, R, r, (r, 1), (1, r), R, batch=g.nb, batch_strides=(ldw * r, 0, ldw * R),
-				          kscale=Arows, kscale_batch=r)
+				W = self._build_W(ci, b)
 				X = self._impute_good(ci, b, do_conv, do_rwr, do_col)
 				_lib.gemm(X, W, MT, ds.num_cell, R, P, (P, 1), (R, 1), R, beta=1.0, dtype=gd)
 				nbad = ds.total_cell_num - ds.num_cell
@@ -639,7 +664,7 @@ class Fast_Higashi_core:
 						              bin_cov=self._cov_all[ci] if do_col else None, use_tc=self.use_tc)
 						_lib.gemm(Xb, W, MT[ds.num_cell + c0:], nc, R, P, (P, 1), (R, 1), R, beta=1.0, dtype=gd)
 						del Xb
-				del W, UB
+				del W
 		meta = polar_tall(MT, self.group)
 		self.A_list = [a.cpu() for a in self.A_dev]
 		return (None, (self.A_list, self.B_dict.values(), self.D_dict.values(), meta), self.projection_list)

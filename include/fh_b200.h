@@ -158,6 +158,12 @@ int fh_cp_als(const float* Y, int n, int r, int R, float* A, float* B, float* D,
 int fh_cp_core_sqnorm(const float* A, int n, const float* B, const float* D, int R, int r,
                       double* ws, double* acc, void* stream);
 
+/* out[i][j][p] = F[j][p] * Arows[i][p] (p < r), zero in the pad columns r..ldo-1: the per-bin scaled
+ * factor copies (B diag(A_i), D diag(A_i)) of the 'ir,jr,kr->...' contractions at
+ * parafac2_intergrative.py:374,422. F: rows x r (row pitch ldf); Arows: nb x r; out: (nb, rows, ldo). */
+int fh_scale_cols_batched(const float* F, int rows, int r, long long ldf, const float* Arows, int nb, int ldo,
+                          float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
