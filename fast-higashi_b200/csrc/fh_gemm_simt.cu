@@ -48,8 +48,9 @@ gemm_simt_kernel(GemmP p, const TA* __restrict__ A, const TB* __restrict__ B, TC
 
 	for (int k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
-		for (int it = 0; it < (BM * BK) / NT; ++it) {
+		for (int it = 0; it < (BM * BK + NT - 1) / NT; ++it) {
 			int idx = tid + it * NT;
+			if ((BM * BK) % NT != 0 && idx >= BM * BK) break;
 			int kk, mm;
 			if (a_kc) { kk = idx % BK; mm = idx / BK; } else { mm = idx % BM; kk = idx / BM; }
 			int m = m0 + mm, k = k0 + kk;
@@ -61,8 +62,9 @@ gemm_simt_kernel(GemmP p, const TA* __restrict__ A, const TB* __restrict__ B, TC
 			As[kk][mm] = v;
 		}
 #pragma unroll
-		for (int it = 0; it < (BN * BK) / NT; ++it) {
+		for (int it = 0; it < (BN * BK + NT - 1) / NT; ++it) {
 			int idx = tid + it * NT;
+			if ((BN * BK) % NT != 0 && idx >= BN * BK) break;
 			int kk, nn;
 			if (b_nc) { nn = idx % BN; kk = idx / BN; } else { kk = idx % BK; nn = idx / BK; }
 			int n = n0 + nn, k = k0 + kk;
@@ -132,11 +134,19 @@ int launch(GemmP p, const void* A, const void* B, void* C, cudaStream_t st) {
 		dim3 g(fh_cdiv(p.N, 128), fh_cdiv(p.M, 128), p.batch);
 		gemm_simt_kernel<TA, TB, TC, TAcc, 128, 128, 8, 8, 8><<<g, 256, 0, st>>>(p, (const TA*)A, (const TB*)B, (TC*)C);
 	} else {
-		dim3 g(fh_cdiv(p.N, 64), fh_cdiv(p.M, 64), p.batch * p.splits);
-		if (dbl)
-			gemm_simt_kernel<TA, TB, TC, TAcc, 64, 64, 8, 4, 4><<<g, 256, 0, st>>>(p, (const TA*)A, (const TB*)B, (TC*)C);
-		else
-			gemm_simt_kernel<TA, TB, TC, TAcc, 64, 64, 16, 4, 4><<<g, 256, 0, st>>>(p, (const TA*)A, (const TB*)B, (TC*)C);
+		// 64 x 64 or 48 x 48 tiles, whichever pads the problem less (r = 137 -> 3 x 48 = 144 instead of 3 x 64 = 192)
+		const long long pad64 = (long long)fh_cdiv(p.M, 64) * 64 * fh_cdiv(p.N, 64) * 64;
+		const long long pad48 = (long long)fh_cdiv(p.M, 48) * 48 * fh_cdiv(p.N, 48) * 48;
+		if (dbl && pad48 * 10 < pad64 * 9) {
+			dim3 g(fh_cdiv(p.N, 48), fh_cdiv(p.M, 48), p.batch * p.splits);
+			gemm_simt_kernel<TA, TB, TC, TAcc, 48, 48, 8, 3, 3><<<g, 256, 0, st>>>(p, (const TA*)A, (const TB*)B, (TC*)C);
+		} else {
+			dim3 g(fh_cdiv(p.N, 64), fh_cdiv(p.M, 64), p.batch * p.splits);
+			if (dbl)
+				gemm_simt_kernel<TA, TB, TC, TAcc, 64, 64, 8, 4, 4><<<g, 256, 0, st>>>(p, (const TA*)A, (const TB*)B, (TC*)C);
+			else
+				gemm_simt_kernel<TA, TB, TC, TAcc, 64, 64, 16, 4, 4><<<g, 256, 0, st>>>(p, (const TA*)A, (const TB*)B, (TC*)C);
+		}
 	}
 	FH_LAUNCH_CHECK();
 	return FH_OK;

@@ -34,13 +34,13 @@ __device__ __forceinline__ void rr_pair(int m, int s, int t, int& p, int& q) {
 }
 
 constexpr int MAXPL = 6;        // n <= 32 * MAXPL = 192 (shared memory caps n at ~166 anyway)
-constexpr int MAXPL16 = 12;     // column elements per lane of a half warp
 
 // One CTA per matrix (problem b: size prob_n[b], data at prob_off[b] doubles into Gall / WTall).
 // Shared memory holds R (n x ld, row-major): first the symmetric G, then its pivoted Cholesky factor
 // as the UPPER triangle R = L^T (row j of R = column j of L), then the rows are orthogonalised in
 // place. Output WT (n x n): row j = w_j * lambda_j^{-3/4} in the ORIGINAL index order;
 // sigma[prob_sig[b] + j] = sqrt(lambda_j); sigma_sum[prob_slot[b]] = sum_j sqrt(lambda_j).
+template <int MAXPL16>  // column elements per lane of a half warp: n <= 16 * MAXPL16
 __global__ void __launch_bounds__(1024)
 chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob_n, const long long* __restrict__ prob_off,
                    const int* __restrict__ prob_slot, const long long* __restrict__ prob_sig, int uniform_n,
@@ -278,6 +278,25 @@ constexpr int kMaxSweeps = 30;
 
 int jacobi_threads(int n) { return n > 83 ? 1024 : (n > 58 ? 512 : 256); }
 
+template <int PL>
+int launch_jacobi_pl(int grid, int nmax, size_t smem, cudaStream_t st, const double* G, const int* pn, const long long* po,
+                     const int* ps, int uniform_n, int max_sweeps, double* WT, double* sigma, double* sigma_sum, int* nsweep) {
+	FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	chol_jacobi_kernel<PL><<<grid, jacobi_threads(nmax), smem, st>>>(G, pn, po, ps, nullptr, uniform_n, max_sweeps, WT, sigma,
+	                                                              sigma_sum, nsweep);
+	FH_LAUNCH_CHECK();
+	return FH_OK;
+}
+// the half-warp register tile is sized to the largest problem of the launch (fewer predicated iterations)
+int launch_jacobi(int grid, int nmax, size_t smem, cudaStream_t st, const double* G, const int* pn, const long long* po,
+                  const int* ps, int uniform_n, int max_sweeps, double* WT, double* sigma, double* sigma_sum, int* nsweep) {
+	if (nmax <= 64) return launch_jacobi_pl<4>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, WT, sigma, sigma_sum, nsweep);
+	if (nmax <= 96) return launch_jacobi_pl<6>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, WT, sigma, sigma_sum, nsweep);
+	if (nmax <= 128) return launch_jacobi_pl<8>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, WT, sigma, sigma_sum, nsweep);
+	if (nmax <= 144) return launch_jacobi_pl<9>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, WT, sigma, sigma_sum, nsweep);
+	return launch_jacobi_pl<12>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, WT, sigma, sigma_sum, nsweep);
+}
+
 size_t jacobi_smem(int n) { return ((size_t)n * (n | 1) + 64 + (n + 1) / 2 + n) * 8 + 16; }
 
 }  // namespace
@@ -310,10 +329,8 @@ extern "C" int fh_polar_batched(const float* T, float* U, int batch, int rows, i
 	if (tall) rc = gemm(FH_GEMM_F32_ACC64, n, n, rows, batch, T, 1, ld, batch_stride, T, ld, 1, batch_stride, ws.G, n, nn, stream);
 	else rc = gemm(FH_GEMM_F32_ACC64, n, n, cols, batch, T, ld, 1, batch_stride, T, 1, ld, batch_stride, ws.G, n, nn, stream);
 	if (rc) return rc;
-	FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	chol_jacobi_kernel<<<batch, jacobi_threads(n), smem, st>>>(ws.G, nullptr, nullptr, nullptr, nullptr, n, max_sweeps, ws.WT, sigma,
-	                                                             sigma_sum, ws.nsweep);
-	FH_LAUNCH_CHECK();
+	rc = launch_jacobi(batch, n, smem, st, ws.G, nullptr, nullptr, nullptr, n, max_sweeps, ws.WT, sigma, sigma_sum, ws.nsweep);
+	if (rc) return rc;
 	if (host_max_sweeps) {  // diagnostics only: synchronises
 		int* h = (int*)malloc(sizeof(int) * batch);
 		if (h) {
@@ -358,10 +375,9 @@ extern "C" int fh_polar_isqrt_multi(const double* G_all, double* WT_all, const i
 			++j;
 		}
 		const size_t smem = jacobi_smem(nmax);
-		FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		chol_jacobi_kernel<<<j - i, jacobi_threads(nmax), smem, st>>>(G_all, dev_prob_n + i, dev_prob_off + i, dev_prob_slot + i,
-		                                                            nullptr, 0, max_sweeps, WT_all, nullptr, sigma_sum, dev_nsweep);
-		FH_LAUNCH_CHECK();
+		int rc = launch_jacobi(j - i, nmax, smem, st, G_all, dev_prob_n + i, dev_prob_off + i, dev_prob_slot + i, 0, max_sweeps,
+		                       WT_all, nullptr, sigma_sum, dev_nsweep);
+		if (rc) return rc;
 		i = j;
 	}
 	return FH_OK;
