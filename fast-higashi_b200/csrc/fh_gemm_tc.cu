@@ -248,14 +248,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
 					for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
 						float4 v = hi[t + 128 * i];
-						uint4 h, l;
-						// tf32 round-to-nearest (ties away, = cvt.rna.tf32.f32) with two integer ops; ptxas expands
-						// the cvt itself to ~10 instructions and the splitters were the busiest warps (ncu)
-						h.x = tf32_rn(__float_as_uint(v.x)); h.y = tf32_rn(__float_as_uint(v.y));
-						h.z = tf32_rn(__float_as_uint(v.z)); h.w = tf32_rn(__float_as_uint(v.w));
-						l.x = tf32_rn(__float_as_uint(v.x - __uint_as_float(h.x))); l.y = tf32_rn(__float_as_uint(v.y - __uint_as_float(h.y)));
-						l.z = tf32_rn(__float_as_uint(v.z - __uint_as_float(h.z))); l.w = tf32_rn(__float_as_uint(v.w - __uint_as_float(h.w)));
-						((uint4*)hi)[t + 128 * i] = h;
+						uint4 l;
+						// The tensor core reads only the upper 19 bits of a tf32 operand (truncation), so the raw
+						// fp32 tile IS the hi operand and is left untouched in shared memory (one 16-byte store per
+						// element quad saved: the kernel is shared-memory-bandwidth bound). lo = a - trunc(a) is exact
+						// in fp32 and rounded to tf32 (ties away, two integer ops).
+						l.x = tf32_rn(__float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u)));
+						l.y = tf32_rn(__float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u)));
+						l.z = tf32_rn(__float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u)));
+						l.w = tf32_rn(__float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u)));
 						((uint4*)lo)[t + 128 * i] = l;
 					}
 				}
