@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int RT = 16;  // output rows per CTA in densify/conv
+constexpr int RT = 32;  // output rows per CTA in densify/conv
 
 // ---------------------------------------------------------------------------------------------
 // K1+K2: CSR -> dense (floor 1e-8) [-> 3x3 mean, zero padding counted, floor 1e-8]
@@ -34,11 +34,14 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 	const int ra = max(r0 - halo, 0), rb = min(r0 + RT + halo, nb);  // staged global rows [ra, rb)
 	const int tid = threadIdx.x;
 
-	// 1. background: floor inside the block, 0 in the zero padding ring
-	for (int i = tid; i < (RT + 2) * tw; i += blockDim.x) {
-		int tr = i / tw, tc = i - tr * tw;
-		int gr = r0 - 1 + tr, gc = tc - 1;
-		tile[i] = (gr >= 0 && gr < nb && gc >= 0 && gc < w) ? FH_FLOOR : 0.f;
+	// 1. background: floor inside the block, 0 in the zero padding ring (warp per tile row: no integer
+	// division in any per-element loop of this kernel - they dominated its instruction count)
+	const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+	for (int tr = warp; tr < RT + 2; tr += nwarp) {
+		const int gr = r0 - 1 + tr;
+		const bool rin = gr >= 0 && gr < nb;
+		float* trow = tile + tr * tw;
+		for (int tc = lane; tc < tw; tc += 32) trow[tc] = (rin && tc >= 1 && tc <= w) ? FH_FLOOR : 0.f;
 	}
 	if (!FROM_DENSE) {
 		const long long base = (long long)(cell0 + cell) * nb;
@@ -47,10 +50,10 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 	__syncthreads();
 	if (FROM_DENSE) {
 		const float* src = dense_in + (long long)cell * in_cell_stride;
-		for (int i = tid; i < (rb - ra) * w; i += blockDim.x) {
-			int rr = i / w, c = i - rr * w;
-			int gr = ra + rr;
-			tile[(gr - r0 + 1) * tw + c + 1] = fmaxf(src[(long long)gr * ldw + c], FH_FLOOR);
+		for (int gr = ra + warp; gr < rb; gr += nwarp) {
+			float* trow = tile + (gr - r0 + 1) * tw + 1;
+			const float* srow = src + (long long)gr * ldw;
+			for (int c = lane; c < w; c += 32) trow[c] = fmaxf(srow[c], FH_FLOOR);
 		}
 	} else {
 		// 2. scatter the CSR entries of rows [ra, rb): 8 entries per thread and step through one
@@ -95,25 +98,44 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 		}
 	}
 	__syncthreads();
-	// 3. stencil + write (coalesced rows); pad columns [w, ldw) are written as 0
+	// 3. stencil + write; pad columns [w, ldw) are written as 0. One work unit = one column x 8 rows:
+	// the 3x3 window slides down the column on per-row triple sums (3 shared loads per output instead
+	// of 9); consecutive threads own consecutive columns, so shared reads are conflict free and every
+	// global store instruction writes a contiguous row segment.
 	float* dst = out + (long long)cell * out_cell_stride;
 	const int rows = min(RT, nb - r0);
-	for (int i = tid; i < rows * ldw; i += blockDim.x) {
-		int tr = i / ldw, c = i - tr * ldw;
-		float v = 0.f;
-		if (c < w) {
-			const float* t = tile + (tr + 1) * tw + (c + 1);
-			if (do_conv) {
-				float s = t[-tw - 1];
-				s += t[-tw]; s += t[-tw + 1];
-				s += t[-1]; s += t[0]; s += t[1];
-				s += t[tw - 1]; s += t[tw]; s += t[tw + 1];
-				v = fmaxf(s / 9.0f, FH_FLOOR);
-			} else {
-				v = t[0];
+	if (do_conv) {
+		const int nstrip = (rows + 7) >> 3;            // <= 4 strips of 8 rows
+		const int per = nwarp / 4 > 0 ? nwarp / 4 : 1;  // warps per strip
+		for (int strip = warp & 3; strip < nstrip; strip += 4) {
+			const int tr0 = strip * 8;
+			const int nr = min(8, rows - tr0);
+			for (int c = (warp >> 2) * 32 + lane; c < ldw; c += 32 * per) {
+				float* drow = dst + (long long)(r0 + tr0) * ldw + c;
+				if (c >= w) {
+					for (int k = 0; k < nr; ++k) drow[(long long)k * ldw] = 0.f;
+					continue;
+				}
+				const float* t = tile + tr0 * tw + (c + 1);  // tile row tr0 = global row r0 + tr0 - 1
+				float h0 = (t[-1] + t[0]) + t[1];
+				float h1 = (t[tw - 1] + t[tw]) + t[tw + 1];
+#pragma unroll
+				for (int k = 0; k < 8; ++k) {
+					if (k < nr) {
+						const float* tn = t + (k + 2) * tw;
+						const float h2 = (tn[-1] + tn[0]) + tn[1];
+						drow[(long long)k * ldw] = fmaxf(((h0 + h1) + h2) / 9.0f, FH_FLOOR);
+						h0 = h1; h1 = h2;
+					}
+				}
 			}
 		}
-		dst[(long long)(r0 + tr) * ldw + c] = v;
+	} else {
+		for (int tr = warp; tr < rows; tr += nwarp) {
+			float* drow = dst + (long long)(r0 + tr) * ldw;
+			const float* trow = tile + (tr + 1) * tw + 1;
+			for (int c = lane; c < ldw; c += 32) drow[c] = (c < w) ? trow[c] : 0.f;
+		}
 	}
 }
 

@@ -259,8 +259,8 @@ def test_midsize_parity_vs_oracle_realistic_windows():
 	# with the SAME ||X||^2 on both sides, and ||X||^2 itself to the fp32 summation error.
 	for tg, to in zip(core.loss_terms, ocore.loss_terms):
 		assert np.max(np.abs(tg["xnorm"] - to["xnorm"]) / to["xnorm"]) < 1e-3
-		assert np.max(np.abs(tg["x_U"] - to["x_U"]) / to["x_U"]) < 1e-5
-		assert abs(tg["x_V"] - to["x_V"]) / to["x_V"] < 2e-5
+		assert np.max(np.abs(tg["x_U"] - to["x_U"]) / to["x_U"]) < 5e-5   # both sides are fp32 pipelines
+		assert abs(tg["x_V"] - to["x_V"]) / to["x_V"] < 5e-5
 		assert np.max(np.abs(tg["core"] - to["core"]) / to["core"]) < 1e-4
 		xn = to["xnorm"].sum()
 		re_g = np.sqrt(xn + tg["core"].sum() - 2 * tg["x_V"]) / np.sqrt(xn)
