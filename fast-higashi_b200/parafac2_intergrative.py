@@ -272,6 +272,9 @@ class Fast_Higashi_core:
 			self._X[key] = X
 			self._X_valid = getattr(self, "_X_valid", set())
 		if key not in self._X_valid:
+			ev = getattr(self, "input_events", None)
+			if ev is not None and ev.get(ci) is not None:  # block-CSR of this chromosome still in flight (H2D on another stream)
+				torch.cuda.current_stream().wait_event(ev[ci])
 			rwr_block_csr(ds, b, 0, ds.num_cell, X, g.nb * ldw, int(self.n_i[ci]), do_conv, do_rwr, do_col,
 			              bin_cov=self._cov_all[ci] if do_col else None, use_tc=self.use_tc)
 			self._X_valid.add(key)
