@@ -99,12 +99,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ uint32_t tf32_rn(uint32_t bits) { return (bits + 0x1000u) & 0xFFFFE000u; }
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-	uint32_t r;
-	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-	return r;
-}
-
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcP p,
