@@ -306,6 +306,7 @@ class Fast_Higashi_core:
 		                  off_dev=torch.from_numpy(np.asarray(off_list, dtype=np.int64)[order].copy()).to(dev),
 		                  slot_dev=torch.from_numpy(order.astype(np.int32)).to(dev),
 		                  ssum=torch.zeros(len(n_list), dtype=torch.float64, device=dev),
+		                  nsweep=torch.zeros(len(n_list), dtype=torch.int32, device=dev),  # Jacobi sweeps per bin (diagnostics)
 		                  chrom_lengths=torch.tensor(lengths, device=dev),
 		                  G=torch.empty(off, dtype=torch.float64, device=dev), WT=torch.empty(off, dtype=torch.float64, device=dev))
 		return self._ptab
@@ -410,8 +411,8 @@ class Fast_Higashi_core:
 		t = self._tic()
 		_lib.check(_lib.lib().fh_polar_isqrt_multi(G_all.data_ptr(), WT_all.data_ptr(), tab["n_dev"].data_ptr(),
 		                                           tab["off_dev"].data_ptr(), tab["slot_dev"].data_ptr(),
-		                                           tab["n_host"].ctypes.data, tab["count"], tab["ssum"].data_ptr(), 0, None,
-		                                           _lib.stream_ptr()))
+		                                           tab["n_host"].ctypes.data, tab["count"], tab["ssum"].data_ptr(), 0,
+		                                           tab["nsweep"].data_ptr(), _lib.stream_ptr()))
 		stats[:nch] = torch.segment_reduce(tab["ssum"], "sum", lengths=tab["chrom_lengths"])
 		self._toc("polar_bins", t)
 		# ---- phase C: U_i = temp_i M_i, P3
