@@ -22,14 +22,121 @@ namespace {
 
 __host__ __device__ inline int even_up(int n) { return (n + 1) & ~1; }
 
-constexpr int MAXPL = 6;        // n <= 32 * MAXPL = 192 (shared memory caps n at ~166 anyway)
+constexpr int kMaxGram = 160;   // shared memory: 160 x 160 fp64 = 200 KB
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v, unsigned mask) {
+#pragma unroll
+	for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+	return v;
+}
+
+// tan(theta) of the rotation that annihilates gamma = <w_p, w_q> given alpha = |w_p|^2, beta = |w_q|^2:
+// t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (beta - alpha) / (2 gamma). Evaluated in fp32
+// with approximate div/sqrt (an fp32-accurate angle only leaves a 1e-7 relative residual, removed
+// quadratically by the next sweep); cos = rsqrt(1 + t^2) in fp64 keeps the rotation orthogonal to
+// fp64 rounding.
+__device__ __forceinline__ double jacobi_tan(double al, double be, double ga) {
+	const double d = be - al;
+	const double big = fmax(fabs(d), fabs(ga));  // common power-of-two scale: no fp32 over/underflow
+	const int ex = (__double2hiint(big) >> 20) & 0x7ff;
+	const double scale = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023 - ex)
+	const float ds = (float)(fabs(d) * scale), gs = (float)(2.0 * fabs(ga) * scale);
+	const float z = __fdividef(ds, gs);          // gs == 0 -> inf -> t = 0
+	float sq;
+	asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(fmaf(z, z, 1.f)));
+	float tf = (z > 1e18f) ? __fdividef(0.5f, z) : __fdividef(1.f, z + sq);
+	if (!(tf <= 1.f)) tf = 1.f;                  // nan guard: 45 degrees
+	return ((d >= 0.0) == (ga >= 0.0)) ? (double)tf : -(double)tf;
+}
+
+// One-sided Jacobi sweeps over the rows of R (n x ld, ld a multiple of 16, pad columns zero).
+// A half-warp (G = 16 lanes) owns one row pair and keeps row p in registers (PL = ld / 16 elements per
+// lane). Measured and rejected: quarter-warp groups streaming both rows (one round per step for
+// n > 128, but 4 rows per warp request collide on the same banks: 73 vs 62 ms). Returns the sweep count.
+template <int PL, int G>
+__device__ __forceinline__ int jacobi_sweeps(double* __restrict__ R, const int n, const int ld, double* __restrict__ nrm,
+                                             double* __restrict__ red, const int max_sweeps) {
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+	const int m = even_up(n), half = m >> 1, mm = m - 1;
+	const double tol2 = 1e-30 * (double)n;       // (1e-15 sqrt(n))^2 on gamma^2 / (alpha beta)
+	constexpr int GPW = 32 / G;                  // groups per warp
+	const int hw = lane / G, hl = lane % G;
+	const unsigned hmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (hw * G));
+	const int nslot = nw * GPW;
+	int sweep = 0;
+	for (; sweep < max_sweeps; ++sweep) {
+		for (int j = warp; j < n; j += nw) {        // refresh the tracked norms
+			double s2 = 0.0;
+			for (int i = lane; i < ld; i += 32) { double v = R[j * ld + i]; s2 += v * v; }
+			s2 = fh_warp_sum(s2);
+			if (lane == 0) nrm[j] = s2;
+		}
+		__syncthreads();
+		double worst = 0.0;                        // largest gamma^2/(alpha beta) met in this sweep
+		for (int step = 0; step < mm; ++step) {
+			for (int t = warp * GPW + hw; t < half; t += nslot) {
+				int p, q;
+				if (t == 0) { p = mm; q = step; }
+				else {
+					p = step + t; if (p >= mm) p -= mm;
+					q = step - t + mm; if (q >= mm) q -= mm;
+				}
+				if (p >= n || q >= n) continue;      // the padding player of an odd n
+				if (p > q) { int x = p; p = q; q = x; }
+				double* rp = R + p * ld + hl;
+				double* rq = R + q * ld + hl;
+				double ga = 0.0, gb = 0.0;
+				double a[PL];
+#pragma unroll
+				for (int e = 0; e < PL; ++e) {
+					a[e] = rp[G * e];
+					if (e & 1) gb += a[e] * rq[G * e]; else ga += a[e] * rq[G * e];
+				}
+				ga = group_sum<G>(ga + gb, hmask);
+				const double al = nrm[p], be = nrm[q];
+				const double g2 = ga * ga, ab = al * be;
+				if (g2 > tol2 * ab && ga != 0.0) {
+					worst = fmax(worst, g2 / ab);
+					const double tt = jacobi_tan(al, be, ga);
+					const double cs = rsqrt(tt * tt + 1.0), sn = tt * cs;
+#pragma unroll
+					for (int e = 0; e < PL; ++e) {
+						const double c = rq[G * e];
+						rp[G * e] = cs * a[e] - sn * c;
+						rq[G * e] = sn * a[e] + cs * c;
+					}
+					if (hl == 0) {  // |w_p|^2, |w_q|^2 after the rotation
+						nrm[p] = fmax(al - tt * ga, 0.0);
+						nrm[q] = be + tt * ga;
+					}
+				}
+			}
+			__syncthreads();
+		}
+		// block max of `worst`
+#pragma unroll
+		for (int o = 16; o >= G; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+		if (lane == 0) red[warp] = worst;
+		__syncthreads();
+		double wmax = 0.0;
+		for (int i = 0; i < nw; ++i) wmax = fmax(wmax, red[i]);
+		__syncthreads();
+		// convergence: the largest scaled off-diagonal met in the sweep was <= 3e-6, its rotations leave
+		// ~1e-11 behind (quadratic convergence), far below the fp32 output rounding - no confirming sweep
+		if (wmax <= 1e-11) { ++sweep; break; }
+	}
+	return sweep;
+}
+
+__host__ __device__ inline int jacobi_ld(int n) { return (n + 15) & ~15; }
 
 // One CTA per matrix (problem b: size prob_n[b], data at prob_off[b] doubles into Gall / WTall).
-// Shared memory holds R (n x ld, row-major): first the symmetric G, then its pivoted Cholesky factor
-// as the UPPER triangle R = L^T (row j of R = column j of L), then the rows are orthogonalised in
-// place. Output WT (n x n): row j = w_j * lambda_j^{-3/4} in the ORIGINAL index order;
-// sigma[prob_sig[b] + j] = sqrt(lambda_j); sigma_sum[prob_slot[b]] = sum_j sqrt(lambda_j).
-template <int MAXPL16>  // column elements per lane of a half warp: n <= 16 * MAXPL16
+// Shared memory holds R (n x ld, row-major, ld = n rounded up to 16 with zero pad columns): first the
+// symmetric G, then its pivoted Cholesky factor as the UPPER triangle R = L^T (row j of R = column j
+// of L), then the rows are orthogonalised in place. Output WT (n x n): row j = w_j * lambda_j^{-3/4}
+// in the ORIGINAL index order; sigma[prob_sig[b] + j] = sqrt(lambda_j);
+// sigma_sum[prob_slot[b]] = sum_j sqrt(lambda_j).
 __global__ void __launch_bounds__(1024)
 chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob_n, const long long* __restrict__ prob_off,
                    const int* __restrict__ prob_slot, const long long* __restrict__ prob_sig, int uniform_n,
@@ -41,7 +148,7 @@ chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob
 	const long long off = prob_off ? prob_off[b] : (long long)b * n * n;
 	const int slot = prob_slot ? prob_slot[b] : b;
 	const long long sig_off = prob_sig ? prob_sig[b] : (long long)b * n;
-	const int ld = n | 1;
+	const int ld = jacobi_ld(n);
 	double* R = sm;                          // n x ld
 	double* red = R + (size_t)n * ld;        // 64 doubles scratch
 	int* perm = (int*)(red + 64);            // n
@@ -50,7 +157,10 @@ chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob
 	const int JT = blockDim.x;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = JT >> 5;
 	const double* Gg = Gall + off;
-	for (int i = tid; i < n * n; i += JT) R[(i / n) * ld + (i % n)] = Gg[i];
+	for (int i = tid; i < n * ld; i += JT) {
+		const int r = i / ld, c = i - r * ld;
+		R[i] = (c < n) ? Gg[r * n + c] : 0.0;
+	}
 	for (int i = tid; i < n; i += JT) perm[i] = i;
 	__syncthreads();
 	// ---------------- diagonally pivoted Cholesky, upper factor in place ----------------
@@ -112,96 +222,23 @@ chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob
 	}
 	__syncthreads();
 	// ---------------- one-sided Jacobi on the rows of R (columns of L) ----------------
-	// ncu: the first version was instruction-issue bound (32 warps x ~250 instructions per pair, mostly
-	// fp64 reductions and the sqrt/div chain). Now: a HALF-warp per pair (two pairs share every
-	// instruction), squared norms tracked incrementally (one dot product per pair, norms refreshed every
-	// sweep), tan(theta) from fp32 arithmetic (cos = rsqrt(1+t^2) in fp64 keeps the rotation orthogonal to
-	// fp64 rounding; an fp32-accurate angle only leaves a 1e-7 relative residual), no integer division.
-	const int m = even_up(n), half = m >> 1, mm = m - 1;
-	const double tol2 = 1e-30 * (double)n;       // (1e-15 sqrt(n))^2 on gamma^2 / (alpha beta)
+	// ncu: instruction-issue bound (32 warps x ~300 issue slots per pair). So: a half-warp per pair
+	// (two pairs share every instruction), squared norms tracked incrementally (one dot product per
+	// pair, refreshed every sweep), fp32 angle with approximate div/sqrt, rows padded to 16 so the
+	// element loops carry no predicates.
 	double* nrm = red + 64 + ((n + 1) >> 1);     // n squared norms, after perm (ints) in the scratch area
-	const int hw = lane >> 4, hl = lane & 15;
-	const unsigned hmask = hw ? 0xffff0000u : 0x0000ffffu;
-	const int nslot = nw * 2;
-	int sweep = 0;
-	for (; sweep < max_sweeps; ++sweep) {
-		for (int j = warp; j < n; j += nw) {        // refresh the tracked norms
-			double s2 = 0.0;
-			for (int i = lane; i < n; i += 32) { double v = R[j * ld + i]; s2 += v * v; }
-			s2 = fh_warp_sum(s2);
-			if (lane == 0) nrm[j] = s2;
-		}
-		__syncthreads();
-		double worst = 0.0;                        // largest gamma^2/(alpha beta) met in this sweep
-		for (int step = 0; step < mm; ++step) {
-			for (int t = warp * 2 + hw; t < half; t += nslot) {
-				int p, q;
-				if (t == 0) { p = mm; q = step; }
-				else {
-					p = step + t; if (p >= mm) p -= mm;
-					q = step - t + mm; if (q >= mm) q -= mm;
-				}
-				if (p >= n || q >= n) continue;      // the padding player of an odd n
-				if (p > q) { int x = p; p = q; q = x; }
-				double* rp = R + p * ld;
-				double* rq = R + q * ld;
-				double a[MAXPL16];
-				double ga = 0.0;
-#pragma unroll
-				for (int e = 0; e < MAXPL16; ++e) {
-					int i = hl + 16 * e;
-					a[e] = (i < n) ? rp[i] : 0.0;
-					ga += a[e] * ((i < n) ? rq[i] : 0.0);
-				}
-#pragma unroll
-				for (int o = 8; o > 0; o >>= 1) ga += __shfl_xor_sync(hmask, ga, o);
-				const double al = nrm[p], be = nrm[q];
-				const double g2 = ga * ga, ab = al * be;
-				if (g2 > tol2 * ab && ga != 0.0) {
-					worst = fmax(worst, g2 / ab);
-					// t = sign(d) rho / (1 + sqrt(1 + rho^2)), rho = 2 gamma / |d|, d = beta - alpha (fp32)
-					const double d = be - al;
-					// common power-of-two scale so the fp32 ratio cannot over/underflow
-					const double big = fmax(fabs(d), fabs(ga));
-					const int ex = (__double2hiint(big) >> 20) & 0x7ff;
-					const double scale = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023 - ex)
-					const float rho = (float)(2.0 * ga * scale) / fmaxf((float)(fabs(d) * scale), 1e-30f);
-					float tf;
-					if (fabsf(rho) <= 1.f) tf = rho / (1.f + sqrtf(1.f + rho * rho));
-					else {
-						const float ir = 1.f / fabsf(rho);
-						tf = copysignf(1.f / (ir + sqrtf(1.f + ir * ir)), rho);
-					}
-					if (!(fabsf(tf) <= 1.f)) tf = copysignf(1.f, rho);  // inf/nan guard: 45 degrees
-					const double tt = (d >= 0.0) ? (double)tf : -(double)tf;
-					const double cs = rsqrt(tt * tt + 1.0), sn = tt * cs;
-#pragma unroll
-					for (int e = 0; e < MAXPL16; ++e) {
-						int i = hl + 16 * e;
-						if (i < n) {
-							const double c = rq[i];
-							rp[i] = cs * a[e] - sn * c;
-							rq[i] = sn * a[e] + cs * c;
-						}
-					}
-					if (hl == 0) {  // |w_p|^2, |w_q|^2 after the rotation
-						nrm[p] = fmax(al - tt * ga, 0.0);
-						nrm[q] = be + tt * ga;
-					}
-				}
-			}
-			__syncthreads();
-		}
-		// block max of `worst`
-		worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, 16));
-		if (lane == 0) red[warp] = worst;
-		__syncthreads();
-		double wmax = 0.0;
-		for (int i = 0; i < nw; ++i) wmax = fmax(wmax, red[i]);
-		__syncthreads();
-		// convergence: the largest scaled off-diagonal met in the sweep was <= 3e-6, its rotations leave
-		// ~1e-11 behind (quadratic convergence), far below the fp32 output rounding - no confirming sweep
-		if (wmax <= 1e-11) { ++sweep; break; }
+	int sweep;
+	switch (ld >> 4) {
+		case 1: sweep = jacobi_sweeps<1, 16>(R, n, ld, nrm, red, max_sweeps); break;
+		case 2: sweep = jacobi_sweeps<2, 16>(R, n, ld, nrm, red, max_sweeps); break;
+		case 3: sweep = jacobi_sweeps<3, 16>(R, n, ld, nrm, red, max_sweeps); break;
+		case 4: sweep = jacobi_sweeps<4, 16>(R, n, ld, nrm, red, max_sweeps); break;
+		case 5: sweep = jacobi_sweeps<5, 16>(R, n, ld, nrm, red, max_sweeps); break;
+		case 6: sweep = jacobi_sweeps<6, 16>(R, n, ld, nrm, red, max_sweeps); break;
+		case 7: sweep = jacobi_sweeps<7, 16>(R, n, ld, nrm, red, max_sweeps); break;
+		case 8: sweep = jacobi_sweeps<8, 16>(R, n, ld, nrm, red, max_sweeps); break;
+		case 9: sweep = jacobi_sweeps<9, 16>(R, n, ld, nrm, red, max_sweeps); break;
+		default: sweep = jacobi_sweeps<10, 16>(R, n, ld, nrm, red, max_sweeps); break;
 	}
 	if (tid == 0 && nsweep_out) nsweep_out[slot] = sweep;
 	// ---------------- lambda_j = |w_j|^2, outputs ----------------
@@ -267,26 +304,16 @@ constexpr int kMaxSweeps = 30;
 
 int jacobi_threads(int n) { return n > 83 ? 1024 : (n > 58 ? 512 : 256); }
 
-template <int PL>
-int launch_jacobi_pl(int grid, int nmax, size_t smem, cudaStream_t st, const double* G, const int* pn, const long long* po,
-                     const int* ps, int uniform_n, int max_sweeps, double* WT, double* sigma, double* sigma_sum, int* nsweep) {
-	FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	chol_jacobi_kernel<PL><<<grid, jacobi_threads(nmax), smem, st>>>(G, pn, po, ps, nullptr, uniform_n, max_sweeps, WT, sigma,
-	                                                              sigma_sum, nsweep);
+int launch_jacobi(int grid, int nmax, size_t smem, cudaStream_t st, const double* G, const int* pn, const long long* po,
+                  const int* ps, int uniform_n, int max_sweeps, double* WT, double* sigma, double* sigma_sum, int* nsweep) {
+	FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	chol_jacobi_kernel<<<grid, jacobi_threads(nmax), smem, st>>>(G, pn, po, ps, nullptr, uniform_n, max_sweeps,
+	                                                           WT, sigma, sigma_sum, nsweep);
 	FH_LAUNCH_CHECK();
 	return FH_OK;
 }
-// the half-warp register tile is sized to the largest problem of the launch (fewer predicated iterations)
-int launch_jacobi(int grid, int nmax, size_t smem, cudaStream_t st, const double* G, const int* pn, const long long* po,
-                  const int* ps, int uniform_n, int max_sweeps, double* WT, double* sigma, double* sigma_sum, int* nsweep) {
-	if (nmax <= 64) return launch_jacobi_pl<4>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, WT, sigma, sigma_sum, nsweep);
-	if (nmax <= 96) return launch_jacobi_pl<6>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, WT, sigma, sigma_sum, nsweep);
-	if (nmax <= 128) return launch_jacobi_pl<8>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, WT, sigma, sigma_sum, nsweep);
-	if (nmax <= 144) return launch_jacobi_pl<9>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, WT, sigma, sigma_sum, nsweep);
-	return launch_jacobi_pl<12>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, WT, sigma, sigma_sum, nsweep);
-}
 
-size_t jacobi_smem(int n) { return ((size_t)n * (n | 1) + 64 + (n + 1) / 2 + n) * 8 + 16; }
+size_t jacobi_smem(int n) { return ((size_t)n * jacobi_ld(n) + 64 + (n + 1) / 2 + n) * 8 + 16; }
 
 }  // namespace
 
@@ -307,7 +334,7 @@ extern "C" int fh_polar_batched(const float* T, float* U, int batch, int rows, i
 	const bool tall = rows >= cols;
 	const int n = tall ? cols : rows;
 	const size_t smem = jacobi_smem(n);
-	FH_CHECK_ARG(smem <= 227 * 1024 && n <= 32 * MAXPL, "fh_polar_batched: Gram side %d does not fit shared memory (max ~166)", n);
+	FH_CHECK_ARG(smem <= 227 * 1024 && n <= kMaxGram, "fh_polar_batched: Gram side %d does not fit shared memory (max 160)", n);
 	FH_CHECK_ARG(workspace && workspace_bytes >= fh_polar_workspace_bytes(batch, rows, cols),
 	             "fh_polar_batched: workspace too small");
 	PolarWs ws = carve(batch, n, workspace);
@@ -349,12 +376,12 @@ extern "C" int fh_polar_isqrt_multi(const double* G_all, double* WT_all, const i
 	             "fh_polar_isqrt_multi: null argument");
 	if (max_sweeps <= 0 || max_sweeps > kMaxSweeps) max_sweeps = kMaxSweeps;
 	cudaStream_t st = (cudaStream_t)stream;
-	const int bounds[4] = {117, 83, 58, 0};  // class lower bounds (exclusive): (117,166], (83,117], (58,83], (0,58]
+	const int bounds[4] = {117, 83, 58, 0};  // class lower bounds (exclusive): (117,160], (83,117], (58,83], (0,58]
 	int i = 0;
 	while (i < count) {
 		const int nmax = host_prob_n[i];
-		FH_CHECK_ARG(nmax > 0 && jacobi_smem(nmax) <= 227 * 1024 && nmax <= 32 * MAXPL,
-		             "fh_polar_isqrt_multi: Gram side %d does not fit shared memory (max ~166)", nmax);
+		FH_CHECK_ARG(nmax > 0 && jacobi_smem(nmax) <= 227 * 1024 && nmax <= kMaxGram,
+		             "fh_polar_isqrt_multi: Gram side %d does not fit shared memory (max 160)", nmax);
 		int lb = 0;
 		for (int c = 0; c < 4; ++c)
 			if (nmax > bounds[c]) { lb = bounds[c]; break; }

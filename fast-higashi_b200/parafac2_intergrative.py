@@ -39,7 +39,7 @@ def _as_block_csr(ds, device):
 
 
 class Fast_Higashi_core:
-	def __init__(self, rank, off_diag, res_list, cache="sweep", use_tc=None, group=None, warm_polar=True):
+	def __init__(self, rank, off_diag, res_list, cache="sweep", use_tc=None, group=None):
 		self.rank = rank
 		self.off_diag = off_diag
 		self.res_list = res_list
@@ -47,7 +47,6 @@ class Fast_Higashi_core:
 		self.cache = cache            # "sweep": one RWR pass per ALS sweep; "run": one per run
 		self.use_tc = use_tc          # None -> decided in .to()
 		self.group = group            # torch.distributed process group when cell-sharded
-		self.warm_polar = warm_polar
 		self.verbose = True
 		self.n_rwr_passes = 0
 		self._X = {}

@@ -12,7 +12,7 @@ import os
 import torch
 from . import _lib
 
-JACOBI_MAX_SIDE = 166  # Gram side that still fits shared memory (fh_polar.cu)
+JACOBI_MAX_SIDE = 160  # Gram side that still fits shared memory (fh_polar.cu)
 
 
 def polar_batched(T, rows, cols, ld, out=None, want_sigma=False, want_sweeps=False):
