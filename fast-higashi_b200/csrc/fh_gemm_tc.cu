@@ -19,11 +19,11 @@
 //               (tcgen05.ld), which keeps the error at the fp32 level for any K; the final sum goes
 //               through alpha/beta/diag/column-scale and coalesced stores
 //   warp 2      TMEM allocation (256 columns: two 128-column accumulators)
-#include <cuda.h>
-#include "fh_common.cuh"
+#include "fh_tc.cuh"
 #include "../../include/fh_b200.h"
 
 namespace {
+using namespace fh_tc;
 
 constexpr int BM = 128, BN = 128, BK = 32;       // tile (BK fp32 = one 128-byte swizzle row)
 constexpr int STAGES = 3;
@@ -43,62 +43,9 @@ struct TcP {
 	int a_bcast, b_bcast;  // operand shared by all batch items (batch stride 0)
 	int vec_ok;            // C rows are 16-byte aligned: 128-bit epilogue accesses allowed
 	int ksplit, kb_per_split;  // split-K: work item = (tile, k range); partial sums are atomically added to C
+	int dbg;               // FH_TC_DEBUG bits (timing experiments only, results wrong): 1 no C stores, 2 no split, 4 no MMA
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-	asm volatile(
-		"{\n"
-		".reg .pred p;\n"
-		"LAB_WAIT:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-		"@p bra LAB_DONE;\n"
-		"bra LAB_WAIT;\n"
-		"LAB_DONE:\n"
-		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-	asm volatile(
-		"cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-			smem_u32(dst)),
-		"l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-		: "memory");
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
-	// cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
-	// layout type [61,64): SWIZZLE_128B = 2 (K-major), SWIZZLE_128B_BASE32B = 1 (the only MN-major
-	// layout tf32 operands have: 32-byte chunks swizzled inside 128-byte rows, 4-row atoms)
-	uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
-	d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-	d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-	d |= 1ull << 46;
-	d |= (uint64_t)layout_type << 61;
-	return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-	asm volatile(
-		"{\n"
-		".reg .pred p;\n"
-		"setp.ne.b32 p, %4, 0;\n"
-		"tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-		"}\n" ::"r"(tmem_d),
-		"l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-		: "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ uint32_t tf32_rn(uint32_t bits) { return (bits + 0x1000u) & 0xFFFFE000u; }
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcP p,
@@ -209,6 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 					const uint32_t b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
 #pragma unroll
 					for (int k = 0; k < BK / 8; ++k) {
+						if (p.dbg & 4) break;
 						const uint64_t dah = make_desc(a_hi + k * a_step, a_lbo, a_sbo, a_lt), dal = make_desc(a_lo + k * a_step, a_lbo, a_sbo, a_lt);
 						const uint64_t dbh = make_desc(b_hi + k * b_step, b_lbo, b_sbo, b_lt), dbl = make_desc(b_lo + k * b_step, b_lbo, b_sbo, b_lt);
 						umma_tf32(acc, dal, dbh, idesc, ((kb % CHUNK_KB) | k) ? 1u : 0u);  // small terms first
@@ -237,6 +185,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 				uint8_t* st = smem + s * STAGE_BYTES;
 #pragma unroll
 				for (int op = 0; op < 2; ++op) {
+					if (p.dbg & 2) break;
 					float4* hi = (float4*)(st + op * 2 * TILE_BYTES);
 					float4* lo = (float4*)(st + op * 2 * TILE_BYTES + TILE_BYTES);
 #pragma unroll
@@ -314,7 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 				for (int j = 0; j < 32; ++j) tile_s[lane * 33 + j] = sum[c * 32 + j];
 				__syncwarp();
 				const int n = n0 + h * 64 + c * 32 + 4 * cg;  // first of this lane's 4 columns
-				if (n < p.N) {
+				if (n < p.N && !(p.dbg & 1)) {
 					float csv[4] = {1.f, 1.f, 1.f, 1.f};
 					if (cs) {
 #pragma unroll
@@ -367,35 +316,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 	}
 }
 
-typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeFn get_encode() {
-	static EncodeFn fn = nullptr;
-	if (!fn) {
-		void* p = nullptr;
-		cudaDriverEntryPointQueryResult q;
-		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-			fn = (EncodeFn)p;
-	}
-	return fn;
-}
-
-// operand viewed as (rows x contiguous) with an optional batch dimension
-bool make_map(CUtensorMap* m, const float* base, long long contig_extent, long long rows, long long row_stride,
-              int batch, long long batch_stride, int box_contig, int box_rows, bool mn_major) {
-	EncodeFn enc = get_encode();
-	if (!enc) return false;
-	cuuint64_t dims[3] = {(cuuint64_t)contig_extent, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
-	long long bs = batch_stride > 0 ? batch_stride : row_stride * rows;
-	cuuint64_t strides[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)bs * 4};
-	cuuint32_t box[3] = {(cuuint32_t)box_contig, (cuuint32_t)box_rows, 1};
-	cuuint32_t es[3] = {1, 1, 1};
-	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-	                 mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-	return r == CUDA_SUCCESS;
-}
-
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace
@@ -440,6 +360,9 @@ int fh_gemm_tc(const fh_gemm_desc* d, const float* A, const float* B, float* C, 
 	}
 	// long-K problems with few output tiles (P3: cells x 256 outputs, K = nb*ldw ~ 36k): split K so every SM
 	// has work; partial sums are added with fp32 atomics (C pre-scaled by beta here)
+	static int dbg = -1;
+	if (dbg < 0) { const char* e = getenv("FH_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+	p.dbg = dbg;
 	const int nkb_h = fh_cdiv(d->K, BK);
 	p.ksplit = 1; p.kb_per_split = nkb_h;
 	if (total_tiles * 2 <= num_sms + 12 && nkb_h >= 64 && !d->cscale && d->epilogue == FH_EPI_NONE && (d->beta == 0.0 || d->beta == 1.0)) {

@@ -314,6 +314,12 @@ sqnorm_kernel(const float* __restrict__ x, const float* __restrict__ y, long lon
 	if (threadIdx.x == 0) atomicAdd(acc, a);
 }
 
+}  // namespace
+extern "C" void fh_count_tc_fallback(void);
+int fh_rwr_chain(const float* P, const float* A, float* out, int nb, int w, int ldw, int ldp, int k, int ncell,
+                 long long p_cell_stride, long long a_cell_stride, long long out_cell_stride, void* stream);
+namespace {
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct RwrWs {
@@ -359,6 +365,12 @@ int gemm_f32(int use_tc, int M, int N, int K, int batch, const float* A, long lo
 	return FH_OK;
 }
 
+bool rwr_fused_enabled() {  // FH_RWR_FUSED=0: keep the per-step GEMM chain (A/B measurements, tests)
+	static int v = -1;
+	if (v < 0) { const char* e = getenv("FH_RWR_FUSED"); v = (e && e[0] == '0') ? 0 : 1; }
+	return v != 0;
+}
+
 // the RWR pipeline from the conv'd panel A (in ws.A, or already in `out` when !do_rwr)
 int rwr_from_panel(const fh_rwr_desc* d, const RwrWs& ws, const float* bin_cov, long long bin_cov_ld,
                    float* out, long long out_cell_stride, int* host_n_iter, cudaStream_t st) {
@@ -373,10 +385,24 @@ int rwr_from_panel(const fh_rwr_desc* d, const RwrWs& ws, const float* bin_cov, 
 	              nullptr, 0, 0, st);
 	if (rc) return rc;
 	FH_CHECK_ARG(nb <= 256, "fh_rwr: bin block of %d rows (max 256: recommend_bs_bin, FastHigashi_Wrapper.py:501)", nb);
-	const bool fuse_q1 = d->k >= 1;  // forced mode: Q1 comes out of the transition kernel
+	// forced step count without do_col on the tensor cores: the remaining steps and Q A run as ONE
+	// kernel with Q resident in tensor memory (fh_rwr_chain.cu)
+	const bool fused = tc && d->k >= 1 && !d->do_col && nb <= 128 && rwr_fused_enabled();
+	const bool fuse_q1 = d->k >= 1 && !fused;  // forced mode: Q1 comes out of the transition kernel
 	if (nb <= 128) transition_kernel<16><<<nc, 256, 0, st>>>(ws.A, acs, ldw, d->s, ws.P, nb, ldp, fuse_q1 ? ws.Q0 : nullptr);
 	else transition_kernel<32><<<nc, 256, 0, st>>>(ws.A, acs, ldw, d->s, ws.P, nb, ldp, fuse_q1 ? ws.Q0 : nullptr);
 	FH_LAUNCH_CHECK();
+	if (fused) {
+		rc = fh_rwr_chain(ws.P, ws.A, out, nb, w, ldw, ldp, d->k, nc, pcs, acs, out_cell_stride, st);
+		if (rc == FH_OK) {
+			if (host_n_iter) *host_n_iter = d->k;
+			return FH_OK;
+		}
+		if (rc != FH_ERR_UNSUPPORTED) return rc;
+		fh_count_tc_fallback();
+		first_step_kernel<<<fh_cdiv(ptotal, 256), 256, 0, st>>>(ws.P, ws.Q0, nb, ldp, ptotal);  // Q1 for the GEMM chain
+		FH_LAUNCH_CHECK();
+	}
 	float* Q = ws.Q0;
 	float* Qn = ws.Q1;
 	int n_iter = 0;

@@ -392,3 +392,39 @@ def test_gemm_tcgen05_split_k(beta):
 	Cd = C0.clone().to(DEV)
 	L.gemm(Ad.to(DEV), B.to(DEV), Cd, M, N, K, (lda, 1), (N, 1), N, beta=beta, dtype=L.GEMM_TF32X3)
 	assert rel_fro(Cd.cpu().numpy(), ref.numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("k", [1, 2, 4])
+def test_rwr_fused_chain_kernel(k):
+	"""The fused tcgen05 RWR tail (Q resident in tensor memory, fh_rwr_chain.cu) against the CPU oracle and
+	the fp32 SIMT GEMM chain: realistic windows (nb up to 128, w up to 328), more cells than SMs so every
+	CTA walks several cells, bin blocks with 2, 3 and 4 k-blocks."""
+	import math
+	from fasthigashi_b200 import synth, _lib
+	from fasthigashi_b200.partial_rwr import rwr_block_csr, pad4
+	from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset
+	bins, ncell = [250, 256, 60, 90], 330
+	chroms, _ = synth.synth_dataset(bins, ncell, 0.10, off_diag=100, seed=2, num_cluster=4)
+	fb0 = _lib.lib().fh_tc_fallback_count()
+	for ch in chroms:
+		n = ch["n"]
+		bb = math.ceil(n / max(math.ceil(n / 128), 1))
+		mk = lambda device: Chrom_Dataset(Sparse(ch["indices"], ch["values"], ch["shape"]), bs_bin=bb, bs_cell=ncell, compact=True,
+		                                  flank=100, chrom=ch["chrom"], resolution=1000000, device=device)
+		ds_c, ds_g = mk("cpu"), mk(DEV)
+		for b, g in enumerate(ds_c.geoms):
+			ldw = pad4(g.w)
+			out = torch.full((ncell, g.nb * ldw), float("nan"), device=DEV)
+			ref32 = torch.full((ncell, g.nb * ldw), float("nan"), device=DEV)
+			rwr_block_csr(ds_g, b, 0, ncell, out, g.nb * ldw, k, True, True, False, use_tc=True)
+			rwr_block_csr(ds_g, b, 0, ncell, ref32, g.nb * ldw, k, True, True, False, use_tc=False)
+			got = out.view(ncell, g.nb, ldw)
+			assert torch.isfinite(got).all()
+			assert float(got[:, :, g.w:].abs().sum()) == 0.0
+			assert rel_fro(got.cpu().numpy(), ref32.view(ncell, g.nb, ldw).cpu().numpy()) < 5e-6, (n, b)  # 3xTF32 vs fp32 FMA
+			per_cell = (got - ref32.view(ncell, g.nb, ldw)).flatten(1).norm(dim=1) / ref32.view(ncell, -1).norm(dim=1)
+			assert float(per_cell.max()) < 1e-5, (n, b, int(per_cell.argmax()))
+			sel = [0, 1, 147, 148, 149, 296, 329]
+			ref, _ = O.partial_rwr(O.densify_block(ds_c, b, 0, ncell)[sel], g.s, g.e, True, True, False, None, k)
+			assert rel_fro(got[sel][:, :, :g.w].cpu().numpy(), ref.numpy()) < 1e-5, (n, b)
+	assert _lib.lib().fh_tc_fallback_count() == fb0  # the tensor-core path really ran
