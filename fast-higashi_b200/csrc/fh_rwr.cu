@@ -316,14 +316,16 @@ sqnorm_kernel(const float* __restrict__ x, const float* __restrict__ y, long lon
 
 }  // namespace
 extern "C" void fh_count_tc_fallback(void);
-int fh_rwr_chain(const float* P, const float* A, float* out, int nb, int w, int ldw, int ldp, int k, int ncell,
-                 long long p_cell_stride, long long a_cell_stride, long long out_cell_stride, void* stream);
+size_t fh_rwr_chain_scratch_bytes();
+int fh_rwr_chain(const float* P, const float* A, float* out, int nb, int w, int ldw, int ldp, int s, int k, int ncell,
+                 long long p_cell_stride, long long a_cell_stride, long long out_cell_stride, float* scratch,
+                 void* stream);
 namespace {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct RwrWs {
-	float *A, *P, *Q0, *Q1, *delta;
+	float *A, *P, *Q0, *Q1, *delta, *scratch;
 	size_t bytes;
 };
 
@@ -338,6 +340,7 @@ RwrWs carve(const fh_rwr_desc* d, void* ws) {
 	r.Q0 = (float*)b; b += p;
 	r.Q1 = (float*)b; b += p;
 	r.delta = (float*)b; b += align_up((size_t)d->ncell * 4, 256);
+	r.scratch = (float*)b; b += align_up(fh_rwr_chain_scratch_bytes(), 256);
 	r.bytes = (size_t)(b - (char*)ws);
 	return r;
 }
@@ -365,10 +368,12 @@ int gemm_f32(int use_tc, int M, int N, int K, int batch, const float* A, long lo
 	return FH_OK;
 }
 
-bool rwr_fused_enabled() {  // FH_RWR_FUSED=0: keep the per-step GEMM chain (A/B measurements, tests)
+// FH_RWR_FUSED: 2 (default) S2 + transition + steps + Q A in one kernel; 1 steps + Q A fused; 0 per-step
+// kernels (A/B measurements)
+int rwr_fused_level() {
 	static int v = -1;
-	if (v < 0) { const char* e = getenv("FH_RWR_FUSED"); v = (e && e[0] == '0') ? 0 : 1; }
-	return v != 0;
+	if (v < 0) { const char* e = getenv("FH_RWR_FUSED"); v = e ? atoi(e) : 2; }
+	return v;
 }
 
 // the RWR pipeline from the conv'd panel A (in ws.A, or already in `out` when !do_rwr)
@@ -380,20 +385,28 @@ int rwr_from_panel(const fh_rwr_desc* d, const RwrWs& ws, const float* bin_cov, 
 	const long long ptotal = (long long)nc * pcs;
 	const int tc = d->use_tensor_cores;
 	int rc;
+	// forced step count without do_col on the tensor cores: one fused kernel (fh_rwr_chain.cu)
+	const int fused = (tc && d->k >= 1 && !d->do_col && nb <= 128) ? rwr_fused_level() : 0;
+	FH_CHECK_ARG(nb <= 256, "fh_rwr: bin block of %d rows (max 256: recommend_bs_bin, FastHigashi_Wrapper.py:501)", nb);
+	if (fused >= 2) {
+		rc = fh_rwr_chain(nullptr, ws.A, out, nb, w, ldw, ldp, d->s, d->k, nc, pcs, acs, out_cell_stride, ws.scratch, st);
+		if (rc == FH_OK) {
+			if (host_n_iter) *host_n_iter = d->k;
+			return FH_OK;
+		}
+		if (rc != FH_ERR_UNSUPPORTED) return rc;
+		fh_count_tc_fallback();
+	}
 	// S2 = A A^T  (partial_rwr.py:85)
 	rc = gemm_f32(tc, nb, nb, w, nc, ws.A, ldw, 1, acs, ws.A, 1, ldw, acs, ws.P, ldp, pcs, 1.0, FH_EPI_NONE, 0.0,
 	              nullptr, 0, 0, st);
 	if (rc) return rc;
-	FH_CHECK_ARG(nb <= 256, "fh_rwr: bin block of %d rows (max 256: recommend_bs_bin, FastHigashi_Wrapper.py:501)", nb);
-	// forced step count without do_col on the tensor cores: the remaining steps and Q A run as ONE
-	// kernel with Q resident in tensor memory (fh_rwr_chain.cu)
-	const bool fused = tc && d->k >= 1 && !d->do_col && nb <= 128 && rwr_fused_enabled();
-	const bool fuse_q1 = d->k >= 1 && !fused;  // forced mode: Q1 comes out of the transition kernel
+	const bool fuse_q1 = d->k >= 1 && fused != 1;  // forced mode: Q1 comes out of the transition kernel
 	if (nb <= 128) transition_kernel<16><<<nc, 256, 0, st>>>(ws.A, acs, ldw, d->s, ws.P, nb, ldp, fuse_q1 ? ws.Q0 : nullptr);
 	else transition_kernel<32><<<nc, 256, 0, st>>>(ws.A, acs, ldw, d->s, ws.P, nb, ldp, fuse_q1 ? ws.Q0 : nullptr);
 	FH_LAUNCH_CHECK();
-	if (fused) {
-		rc = fh_rwr_chain(ws.P, ws.A, out, nb, w, ldw, ldp, d->k, nc, pcs, acs, out_cell_stride, st);
+	if (fused == 1) {
+		rc = fh_rwr_chain(ws.P, ws.A, out, nb, w, ldw, ldp, d->s, d->k, nc, pcs, acs, out_cell_stride, nullptr, st);
 		if (rc == FH_OK) {
 			if (host_n_iter) *host_n_iter = d->k;
 			return FH_OK;

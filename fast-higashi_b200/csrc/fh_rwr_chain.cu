@@ -1,4 +1,5 @@
-// Fused tail of the RWR imputation of one bin block (reference: partial_rwr.py:99-126 and :138):
+// Fused RWR imputation of one bin block from the conv'd panel A (reference: partial_rwr.py:80-126, :138):
+//   S2 = A A^T;  P = colnorm(3/4 colnorm(A_diag_block) + 1/4 colnorm(S2 - diag))     [PANEL mode only]
 //   Q_1 = 0.5 P + 0.5 I,   Q_{t+1} = 0.5 Q_t P + 0.5 I  (t = 1 .. k-1),   X = Q_k A
 // for every cell of the chunk in ONE persistent tcgen05 kernel. The per-launch GEMM chain it replaces
 // (k-1 launches of Q P plus Q A) is HBM-bound: each 128 x 128 x 128 step re-reads Q and P and re-writes Q
@@ -13,6 +14,12 @@
 //     first A tiles. During X = Q A the whole ring streams A (MN-major B tiles), so the next cell's P
 //     arrives while this cell's product is still running.
 //   * HBM traffic per cell: P + A in, X out (343 KB at nb=115, w=316) instead of ~1.1 MB.
+//   * PANEL mode also forms S2 on the tensor cores (each landed K-major A tile is BOTH operands) and runs
+//     the transition-matrix normalisation in the drain warps: thread = row, S2 / first-order values parked
+//     in the idle accumulator columns of TMEM between passes, column sums through the warps' private
+//     staging tiles (fixed order: deterministic), the symmetric S2 column sums taken as row sums. P goes
+//     to a per-CTA 64 KB global scratch (L2 resident) and comes back through TMA as the chain's B operand;
+//     Q_1 is written straight into TMEM. HBM traffic per cell: A twice in (second read mostly L2), X out.
 // Arithmetic is the same 3xTF32 split, MMA order and fp32 epilogue as fh_gemm_tc.cu (K = nb <= 128 is a
 // single accumulation chunk), so results match the unfused path.
 // TMEM (512 columns): Q_hi [0,128) | Q_lo [128,256) | accumulator 0 [256,384) | accumulator 1 [384,512)
@@ -25,39 +32,55 @@ namespace {
 using namespace fh_tc;
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int SLOTS = 6;
-constexpr int TILE_BYTES = BK * BN * 4;         // 16 KB: 32 k-rows x 128 n (four 32-wide TMA boxes)
+constexpr int TILE_BYTES = BK * BN * 4;         // 16 KB: 32 k-rows x 128 n (four 32-wide TMA boxes) or 128 rows x 32 k
 constexpr int SLOT_BYTES = 2 * TILE_BYTES;      // hi (raw fp32 as landed), lo
 constexpr int EPI_BYTES = 8 * 32 * 32 * 4;      // 8 drain warps x (32 x 32 floats, XOR-swizzled)
-constexpr int SMEM_BYTES = SLOTS * SLOT_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int XCH_FLOATS = 4 * 128 + 2 * 128 + 3 * 128;  // PANEL: column partials [4][128], row sums [2][128], rc1/rc2/flag [128]
 constexpr int NTHREADS = 512;
+constexpr int CHUNK_KB = 4;                     // S2: k-blocks accumulated in TMEM before a drain (as fh_gemm_tc.cu)
+constexpr float EPS = 1e-15f;                   // partial_rwr.py:88-97
+template <bool PANEL> struct Cfg {
+	static constexpr int SLOTS = PANEL ? 5 : 6;
+	static constexpr int SMEM_BYTES = SLOTS * SLOT_BYTES + EPI_BYTES + (PANEL ? XCH_FLOATS * 4 : 0) + 1024 /*align*/ + 256 /*barriers*/;
+};
 constexpr uint32_t TM_QHI = 0, TM_QLO = 128, TM_ACC = 256;
 
 struct ChainP {
 	int nb, w, ldw, ldp, k, ncell;
 	long long p_cell_stride, out_cell_stride;
-	const float* P;
+	const float* P;        // !PANEL: transition matrices (Q_1 source). PANEL: per-CTA scratch (gridDim x 128 x 128)
+	const float* A;        // PANEL: the panel, for the first-order block A[:, s:s+nb]
+	long long a_cell_stride;
+	int s;
 	float* out;
 	int vec_ok;
 };
 
+// tmP: P as (k rows x n) MN-major boxes (PANEL: the scratch, one "cell" per CTA); tmA: the panel as MN-major
+// B tiles of Q A; tmK (PANEL): the panel as K-major 128 x 32 tiles for S2
+template <bool PANEL>
 __global__ void __launch_bounds__(NTHREADS, 1)
-rwr_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmA, ChainP p) {
+rwr_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmA,
+                 const __grid_constant__ CUtensorMap tmK, ChainP p) {
+	constexpr int SLOTS = Cfg<PANEL>::SLOTS;
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	uint8_t* stagebuf = smem + SLOTS * SLOT_BYTES;
-	uint64_t* bars = (uint64_t*)(stagebuf + EPI_BYTES);
+	float* xch = (float*)(stagebuf + EPI_BYTES);
+	uint64_t* bars = (uint64_t*)(stagebuf + EPI_BYTES + (PANEL ? XCH_FLOATS * 4 : 0));
 	uint64_t* raw_full = bars;                    // TMA landed              (count 1 + tx)
 	uint64_t* split_full = bars + SLOTS;          // lo half written         (count 4: splitter warps)
 	uint64_t* empty = bars + 2 * SLOTS;           // MMAs reading the slot done (tcgen05.commit)
 	uint64_t* acc_full = bars + 3 * SLOTS;        // [2] accumulator complete (tcgen05.commit)
 	uint64_t* acc_empty = bars + 3 * SLOTS + 2;   // [2] accumulator drained  (count 8: drain warps)
 	uint64_t* q_ready = bars + 3 * SLOTS + 4;     // Q hi/lo stored in TMEM   (count 8: drain warps)
-	uint32_t* tmem_holder = (uint32_t*)(bars + 3 * SLOTS + 5);
+	uint64_t* p_written = bars + 3 * SLOTS + 5;   // PANEL: P of the current cell is in the global scratch (count 1)
+	uint32_t* tmem_holder = (uint32_t*)(bars + 3 * SLOTS + 6);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int nkb = (p.nb + BK - 1) / BK;         // k-blocks of the bin dimension (K of every product)
 	const int NT = (p.ldw + BN - 1) / BN;         // 128-column tiles of the window
+	const int nkw = PANEL ? (p.w + BK - 1) / BK : 0;  // k-blocks of the window (K of S2)
 	const bool chain = p.k > 1;
 
 	if (threadIdx.x == 0) {
@@ -69,11 +92,13 @@ rwr_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant_
 		mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
 		mbar_init(&acc_empty[0], 8); mbar_init(&acc_empty[1], 8);
 		mbar_init(q_ready, 8);
+		mbar_init(p_written, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 0 && lane == 0) {
 		asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmP) : "memory");
 		asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+		if (PANEL) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmK) : "memory");
 	}
 	if (warp == 2) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512) : "memory");
@@ -87,23 +112,30 @@ rwr_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant_
 	if (warp == 0) {
 		// ------------------------------------------------------------------ TMA producer
 		if (lane == 0) {
-			long long it = 0;
-			for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x) {
-				const int nslots = (chain ? nkb : 0) + NT * nkb;
+			long long it = 0, ncell_done = 0;
+			for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x, ++ncell_done) {
+				const int np = chain ? nkb : 0;
+				const int nslots = nkw + np + NT * nkb;
 				for (int j = 0; j < nslots; ++j, ++it) {
 					const int s = (int)(it % SLOTS);
 					mbar_wait(&empty[s], (uint32_t)(((it / SLOTS) & 1) ^ 1));
 					uint8_t* dst = smem + s * SLOT_BYTES;
 					mbar_expect_tx(&raw_full[s], TILE_BYTES);
+					if (j < nkw) {  // S2: one K-major box of 128 rows x 32 window columns
+						tma_load_3d(dst, &tmK, &raw_full[s], j * BK, 0, cell);
+						continue;
+					}
 					const CUtensorMap* tm;
-					int n0, k0;
-					if (chain && j < nkb) { tm = &tmP; n0 = 0; k0 = j * BK; }
-					else {
-						const int t = j - (chain ? nkb : 0);
-						tm = &tmA; n0 = (t / nkb) * BN; k0 = (t % nkb) * BK;
+					int n0, k0, z;
+					if (j < nkw + np) {
+						if (PANEL && j == nkw) mbar_wait(p_written, (uint32_t)(ncell_done & 1));  // transition done
+						tm = &tmP; n0 = 0; k0 = (j - nkw) * BK; z = PANEL ? (int)blockIdx.x : cell;
+					} else {
+						const int t = j - nkw - np;
+						tm = &tmA; n0 = (t / nkb) * BN; k0 = (t % nkb) * BK; z = cell;
 					}
 #pragma unroll
-					for (int b = 0; b < BN / 32; ++b) tma_load_3d(dst + b * (BK * 128), tm, &raw_full[s], n0 + 32 * b, k0, cell);
+					for (int b = 0; b < BN / 32; ++b) tma_load_3d(dst + b * (BK * 128), tm, &raw_full[s], n0 + 32 * b, k0, z);
 				}
 			}
 		}
@@ -126,7 +158,36 @@ rwr_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant_
 					umma_tf32_ts(acc, a_hi, dbh, idesc, 1u);
 				}
 			};
+			const uint32_t idesc_kk = make_idesc_tf32(false, false, BN, BM);
 			for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x) {
+				if (PANEL) {
+					// S2 = A A^T: the landed K-major tile (SWIZZLE_128B: 128-byte rows, 8-row groups 1024 B apart, a K=8
+					// step = +32 B) is both operands; accumulator chunks of CHUNK_KB k-blocks alternate buffers
+					for (int kb = 0; kb < nkw; ++kb, ++it) {
+						const int cb = (int)(ch & 1);
+						if (kb % CHUNK_KB == 0) {
+							mbar_wait(&acc_empty[cb], (uint32_t)(((ch >> 1) & 1) ^ 1));
+							asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+						}
+						const uint32_t acc = tmem + TM_ACC + (uint32_t)(cb * BN);
+						const int s = (int)(it % SLOTS);
+						mbar_wait(&split_full[s], (uint32_t)((it / SLOTS) & 1));
+						asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+						const uint32_t hi = smem_u32(smem + s * SLOT_BYTES), lo = hi + TILE_BYTES;
+#pragma unroll
+						for (int k4 = 0; k4 < BK / 8; ++k4) {
+							const uint64_t dh = make_desc(hi + k4 * 32, 16, 1024, 2), dl = make_desc(lo + k4 * 32, 16, 1024, 2);
+							umma_tf32(acc, dl, dh, idesc_kk, ((kb % CHUNK_KB) | k4) ? 1u : 0u);  // small terms first
+							umma_tf32(acc, dh, dl, idesc_kk, 1u);
+							umma_tf32(acc, dh, dh, idesc_kk, 1u);
+						}
+						umma_commit(&empty[s]);
+						if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkw - 1) {
+							umma_commit(&acc_full[cb]);
+							++ch;
+						}
+					}
+				}
 				if (chain) {
 					const long long p_it = it;  // the cell's P slots: p_it .. p_it + nkb - 1
 					for (int step = 1; step < p.k; ++step) {
@@ -174,7 +235,7 @@ rwr_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant_
 		const int t = threadIdx.x - 128;  // 0..127
 		long long it = 0;
 		for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x) {
-			const int nslots = (chain ? nkb : 0) + NT * nkb;
+			const int nslots = nkw + (chain ? nkb : 0) + NT * nkb;
 			for (int j = 0; j < nslots; ++j, ++it) {
 				const int s = (int)(it % SLOTS);
 				mbar_wait(&raw_full[s], (uint32_t)((it / SLOTS) & 1));
@@ -193,79 +254,237 @@ rwr_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant_
 			}
 		}
 	} else if (warp >= 8) {
-		// ------------------------------------------------------------------ drain: accumulator -> Q / X
+		// ------------------------------------------------------------------ drain: accumulator -> P, Q / X
 		const int q = warp & 3;             // TMEM lane quarter of this warp (rows 32q .. 32q+31)
 		const int h = (warp - 8) >> 2;      // column half (64 columns)
 		const int m = q * 32 + lane;        // this thread's row
 		const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
 		float* tile_s = (float*)(stagebuf + (warp - 8) * (32 * 32 * 4));
-		// Q (this thread's row, this warp's 64 columns) -> TMEM hi / lo, then publish
-		auto store_q = [&](const float (&qv)[64]) {
+		// 32 values of Q (this thread's row, columns 64h + 32c ..) -> TMEM hi / lo
+		auto store_q_chunk = [&](int c, const float (&qv)[32]) {
+			uint32_t hi[32], lo[32];
 #pragma unroll
-			for (int c = 0; c < 2; ++c) {
-				uint32_t hi[32], lo[32];
-#pragma unroll
-				for (int j = 0; j < 32; ++j) { hi[j] = __float_as_uint(qv[c * 32 + j]); lo[j] = tf32_lo(qv[c * 32 + j]); }
-				tmem_st32(tmem + lane_addr + TM_QHI + (uint32_t)(h * 64 + c * 32), hi);
-				tmem_st32(tmem + lane_addr + TM_QLO + (uint32_t)(h * 64 + c * 32), lo);
-			}
+			for (int j = 0; j < 32; ++j) { hi[j] = __float_as_uint(qv[j]); lo[j] = tf32_lo(qv[j]); }
+			tmem_st32(tmem + lane_addr + TM_QHI + (uint32_t)(h * 64 + c * 32), hi);
+			tmem_st32(tmem + lane_addr + TM_QLO + (uint32_t)(h * 64 + c * 32), lo);
+		};
+		auto publish_q = [&]() {
 			tmem_st_wait();
 			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 			__syncwarp();
 			if (lane == 0) mbar_arrive(q_ready);
 		};
-		// Q_1 = 0.5 P + 0.5 I from the transition matrix in global memory (first RWR step, Q_0 = I)
+		// Q_1 = 0.5 P + 0.5 I from the transition matrix in global memory (first RWR step, Q_0 = I)   [!PANEL]
 		auto first_q = [&](int cell) {
-			float qv[64];
 			const float* prow = p.P + (long long)cell * p.p_cell_stride + (long long)m * p.ldp + h * 64;
 #pragma unroll
-			for (int g = 0; g < 16; ++g) {
-				const int col = h * 64 + 4 * g;
-				float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-				if (m < p.nb && col < p.ldp) v = *reinterpret_cast<const float4*>(prow + 4 * g);
-				const float e[4] = {v.x, v.y, v.z, v.w};
+			for (int c = 0; c < 2; ++c) {
+				float qv[32];
 #pragma unroll
-				for (int x = 0; x < 4; ++x) {
-					float r = 0.f;
-					if (m < p.nb && col + x < p.nb) r = 0.5f * e[x] + ((m == col + x) ? 0.5f : 0.f);
-					qv[4 * g + x] = r;
+				for (int g = 0; g < 8; ++g) {
+					const int col = h * 64 + c * 32 + 4 * g;
+					float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+					if (m < p.nb && col < p.ldp) v = *reinterpret_cast<const float4*>(prow + c * 32 + 4 * g);
+					const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+					for (int x = 0; x < 4; ++x) {
+						float r = 0.f;
+						if (m < p.nb && col + x < p.nb) r = 0.5f * e[x] + ((m == col + x) ? 0.5f : 0.f);
+						qv[4 * g + x] = r;
+					}
+				}
+				store_q_chunk(c, qv);
+			}
+			publish_q();
+		};
+		// sum over the warp's 32 rows of a 32-column chunk held one row per lane: lane c gets column c
+		auto col_sum32 = [&](const float (&v)[32]) -> float {
+			__syncwarp();
+#pragma unroll
+			for (int j = 0; j < 32; ++j) tile_s[lane * 32 + (j ^ lane)] = v[j];
+			__syncwarp();
+			float acc = 0.f;
+#pragma unroll
+			for (int r = 0; r < 32; ++r) acc += tile_s[r * 32 + (lane ^ r)];
+			return acc;
+		};
+		auto drain_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };  // the 8 drain warps
+		float* colpart = xch;                  // [4][128] per-row-quarter column sums
+		float* rowsum = xch + 4 * 128;         // [2][128] S2 row sums of the two column halves
+		float* rc1 = xch + 6 * 128;            // 1 / column sum (first order, then of the blend)
+		float* rc2 = xch + 7 * 128;            // 1 / column sum (second order)
+		float* cflag = xch + 8 * 128;          // column of the blend was empty (partial_rwr.py:96-97)
+		const int td = threadIdx.x - 256;      // 0..255 among the drain warps
+		const uint32_t scrA = tmem + lane_addr + TM_ACC + (uint32_t)(h * 64), scrB = scrA + 128;  // TMEM parking (idle accumulators)
+		long long ch = 0;
+		if (!PANEL && (int)blockIdx.x < p.ncell) first_q(blockIdx.x);
+		for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x) {
+			if (PANEL) {
+				// ---- S2 row (this warp's 64 columns): chunks summed with round-to-nearest adds
+				{
+					float sum[64];
+#pragma unroll
+					for (int j = 0; j < 64; ++j) sum[j] = 0.f;
+					const int nchunk = (nkw + CHUNK_KB - 1) / CHUNK_KB;
+					for (int chunk = 0; chunk < nchunk; ++chunk, ++ch) {
+						const int cb = (int)(ch & 1);
+						mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
+						asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+						for (int c = 0; c < 2; ++c) {
+							uint32_t v[32];
+							tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 64 + c * 32), v);
+#pragma unroll
+							for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(v[j]);
+						}
+						asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+						__syncwarp();
+						if (lane == 0) mbar_arrive(&acc_empty[cb]);
+					}
+					// The MMA warp now waits for Q_1, so both accumulators are idle: park values there.
+					// second-order affinity without its diagonal; S2 is symmetric, so its column sums are row sums
+					float rs = 0.f;
+#pragma unroll
+					for (int c = 0; c < 2; ++c) {
+						uint32_t hv[32];
+#pragma unroll
+						for (int j = 0; j < 32; ++j) {
+							const int col = h * 64 + c * 32 + j;
+							const float x = (m < p.nb && col < p.nb && col != m) ? sum[c * 32 + j] : 0.f;
+							rs += x;
+							hv[j] = __float_as_uint(x);
+						}
+						tmem_st32(scrA + (uint32_t)(c * 32), hv);
+					}
+					rowsum[h * 128 + m] = rs;
+				}
+				// ---- first-order block A[m][s + col]: column sums over the rows
+				{
+					const float* arow = p.A + (long long)cell * p.a_cell_stride + (long long)m * p.ldw + p.s + h * 64;
+					const bool vec = ((p.s & 3) == 0);
+#pragma unroll
+					for (int c = 0; c < 2; ++c) {
+						float f[32];
+#pragma unroll
+						for (int g = 0; g < 8; ++g) {
+							const int col = h * 64 + c * 32 + 4 * g;
+							float e[4] = {0.f, 0.f, 0.f, 0.f};
+							if (m < p.nb && col < p.nb) {
+								if (vec && col + 3 < p.nb) {
+									const float4 v = *reinterpret_cast<const float4*>(arow + c * 32 + 4 * g);
+									e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
+								} else {
+#pragma unroll
+									for (int x = 0; x < 4; ++x)
+										if (col + x < p.nb) e[x] = arow[c * 32 + 4 * g + x];
+								}
+							}
+#pragma unroll
+							for (int x = 0; x < 4; ++x) f[4 * g + x] = e[x];
+						}
+						colpart[q * 128 + h * 64 + c * 32 + lane] = col_sum32(f);
+						uint32_t fu[32];
+#pragma unroll
+						for (int j = 0; j < 32; ++j) fu[j] = __float_as_uint(f[j]);
+						tmem_st32(scrB + (uint32_t)(c * 32), fu);
+					}
+				}
+				tmem_st_wait();
+				drain_sync();
+				if (td < 128) rc1[td] = 1.f / (((colpart[td] + colpart[128 + td]) + (colpart[256 + td] + colpart[384 + td])) + EPS);
+				else rc2[td - 128] = 1.f / ((rowsum[td - 128] + rowsum[128 + td - 128]) + EPS);
+				drain_sync();
+				// ---- blend l = 3/4 f / cs1 + 1/4 h / cs2, its column sums
+#pragma unroll
+				for (int c = 0; c < 2; ++c) {
+					uint32_t fu[32], hu[32];
+					tmem_ld32(scrB + (uint32_t)(c * 32), fu);
+					tmem_ld32(scrA + (uint32_t)(c * 32), hu);
+					float l[32];
+#pragma unroll
+					for (int j = 0; j < 32; ++j) {
+						const int col = h * 64 + c * 32 + j;
+						l[j] = (__uint_as_float(fu[j]) * rc1[col]) * 0.75f + (__uint_as_float(hu[j]) * rc2[col]) * 0.25f;
+						fu[j] = __float_as_uint(l[j]);
+					}
+					tmem_st32(scrB + (uint32_t)(c * 32), fu);
+					const float cs = col_sum32(l);
+					colpart[q * 128 + h * 64 + c * 32 + lane] = cs;
+				}
+				tmem_st_wait();
+				drain_sync();
+				if (td < 128) {
+					float csl = (colpart[td] + colpart[128 + td]) + (colpart[256 + td] + colpart[384 + td]);
+					const bool empty = (csl == 0.f) && td < p.nb;  // unreachable after the 1e-8 floor; kept for parity
+					if (empty) csl += 1.f;
+					rc1[td] = 1.f / (csl + EPS);
+					cflag[td] = empty ? 1.f : 0.f;
+				}
+				drain_sync();
+				// ---- P = l / colsum -> global scratch (B operand of the chain, back through TMA); Q_1 -> TMEM
+				float* prow = const_cast<float*>(p.P) + ((long long)blockIdx.x * 128 + m) * 128 + h * 64;
+#pragma unroll
+				for (int c = 0; c < 2; ++c) {
+					uint32_t lu[32];
+					tmem_ld32(scrB + (uint32_t)(c * 32), lu);
+					float qv[32];
+#pragma unroll
+					for (int j = 0; j < 32; ++j) {
+						const int col = h * 64 + c * 32 + j;
+						float l = __uint_as_float(lu[j]);
+						if (m == col && cflag[col] != 0.f) l += 1.f;
+						const float pv = l * rc1[col];
+						lu[j] = __float_as_uint(pv);
+						qv[j] = (m < p.nb && col < p.nb) ? 0.5f * pv + ((m == col) ? 0.5f : 0.f) : 0.f;
+					}
+					if (chain) {
+#pragma unroll
+						for (int g = 0; g < 8; ++g)
+							*reinterpret_cast<uint4*>(prow + c * 32 + 4 * g) = make_uint4(lu[4 * g], lu[4 * g + 1], lu[4 * g + 2], lu[4 * g + 3]);
+					}
+					store_q_chunk(c, qv);
+				}
+				if (chain) {
+					asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy global writes -> async proxy (TMA read)
+					__threadfence_block();
+				}
+				publish_q();
+				if (chain) {
+					drain_sync();
+					if (td == 0) mbar_arrive(p_written);
 				}
 			}
-			store_q(qv);
-		};
-		long long ch = 0;
-		if ((int)blockIdx.x < p.ncell) first_q(blockIdx.x);
-		for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x) {
 			for (int step = 1; step < p.k; ++step) {
 				const int cb = (int)(ch & 1);
 				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-				float qv[64];
 #pragma unroll
 				for (int c = 0; c < 2; ++c) {
 					uint32_t v[32];
 					tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 64 + c * 32), v);
+					float qv[32];
 #pragma unroll
 					for (int j = 0; j < 32; ++j) {
 						float r = 0.5f * __uint_as_float(v[j]);
 						if (m == h * 64 + c * 32 + j && m < p.nb) r += 0.5f;
-						qv[c * 32 + j] = r;
+						qv[j] = r;
 					}
+					store_q_chunk(c, qv);  // every MMA that read the old Q completed before acc_full fired
 				}
 				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 				__syncwarp();
 				if (lane == 0) mbar_arrive(&acc_empty[cb]);
 				++ch;
-				store_q(qv);  // every MMA that read the old Q completed before acc_full fired
+				publish_q();
 			}
 			float* ob = p.out + (long long)cell * p.out_cell_stride;
 			for (int nt = 0; nt < NT; ++nt) {
 				const int cb = (int)(ch & 1);
 				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-				// the last tile's completion frees Q: hand the next cell's Q_1 to the MMA warp first (its
+				// !PANEL: the last tile's completion frees Q: hand the next cell's Q_1 to the MMA warp first (its
 				// first accumulator is the other buffer), then drain this tile
-				if (nt == NT - 1 && cell + (int)gridDim.x < p.ncell) first_q(cell + gridDim.x);
+				if (!PANEL && nt == NT - 1 && cell + (int)gridDim.x < p.ncell) first_q(cell + gridDim.x);
 				float sum[64];
 #pragma unroll
 				for (int c = 0; c < 2; ++c) {
@@ -317,38 +536,60 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace
 
-// P: (ncell, nb, ldp) column-stochastic transition matrices; A: (ncell, nb, ldw) conv'd panels;
-// out: cell c at out + c * out_cell_stride, rows of ldw floats. Returns FH_ERR_UNSUPPORTED (nothing
-// launched) when the shape is outside the fused kernel's range - the caller runs the GEMM chain.
-int fh_rwr_chain(const float* P, const float* A, float* out, int nb, int w, int ldw, int ldp, int k, int ncell,
-                 long long p_cell_stride, long long a_cell_stride, long long out_cell_stride, void* stream) {
+// A: (ncell, nb, ldw) conv'd panels; out: cell c at out + c * out_cell_stride, rows of ldw floats.
+// scratch == nullptr: P (ncell, nb, ldp) holds the column-stochastic transition matrices (chain + Q A only).
+// scratch != nullptr (fh_rwr_chain_scratch_bytes() bytes): P is ignored, S2 and the transition matrix
+// are formed in the kernel from A and the diagonal block offset s.
+// Returns FH_ERR_UNSUPPORTED (nothing launched) when the shape is outside the fused kernel's range -
+// the caller runs the per-step kernels.
+size_t fh_rwr_chain_scratch_bytes() { return (size_t)256 * 128 * 128 * 4; }
+
+int fh_rwr_chain(const float* P, const float* A, float* out, int nb, int w, int ldw, int ldp, int s, int k, int ncell,
+                 long long p_cell_stride, long long a_cell_stride, long long out_cell_stride, float* scratch,
+                 void* stream) {
 	if (ncell <= 0) return FH_OK;
-	if (nb > BM || k < 1 || (ldp & 3) || (ldw & 3) || (p_cell_stride & 3) || (a_cell_stride & 3) || !aligned16(P) ||
-	    !aligned16(A) || ncell > 65535) {
+	const bool panel = scratch != nullptr;
+	if (nb > BM || k < 1 || (ldw & 3) || (a_cell_stride & 3) || !aligned16(A) || ncell > 65535 ||
+	    (!panel && ((ldp & 3) || (p_cell_stride & 3) || !aligned16(P))) || (panel && !aligned16(scratch))) {
 		fh_set_error("fh_rwr_chain: shape outside the fused kernel (nb <= 128, k >= 1, 16-byte aligned rows)");
 		return FH_ERR_UNSUPPORTED;
 	}
-	CUtensorMap tp, ta;
-	// (k rows x n contiguous) MN-major operands; the contiguous extent is the LOGICAL width, so pad columns and
-	// rows beyond nb read as zeros whatever the buffers hold
-	if (!make_map(&tp, P, nb, nb, ldp, ncell, p_cell_stride, 32, BK, true) ||
-	    !make_map(&ta, A, w, nb, ldw, ncell, a_cell_stride, 32, BK, true)) {
-		fh_set_error("fh_rwr_chain: cuTensorMapEncodeTiled failed");
-		return FH_ERR_UNSUPPORTED;
-	}
-	ChainP p;
-	p.nb = nb; p.w = w; p.ldw = ldw; p.ldp = ldp; p.k = k; p.ncell = ncell;
-	p.p_cell_stride = p_cell_stride; p.out_cell_stride = out_cell_stride;
-	p.P = P; p.out = out;
-	p.vec_ok = aligned16(out) && (out_cell_stride % 4 == 0);
 	static int num_sms = 0;
 	if (!num_sms) {
 		int dev = 0;
 		FH_CUDA(cudaGetDevice(&dev));
 		FH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
 	}
-	FH_CUDA(cudaFuncSetAttribute(rwr_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-	rwr_chain_kernel<<<ncell < num_sms ? ncell : num_sms, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tp, ta, p);
+	int grid = ncell < num_sms ? ncell : num_sms;
+	if (grid > 256) grid = 256;  // scratch holds 256 CTAs
+	CUtensorMap tp, ta, tk;
+	// (k rows x n contiguous) MN-major operands; the contiguous extent is the LOGICAL width, so pad columns and
+	// rows beyond nb read as zeros whatever the buffers hold
+	bool ok = make_map(&ta, A, w, nb, ldw, ncell, a_cell_stride, 32, BK, true);
+	if (panel) {
+		ok = ok && make_map(&tp, scratch, nb, nb, 128, grid, 128 * 128, 32, BK, true) &&
+		     make_map(&tk, A, w, nb, ldw, ncell, a_cell_stride, BK, BM, false);
+	} else {
+		ok = ok && make_map(&tp, P, nb, nb, ldp, ncell, p_cell_stride, 32, BK, true);
+		tk = ta;
+	}
+	if (!ok) {
+		fh_set_error("fh_rwr_chain: cuTensorMapEncodeTiled failed");
+		return FH_ERR_UNSUPPORTED;
+	}
+	ChainP p;
+	p.nb = nb; p.w = w; p.ldw = ldw; p.ldp = ldp; p.k = k; p.ncell = ncell;
+	p.p_cell_stride = p_cell_stride; p.out_cell_stride = out_cell_stride;
+	p.P = panel ? scratch : P; p.A = A; p.a_cell_stride = a_cell_stride; p.s = s; p.out = out;
+	p.vec_ok = aligned16(out) && (out_cell_stride % 4 == 0);
+	cudaStream_t st = (cudaStream_t)stream;
+	if (panel) {
+		FH_CUDA(cudaFuncSetAttribute(rwr_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
+		rwr_chain_kernel<true><<<grid, NTHREADS, Cfg<true>::SMEM_BYTES, st>>>(tp, ta, tk, p);
+	} else {
+		FH_CUDA(cudaFuncSetAttribute(rwr_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
+		rwr_chain_kernel<false><<<grid, NTHREADS, Cfg<false>::SMEM_BYTES, st>>>(tp, ta, tk, p);
+	}
 	FH_LAUNCH_CHECK();
 	return FH_OK;
 }
