@@ -62,6 +62,20 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ uint32_t tf32_rn(uint32_t bits) { return (bits + 0x1000u) & 0xFFFFE000u; }
 
+// shared -> global tile store (bulk async group), out-of-range rows / columns clipped by the tensor map
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+	asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map),
+	             "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+	             : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// pull a tile into L2 ahead of its TMA load
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+	asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2)
+	             : "memory");
+}
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b_format TF32
 // [7,10)/[10,13)=2, a_major [15], b_major [16] (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
 __device__ __forceinline__ uint32_t make_idesc_tf32(bool a_mn, bool b_mn, int n, int m) {
