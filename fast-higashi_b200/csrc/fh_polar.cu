@@ -56,10 +56,15 @@ __device__ __forceinline__ double jacobi_tan(double al, double be, double ga) {
 // n > 128, but 4 rows per warp request collide on the same banks: 73 vs 62 ms). Returns the sweep count.
 template <int PL, int G>
 __device__ __forceinline__ int jacobi_sweeps(double* __restrict__ R, const int n, const int ld, double* __restrict__ nrm,
-                                             double* __restrict__ red, const int max_sweeps) {
+                                             double* __restrict__ red, const int max_sweeps, const double skip_tol) {
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
 	const int m = even_up(n), half = m >> 1, mm = m - 1;
-	const double tol2 = 1e-30 * (double)n;       // (1e-15 sqrt(n))^2 on gamma^2 / (alpha beta)
+	// Rotation threshold. With W^T W = Lambda + E the polar factor U = T W Lambda^{-3/2} W^T has
+	// U^T U - I ~ cos(w_a, w_b) sqrt(lambda_big / lambda_small), i.e. |gamma| / min(alpha, beta): a pair is left
+	// alone once gamma^2 <= kSkip min(alpha, beta)^2 (its contribution 3e-9, fp32 output). For equal norms that
+	// is far looser than a cosine test at fp64 rounding, for strongly graded pairs it is stricter - and it
+	// removes most rotations of the last sweeps (FH_JACOBI_SKIP overrides kSkip for experiments).
+	const double tol2 = skip_tol;
 	constexpr int GPW = 32 / G;                  // groups per warp
 	const int hw = lane / G, hl = lane % G;
 	const unsigned hmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (hw * G));
@@ -87,24 +92,44 @@ __device__ __forceinline__ int jacobi_sweeps(double* __restrict__ R, const int n
 				double* rp = R + p * ld + hl;
 				double* rq = R + q * ld + hl;
 				double ga = 0.0, gb = 0.0;
-				double a[PL];
+				double a[PL > 0 ? PL : 1];
+				if (PL > 0) {  // row p in registers
 #pragma unroll
-				for (int e = 0; e < PL; ++e) {
-					a[e] = rp[G * e];
-					if (e & 1) gb += a[e] * rq[G * e]; else ga += a[e] * rq[G * e];
+					for (int e = 0; e < PL; ++e) {
+						a[e] = rp[G * e];
+						if (e & 1) gb += a[e] * rq[G * e]; else ga += a[e] * rq[G * e];
+					}
+				} else {       // streamed (quarter-warp groups: the register tile would not fit 64 registers)
+					int i = 0;
+#pragma unroll 4
+					for (; i + G < ld; i += 2 * G) {
+						ga += rp[i] * rq[i];
+						gb += rp[i + G] * rq[i + G];
+					}
+					if (i < ld) ga += rp[i] * rq[i];
 				}
 				ga = group_sum<G>(ga + gb, hmask);
 				const double al = nrm[p], be = nrm[q];
 				const double g2 = ga * ga, ab = al * be;
-				if (g2 > tol2 * ab && ga != 0.0) {
+				const double mn = fmin(al, be);
+				if (g2 > tol2 * mn * mn && ga != 0.0) {
 					worst = fmax(worst, g2 / ab);
 					const double tt = jacobi_tan(al, be, ga);
 					const double cs = rsqrt(tt * tt + 1.0), sn = tt * cs;
+					if (PL > 0) {
 #pragma unroll
-					for (int e = 0; e < PL; ++e) {
-						const double c = rq[G * e];
-						rp[G * e] = cs * a[e] - sn * c;
-						rq[G * e] = sn * a[e] + cs * c;
+						for (int e = 0; e < PL; ++e) {
+							const double c = rq[G * e];
+							rp[G * e] = cs * a[e] - sn * c;
+							rq[G * e] = sn * a[e] + cs * c;
+						}
+					} else {
+#pragma unroll 4
+						for (int i = 0; i < ld; i += G) {
+							const double x = rp[i], c = rq[i];
+							rp[i] = cs * x - sn * c;
+							rq[i] = sn * x + cs * c;
+						}
 					}
 					if (hl == 0) {  // |w_p|^2, |w_q|^2 after the rotation
 						nrm[p] = fmax(al - tt * ga, 0.0);
@@ -129,7 +154,17 @@ __device__ __forceinline__ int jacobi_sweeps(double* __restrict__ R, const int n
 	return sweep;
 }
 
-__host__ __device__ inline int jacobi_ld(int n) { return (n + 15) & ~15; }
+// Row pitch (doubles), pad columns zero. Half-warp groups: n rounded up to 16 (no predicates in the element
+// loops). Quarter-warp groups (a step has more pairs than the CTA has half-warps: one round per step instead
+// of a second, nearly empty one): an ODD multiple of 8, so that the four rows a warp touches per request
+// fall on both 64-byte halves of the banks (with a multiple of 16 every request is a 4-way conflict:
+// measured 73 vs 62 ms).
+__host__ __device__ inline bool jacobi_quarter(int n, int nthreads) { return (even_up(n) >> 1) > (nthreads >> 5) * 2; }
+__host__ __device__ inline int jacobi_ld(int n, int nthreads) {
+	if (!jacobi_quarter(n, nthreads)) return (n + 15) & ~15;
+	const int l = (n + 7) & ~7;
+	return (l & 8) ? l : l + 8;
+}
 
 // One CTA per matrix (problem b: size prob_n[b], data at prob_off[b] doubles into Gall / WTall).
 // Shared memory holds R (n x ld, row-major, ld = n rounded up to 16 with zero pad columns): first the
@@ -140,7 +175,7 @@ __host__ __device__ inline int jacobi_ld(int n) { return (n + 15) & ~15; }
 __global__ void __launch_bounds__(1024)
 chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob_n, const long long* __restrict__ prob_off,
                    const int* __restrict__ prob_slot, const long long* __restrict__ prob_sig, int uniform_n,
-                   int max_sweeps, double* __restrict__ WTall, double* __restrict__ sigma_all,
+                   int max_sweeps, double skip_tol, double* __restrict__ WTall, double* __restrict__ sigma_all,
                    double* __restrict__ sigma_sum, int* __restrict__ nsweep_out) {
 	extern __shared__ double sm[];
 	const int b = blockIdx.x;
@@ -148,7 +183,7 @@ chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob
 	const long long off = prob_off ? prob_off[b] : (long long)b * n * n;
 	const int slot = prob_slot ? prob_slot[b] : b;
 	const long long sig_off = prob_sig ? prob_sig[b] : (long long)b * n;
-	const int ld = jacobi_ld(n);
+	const int ld = jacobi_ld(n, blockDim.x);
 	double* R = sm;                          // n x ld
 	double* red = R + (size_t)n * ld;        // 64 doubles scratch
 	int* perm = (int*)(red + 64);            // n
@@ -228,17 +263,18 @@ chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob
 	// element loops carry no predicates.
 	double* nrm = red + 64 + ((n + 1) >> 1);     // n squared norms, after perm (ints) in the scratch area
 	int sweep;
-	switch (ld >> 4) {
-		case 1: sweep = jacobi_sweeps<1, 16>(R, n, ld, nrm, red, max_sweeps); break;
-		case 2: sweep = jacobi_sweeps<2, 16>(R, n, ld, nrm, red, max_sweeps); break;
-		case 3: sweep = jacobi_sweeps<3, 16>(R, n, ld, nrm, red, max_sweeps); break;
-		case 4: sweep = jacobi_sweeps<4, 16>(R, n, ld, nrm, red, max_sweeps); break;
-		case 5: sweep = jacobi_sweeps<5, 16>(R, n, ld, nrm, red, max_sweeps); break;
-		case 6: sweep = jacobi_sweeps<6, 16>(R, n, ld, nrm, red, max_sweeps); break;
-		case 7: sweep = jacobi_sweeps<7, 16>(R, n, ld, nrm, red, max_sweeps); break;
-		case 8: sweep = jacobi_sweeps<8, 16>(R, n, ld, nrm, red, max_sweeps); break;
-		case 9: sweep = jacobi_sweeps<9, 16>(R, n, ld, nrm, red, max_sweeps); break;
-		default: sweep = jacobi_sweeps<10, 16>(R, n, ld, nrm, red, max_sweeps); break;
+	if (jacobi_quarter(n, blockDim.x)) sweep = jacobi_sweeps<0, 8>(R, n, ld, nrm, red, max_sweeps, skip_tol);
+	else switch (ld >> 4) {
+		case 1: sweep = jacobi_sweeps<1, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
+		case 2: sweep = jacobi_sweeps<2, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
+		case 3: sweep = jacobi_sweeps<3, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
+		case 4: sweep = jacobi_sweeps<4, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
+		case 5: sweep = jacobi_sweeps<5, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
+		case 6: sweep = jacobi_sweeps<6, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
+		case 7: sweep = jacobi_sweeps<7, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
+		case 8: sweep = jacobi_sweeps<8, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
+		case 9: sweep = jacobi_sweeps<9, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
+		default: sweep = jacobi_sweeps<10, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
 	}
 	if (tid == 0 && nsweep_out) nsweep_out[slot] = sweep;
 	// ---------------- lambda_j = |w_j|^2, outputs ----------------
@@ -307,13 +343,15 @@ int jacobi_threads(int n) { return n > 83 ? 1024 : (n > 58 ? 512 : 256); }
 int launch_jacobi(int grid, int nmax, size_t smem, cudaStream_t st, const double* G, const int* pn, const long long* po,
                   const int* ps, int uniform_n, int max_sweeps, double* WT, double* sigma, double* sigma_sum, int* nsweep) {
 	FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	chol_jacobi_kernel<<<grid, jacobi_threads(nmax), smem, st>>>(G, pn, po, ps, nullptr, uniform_n, max_sweeps,
+	static double skip = -1.0;
+	if (skip < 0.0) { const char* e = getenv("FH_JACOBI_SKIP"); skip = e ? atof(e) : 1e-17; }
+	chol_jacobi_kernel<<<grid, jacobi_threads(nmax), smem, st>>>(G, pn, po, ps, nullptr, uniform_n, max_sweeps, skip,
 	                                                           WT, sigma, sigma_sum, nsweep);
 	FH_LAUNCH_CHECK();
 	return FH_OK;
 }
 
-size_t jacobi_smem(int n) { return ((size_t)n * jacobi_ld(n) + 64 + (n + 1) / 2 + n) * 8 + 16; }
+size_t jacobi_smem(int n) { return ((size_t)n * jacobi_ld(n, jacobi_threads(n)) + 64 + (n + 1) / 2 + n) * 8 + 16; }
 
 }  // namespace
 
