@@ -308,6 +308,20 @@ class Fast_Higashi_core:
 		                  nsweep=torch.zeros(len(n_list), dtype=torch.int32, device=dev),  # Jacobi sweeps per bin (diagnostics)
 		                  chrom_lengths=torch.tensor(lengths, device=dev),
 		                  G=torch.empty(off, dtype=torch.float64, device=dev), WT=torch.empty(off, dtype=torch.float64, device=dev))
+		# Multi-GPU: the bins are independent problems and every rank holds every (all-reduced) Gram matrix, so
+		# rank k factorises problems k, k + world, ... of the size-sorted list (balanced by construction); the
+		# factors are exchanged with ONE all-reduce over the zero-initialised WT buffer (x + 0 is exact, every
+		# rank ends with identical bits).
+		d = self._dist()
+		world = d.get_world_size(self.group) if d is not None else 1
+		self._ptab["world"] = world
+		if world > 1:
+			mine = np.arange(d.get_rank(self.group), len(n_list), world)
+			sub = order[mine]
+			self._ptab.update(count=len(sub), n_host=np.ascontiguousarray(n_arr[sub]),
+			                  n_dev=torch.from_numpy(np.ascontiguousarray(n_arr[sub])).to(dev),
+			                  off_dev=torch.from_numpy(np.asarray(off_list, dtype=np.int64)[sub].copy()).to(dev),
+			                  slot_dev=torch.from_numpy(sub.astype(np.int32)).to(dev))
 		return self._ptab
 
 	def _padded_factors(self, chrom):
@@ -408,10 +422,15 @@ class Fast_Higashi_core:
 				del T1, Bsc
 		# ---- phase B: G^{-1/2} of all bins of all chromosomes at once (P2b)
 		t = self._tic()
+		if tab["world"] > 1:
+			WT_all.zero_(); tab["ssum"].zero_()
 		_lib.check(_lib.lib().fh_polar_isqrt_multi(G_all.data_ptr(), WT_all.data_ptr(), tab["n_dev"].data_ptr(),
 		                                           tab["off_dev"].data_ptr(), tab["slot_dev"].data_ptr(),
 		                                           tab["n_host"].ctypes.data, tab["count"], tab["ssum"].data_ptr(), 0,
 		                                           tab["nsweep"].data_ptr(), _lib.stream_ptr()))
+		if tab["world"] > 1:
+			self._allreduce(WT_all)
+			self._allreduce(tab["ssum"])
 		stats[:nch] = torch.segment_reduce(tab["ssum"], "sum", lengths=tab["chrom_lengths"])
 		self._toc("polar_bins", t)
 		# ---- phase C: U_i = temp_i M_i, P3
