@@ -8,17 +8,20 @@
 // ring and the two TMEM accumulators keep rolling across tiles, so the epilogue of one tile overlaps
 // the loads / MMAs of the next. Roles inside a CTA:
 //   warp 0      TMA producer: raw fp32 operand tiles (K-major or MN-major, 128-byte swizzle) from
-//               HBM/L2 into a 3-stage shared-memory ring (cp.async.bulk.tensor, mbarrier tx-count)
-//   warps 4-7   splitters: turn each landed tile into its hi / lo TF32 halves in place (+ a second
-//               buffer), fence to the async proxy, hand the stage to the MMA warp
-//   warp 1      MMA issuer: one thread issues 3 x 4 tcgen05.mma.kind::tf32 (M=128, N=128, K=8) per
-//               stage; tcgen05.commit releases the stage / publishes the accumulator
+//               HBM/L2 into a 4-stage shared-memory ring (cp.async.bulk.tensor, mbarrier tx-count)
+//   warps 4-7   splitters. A: each thread owns one row of the landed tile (= one TMEM lane), un-swizzles it
+//               and writes the hi (raw fp32: the tensor core truncates) and lo TF32 halves straight into
+//               TENSOR MEMORY (tcgen05.st) - A is the TMEM operand of the MMAs, which takes its lo copy and
+//               its three reads per k-block off shared memory (the kernel was shared-memory-bandwidth
+//               bound: contractions 55 -> 48 ms per sweep). B: lo half written next to the raw tile.
+//   warp 1      MMA issuer: one thread issues 3 x 4 tcgen05.mma.kind::tf32 (M=128, N=128, K=8, A from
+//               TMEM) per stage; tcgen05.commit releases the stage / publishes the accumulator
 //   warps 8-15  drain + epilogue. The tensor core accumulates with truncation, so a long K run drifts
 //               by ~7e-9*K (measured). The accumulator is therefore double-buffered in TMEM and
 //               drained every CHUNK_KB k-blocks (K=128) into fp32 registers with round-to-nearest adds
 //               (tcgen05.ld), which keeps the error at the fp32 level for any K; the final sum goes
 //               through alpha/beta/diag/column-scale and coalesced stores
-//   warp 2      TMEM allocation (256 columns: two 128-column accumulators)
+//   warp 2      TMEM allocation (512 columns: two 128-column accumulators + 4 stages x (A_hi | A_lo))
 #include "fh_tc.cuh"
 #include "../../include/fh_b200.h"
 
@@ -26,10 +29,11 @@ namespace {
 using namespace fh_tc;
 
 constexpr int BM = 128, BN = 128, BK = 32;       // tile (BK fp32 = one 128-byte swizzle row)
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;
 constexpr int TILE_BYTES = BM * BK * 4;          // 16 KB per operand tile
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
-constexpr int EPI_BYTES = 8 * 32 * 33 * 4;         // epilogue transposes: 8 drain warps x 32 rows x 33 floats
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;      // A (raw fp32 as landed), B_hi (raw), B_lo
+constexpr int EPI_BYTES = 8 * 32 * 32 * 4;       // epilogue transposes: 8 drain warps x (32 x 32 floats, XOR-swizzled)
+constexpr uint32_t TM_A = 2 * BN;                // TMEM: accumulators [0, 2 BN), then per stage A_hi (32 cols) | A_lo (32 cols)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NTHREADS = 512;
 constexpr int CHUNK_KB = 4;                      // k-blocks accumulated in TMEM before a drain (K = 128)
@@ -52,7 +56,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                float* __restrict__ C) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-	uint8_t* stagebuf = smem + STAGES * STAGE_BYTES;           // 8 warps x 16 x 33 floats (epilogue transposes)
+	uint8_t* stagebuf = smem + STAGES * STAGE_BYTES;           // 8 warps x 32 x 32 floats (epilogue transposes)
 	uint64_t* bars = (uint64_t*)(stagebuf + EPI_BYTES);
 	uint64_t* raw_full = bars;                 // TMA landed            (count 1 + tx)
 	uint64_t* split_full = bars + STAGES;      // hi/lo written         (count 4: one per splitter warp)
@@ -82,7 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 		asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
 	}
 	if (warp == 2) {
-		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(2 * BN) : "memory");
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512) : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -115,7 +119,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 					} else {     // global (M rows x K contiguous): one box of 32 x 128
 						tma_load_3d(st, &tmA, &raw_full[s], k0, m0, za);
 					}
-					uint8_t* sb = st + 2 * TILE_BYTES;
+					uint8_t* sb = st + TILE_BYTES;
 					if (B_MN) {
 #pragma unroll
 						for (int j = 0; j < BN / 32; ++j) tma_load_3d(sb + j * (BK * 128), &tmB, &raw_full[s], n0 + 32 * j, k0, zb);
@@ -130,12 +134,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 		if (lane == 0) {
 			// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b_format TF32 [7,10)/[10,13)=2,
 			// a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
-			const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-			                       ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-			// K-major tile (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO); a K=8 step = +32 B.
-			// MN-major tile (SWIZZLE_128B_BASE32B): k rows of 128 B (32 MN elements), 4-row atoms 512 B apart
-			// (SBO), 32-element MN groups BK*128 B apart (LBO); a K=8 step = 8 rows = +1024 B.
-			const uint32_t a_lbo = A_MN ? BK * 128 : 16, a_sbo = A_MN ? 512 : 1024, a_step = A_MN ? 1024 : 32, a_lt = A_MN ? 1 : 2;
+			const uint32_t idesc = make_idesc_tf32(false, B_MN, BN, BM);  // A comes from TMEM (always "K-major")
+			// K-major B tile (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO); a K=8 step = +32 B.
+			// MN-major B tile (SWIZZLE_128B_BASE32B): k rows of 128 B (32 N elements), 4-row atoms 512 B apart
+			// (SBO), 32-element N groups BK*128 B apart (LBO); a K=8 step = 8 rows = +1024 B.
 			const uint32_t b_lbo = B_MN ? BK * 128 : 16, b_sbo = B_MN ? 512 : 1024, b_step = B_MN ? 1024 : 32, b_lt = B_MN ? 1 : 2;
 			long long it = 0, ch = 0;  // k-blocks / accumulator chunks consumed by this CTA so far
 			for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -152,16 +154,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 					const uint32_t acc = tmem_acc + (uint32_t)(cb * BN);
 					mbar_wait(&split_full[s], ph);
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-					const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES;
-					const uint32_t b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
+					const uint32_t b_hi = smem_u32(smem + s * STAGE_BYTES) + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+					const uint32_t ta = tmem_acc + TM_A + (uint32_t)(s * 64);
 #pragma unroll
 					for (int k = 0; k < BK / 8; ++k) {
 						if (p.dbg & 4) break;
-						const uint64_t dah = make_desc(a_hi + k * a_step, a_lbo, a_sbo, a_lt), dal = make_desc(a_lo + k * a_step, a_lbo, a_sbo, a_lt);
+						const uint32_t a_hi = ta + (uint32_t)(k * 8), a_lo = a_hi + 32;
 						const uint64_t dbh = make_desc(b_hi + k * b_step, b_lbo, b_sbo, b_lt), dbl = make_desc(b_lo + k * b_step, b_lbo, b_sbo, b_lt);
-						umma_tf32(acc, dal, dbh, idesc, ((kb % CHUNK_KB) | k) ? 1u : 0u);  // small terms first
-						umma_tf32(acc, dah, dbl, idesc, 1u);
-						umma_tf32(acc, dah, dbh, idesc, 1u);
+						umma_tf32_ts(acc, a_lo, dbh, idesc, ((kb % CHUNK_KB) | k) ? 1u : 0u);  // small terms first
+						umma_tf32_ts(acc, a_hi, dbl, idesc, 1u);
+						umma_tf32_ts(acc, a_hi, dbh, idesc, 1u);
 					}
 					umma_commit(&empty[s]);
 					if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb_t - 1) {
@@ -183,25 +185,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 				const uint32_t ph = (uint32_t)((it / STAGES) & 1);
 				mbar_wait(&raw_full[s], ph);
 				uint8_t* st = smem + s * STAGE_BYTES;
+				if (!(p.dbg & 2)) {
+					// A: thread t owns row m = t of the tile (= TMEM lane t). The raw fp32 row is the hi operand (the
+					// tensor core truncates to tf32), lo = tf32(a - trunc(a)); both go straight to TENSOR MEMORY
+					// (tcgen05.st) and are the A operand of the MMAs - the kernel is shared-memory-bandwidth bound and
+					// this removes the A_lo write and the three A reads per k-block from shared memory.
+					uint32_t hi[32], lo[32];
+					if (A_MN) {
+						// MN-major landing (SWIZZLE_128B_ATOM_32B): 32-row m groups BK*128 B apart; k row = 128 B holding
+						// 32 m elements, its 32-byte chunks XOR-ed with (k & 3)
+						const uint8_t* g = st + (t >> 5) * (BK * 128);
+						const int ml = t & 31;
 #pragma unroll
-				for (int op = 0; op < 2; ++op) {
-					if (p.dbg & 2) break;
-					float4* hi = (float4*)(st + op * 2 * TILE_BYTES);
-					float4* lo = (float4*)(st + op * 2 * TILE_BYTES + TILE_BYTES);
+						for (int k = 0; k < 32; ++k)
+							hi[k] = *reinterpret_cast<const uint32_t*>(g + k * 128 + ((((ml >> 3) ^ (k & 3)) << 5) | ((ml & 7) << 2)));
+					} else {
+						// K-major landing (SWIZZLE_128B): row m = 128 B holding 32 k elements, 16-byte chunks XOR-ed with (m & 7)
+						const uint4* g = reinterpret_cast<const uint4*>(st + t * 128);
+#pragma unroll
+						for (int c = 0; c < 8; ++c) {
+							const uint4 v = g[c ^ (t & 7)];
+							hi[4 * c] = v.x; hi[4 * c + 1] = v.y; hi[4 * c + 2] = v.z; hi[4 * c + 3] = v.w;
+						}
+					}
+#pragma unroll
+					for (int k = 0; k < 32; ++k) lo[k] = tf32_lo(__uint_as_float(hi[k]));
+					const uint32_t ta = tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + TM_A + (uint32_t)(s * 64);
+					tmem_st32(ta, hi);
+					tmem_st32(ta + 32, lo);
+					// B: lo half next to the raw tile in shared memory
+					const float4* bh = (const float4*)(st + TILE_BYTES);
+					uint4* bl = (uint4*)(st + 2 * TILE_BYTES);
 #pragma unroll
 					for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
-						float4 v = hi[t + 128 * i];
+						const float4 v = bh[t + 128 * i];
 						uint4 l;
-						// The tensor core reads only the upper 19 bits of a tf32 operand (truncation), so the raw
-						// fp32 tile IS the hi operand and is left untouched in shared memory (one 16-byte store per
-						// element quad saved: the kernel is shared-memory-bandwidth bound). lo = a - trunc(a) is exact
-						// in fp32 and rounded to tf32 (ties away, two integer ops).
-						l.x = tf32_rn(__float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u)));
-						l.y = tf32_rn(__float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u)));
-						l.z = tf32_rn(__float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u)));
-						l.w = tf32_rn(__float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u)));
-						((uint4*)lo)[t + 128 * i] = l;
+						l.x = tf32_lo(v.x); l.y = tf32_lo(v.y); l.z = tf32_lo(v.z); l.w = tf32_lo(v.w);
+						bl[t + 128 * i] = l;
 					}
+					tmem_st_wait();
+					asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 				}
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
 				__syncwarp();
@@ -212,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 		// ------------------------------------------------------------------ drain + epilogue
 		const int q = warp & 3;             // TMEM lane quarter of this warp (rows 32q .. 32q+31)
 		const int h = (warp - 8) >> 2;      // column half (64 columns)
-		float* tile_s = (float*)(stagebuf + (warp - 8) * (32 * 33 * 4));
+		float* tile_s = (float*)(stagebuf + (warp - 8) * (32 * 32 * 4));
 		long long ch = 0;
 		for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 			const long long tl = tile / p.ksplit;
@@ -260,7 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 			for (int c = 0; c < 2; ++c) {
 				__syncwarp();
 #pragma unroll
-				for (int j = 0; j < 32; ++j) tile_s[lane * 33 + j] = sum[c * 32 + j];
+				for (int j = 0; j < 32; ++j) tile_s[lane * 32 + (j ^ lane)] = sum[c * 32 + j];  // word (r, j) at r*32 + (j ^ r)
 				__syncwarp();
 				const int n = n0 + h * 64 + c * 32 + 4 * cg;  // first of this lane's 4 columns
 				if (n < p.N && !(p.dbg & 1)) {
@@ -281,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 						float x[4];
 #pragma unroll
 						for (int e = 0; e < 4; ++e) {
-							x[e] = p.alpha * tile_s[rr * 33 + 4 * cg + e];
+							x[e] = p.alpha * tile_s[rr * 32 + ((4 * cg + e) ^ rr)];
 							if (p.epilogue == FH_EPI_DIAG_ADD && r == n + e) x[e] += p.diag;
 							if (cs) x[e] = p.cscale_recip ? x[e] / csv[e] : x[e] * csv[e];
 						}
@@ -312,7 +335,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 	__syncthreads();
 	if (warp == 2) {
-		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(2 * BN) : "memory");
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512) : "memory");
 	}
 }
 
