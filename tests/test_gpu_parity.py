@@ -428,3 +428,20 @@ def test_rwr_fused_chain_kernel(k):
 			ref, _ = O.partial_rwr(O.densify_block(ds_c, b, 0, ncell)[sel], g.s, g.e, True, True, False, None, k)
 			assert rel_fro(got[sel][:, :, :g.w].cpu().numpy(), ref.numpy()) < 1e-5, (n, b)
 	assert _lib.lib().fh_tc_fallback_count() == fb0  # the tensor-core path really ran
+
+
+@pytest.mark.parametrize("env", [{"FH_RWR_FUSED": "1"}, {"FH_RWR_FUSED": "0"}, {"FH_CHAIN_DEBUG": "2"}])
+def test_rwr_alternative_paths(env):
+	"""The library reads its path switches once per process, so the other RWR paths are exercised in a child
+	process: chain-only fusion (S2 / transition as separate kernels), the per-op tcgen05 GEMM chain, and the
+	fused kernel with the non-TMA epilogue (outputs TMA cannot describe)."""
+	import subprocess
+	import sys
+	e = dict(os.environ)
+	e.update(env)
+	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
+	                    "-k", "test_rwr_fused_chain_kernel and 4", "-p", "no:cacheprovider"], env=e, cwd=root, capture_output=True, text=True,
+	                   timeout=600)
+	assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+	assert "1 passed" in r.stdout, r.stdout[-2000:]
