@@ -28,6 +28,7 @@ from .partial_rwr import rwr_block_csr, pad4, cells_per_chunk
 from .project2orthogonal import polar_batched, polar_tall
 from .parafac_integrative import cp_als_, core_sqnorm_accum
 from .sparse_for_schic import Chrom_Dataset
+from .sharding import polar_partition
 
 
 def _as_block_csr(ds, device):
@@ -299,7 +300,9 @@ class Fast_Higashi_core:
 				cnt += g.nb
 			lengths.append(cnt)
 		n_arr = np.asarray(n_list, dtype=np.int32)
-		order = np.argsort(-n_arr, kind="stable")
+		d = self._dist()
+		world = d.get_world_size(self.group) if d is not None else 1
+		order, sub = polar_partition(n_arr, world, d.get_rank(self.group) if d is not None else 0)
 		self._ptab = dict(block=block, count=len(n_list), n_host=np.ascontiguousarray(n_arr[order]),
 		                  n_dev=torch.from_numpy(np.ascontiguousarray(n_arr[order])).to(dev),
 		                  off_dev=torch.from_numpy(np.asarray(off_list, dtype=np.int64)[order].copy()).to(dev),
@@ -312,12 +315,8 @@ class Fast_Higashi_core:
 		# rank k factorises problems k, k + world, ... of the size-sorted list (balanced by construction); the
 		# factors are exchanged with ONE all-reduce over the zero-initialised WT buffer (x + 0 is exact, every
 		# rank ends with identical bits).
-		d = self._dist()
-		world = d.get_world_size(self.group) if d is not None else 1
 		self._ptab["world"] = world
 		if world > 1:
-			mine = np.arange(d.get_rank(self.group), len(n_list), world)
-			sub = order[mine]
 			self._ptab.update(count=len(sub), n_host=np.ascontiguousarray(n_arr[sub]),
 			                  n_dev=torch.from_numpy(np.ascontiguousarray(n_arr[sub])).to(dev),
 			                  off_dev=torch.from_numpy(np.asarray(off_list, dtype=np.int64)[sub].copy()).to(dev),
