@@ -124,7 +124,7 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 					if (k < nr) {
 						const float* tn = t + (k + 2) * tw;
 						const float h2 = (tn[-1] + tn[0]) + tn[1];
-						drow[(long long)k * ldw] = fmaxf(((h0 + h1) + h2) / 9.0f, FH_FLOOR);
+						drow[(long long)k * ldw] = fmaxf(((h0 + h1) + h2) * (1.0f / 9.0f), FH_FLOOR);  // 1 ulp from sum / 9: an IEEE division is ~9 instructions of the ~22 per output
 						h0 = h1; h1 = h2;
 					}
 				}

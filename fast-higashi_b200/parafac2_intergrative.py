@@ -555,7 +555,7 @@ class Fast_Higashi_core:
 		acc = torch.zeros(nch, dtype=torch.float64, device=self.device)
 		main = torch.cuda.current_stream()
 		if getattr(self, "_cp_streams", None) is None:
-			self._cp_streams = [torch.cuda.Stream(device=self.device) for _ in range(6)]
+			self._cp_streams = [torch.cuda.Stream(device=self.device) for _ in range(11)]
 		ready = torch.cuda.Event()
 		ready.record(main)
 		for k, (chrom, ids) in enumerate(self.chrom2id.items()):
@@ -576,13 +576,17 @@ class Fast_Higashi_core:
 						core_sqnorm_accum(self.A_dev[i], self.B_dict[chrom], self.D_dict[chrom], acc[i:], tag=tag)
 		for st in self._cp_streams:
 			main.wait_stream(st)
-		if dist is not None:  # keep replicas bit-identical (split-K atomics are unordered)
+		if dist is not None:  # keep replicas bit-identical (split-K atomics are unordered): ONE packed broadcast
 			src = dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0
+			parts = []
 			for chrom, ids in self.chrom2id.items():
-				for i in ids:
-					dist.broadcast(self.A_dev[i], src=src, group=self.group)
-				dist.broadcast(self.B_dict[chrom], src=src, group=self.group)
-				dist.broadcast(self.D_dict[chrom], src=src, group=self.group)
+				parts += [self.A_dev[i] for i in ids] + [self.B_dict[chrom], self.D_dict[chrom]]
+			flat = torch.cat([p_.reshape(-1) for p_ in parts])
+			dist.broadcast(flat, src=src, group=self.group)
+			off = 0
+			for p_ in parts:
+				p_.copy_(flat[off:off + p_.numel()].view_as(p_))
+				off += p_.numel()
 			self._core_norm = self._core_norms()
 		else:
 			self._core_norm = acc.cpu().numpy().reshape(-1, 1)
