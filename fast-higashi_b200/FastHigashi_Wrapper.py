@@ -7,19 +7,22 @@ kept signature-for-signature for the decomposition hot path:
     .run_model(dim1=.6, rank=256, n_iter_parafac=1, n_iter_max=None, tol=2e-5, extra="",
                run_init=True)                                              (:657-663)
     .fetch_cell_embedding(final_dim=None, restore_order=False)             (:750)
-    .load_model(...), .correct_batch_linear(...)                           (:704, :815)
+    .load_model(...), .correct_batch_linear(...), .only_partial_rwr()      (:704, :815, :569)
+    .get_qc(), .pack_training_data_one_process(...)                        (:428, :221)
 
 `run_model` drives the B200 core (parafac2_intergrative.Fast_Higashi_core of this package) instead
 of the reference's torch path; it fills the same attributes and writes the same pickles.
 
-Scope: raw-file ingest, QC and normalisation (`pack_training_data_one_process`,
-preprocessing.py, Fast_process.py) are NOT part of the hot path. `prep_dataset` therefore accepts the
-tensors in one of three ways, in this order:
+Scope: the tensor stage of the reference's ingest (`get_qc`,
+`pack_training_data_one_process`, the per-resolution cache) is provided by `ingest.py`; contact-pair
+parsing (`Fast_process.py`) is not. `prep_dataset` takes the tensors from, in this order:
   1. `set_tensors(...)`: in-memory COO tensors per chromosome (what `pack_training_data_one_process`
-     returns, FastHigashi_Wrapper.py:366) - the native entry;
-  2. the reference's own input cache `cache_intra_{res}_offdiag_{off_diag}_.pkl` (:482-483) holding its
-     `Sparse` objects, if a reference installation wrote one (needs the reference importable to unpickle);
-  3. otherwise it raises: run the reference's ingest first (documented in INTEGRATION.md).
+     returns, FastHigashi_Wrapper.py:366);
+  2. this package's cache `cache_intra_{res}_offdiag_{off_diag}_b200.pkl`, else the reference's own
+     `cache_intra_{res}_offdiag_{off_diag}_.pkl` (:482-483; needs the reference importable to unpickle);
+  3. `{temp_dir}/raw/{chrom}_sparse_adj.npy` (per-cell scipy CSR, what the reference's `extract_table`
+     writes) through `ingest.preprocess_contact_map`;
+  4. otherwise it raises.
 """
 import json
 import math
@@ -31,6 +34,7 @@ import time
 import numpy as np
 import torch
 
+from . import ingest
 from .parafac2_intergrative import Fast_Higashi_core
 from .sparse_for_schic import Sparse, Chrom_Dataset
 
@@ -86,8 +90,7 @@ class FastHigashi:
 			qc = np.load(os.path.join(self.path2input_cache, "qc.npy"))
 			readcount = np.load(os.path.join(self.path2input_cache, "read_count_all.npy"))
 		if qc is None:
-			raise RuntimeError("no QC information: pass qc/readcount to set_tensors() or provide the reference's "
-			                   "qc.npy / read_count_all.npy in path2input_cache (get_qc is offline ingest, out of scope)")
+			qc, readcount = self.get_qc()
 		qc = np.asarray(qc)
 		readcount = np.asarray(readcount)
 		good, bad = np.where(qc > 0)[0], np.where(qc <= 0)[0]
@@ -102,7 +105,29 @@ class FastHigashi:
 		np.save(os.path.join(self.path2input_cache, "reorder.npy"), reorder)
 		if "batch_id" in self.config:
 			self.batch_id = np.asarray(label_info[self.config["batch_id"]])
+		np.save(os.path.join(self.path2input_cache, "qc.npy"), qc)  # :208-209
+		np.save(os.path.join(self.path2input_cache, "read_count_all.npy"), readcount)
 		return label_info, reorder, readcount, qc
+
+	def get_qc(self):
+		"""FastHigashi_Wrapper.py:428-458 over `{temp_dir}/raw/{chrom}_sparse_adj.npy`."""
+		raw_dir = os.path.join(self.temp_dir, "raw")
+		if not os.path.isdir(raw_dir):
+			raise RuntimeError("no QC information: pass qc/readcount to set_tensors(), provide qc.npy / read_count_all.npy in "
+			                   "path2input_cache, or the per-cell matrices under %s" % raw_dir)
+		return ingest.get_qc(raw_dir, self.chrom_list, self.config["resolution"])
+
+	def pack_training_data_one_process(self, raw_dir, chrom, reorder, off_diag=None, fac_size=None, merge_fac_row=1,
+	                                   merge_fac_col=1, is_sym=True, filename_pattern="%s_sparse_adj.npy", force_shift=None,
+	                                   batch_norm=True, bar=None):
+		"""Reference signature (FastHigashi_Wrapper.py:221-231); only the options the wrapper itself
+		uses are supported (fac_size 1, is_sym, no forced shift)."""
+		if (fac_size not in (None, 1)) or not is_sym or force_shift:
+			raise NotImplementedError("fac_size != 1, is_sym=False and force_shift are never used by prep_dataset (:484-494)")
+		return ingest.pack_training_data_one_process(
+			raw_dir, chrom, reorder, self.off_diag if off_diag is None else off_diag, merge_fac_row, merge_fac_col,
+			getattr(self, "batch_id", None) if "batch_id" in self.config else None, batch_norm,
+			ingest.load_blacklist(self.temp_dir), filename_pattern)
 
 	def _load_tensors(self, res, reorder):
 		if self._tensors is not None:
@@ -114,19 +139,26 @@ class FastHigashi:
 				idx[2] = torch.as_tensor(inv)[idx[2]]  # cell ids follow `reorder` (:233)
 				out.append(Sparse(idx, torch.as_tensor(np.asarray(val)).float(), shape, copy=False))
 			return out
+		ours = os.path.join(self.path2input_cache, "cache_intra_%d_offdiag_%d_b200.pkl" % (res, self.off_diag))
 		path = os.path.join(self.path2input_cache, "cache_intra_%d_offdiag_%d_%s.pkl" % (res, self.off_diag, ""))
-		if os.path.exists(path):
+		if not os.path.exists(ours) and os.path.exists(path):
 			out = []
 			with open(path, "rb") as f:
 				for _ in self.chrom_list:
 					out.append(pickle.load(f))  # the reference's Sparse objects (reference must be importable)
 			return out
-		raise RuntimeError("no input tensors: call set_tensors() or let the reference's prep_dataset write %s first "
-		                   "(contact-pair ingest and normalisation are outside the hot path, INTEGRATION.md)" % path)
+		if os.path.exists(ours) or os.path.isdir(os.path.join(self.temp_dir, "raw")):
+			packed = ingest.preprocess_contact_map(self.config, reorder, ours, self.off_diag, res,
+			                                       getattr(self, "batch_id", None) if "batch_id" in self.config else None,
+			                                       self._batch_norm)
+			return [Sparse(torch.as_tensor(idx.astype(np.int64)), torch.as_tensor(val), shape, copy=False) for idx, val, shape in packed]
+		raise RuntimeError("no input tensors: call set_tensors(), or provide %s/raw/{chrom}_sparse_adj.npy, or a cache file %s"
+		                   % (self.temp_dir, ours))
 
 	def prep_dataset(self, meta_only=False, batch_norm=True):
 		"""FastHigashi_Wrapper.py:460-567 from the tensor stage on: batch sizes (:500-517), auto do_col
 		(:545-551), one device-resident block-CSR `Chrom_Dataset` per (resolution, chromosome)."""
+		self._batch_norm = batch_norm
 		self.label_info, reorder, readcount, qc = self.preprocess_meta()
 		self.reorder = reorder
 		self.coverage_feats = readcount[reorder].reshape((-1, 1))
@@ -167,6 +199,70 @@ class FastHigashi:
 				raise EOFError
 		self.good_qc_num = good_qc_num
 		self.all_matrix = datasets
+
+	def only_partial_rwr(self, out_format=None):
+		"""FastHigashi_Wrapper.py:569-655: impute every cell (good and bad QC) with conv + auto-stopped RWR
+		(`force_rwr_epochs=-1`, `do_col=False`, one stop decision per (bin-block, cell batch) as in the
+		reference), paste the block windows into the full (n, n) map, symmetrise (`m + m^T` with the
+		diagonal halved) and write one fp32 dataset per cell named by its ORIGINAL cell id.
+		Output: `{path2result_dir}/impute_prwr.hdf5` with the reference's layout (group per chromosome:
+		"shape" + one dataset per cell) when h5py is importable or out_format="hdf5"; otherwise one
+		`impute_prwr_{chrom}.npz` per chromosome with the same keys (h5py is not part of this image).
+		Everything up to the final device->host copy runs on the GPU: fh_rwr_batched per block, the paste and the
+		symmetrisation in fp32 (x + y and 2x/2 are exact in fp32, so the result equals the reference's
+		float64-then-cast arithmetic bit for bit)."""
+		from .partial_rwr import rwr_block_csr, pad4
+		if out_format is None:
+			try:
+				import h5py  # noqa: F401
+				out_format = "hdf5"
+			except ImportError:
+				out_format = "npz"
+		h5 = None
+		if out_format == "hdf5":
+			import h5py
+			h5 = h5py.File(os.path.join(self.path2result_dir, "impute_prwr.hdf5"), "w")
+		elif out_format != "npz":
+			raise ValueError("out_format must be 'hdf5' or 'npz'")
+		written = []
+		for ds in self.all_matrix:
+			n = ds.num_bin
+			maps = {"shape": np.asarray([n, n])}
+			for sl in ds.cell_slice_list:
+				c0, nc = sl.start, sl.stop - sl.start
+				if nc <= 0:
+					continue
+				panels = []
+				for b, g in enumerate(ds.geoms):
+					ldw = pad4(g.w)
+					X = torch.zeros(nc, g.nb * ldw, dtype=torch.float32, device=self.device)
+					rwr_block_csr(ds, b, c0, nc, X, g.nb * ldw, -1, self.do_conv, self.do_rwr, False)
+					panels.append(X.view(nc, g.nb, ldw))
+				step = max(1, min(nc, (1 << 30) // (4 * n * n)))
+				for s0 in range(0, nc, step):
+					s1 = min(s0 + step, nc)
+					full = torch.zeros(s1 - s0, n, n, dtype=torch.float32, device=self.device)
+					for X, g in zip(panels, ds.geoms):
+						full[:, g.row0:g.row0 + g.nb, g.col0:g.col0 + g.w] = X[s0:s1, :, :g.w]
+					full = full + full.transpose(1, 2)
+					d = torch.diagonal(full, dim1=1, dim2=2)
+					d.sub_(d / 2)
+					host = full.cpu().numpy()
+					for i in range(s1 - s0):
+						maps[str(self.reorder[c0 + s0 + i])] = host[i]
+				del panels
+			if h5 is not None:
+				group = h5.create_group(ds.chrom)
+				for k, v in maps.items():
+					group.create_dataset(k, data=v)
+			else:
+				path = os.path.join(self.path2result_dir, "impute_prwr_%s.npz" % ds.chrom)
+				np.savez(path, **maps)
+				written.append(path)
+		if h5 is not None:
+			h5.close()
+			return os.path.join(self.path2result_dir, "impute_prwr.hdf5")
+		return written
 
 	def run_model(self, dim1=.6, rank=256, n_iter_parafac=1, n_iter_max=None, tol=2e-5, extra="", run_init=True):
 		"""FastHigashi_Wrapper.py:657-701."""

@@ -1,0 +1,83 @@
+"""Host-side methods of the `FastHigashi` wrapper that never touch the device (meta/QC, raw ingest,
+embedding post-processing), against reference fixtures (tests/golden/make_golden_ingest.py).
+The constructor itself demands a CUDA device, so the object is assembled with __new__ here."""
+import os
+import numpy as np
+import pandas as pd
+import pytest
+from conftest import GOLDEN
+from fasthigashi_b200.FastHigashi_Wrapper import FastHigashi
+from test_ingest_golden import G, CHROMS, NCELL, RES, raw_dir  # noqa: F401  (fixture)
+
+
+def host_only_wrapper(tmp, cache, with_batch=False):
+	fh = FastHigashi.__new__(FastHigashi)
+	fh.config = {"chrom_list": CHROMS, "temp_dir": tmp, "data_dir": tmp, "resolution": RES, "resolution_fh": [RES]}
+	if with_batch:
+		fh.config["batch_id"] = "batch"
+	fh.chrom_list, fh.temp_dir, fh.data_dir = CHROMS, tmp, tmp
+	fh.path2input_cache = fh.path2result_dir = cache
+	fh.off_diag, fh.filter, fh.fh_resolutions = 12, True, [RES]
+	fh._tensors, fh._meta, fh._batch_norm = None, None, True
+	fh.embedding_storage = None
+	return fh
+
+
+def test_constructor_refuses_cpu(tmp_path):
+	import torch
+	if torch.cuda.is_available():
+		pytest.skip("CUDA present")
+	with pytest.raises(RuntimeError, match="CUDA"):
+		FastHigashi({"chrom_list": CHROMS, "temp_dir": str(tmp_path), "resolution": RES, "resolution_fh": [RES]},
+		            None, None, 12, True, True, True, False, False)
+
+
+def test_preprocess_meta_and_raw_ingest(raw_dir, tmp_path):  # noqa: F811
+	import pickle
+	pickle.dump({"batch": list(G["batch"])}, open(os.path.join(raw_dir, "label_info.pickle"), "wb"))
+	fh = host_only_wrapper(raw_dir, str(tmp_path), with_batch=True)
+	label_info, reorder, readcount, qc = fh.preprocess_meta()
+	assert np.array_equal(reorder, G["reorder"]) and np.array_equal(qc, G["qc"])
+	assert np.array_equal(fh.batch_id, G["batch"][reorder])
+	for f in ("qc.npy", "read_count_all.npy", "reorder.npy"):  # the reference writes these too (:205-209)
+		assert os.path.exists(os.path.join(str(tmp_path), f))
+	# second call takes the cached QC
+	assert np.array_equal(fh.preprocess_meta()[3], qc)
+	mats = fh._load_tensors(RES, reorder)
+	assert os.path.exists(os.path.join(str(tmp_path), "cache_intra_%d_offdiag_12_b200.pkl" % RES))
+	for ch, m in zip(CHROMS, mats):
+		assert tuple(int(x) for x in m.shape) == tuple(int(x) for x in G["batch_%s_shape" % ch])
+		assert len(m.values) == len(G["batch_%s_val" % ch])
+		np.testing.assert_allclose(np.sort(m.values.numpy()), np.sort(G["batch_%s_val" % ch]), rtol=2e-6, atol=1e-7)
+	# method with the reference signature
+	idx, val, shape = fh.pack_training_data_one_process(os.path.join(raw_dir, "raw"), "chr1", reorder, off_diag=12, fac_size=1,
+	                                                    merge_fac_row=1, merge_fac_col=1, is_sym=True, force_shift=False)
+	assert idx.shape[1] == len(G["batch_chr1_val"])
+	with pytest.raises(NotImplementedError):
+		fh.pack_training_data_one_process(os.path.join(raw_dir, "raw"), "chr1", reorder, fac_size=2)
+
+
+def test_fetch_cell_embedding_matches_reference(tmp_path):
+	fh = host_only_wrapper(str(tmp_path), str(tmp_path))
+	reorder = G["reorder"]
+	fh.rank = 8
+	fh.meta_embedding = G["emb_meta"]
+	fh.D_list = [G["emb_D0"], G["emb_D1"]]
+	fh.coverage_feats = G["readcount"][reorder].reshape(-1, 1)
+	fh.reorder = reorder
+	fh.label_info = pd.DataFrame({"batch": G["batch"]}).iloc[reorder].reset_index()
+	np.random.seed(0)
+	store = fh.fetch_cell_embedding(final_dim=6, restore_order=True)
+	np.random.seed(1)
+	store = fh.correct_batch_linear("batch", add_intercept_back=True)
+	assert set(store) == {"embed_all", "embed_raw", "embed_l2_norm", "restore_order", "embed_correct_coverage_fh",
+	                      "embed_l2_norm_correct_coverage_fh", "embed_correct_batch", "embed_l2_norm_correct_batch"}
+	np.testing.assert_allclose(store["embed_all"], G["emb_out_embed_all"], rtol=1e-10, atol=1e-12)
+	np.testing.assert_allclose(np.asarray(fh.label_info["coverage_fh"]), G["emb_coverage_fh"], rtol=1e-10)
+	for k in ("embed_raw", "embed_l2_norm", "embed_correct_coverage_fh", "embed_correct_batch", "embed_l2_norm_correct_batch"):
+		a, b = store[k], G["emb_out_" + k]
+		assert a.shape == b.shape
+		# randomized SVD: same seed gives the same basis; allow a per-component sign and a loose tolerance
+		sgn = np.sign(np.sum(a * b, axis=0))
+		np.testing.assert_allclose(a * sgn, b, rtol=1e-5, atol=1e-7)
+	assert fh.correct_batch_linear("missing") is None
