@@ -8,8 +8,8 @@ import torch
 from conftest import ROOT
 
 
-def _declared():
-	src = open(os.path.join(ROOT, "include", "fh_b200.h")).read()
+def _declared(header="fh_b200.h"):
+	src = open(os.path.join(ROOT, "include", header)).read()
 	src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
 	return sorted(set(re.findall(r"\b(fh_[a-z0-9_]+)\s*\(", src)))
 
@@ -24,6 +24,19 @@ def test_library_exports_every_declared_symbol():
 		assert hasattr(lib, n), "missing export %s" % n
 	from fasthigashi_b200 import _lib
 	assert sorted(_lib.EXPORTS) == names
+
+
+def test_host_library_exports_every_declared_symbol():
+	import __graft_entry__ as ge
+	ge.build_host()
+	lib = ctypes.CDLL(ge.HOST_LIB)
+	names = _declared("fh_host.h")
+	assert len(names) >= 6
+	for n in names:
+		assert hasattr(lib, n), "missing export %s" % n
+	from fasthigashi_b200 import ingest
+	assert sorted(ingest.EXPORTS) == names
+	assert ingest.lib().fh_host_version() >= 100
 
 
 def test_version_and_error_string():
