@@ -29,6 +29,7 @@ from .project2orthogonal import polar_batched, polar_tall
 from .parafac_integrative import cp_als_, core_sqnorm_accum
 from .sparse_for_schic import Chrom_Dataset
 from .sharding import polar_partition
+from .dist_svd import sharded_truncated_svd, sharded_svd_gram
 
 
 def _as_block_csr(ds, device):
@@ -40,7 +41,7 @@ def _as_block_csr(ds, device):
 
 
 class Fast_Higashi_core:
-	def __init__(self, rank, off_diag, res_list, cache="sweep", use_tc=None, group=None):
+	def __init__(self, rank, off_diag, res_list, cache="sweep", use_tc=None, group=None, init_svd="host"):
 		self.rank = rank
 		self.off_diag = off_diag
 		self.res_list = res_list
@@ -48,6 +49,9 @@ class Fast_Higashi_core:
 		self.cache = cache            # "sweep": one RWR pass per ALS sweep; "run": one per run
 		self.use_tc = use_tc          # None -> decided in .to()
 		self.group = group            # torch.distributed process group when cell-sharded
+		if init_svd not in ("host", "device"):
+			raise ValueError("init_svd must be 'host' (the reference's sklearn SVD, features gathered to rank 0) or 'device'")
+		self.init_svd = init_svd      # "device": cell-sharded randomized SVD (dist_svd.py), nothing gathered
 		self.verbose = True
 		self.n_rwr_passes = 0
 		self._X = {}
@@ -187,16 +191,25 @@ class Fast_Higashi_core:
 			r = self.chrom2size[ds.chrom]
 			# host randomized SVD exactly as the reference (:257-258, numpy global RNG); with cell
 			# sharding the features are gathered to rank 0 (SURVEY.md 8e "init")
-			f_host = feats[:, :fstart].cpu().numpy().astype(np.float64)
-			if dist is not None:
-				gathered = [None] * dist.get_world_size(self.group)
-				dist.all_gather_object(gathered, f_host, group=self.group)
-				f_host = np.concatenate(gathered, 0)
-			if rank0:
-				emb = TruncatedSVD(n_components=r, n_iter=2).fit_transform(f_host)
+			if self.init_svd == "device":
+				# cell-sharded randomized SVD on the device: only (features x k) sketches and k x k Grams are
+				# all-reduced, the embedding rows stay with their cells (dist_svd.py)
+				emb, _, _ = sharded_truncated_svd(feats[:, :fstart], r, n_iter=2, group=self.group if dist is not None else None,
+				                                  seed=1000 + ci)
 				if C is None:
-					C = np.empty((f_host.shape[0], cum[-1]))
+					C = torch.zeros(ds.num_cell, int(cum[-1]), dtype=torch.float64, device=dev)
 				C[:, cstart:cstart + emb.shape[1]] = emb
+			else:
+				f_host = feats[:, :fstart].cpu().numpy().astype(np.float64)
+				if dist is not None:
+					gathered = [None] * dist.get_world_size(self.group)
+					dist.all_gather_object(gathered, f_host, group=self.group)
+					f_host = np.concatenate(gathered, 0)
+				if rank0:
+					emb = TruncatedSVD(n_components=r, n_iter=2).fit_transform(f_host)
+					if C is None:
+						C = np.empty((f_host.shape[0], cum[-1]))
+					C[:, cstart:cstart + emb.shape[1]] = emb
 			cstart += r
 			ni = torch.tensor([max(n_i_list) if n_i_list else 0], device=dev)
 			if dist is not None:
@@ -211,12 +224,17 @@ class Fast_Higashi_core:
 		self.n_i = np.array(n_i_all)
 		self._log("rwr iters:", self.n_i)
 		# joint SVD of the per-chromosome embeddings (:283-290); one-off, cuSOLVER through torch
-		if rank0:
+		if self.init_svd == "device":
+			meta, SVh = sharded_svd_gram(C, R, self.group if dist is not None else None)
+			meta, SVh = meta.float().contiguous(), SVh.float().contiguous()
+		elif rank0:
 			Ct = torch.from_numpy(C).float().to(dev)
 			U, S, Vh = torch.linalg.svd(Ct, full_matrices=False)
 			meta_all = U[:, :R].contiguous()
 			SVh = (Vh[:R] * S[:R, None]).contiguous()
-		if dist is not None:
+		if self.init_svd == "device":
+			pass  # meta rows are already the local cells', SVh is replicated
+		elif dist is not None:
 			sizes_all = [None] * dist.get_world_size(self.group)
 			dist.all_gather_object(sizes_all, self.num_cell, group=self.group)
 			if not rank0:

@@ -91,3 +91,19 @@ def test_wrapper_from_raw_files(tmp_path):
 	Eo = O.embed_all(Vo.numpy(), [x.numpy() for x in oc.D_dict.values()])
 	pear = [abs(np.corrcoef(emb["embed_all"][:, j], Eo[:, j])[0, 1]) for j in range(Eo.shape[1])]
 	assert min(pear) > 0.999, min(pear)
+
+
+def test_device_init_svd_reaches_the_host_init_loss():
+	"""init_svd="device" (cell-sharded randomized SVD, dist_svd.py) is a different random start than the
+	reference's sklearn SVD: after a few sweeps the reconstruction loss must be as good (within 1 %)."""
+	from conftest import load_small_dataset
+	from fasthigashi_b200.parafac2_intergrative import Fast_Higashi_core
+	losses = {}
+	for mode in ("host", "device"):
+		ds = load_small_dataset(device="cuda:0")
+		core = Fast_Higashi_core(16, 12, [1000000], init_svd=mode).to("cuda:0")
+		torch.manual_seed(0); np.random.seed(0)
+		core.fit(ds, 0.3, 6, 1, True, True, False, 0.0, verbose=False)
+		losses[mode] = core.re_trace[-1]
+		assert np.all(np.diff(core.re_trace[1:]) <= 1e-6)
+	assert abs(losses["device"] - losses["host"]) <= 0.01 * losses["host"], losses
