@@ -55,3 +55,24 @@ def test_empty_cells_and_select_cells():
 	assert sub.total_cell_num == 2 and sub.nnz() == 3
 	sub0 = ds.select_cells(0, 2)
 	assert sub0.nnz() == 0 and all(int(r[-1]) == 0 for r in sub0.rowptr)
+
+
+def test_geometry_matches_reference_at_full_baseline_sizes():
+	"""All four BASELINE geometries (PFC @500 kb, hg19 @1 Mb / 500 kb / 100 kb, off_diag 100, the wrapper's GPU
+	batching rule): the slice lists of the unmodified reference's Chrom_Dataset (tests/golden/make_golden_geometry.py)."""
+	import math, os
+	from conftest import GOLDEN
+	from fasthigashi_b200 import synth
+	G = np.load(os.path.join(GOLDEN, "geometry_cases.npz"))
+	blocks = 0
+	for case, (kind, res) in {"pfc_500kb": ("pfc", 500000), "hg19_1mb": ("hg19", 1000000), "hg19_500kb": ("hg19", 500000),
+	                          "hg19_100kb": ("hg19", 100000)}.items():
+		for ci, n in enumerate(synth.chrom_bins(kind, res)):
+			ref = G["%s_chr%d" % (case, ci + 1)]
+			assert int(G["%s_chr%d_n" % (case, ci + 1)]) == n
+			rec = min(max(int(15000000 / res), 128), 256)
+			bs = math.ceil(n / max(math.ceil(n / rec), 1))
+			mine = np.asarray([[g.row0, g.row0 + g.nb, g.s, g.e, g.col0, g.col0 + g.w] for g in block_geometry(n, bs, 100)])
+			assert np.array_equal(mine, ref), (case, ci)
+			blocks += len(mine)
+	assert blocks == 348
