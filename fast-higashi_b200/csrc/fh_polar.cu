@@ -17,6 +17,7 @@
 #include "fh_common.cuh"
 #include "../../include/fh_b200.h"
 #include <math.h>
+#include "fh_polar_block.cuh"  // block one-sided Jacobi, opt-in (FH_POLAR_BLOCK=1)
 
 namespace {
 
@@ -172,29 +173,35 @@ __host__ __device__ inline int jacobi_ld(int n, int nthreads) {
 // of L), then the rows are orthogonalised in place. Output WT (n x n): row j = w_j * lambda_j^{-3/4}
 // in the ORIGINAL index order; sigma[prob_sig[b] + j] = sqrt(lambda_j);
 // sigma_sum[prob_slot[b]] = sum_j sqrt(lambda_j).
+// BLK: the block one-sided Jacobi of fh_polar_block.cuh instead of the scalar sweeps (a separate instantiation, so
+// the default kernel's code generation is untouched by the opt-in variant).
+template <bool BLK>
 __global__ void __launch_bounds__(1024)
 chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob_n, const long long* __restrict__ prob_off,
                    const int* __restrict__ prob_slot, const long long* __restrict__ prob_sig, int uniform_n,
                    int max_sweeps, double skip_tol, double* __restrict__ WTall, double* __restrict__ sigma_all,
                    double* __restrict__ sigma_sum, int* __restrict__ nsweep_out) {
-	extern __shared__ double sm[];
+	extern __shared__ __align__(16) double sm[];
 	const int b = blockIdx.x;
 	const int n = prob_n ? prob_n[b] : uniform_n;
 	const long long off = prob_off ? prob_off[b] : (long long)b * n * n;
 	const int slot = prob_slot ? prob_slot[b] : b;
 	const long long sig_off = prob_sig ? prob_sig[b] : (long long)b * n;
-	const int ld = jacobi_ld(n, blockDim.x);
-	double* R = sm;                          // n x ld
-	double* red = R + (size_t)n * ld;        // 64 doubles scratch
+	// block mode (fh_polar_block.cuh): rows padded to a multiple of 8 with zero rows, even pitch
+	const bool blk = BLK && n <= kBJMaxSide;
+	const int ld = blk ? bj_ld(n) : jacobi_ld(n, blockDim.x);
+	const int nrow = blk ? bj_rows(n) : n;
+	double* R = sm;                          // nrow x ld
+	double* red = R + (size_t)nrow * ld;     // 64 doubles scratch
 	int* perm = (int*)(red + 64);            // n
 	__shared__ int s_piv;
 	__shared__ double s_val;
 	const int JT = blockDim.x;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = JT >> 5;
 	const double* Gg = Gall + off;
-	for (int i = tid; i < n * ld; i += JT) {
+	for (int i = tid; i < nrow * ld; i += JT) {
 		const int r = i / ld, c = i - r * ld;
-		R[i] = (c < n) ? Gg[r * n + c] : 0.0;
+		R[i] = (c < n && (!BLK || r < n)) ? Gg[r * n + c] : 0.0;
 	}
 	for (int i = tid; i < n; i += JT) perm[i] = i;
 	__syncthreads();
@@ -262,8 +269,18 @@ chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob
 	// pair, refreshed every sweep), fp32 angle with approximate div/sqrt, rows padded to 16 so the
 	// element loops carry no predicates.
 	double* nrm = red + 64 + ((n + 1) >> 1);     // n squared norms, after perm (ints) in the scratch area
-	int sweep;
-	if (jacobi_quarter(n, blockDim.x)) sweep = jacobi_sweeps<0, 8>(R, n, ld, nrm, red, max_sweeps, skip_tol);
+	int sweep = 0;
+	bool done = false;
+	if constexpr (BLK) {
+		if (blk) {
+			// scratch behind the norms, on a 16-byte boundary (red starts on one: nrow * ld is even)
+			double* bjs = nrm + n + ((64 + ((n + 1) >> 1) + n) & 1);
+			sweep = block_jacobi_sweeps(R, n, ld, bjs, blockDim.x, max_sweeps, skip_tol);
+			done = true;
+		}
+	}
+	if (done) {}
+	else if (jacobi_quarter(n, blockDim.x)) sweep = jacobi_sweeps<0, 8>(R, n, ld, nrm, red, max_sweeps, skip_tol);
 	else switch (ld >> 4) {
 		case 1: sweep = jacobi_sweeps<1, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
 		case 2: sweep = jacobi_sweeps<2, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
@@ -340,18 +357,40 @@ constexpr int kMaxSweeps = 30;
 
 int jacobi_threads(int n) { return n > 83 ? 1024 : (n > 58 ? 512 : 256); }
 
+// FH_POLAR_BLOCK=1: block one-sided Jacobi (fh_polar_block.cuh) for Gram sides <= kBJMaxSide. Default off: the
+// variant was written and checked through its host emulation after the round's GPU time was spent.
+int polar_block_mode() {
+	static int mode = -1;
+	if (mode < 0) { const char* e = getenv("FH_POLAR_BLOCK"); mode = (e && e[0] == '1') ? 1 : 0; }
+	return mode;
+}
+
 int launch_jacobi(int grid, int nmax, size_t smem, cudaStream_t st, const double* G, const int* pn, const long long* po,
                   const int* ps, int uniform_n, int max_sweeps, double* WT, double* sigma, double* sigma_sum, int* nsweep) {
-	FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const bool blkmode = polar_block_mode() != 0;
+	if (blkmode) FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	else FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	static double skip = -1.0;
 	if (skip < 0.0) { const char* e = getenv("FH_JACOBI_SKIP"); skip = e ? atof(e) : 1e-17; }
-	chol_jacobi_kernel<<<grid, jacobi_threads(nmax), smem, st>>>(G, pn, po, ps, nullptr, uniform_n, max_sweeps, skip,
-	                                                           WT, sigma, sigma_sum, nsweep);
+	if (blkmode)
+		chol_jacobi_kernel<true><<<grid, jacobi_threads(nmax), smem, st>>>(G, pn, po, ps, nullptr, uniform_n, max_sweeps, skip,
+		                                                                  WT, sigma, sigma_sum, nsweep);
+	else
+		chol_jacobi_kernel<false><<<grid, jacobi_threads(nmax), smem, st>>>(G, pn, po, ps, nullptr, uniform_n, max_sweeps, skip,
+		                                                                   WT, sigma, sigma_sum, nsweep);
 	FH_LAUNCH_CHECK();
 	return FH_OK;
 }
 
-size_t jacobi_smem(int n) { return ((size_t)n * jacobi_ld(n, jacobi_threads(n)) + 64 + (n + 1) / 2 + n) * 8 + 16; }
+// A launch covers problems of side <= n with one shared-memory size: the scalar layout of the largest, and in
+// block mode also the block layout of the largest side that uses it.
+size_t jacobi_smem(int n) {
+	size_t scalar = ((size_t)n * jacobi_ld(n, jacobi_threads(n)) + 64 + (n + 1) / 2 + n) * 8 + 16;
+	if (!polar_block_mode()) return scalar;
+	const int nb = n < kBJMaxSide ? n : kBJMaxSide;
+	size_t block = ((size_t)bj_rows(nb) * bj_ld(nb) + 64 + (nb + 1) / 2 + nb + 1 + bj_scratch_doubles(nb)) * 8 + 16;
+	return block > scalar ? block : scalar;
+}
 
 }  // namespace
 

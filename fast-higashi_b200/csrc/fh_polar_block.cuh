@@ -1,0 +1,282 @@
+// Block one-sided Jacobi for the per-bin polar step (alternative inner loop of chol_jacobi_kernel,
+// fh_polar.cu; opt-in with FH_POLAR_BLOCK=1 until it has been timed on a B200).
+//
+// Why: the scalar kernel moves every row of R through shared memory ~2.5 times per round-robin step,
+// n-1 steps per sweep (ncu: 24 ms for 938 problems of n ~ 140, i.e. ~3.3 us per step of which ~2 us is
+// the 525 KB of shared-memory traffic). Here rows are grouped in blocks of 8; a step pairs blocks, and
+// for every pair (16 rows X):  S = X X^T (16 x 16)  ->  S = Z Lambda Z^T by a two-sided cyclic Jacobi on
+// the small matrix  ->  X <- Z^T X.  One sweep has ceil(n/8)-1 steps instead of n-1, each moving the rows
+// three times: ~7x less shared-memory traffic per sweep. Numerics checked on the CPU (numpy prototype and
+// the host emulation of THIS file, tests/test_polar_block_emulation.py): same outer sweep count (7-8) and
+// the same polar-factor error as the scalar kernel on graded spectra up to kappa 3e6; 2.7 inner sweeps
+// per block pair on average.
+//
+// The file is written in barrier-separated PHASES whose bodies depend only on the thread / lane index and
+// on shared memory (no warp shuffles, no per-lane state across a barrier). With FH_EMU defined the phase
+// macros become plain loops over threads, so the same source runs on the host (tests/emu/) - in forward and
+// reverse thread order, which must give bit-identical results: any dependence between two threads inside
+// one phase (a missing barrier) shows up as a difference.
+#pragma once
+
+#ifdef FH_EMU
+#include <cmath>
+struct fh_d2 { double x, y; };
+extern int fh_emu_reverse;
+#define FH_DEV inline
+#define FH_FOR_THREADS(v, cnt) for (int _i##v = 0, v = 0; _i##v < (cnt) && ((v = fh_emu_reverse ? (cnt) - 1 - _i##v : _i##v), true); ++_i##v)
+#define FH_FOR_WARPS(v, cnt) FH_FOR_THREADS(v, cnt)
+#define FH_FOR_LANES(v) FH_FOR_THREADS(v, 32)
+#define FH_WARP_SYNC() ((void)0)
+#define FH_CTA_SYNC() ((void)0)
+#define FH_LD2(p) (*(const fh_d2*)(p))
+#else
+typedef double2 fh_d2;
+#define FH_DEV __device__ __forceinline__
+#define FH_FOR_THREADS(v, cnt) for (int v = threadIdx.x, _o##v = 1; _o##v; _o##v = 0)
+#define FH_FOR_WARPS(v, cnt) for (int v = threadIdx.x >> 5, _o##v = 1; _o##v; _o##v = 0)
+#define FH_FOR_LANES(v) for (int v = threadIdx.x & 31, _o##v = 1; _o##v; _o##v = 0)
+#define FH_WARP_SYNC() __syncwarp()
+#define FH_CTA_SYNC() __syncthreads()
+#define FH_LD2(p) (*reinterpret_cast<const double2*>(p))
+#endif
+
+constexpr int kBJRows = 8;            // rows per block
+constexpr int kBJSlot = 536;          // doubles of scratch per block pair: S 256 | Z 256 | cs 16 | worst 1 | ctl 7 (14 ints)
+constexpr int kBJInnerMax = 12;       // inner sweep cap (2.7 on average, measured on the CPU)
+constexpr double kBJInnerTol = 1e-22; // inner rotation threshold on s_pq^2 / (s_pp s_qq)
+constexpr int kBJMaxSide = 152;       // largest Gram side whose rows + scratch fit 227 KB of shared memory
+
+struct BJSlot {
+	double *S, *Z, *cs, *worst;
+	int* ctl;  // [0],[1] "a rotation happened" flags of even / odd inner sweeps, [2] pair active, [3] valid rows (8 | 16), [4],[5] block ids
+};
+FH_DEV BJSlot bj_slot(double* scratch, int t) {
+	double* b = scratch + (size_t)t * kBJSlot;
+	BJSlot s;
+	s.S = b; s.Z = b + 256; s.cs = b + 512; s.worst = b + 528; s.ctl = (int*)(b + 529);
+	return s;
+}
+inline __host__ __device__ int bj_blocks(int n) { return (n + kBJRows - 1) / kBJRows; }
+inline __host__ __device__ int bj_slots(int n) { return (bj_blocks(n) + 1) >> 1; }
+inline __host__ __device__ int bj_rows(int n) { return bj_blocks(n) * kBJRows; }     // rows of R incl. zero padding
+inline __host__ __device__ int bj_ld(int n) { return (n + 1) & ~1; }                 // even: 16-byte row pairs
+inline __host__ __device__ size_t bj_scratch_doubles(int n) { return (size_t)bj_slots(n) * kBJSlot + 2; }
+
+// pair `t` of round-robin step `s` among m = mm + 1 players (player mm fixed): p < q
+FH_DEV void bj_pair(int t, int s, int mm, int& p, int& q) {
+	if (t == 0) { p = mm; q = s; }
+	else {
+		p = s + t; if (p >= mm) p -= mm;
+		q = s - t + mm; if (q >= mm) q -= mm;
+	}
+	if (p > q) { int x = p; p = q; q = x; }
+}
+
+// Orthogonalises the rows of R (n x ld, rows n..bj_rows(n) and the pad columns zero) in place.
+// scratch: bj_scratch_doubles(n) doubles, 16-byte aligned. Returns the number of sweeps.
+FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scratch, const int nthreads,
+                               const int max_sweeps, const double skip_tol) {
+	const int nw = nthreads >> 5;
+	const int nblk = bj_blocks(n);
+	const int m = (nblk + 1) & ~1, mm = m - 1, nslot = m >> 1;
+	double* sweep_worst = scratch + (size_t)nslot * kBJSlot;  // [2], ping-pong by sweep parity
+	const int nchunk = (ld + 31) >> 5;
+	FH_FOR_THREADS(tid, nthreads) {
+		if (tid < 2) sweep_worst[tid] = 0.0;
+	}
+	FH_CTA_SYNC();
+	int sweep = 0;
+	for (; sweep < max_sweeps; ++sweep) {
+		double* sw_cur = sweep_worst + (sweep & 1);
+		for (int step = 0; step < mm; ++step) {
+			// ---------------- P1: Gram of every block pair of this step, one warp per pair ----------------
+			FH_FOR_WARPS(w, nw) {
+				for (int t = w; t < nslot; t += nw) {
+					BJSlot sl = bj_slot(scratch, t);
+					int P, Q;
+					bj_pair(t, step, mm, P, Q);
+					const int nv = (Q < nblk) ? 16 : 8;  // the dummy player of an odd block count: P alone
+					FH_FOR_LANES(lane) {
+						const int a = lane >> 3, bq = lane & 7;  // rows 4a..4a+3 against rows 2bq, 2bq+1
+						const double* pi[4];
+						const double* pj[2];
+#pragma unroll
+						for (int u = 0; u < 4; ++u) {
+							const int l = 4 * a + u;
+							pi[u] = (l < nv) ? R + (size_t)((l < 8) ? P * 8 + l : Q * 8 + (l - 8)) * ld : nullptr;
+						}
+#pragma unroll
+						for (int v = 0; v < 2; ++v) {
+							const int l = 2 * bq + v;
+							pj[v] = (l < nv) ? R + (size_t)((l < 8) ? P * 8 + l : Q * 8 + (l - 8)) * ld : nullptr;
+						}
+						double acc[4][2];
+#pragma unroll
+						for (int u = 0; u < 4; ++u) { acc[u][0] = 0.0; acc[u][1] = 0.0; }
+						for (int c = 0; c < ld; c += 2) {
+							fh_d2 xi[4], xj[2];
+#pragma unroll
+							for (int u = 0; u < 4; ++u) {
+								if (pi[u]) xi[u] = FH_LD2(pi[u] + c);
+								else { xi[u].x = 0.0; xi[u].y = 0.0; }
+							}
+#pragma unroll
+							for (int v = 0; v < 2; ++v) {
+								if (pj[v]) xj[v] = FH_LD2(pj[v] + c);
+								else { xj[v].x = 0.0; xj[v].y = 0.0; }
+							}
+#pragma unroll
+							for (int u = 0; u < 4; ++u)
+#pragma unroll
+								for (int v = 0; v < 2; ++v) {
+									acc[u][v] = fma(xi[u].x, xj[v].x, acc[u][v]);
+									acc[u][v] = fma(xi[u].y, xj[v].y, acc[u][v]);
+								}
+						}
+#pragma unroll
+						for (int u = 0; u < 4; ++u)
+#pragma unroll
+							for (int v = 0; v < 2; ++v) sl.S[(4 * a + u) * 16 + 2 * bq + v] = acc[u][v];
+					}
+					FH_WARP_SYNC();
+					// does any entry still need a rotation? same rule as the scalar kernel: s_ij^2 > skip * min(d_i, d_j)^2
+					FH_FOR_LANES(lane) {
+						if (lane < 16) {
+							const double di = sl.S[lane * 16 + lane];
+							double worst = 0.0;
+							for (int j = 0; j < 16; ++j) {
+								if (j == lane) continue;
+								const double sij = sl.S[lane * 16 + j], dj = sl.S[j * 16 + j];
+								const double mn = fmin(di, dj), g2 = sij * sij;
+								if (g2 > skip_tol * mn * mn) worst = fmax(worst, g2 / (di * dj));
+							}
+							sl.cs[lane] = worst;
+						}
+					}
+					FH_WARP_SYNC();
+					FH_FOR_LANES(lane) {
+						if (lane == 0) {
+							double wmax = 0.0;
+							for (int i = 0; i < 16; ++i) wmax = fmax(wmax, sl.cs[i]);
+							sl.worst[0] = wmax;
+							sl.ctl[0] = 0; sl.ctl[1] = 0;
+							sl.ctl[2] = wmax > 0.0;
+							sl.ctl[3] = nv; sl.ctl[4] = P; sl.ctl[5] = Q;
+						}
+					}
+					FH_WARP_SYNC();
+				}
+			}
+			FH_CTA_SYNC();
+			// ---------------- P2: S = Z Lambda Z^T, two-sided cyclic Jacobi, one warp per active pair ----------------
+			FH_FOR_WARPS(w, nw) {
+				for (int t = w; t < nslot; t += nw) {
+					BJSlot sl = bj_slot(scratch, t);
+					if (sl.ctl[2] == 0) continue;
+					FH_FOR_LANES(lane) {
+						for (int e = lane; e < 256; e += 32) sl.Z[e] = ((e >> 4) == (e & 15)) ? 1.0 : 0.0;
+					}
+					FH_WARP_SYNC();
+					for (int isw = 0; isw < kBJInnerMax; ++isw) {
+						for (int s = 0; s < 15; ++s) {
+							// J1: the 8 disjoint rotations of this step
+							FH_FOR_LANES(lane) {
+								if (lane < 8) {
+									int p, q;
+									bj_pair(lane, s, 15, p, q);
+									const double app = sl.S[p * 16 + p], aqq = sl.S[q * 16 + q], apq = sl.S[p * 16 + q];
+									double c = 1.0, sn = 0.0;
+									if (apq != 0.0 && apq * apq > kBJInnerTol * fabs(app * aqq)) {
+										const double zeta = (aqq - app) / (2.0 * apq);
+										const double tt = (zeta == 0.0) ? 1.0 : copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+										c = 1.0 / sqrt(1.0 + tt * tt);
+										sn = tt * c;
+										sl.ctl[isw & 1] = 1;
+									}
+									sl.cs[2 * lane] = c;
+									sl.cs[2 * lane + 1] = sn;
+								}
+							}
+							FH_WARP_SYNC();
+							// J2: columns p, q of S and Z (S <- S J, Z <- Z J); 16 rows x 8 rotations = 4 per lane
+							FH_FOR_LANES(lane) {
+								if (s == 0 && lane == 0) sl.ctl[(isw + 1) & 1] = 0;  // next sweep's flag; its last reader is a barrier behind
+#pragma unroll
+								for (int e = 0; e < 4; ++e) {
+									const int combo = lane * 4 + e, i = combo >> 3, tt = combo & 7;
+									const double c = sl.cs[2 * tt], sn = sl.cs[2 * tt + 1];
+									if (sn == 0.0) continue;
+									int p, q;
+									bj_pair(tt, s, 15, p, q);
+									const double sp = sl.S[i * 16 + p], sq = sl.S[i * 16 + q];
+									sl.S[i * 16 + p] = c * sp - sn * sq;
+									sl.S[i * 16 + q] = sn * sp + c * sq;
+									const double zp = sl.Z[i * 16 + p], zq = sl.Z[i * 16 + q];
+									sl.Z[i * 16 + p] = c * zp - sn * zq;
+									sl.Z[i * 16 + q] = sn * zp + c * zq;
+								}
+							}
+							FH_WARP_SYNC();
+							// J3: rows p, q of S (S <- J^T S)
+							FH_FOR_LANES(lane) {
+#pragma unroll
+								for (int e = 0; e < 4; ++e) {
+									const int combo = lane * 4 + e, j = combo >> 3, tt = combo & 7;
+									const double c = sl.cs[2 * tt], sn = sl.cs[2 * tt + 1];
+									if (sn == 0.0) continue;
+									int p, q;
+									bj_pair(tt, s, 15, p, q);
+									const double sp = sl.S[p * 16 + j], sq = sl.S[q * 16 + j];
+									sl.S[p * 16 + j] = c * sp - sn * sq;
+									sl.S[q * 16 + j] = sn * sp + c * sq;
+								}
+							}
+							FH_WARP_SYNC();
+						}
+						if (sl.ctl[isw & 1] == 0) break;  // a full inner sweep without a rotation (warp-uniform read)
+					}
+				}
+			}
+			FH_CTA_SYNC();
+			// ---------------- P3: X <- Z^T X for every active pair, all warps, a lane per column ----------------
+			FH_FOR_THREADS(tid, nthreads) {
+				const int w = tid >> 5, lane = tid & 31;
+				for (int item = w; item < nslot * nchunk; item += nw) {
+					const int t = item / nchunk, c = (item - t * nchunk) * 32 + lane;
+					BJSlot sl = bj_slot(scratch, t);
+					if (sl.ctl[2] == 0 || c >= ld) continue;
+					const int nv = sl.ctl[3], P = sl.ctl[4], Q = sl.ctl[5];
+					double x[16];
+#pragma unroll
+					for (int k = 0; k < 16; ++k)
+						x[k] = (k < nv) ? R[(size_t)((k < 8) ? P * 8 + k : Q * 8 + (k - 8)) * ld + c] : 0.0;
+#pragma unroll
+					for (int h = 0; h < 4; ++h) {
+						double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
+#pragma unroll
+						for (int k = 0; k < 16; ++k) {
+							const fh_d2 za = FH_LD2(sl.Z + k * 16 + 4 * h), zb = FH_LD2(sl.Z + k * 16 + 4 * h + 2);
+							o0 = fma(za.x, x[k], o0); o1 = fma(za.y, x[k], o1);
+							o2 = fma(zb.x, x[k], o2); o3 = fma(zb.y, x[k], o3);
+						}
+						const int l = 4 * h;
+						if (l < nv) {
+							double* dst = R + (size_t)((l < 8) ? P * 8 + l : Q * 8 + (l - 8)) * ld + c;
+							dst[0] = o0; dst[ld] = o1; dst[2 * (size_t)ld] = o2; dst[3 * (size_t)ld] = o3;
+						}
+					}
+				}
+				if (tid == 0) {
+					double wm = *sw_cur;
+					for (int t = 0; t < nslot; ++t) wm = fmax(wm, bj_slot(scratch, t).worst[0]);
+					*sw_cur = wm;
+					if (step == 0) sweep_worst[(sweep + 1) & 1] = 0.0;  // its last reader is two barriers behind
+				}
+			}
+			FH_CTA_SYNC();
+		}
+		// the largest scaled off-diagonal met in the sweep (CTA-uniform read): same stopping rule as the scalar kernel
+		if (*sw_cur <= 1e-11) { ++sweep; break; }
+	}
+	return sweep;
+}
