@@ -8,8 +8,8 @@
 // the small matrix  ->  X <- Z^T X.  One sweep has ceil(n/8)-1 steps instead of n-1, each moving the rows
 // three times: ~7x less shared-memory traffic per sweep. Numerics checked on the CPU (numpy prototype and
 // the host emulation of THIS file, tests/test_polar_block_emulation.py): same outer sweep count (7-8) and
-// the same polar-factor error as the scalar kernel on graded spectra up to kappa 3e6; 2.7 inner sweeps
-// per block pair on average.
+// the same polar-factor error as the scalar kernel on graded spectra up to kappa 3e6 with ONE cyclic sweep over
+// the 16 x 16 problem per visit (iterating it to convergence, 2.7 inner sweeps on average, saves no outer sweep).
 //
 // The file is written in barrier-separated PHASES whose bodies depend only on the thread / lane index and
 // on shared memory (no warp shuffles, no per-lane state across a barrier). With FH_EMU defined the phase
@@ -42,13 +42,24 @@ typedef double2 fh_d2;
 
 constexpr int kBJRows = 8;            // rows per block
 constexpr int kBJSlot = 536;          // doubles of scratch per block pair: S 256 | Z 256 | cs 16 | worst 1 | ctl 7 (14 ints)
-constexpr int kBJInnerMax = 12;       // inner sweep cap (2.7 on average, measured on the CPU)
-constexpr double kBJInnerTol = 1e-22; // inner rotation threshold on s_pq^2 / (s_pp s_qq)
+#ifdef FH_EMU
+// the emulation can vary the inner-solve policy and counts phases (tests/emu, design studies)
+extern int fh_emu_cross_only;
+extern long long fh_emu_count[4];      // [0] block-pair visits, [1] J1 phases, [2] J2+J3 phase pairs
+#define kBJCrossOnly fh_emu_cross_only
+#define FH_EMU_COUNT(i) (++fh_emu_count[i])
+#else
+// 1: after the first step of a sweep only the 64 cross pairs (row of block P, row of block Q) are rotated - the
+// within-block pairs have had their visit of this sweep at step 0, exactly as in a cyclic scalar sweep.
+constexpr int kBJCrossOnly = 1;
+#define FH_EMU_COUNT(i) ((void)0)
+#endif
+constexpr double kBJInnerTol = 1e-22;   // rotation threshold on s_pq^2 / (s_pp s_qq)
 constexpr int kBJMaxSide = 152;       // largest Gram side whose rows + scratch fit 227 KB of shared memory
 
 struct BJSlot {
 	double *S, *Z, *cs, *worst;
-	int* ctl;  // [0],[1] "a rotation happened" flags of even / odd inner sweeps, [2] pair active, [3] valid rows (8 | 16), [4],[5] block ids
+	int* ctl;  // [2] pair active, [3] valid rows (8 | 16), [4],[5] block ids
 };
 FH_DEV BJSlot bj_slot(double* scratch, int t) {
 	double* b = scratch + (size_t)t * kBJSlot;
@@ -70,6 +81,12 @@ FH_DEV void bj_pair(int t, int s, int mm, int& p, int& q) {
 		q = s - t + mm; if (q >= mm) q -= mm;
 	}
 	if (p > q) { int x = p; p = q; q = x; }
+}
+
+// rotation `t` (0..7) of inner step `s`: the round-robin over all 16 rows (15 steps), or the cross pairs only (8 steps)
+FH_DEV void bj_inner_pair(int t, int s, bool cross, int& p, int& q) {
+	if (cross) { p = t; q = 8 + ((t + s) & 7); }
+	else bj_pair(t, s, 15, p, q);
 }
 
 // Orthogonalises the rows of R (n x ld, rows n..bj_rows(n) and the pad columns zero) in place.
@@ -140,12 +157,13 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 					}
 					FH_WARP_SYNC();
 					// does any entry still need a rotation? same rule as the scalar kernel: s_ij^2 > skip * min(d_i, d_j)^2
+					const bool cross = kBJCrossOnly && step != 0;
 					FH_FOR_LANES(lane) {
 						if (lane < 16) {
 							const double di = sl.S[lane * 16 + lane];
 							double worst = 0.0;
 							for (int j = 0; j < 16; ++j) {
-								if (j == lane) continue;
+								if (j == lane || (cross && ((j < 8) == (lane < 8)))) continue;
 								const double sij = sl.S[lane * 16 + j], dj = sl.S[j * 16 + j];
 								const double mn = fmin(di, dj), g2 = sij * sij;
 								if (g2 > skip_tol * mn * mn) worst = fmax(worst, g2 / (di * dj));
@@ -159,7 +177,6 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 							double wmax = 0.0;
 							for (int i = 0; i < 16; ++i) wmax = fmax(wmax, sl.cs[i]);
 							sl.worst[0] = wmax;
-							sl.ctl[0] = 0; sl.ctl[1] = 0;
 							sl.ctl[2] = wmax > 0.0;
 							sl.ctl[3] = nv; sl.ctl[4] = P; sl.ctl[5] = Q;
 						}
@@ -173,67 +190,74 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 				for (int t = w; t < nslot; t += nw) {
 					BJSlot sl = bj_slot(scratch, t);
 					if (sl.ctl[2] == 0) continue;
+					FH_EMU_COUNT(0);
 					FH_FOR_LANES(lane) {
 						for (int e = lane; e < 256; e += 32) sl.Z[e] = ((e >> 4) == (e & 15)) ? 1.0 : 0.0;
 					}
 					FH_WARP_SYNC();
-					for (int isw = 0; isw < kBJInnerMax; ++isw) {
-						for (int s = 0; s < 15; ++s) {
-							// J1: the 8 disjoint rotations of this step
-							FH_FOR_LANES(lane) {
-								if (lane < 8) {
-									int p, q;
-									bj_pair(lane, s, 15, p, q);
-									const double app = sl.S[p * 16 + p], aqq = sl.S[q * 16 + q], apq = sl.S[p * 16 + q];
-									double c = 1.0, sn = 0.0;
-									if (apq != 0.0 && apq * apq > kBJInnerTol * fabs(app * aqq)) {
-										const double zeta = (aqq - app) / (2.0 * apq);
-										const double tt = (zeta == 0.0) ? 1.0 : copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-										c = 1.0 / sqrt(1.0 + tt * tt);
-										sn = tt * c;
-										sl.ctl[isw & 1] = 1;
-									}
-									sl.cs[2 * lane] = c;
-									sl.cs[2 * lane + 1] = sn;
+					// ONE cyclic sweep over the pair's rotations per visit (measured on the CPU: iterating the 16 x 16 problem to
+					// convergence triples the phases per visit and does not save a single outer sweep)
+					const bool cross = kBJCrossOnly && step != 0;
+					const int nsteps = cross ? 8 : 15;
+					for (int s = 0; s < nsteps; ++s) {
+						// J1: the 8 disjoint rotations of this step
+						FH_FOR_LANES(lane) {
+							if (lane < 8) {
+								int p, q;
+								bj_inner_pair(lane, s, cross, p, q);
+								const double app = sl.S[p * 16 + p], aqq = sl.S[q * 16 + q], apq = sl.S[p * 16 + q];
+								double c = 1.0, sn = 0.0;
+								if (apq != 0.0 && apq * apq > kBJInnerTol * fabs(app * aqq)) {
+									const double zeta = (aqq - app) / (2.0 * apq);
+									const double tt = (zeta == 0.0) ? 1.0 : copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+									c = 1.0 / sqrt(1.0 + tt * tt);
+									sn = tt * c;
 								}
+								sl.cs[2 * lane] = c;
+								sl.cs[2 * lane + 1] = sn;
 							}
-							FH_WARP_SYNC();
-							// J2: columns p, q of S and Z (S <- S J, Z <- Z J); 16 rows x 8 rotations = 4 per lane
-							FH_FOR_LANES(lane) {
-								if (s == 0 && lane == 0) sl.ctl[(isw + 1) & 1] = 0;  // next sweep's flag; its last reader is a barrier behind
-#pragma unroll
-								for (int e = 0; e < 4; ++e) {
-									const int combo = lane * 4 + e, i = combo >> 3, tt = combo & 7;
-									const double c = sl.cs[2 * tt], sn = sl.cs[2 * tt + 1];
-									if (sn == 0.0) continue;
-									int p, q;
-									bj_pair(tt, s, 15, p, q);
-									const double sp = sl.S[i * 16 + p], sq = sl.S[i * 16 + q];
-									sl.S[i * 16 + p] = c * sp - sn * sq;
-									sl.S[i * 16 + q] = sn * sp + c * sq;
-									const double zp = sl.Z[i * 16 + p], zq = sl.Z[i * 16 + q];
-									sl.Z[i * 16 + p] = c * zp - sn * zq;
-									sl.Z[i * 16 + q] = sn * zp + c * zq;
-								}
-							}
-							FH_WARP_SYNC();
-							// J3: rows p, q of S (S <- J^T S)
-							FH_FOR_LANES(lane) {
-#pragma unroll
-								for (int e = 0; e < 4; ++e) {
-									const int combo = lane * 4 + e, j = combo >> 3, tt = combo & 7;
-									const double c = sl.cs[2 * tt], sn = sl.cs[2 * tt + 1];
-									if (sn == 0.0) continue;
-									int p, q;
-									bj_pair(tt, s, 15, p, q);
-									const double sp = sl.S[p * 16 + j], sq = sl.S[q * 16 + j];
-									sl.S[p * 16 + j] = c * sp - sn * sq;
-									sl.S[q * 16 + j] = sn * sp + c * sq;
-								}
-							}
-							FH_WARP_SYNC();
 						}
-						if (sl.ctl[isw & 1] == 0) break;  // a full inner sweep without a rotation (warp-uniform read)
+						FH_WARP_SYNC();
+						FH_EMU_COUNT(1);
+						// a step without any rotation: nothing to apply. cs is rewritten by the next J1, so its readers must be a
+						// barrier ahead of it.
+						bool any = false;
+						for (int e = 0; e < 8; ++e) any = any || (sl.cs[2 * e + 1] != 0.0);
+						if (!any) { FH_WARP_SYNC(); continue; }
+						FH_EMU_COUNT(2);
+						// J2: columns p, q of S and Z (S <- S J, Z <- Z J); 16 rows x 8 rotations = 4 per lane
+						FH_FOR_LANES(lane) {
+#pragma unroll
+							for (int e = 0; e < 4; ++e) {
+								const int combo = lane * 4 + e, i = combo >> 3, tt = combo & 7;
+								const double c = sl.cs[2 * tt], sn = sl.cs[2 * tt + 1];
+								if (sn == 0.0) continue;
+								int p, q;
+								bj_inner_pair(tt, s, cross, p, q);
+								const double sp = sl.S[i * 16 + p], sq = sl.S[i * 16 + q];
+								sl.S[i * 16 + p] = c * sp - sn * sq;
+								sl.S[i * 16 + q] = sn * sp + c * sq;
+								const double zp = sl.Z[i * 16 + p], zq = sl.Z[i * 16 + q];
+								sl.Z[i * 16 + p] = c * zp - sn * zq;
+								sl.Z[i * 16 + q] = sn * zp + c * zq;
+							}
+						}
+						FH_WARP_SYNC();
+						// J3: rows p, q of S (S <- J^T S)
+						FH_FOR_LANES(lane) {
+#pragma unroll
+							for (int e = 0; e < 4; ++e) {
+								const int combo = lane * 4 + e, j = combo >> 3, tt = combo & 7;
+								const double c = sl.cs[2 * tt], sn = sl.cs[2 * tt + 1];
+								if (sn == 0.0) continue;
+								int p, q;
+								bj_inner_pair(tt, s, cross, p, q);
+								const double sp = sl.S[p * 16 + j], sq = sl.S[q * 16 + j];
+								sl.S[p * 16 + j] = c * sp - sn * sq;
+								sl.S[q * 16 + j] = sn * sp + c * sq;
+							}
+						}
+						FH_WARP_SYNC();
 					}
 				}
 			}

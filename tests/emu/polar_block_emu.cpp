@@ -6,9 +6,15 @@
 #include <cstddef>
 #include <cstring>
 int fh_emu_reverse = 0;
+int fh_emu_cross_only = 1;
+long long fh_emu_count[4] = {0, 0, 0, 0};
 #include "../../fast-higashi_b200/csrc/fh_polar_block.cuh"
 
 extern "C" {
+void fh_emu_set_policy(int cross_only) { fh_emu_cross_only = cross_only; }
+void fh_emu_counters(long long* out, int reset) {
+	for (int i = 0; i < 4; ++i) { out[i] = fh_emu_count[i]; if (reset) fh_emu_count[i] = 0; }
+}
 int fh_emu_bj_rows(int n) { return bj_rows(n); }
 int fh_emu_bj_ld(int n) { return bj_ld(n); }
 long long fh_emu_bj_scratch_doubles(int n) { return (long long)bj_scratch_doubles(n); }
