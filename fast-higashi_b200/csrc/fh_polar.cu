@@ -176,7 +176,7 @@ __host__ __device__ inline int jacobi_ld(int n, int nthreads) {
 // BLK: the block one-sided Jacobi of fh_polar_block.cuh instead of the scalar sweeps (a separate instantiation, so
 // the default kernel's code generation is untouched by the opt-in variant).
 template <bool BLK>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(BLK ? 512 : 1024)  // the block variant wants 128 registers (Gram tiles, 16-row columns)
 chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob_n, const long long* __restrict__ prob_off,
                    const int* __restrict__ prob_slot, const long long* __restrict__ prob_sig, int uniform_n,
                    int max_sweeps, double skip_tol, double* __restrict__ WTall, double* __restrict__ sigma_all,
@@ -355,14 +355,17 @@ PolarWs carve(int batch, int n, void* ws) {
 
 constexpr int kMaxSweeps = 30;
 
-int jacobi_threads(int n) { return n > 83 ? 1024 : (n > 58 ? 512 : 256); }
-
 // FH_POLAR_BLOCK=1: block one-sided Jacobi (fh_polar_block.cuh) for Gram sides <= kBJMaxSide. Default off: the
 // variant was written and checked through its host emulation after the round's GPU time was spent.
 int polar_block_mode() {
 	static int mode = -1;
 	if (mode < 0) { const char* e = getenv("FH_POLAR_BLOCK"); mode = (e && e[0] == '1') ? 1 : 0; }
 	return mode;
+}
+
+int jacobi_threads(int n) {
+	const int t = n > 83 ? 1024 : (n > 58 ? 512 : 256);
+	return (polar_block_mode() && t > 512) ? 512 : t;  // chol_jacobi_kernel<true> is built for <= 512 threads
 }
 
 int launch_jacobi(int grid, int nmax, size_t smem, cudaStream_t st, const double* G, const int* pn, const long long* po,
