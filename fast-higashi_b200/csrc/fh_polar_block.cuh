@@ -225,8 +225,25 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 						for (int e = 0; e < 8; ++e) any = any || (sl.cs[2 * e + 1] != 0.0);
 						if (!any) { FH_WARP_SYNC(); continue; }
 						FH_EMU_COUNT(2);
-						// J2: columns p, q of S and Z (S <- S J, Z <- Z J); 16 rows x 8 rotations = 4 per lane
+						// J2: S <- J^T S J and Z <- Z J in one phase. The 8 disjoint pairs tile S into 8 x 8 blocks of 2 x 2 entries
+						// ({p_a, q_a} x {p_b, q_b}); a block only needs its own entries and the two rotations: 2 blocks per lane.
 						FH_FOR_LANES(lane) {
+#pragma unroll
+							for (int e = 0; e < 2; ++e) {
+								const int bidx = lane * 2 + e, a = bidx >> 3, b = bidx & 7;
+								const double ca = sl.cs[2 * a], sa = sl.cs[2 * a + 1], cb = sl.cs[2 * b], sb = sl.cs[2 * b + 1];
+								if (sa == 0.0 && sb == 0.0) continue;
+								int pa, qa, pb, qb;
+								bj_inner_pair(a, s, cross, pa, qa);
+								bj_inner_pair(b, s, cross, pb, qb);
+								const double bpp = sl.S[pa * 16 + pb], bpq = sl.S[pa * 16 + qb], bqp = sl.S[qa * 16 + pb], bqq = sl.S[qa * 16 + qb];
+								const double tpp = ca * bpp - sa * bqp, tpq = ca * bpq - sa * bqq;  // J_a^T B
+								const double tqp = sa * bpp + ca * bqp, tqq = sa * bpq + ca * bqq;
+								sl.S[pa * 16 + pb] = tpp * cb - tpq * sb;                             // ... J_b
+								sl.S[pa * 16 + qb] = tpp * sb + tpq * cb;
+								sl.S[qa * 16 + pb] = tqp * cb - tqq * sb;
+								sl.S[qa * 16 + qb] = tqp * sb + tqq * cb;
+							}
 #pragma unroll
 							for (int e = 0; e < 4; ++e) {
 								const int combo = lane * 4 + e, i = combo >> 3, tt = combo & 7;
@@ -234,27 +251,9 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 								if (sn == 0.0) continue;
 								int p, q;
 								bj_inner_pair(tt, s, cross, p, q);
-								const double sp = sl.S[i * 16 + p], sq = sl.S[i * 16 + q];
-								sl.S[i * 16 + p] = c * sp - sn * sq;
-								sl.S[i * 16 + q] = sn * sp + c * sq;
 								const double zp = sl.Z[i * 16 + p], zq = sl.Z[i * 16 + q];
 								sl.Z[i * 16 + p] = c * zp - sn * zq;
 								sl.Z[i * 16 + q] = sn * zp + c * zq;
-							}
-						}
-						FH_WARP_SYNC();
-						// J3: rows p, q of S (S <- J^T S)
-						FH_FOR_LANES(lane) {
-#pragma unroll
-							for (int e = 0; e < 4; ++e) {
-								const int combo = lane * 4 + e, j = combo >> 3, tt = combo & 7;
-								const double c = sl.cs[2 * tt], sn = sl.cs[2 * tt + 1];
-								if (sn == 0.0) continue;
-								int p, q;
-								bj_inner_pair(tt, s, cross, p, q);
-								const double sp = sl.S[p * 16 + j], sq = sl.S[q * 16 + j];
-								sl.S[p * 16 + j] = c * sp - sn * sq;
-								sl.S[q * 16 + j] = sn * sp + c * sq;
 							}
 						}
 						FH_WARP_SYNC();
