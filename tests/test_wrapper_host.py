@@ -81,3 +81,53 @@ def test_fetch_cell_embedding_matches_reference(tmp_path):
 		sgn = np.sign(np.sum(a * b, axis=0))
 		np.testing.assert_allclose(a * sgn, b, rtol=1e-5, atol=1e-7)
 	assert fh.correct_batch_linear("missing") is None
+
+
+def test_only_partial_rwr_assembly_logic(tmp_path, monkeypatch):
+	"""only_partial_rwr (FastHigashi_Wrapper.py:569-655) with the device call replaced by the CPU oracle: checks what the
+	wrapper itself does - one auto-stopped call per (bin-block, cell batch), pasting the block windows into the (n, n) map,
+	m + m^T with the diagonal halved, datasets keyed by the ORIGINAL cell id, good and bad cells - against the same steps
+	written as in the reference (float64 maps, then cast). The device call itself is covered by the GPU tests."""
+	import torch
+	from conftest import load_small_dataset
+	from oracle import fh_oracle as O
+	import fasthigashi_b200.partial_rwr as prw
+
+	calls = []
+
+	def fake_rwr_block_csr(ds, b, cell0, ncell, out, out_cell_stride, k, do_conv, do_rwr, do_col, bin_cov=None, use_tc=False, chunk=None):
+		g = ds.geoms[b]
+		x, n_it = O.partial_rwr(O.densify_block(ds, b, cell0, cell0 + ncell), g.s, g.e, do_conv, do_rwr, do_col, None, k)
+		ldw = prw.pad4(g.w)
+		view = out.view(ncell, g.nb, ldw)
+		view[:, :, :g.w] = x
+		calls.append((ds.chrom, b, cell0, ncell, k, do_col))
+		return n_it
+	monkeypatch.setattr(prw, "rwr_block_csr", fake_rwr_block_csr)
+	fh = host_only_wrapper(str(tmp_path), str(tmp_path))
+	fh.device = "cpu"
+	fh.do_conv, fh.do_rwr = True, True
+	fh.all_matrix = load_small_dataset(good_qc_num=44, bs_cell=20)
+	rng = np.random.default_rng(0)
+	fh.reorder = rng.permutation(48)
+	files = fh.only_partial_rwr(out_format="npz")
+	assert [os.path.basename(f) for f in files] == ["impute_prwr_chr1.npz", "impute_prwr_chr2.npz", "impute_prwr_chr3.npz"]
+	assert all(k == -1 and not col for (_, _, _, _, k, col) in calls)          # auto-stop, do_col=False (:606-607)
+	for ds, path in zip(fh.all_matrix, files):
+		got = np.load(path)
+		n = ds.num_bin
+		assert list(got["shape"]) == [n, n] and len(got.files) == 49
+		assert sorted(int(k) for k in got.files if k != "shape") == list(range(48))
+		assert [(c0, nc) for (ch, b, c0, nc, _, _) in calls if ch == ds.chrom and b == 0] == [(0, 20), (20, 20), (40, 4), (44, 4)]
+		for sl in ds.cell_slice_list:
+			nc = sl.stop - sl.start
+			full = np.zeros((nc, n, n))
+			for b, g in enumerate(ds.geoms):
+				x, _ = O.partial_rwr(O.densify_block(ds, b, sl.start, sl.stop), g.s, g.e, True, True, False, None, -1)
+				full[:, g.row0:g.row0 + g.nb, g.col0:g.col0 + g.w] = x.numpy()
+			full = full + full.transpose(0, 2, 1)
+			for i in range(nc):
+				m = (full[i] - np.diag(np.diag(full[i]) / 2)).astype("float32")
+				assert np.array_equal(got[str(fh.reorder[sl.start + i])], m)        # fp32 on the device == float64-then-cast
+	with pytest.raises(ValueError):
+		fh.only_partial_rwr(out_format="csv")
