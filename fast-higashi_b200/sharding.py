@@ -17,11 +17,35 @@ def shard_datasets(datasets, world_size, rank):
 	Good and bad cells are sharded separately so every rank keeps the good-first order."""
 	out = []
 	for ds in datasets:
-		if ds.total_cell_num != ds.num_cell:
-			raise NotImplementedError("shard before adding bad-QC cells (or pass rank-local tensors)")
 		lo, hi = cell_slab(ds.num_cell, world_size, rank)
-		out.append(ds.select_cells(lo, hi))
+		nbad = ds.total_cell_num - ds.num_cell
+		if nbad == 0:
+			out.append(ds.select_cells(lo, hi))
+			continue
+		blo, bhi = cell_slab(nbad, world_size, rank)
+		out.append(ds.select_cell_ranges([(lo, hi), (ds.num_cell + blo, ds.num_cell + bhi)], good_qc_num=hi - lo))
 	return out
+
+
+def gather_cell_rows(local, num_good_local, group=None):
+	"""Inverse of `shard_datasets` for per-cell results (e.g. the rows of meta_embedding returned by `transform`):
+	`local` (cells_local, ...) holds this rank's good cells then its bad cells; returns the rows of ALL cells in the
+	unsharded order (all good cells, then all bad cells) on every rank."""
+	import torch
+	if group is None:
+		return local
+	import torch.distributed as dist
+	world = dist.get_world_size(group)
+	meta = [None] * world
+	dist.all_gather_object(meta, (int(local.shape[0]), int(num_good_local)), group=group)
+	rows = max(m[0] for m in meta)  # slabs differ by at most one cell: pad to a common size for all_gather
+	padded = torch.zeros((rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+	padded[:local.shape[0]] = local
+	parts = [torch.empty_like(padded) for _ in meta]
+	dist.all_gather(parts, padded, group=group)
+	good = [p[:m[1]] for p, m in zip(parts, meta)]
+	bad = [p[m[1]:m[0]] for p, m in zip(parts, meta)]
+	return torch.cat(good + bad, 0)
 
 
 def polar_partition(sizes, world_size, rank):

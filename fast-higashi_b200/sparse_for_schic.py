@@ -223,15 +223,35 @@ class Chrom_Dataset:
 
 	def select_cells(self, cell_start, cell_stop, good_qc_num=None):
 		"""A dataset holding only cells [cell_start, cell_stop) (cell-slab sharding, §8e)."""
+		return self.select_cell_ranges([(cell_start, cell_stop)], good_qc_num)
+
+	def select_cell_ranges(self, ranges, good_qc_num=None):
+		"""A dataset holding the cells of the given [start, stop) ranges, concatenated in that order (a rank's slab of
+		good-QC cells followed by its slab of bad-QC cells). `good_qc_num`: how many of them are good (default: all)."""
 		new = object.__new__(Chrom_Dataset)
 		new.__dict__.update(self.__dict__)
-		n = cell_stop - cell_start
+		n = int(sum(b - a for a, b in ranges))
 		new.total_cell_num = n
-		new.num_cell = n if good_qc_num is None else good_qc_num
+		new.num_cell = n if good_qc_num is None else int(good_qc_num)
 		new.rowptr, new.col, new.val = [], [], []
 		for b in range(len(self.geoms)):
-			rp, c, v = self.cell_range_csr(b, cell_start, cell_stop)
-			new.rowptr.append(rp.clone()); new.col.append(c.clone()); new.val.append(v.clone())
+			parts = [self.cell_range_csr(b, lo, hi) for lo, hi in ranges if hi > lo]
+			if len(parts) == 1:
+				rp, c, v = parts[0]
+				new.rowptr.append(rp.clone()); new.col.append(c.clone()); new.val.append(v.clone())
+				continue
+			if not parts:
+				dev = self.rowptr[b].device
+				new.rowptr.append(torch.zeros(1, dtype=torch.int32, device=dev))
+				new.col.append(self.col[b][:0].clone()); new.val.append(self.val[b][:0].clone())
+				continue
+			rps, off = [parts[0][0][:1].long()], 0
+			for rp, _, _ in parts:
+				rps.append(rp[1:].long() + off)
+				off += int(rp[-1])
+			new.rowptr.append(torch.cat(rps).int())
+			new.col.append(torch.cat([p[1] for p in parts]))
+			new.val.append(torch.cat([p[2] for p in parts]))
 		good = [slice(c, min(c + new.bs_cell, new.num_cell)) for c in range(0, new.num_cell, new.bs_cell)]
 		bad = [slice(c, min(c + new.bs_cell, n)) for c in range(new.num_cell, n, new.bs_cell)]
 		new.cell_slice_list = good + bad

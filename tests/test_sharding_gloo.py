@@ -31,7 +31,25 @@ def _worker(rank, world, port, q):
 		for b, g in enumerate(d_full.geoms):
 			rp, col, val = d_full.cell_range_csr(b, lo, hi)
 			ok &= torch.equal(rp, d_mine.rowptr[b]) and torch.equal(col, d_mine.col[b]) and torch.equal(val, d_mine.val[b])
-	q.put((rank, lo, hi, float(nnz), int(mx), bool(ok), [d.num_cell for d in mine]))
+	# good + bad QC cells (45 good of 48, so both slabs are uneven): every rank gets its good slab then its bad slab, and
+	# gather_cell_rows restores the unsharded order
+	from fasthigashi_b200.sharding import gather_cell_rows
+	fullb = load_small_dataset(good_qc_num=45)
+	mineb = shard_datasets(fullb, world, rank)
+	glo, ghi = cell_slab(45, world, rank)
+	blo, bhi = cell_slab(3, world, rank)
+	okb = True
+	for d_full, d_mine in zip(fullb, mineb):
+		okb &= d_mine.num_cell == ghi - glo and d_mine.total_cell_num == (ghi - glo) + (bhi - blo)
+		for b, g in enumerate(d_full.geoms):
+			for (a0, a1), off in (((glo, ghi), 0), ((45 + blo, 45 + bhi), ghi - glo)):
+				rp, col, val = d_full.cell_range_csr(b, a0, a1)
+				rp2, col2, val2 = d_mine.cell_range_csr(b, off, off + (a1 - a0))
+				okb &= torch.equal(rp, rp2) and torch.equal(col, col2) and torch.equal(val, val2)
+	ids = torch.cat([torch.arange(glo, ghi), 45 + torch.arange(blo, bhi)]).float()[:, None] * torch.ones(1, 3)
+	back = gather_cell_rows(ids, ghi - glo, dist.group.WORLD)
+	okb &= torch.equal(back, torch.arange(48).float()[:, None] * torch.ones(1, 3))
+	q.put((rank, lo, hi, float(nnz), int(mx), bool(ok and okb), [d.num_cell for d in mine]))
 	dist.destroy_process_group()
 
 
