@@ -97,7 +97,7 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 	const int nblk = bj_blocks(n);
 	const int m = (nblk + 1) & ~1, mm = m - 1, nslot = m >> 1;
 	double* sweep_worst = scratch + (size_t)nslot * kBJSlot;  // [2], ping-pong by sweep parity
-	const int nchunk = (ld + 31) >> 5;
+	const int nchunk = (ld + 63) >> 6;  // 64-column chunks of the apply phase
 	FH_FOR_THREADS(tid, nthreads) {
 		if (tid < 2) sweep_worst[tid] = 0.0;
 	}
@@ -261,31 +261,40 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 				}
 			}
 			FH_CTA_SYNC();
-			// ---------------- P3: X <- Z^T X for every active pair, all warps, a lane per column ----------------
+			// ---------------- P3: X <- Z^T X for every active pair, all warps, two columns (c, c + 32) per lane ----------------
+			// (the Z entries are warp-uniform broadcast loads: one load feeds the FMAs of both columns, which halves the
+			// shared-memory instructions per fp64 FMA)
 			FH_FOR_THREADS(tid, nthreads) {
 				const int w = tid >> 5, lane = tid & 31;
 				for (int item = w; item < nslot * nchunk; item += nw) {
-					const int t = item / nchunk, c = (item - t * nchunk) * 32 + lane;
+					const int t = item / nchunk, c0 = (item - t * nchunk) * 64 + lane, c1 = c0 + 32;
 					BJSlot sl = bj_slot(scratch, t);
-					if (sl.ctl[2] == 0 || c >= ld) continue;
+					if (sl.ctl[2] == 0 || c0 >= ld) continue;
+					const bool two = c1 < ld;
 					const int nv = sl.ctl[3], P = sl.ctl[4], Q = sl.ctl[5];
-					double x[16];
+					double x0[16], x1[16];
 #pragma unroll
-					for (int k = 0; k < 16; ++k)
-						x[k] = (k < nv) ? R[(size_t)((k < 8) ? P * 8 + k : Q * 8 + (k - 8)) * ld + c] : 0.0;
+					for (int k = 0; k < 16; ++k) {
+						const double* src = R + (size_t)((k < 8) ? P * 8 + k : Q * 8 + (k - 8)) * ld;
+						x0[k] = (k < nv) ? src[c0] : 0.0;
+						x1[k] = (k < nv && two) ? src[c1] : 0.0;
+					}
 #pragma unroll
 					for (int h = 0; h < 4; ++h) {
-						double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
+						double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
 #pragma unroll
 						for (int k = 0; k < 16; ++k) {
 							const fh_d2 za = FH_LD2(sl.Z + k * 16 + 4 * h), zb = FH_LD2(sl.Z + k * 16 + 4 * h + 2);
-							o0 = fma(za.x, x[k], o0); o1 = fma(za.y, x[k], o1);
-							o2 = fma(zb.x, x[k], o2); o3 = fma(zb.y, x[k], o3);
+							o0 = fma(za.x, x0[k], o0); o1 = fma(za.y, x0[k], o1);
+							o2 = fma(zb.x, x0[k], o2); o3 = fma(zb.y, x0[k], o3);
+							q0 = fma(za.x, x1[k], q0); q1 = fma(za.y, x1[k], q1);
+							q2 = fma(zb.x, x1[k], q2); q3 = fma(zb.y, x1[k], q3);
 						}
 						const int l = 4 * h;
 						if (l < nv) {
-							double* dst = R + (size_t)((l < 8) ? P * 8 + l : Q * 8 + (l - 8)) * ld + c;
-							dst[0] = o0; dst[ld] = o1; dst[2 * (size_t)ld] = o2; dst[3 * (size_t)ld] = o3;
+							double* dst = R + (size_t)((l < 8) ? P * 8 + l : Q * 8 + (l - 8)) * ld;
+							dst[c0] = o0; dst[ld + c0] = o1; dst[2 * (size_t)ld + c0] = o2; dst[3 * (size_t)ld + c0] = o3;
+							if (two) { dst[c1] = q0; dst[ld + c1] = q1; dst[2 * (size_t)ld + c1] = q2; dst[3 * (size_t)ld + c1] = q3; }
 						}
 					}
 				}
