@@ -17,7 +17,6 @@
 #include "fh_common.cuh"
 #include "../../include/fh_b200.h"
 #include <math.h>
-#include "fh_polar_block.cuh"  // block one-sided Jacobi, opt-in (FH_POLAR_BLOCK=1)
 
 namespace {
 
@@ -50,6 +49,8 @@ __device__ __forceinline__ double jacobi_tan(double al, double be, double ga) {
 	if (!(tf <= 1.f)) tf = 1.f;                  // nan guard: 45 degrees
 	return ((d >= 0.0) == (ga >= 0.0)) ? (double)tf : -(double)tf;
 }
+
+#include "fh_polar_block.cuh"  // block one-sided Jacobi, opt-in (FH_POLAR_BLOCK=1); uses jacobi_tan
 
 // One-sided Jacobi sweeps over the rows of R (n x ld, ld a multiple of 16, pad columns zero).
 // A half-warp (G = 16 lanes) owns one row pair and keeps row p in registers (PL = ld / 16 elements per

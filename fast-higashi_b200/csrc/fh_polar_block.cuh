@@ -73,6 +73,21 @@ inline __host__ __device__ int bj_rows(int n) { return bj_blocks(n) * kBJRows; }
 inline __host__ __device__ int bj_ld(int n) { return (n + 1) & ~1; }                 // even: 16-byte row pairs
 inline __host__ __device__ size_t bj_scratch_doubles(int n) { return (size_t)bj_slots(n) * kBJSlot + 2; }
 
+// tan of the rotation angle for alpha = s_pp, beta = s_qq, gamma = s_pq. Device: the scalar kernel's jacobi_tan (fp32 angle
+// with approximate div / sqrt - the residual it leaves is removed quadratically by the next visit); the host emulation
+// evaluates the same formula exactly. cos = rsqrt(1 + t^2) in fp64 keeps every rotation orthogonal either way.
+#ifdef FH_EMU
+extern int fh_emu_fp32_angle;  // 1: round the angle to fp32 as the device's approximate evaluation does
+inline double bj_tan(double al, double be, double ga) {
+	const double zeta = (be - al) / (2.0 * ga);
+	const double t = (zeta == 0.0) ? 1.0 : std::copysign(1.0, zeta) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+	return fh_emu_fp32_angle ? (double)((float)t * (1.0f + 2e-7f)) : t;
+}
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+#else
+#define bj_tan jacobi_tan
+#endif
+
 // pair `t` of round-robin step `s` among m = mm + 1 players (player mm fixed): p < q
 FH_DEV void bj_pair(int t, int s, int mm, int& p, int& q) {
 	if (t == 0) { p = mm; q = s; }
@@ -208,9 +223,8 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 								const double app = sl.S[p * 16 + p], aqq = sl.S[q * 16 + q], apq = sl.S[p * 16 + q];
 								double c = 1.0, sn = 0.0;
 								if (apq != 0.0 && apq * apq > kBJInnerTol * fabs(app * aqq)) {
-									const double zeta = (aqq - app) / (2.0 * apq);
-									const double tt = (zeta == 0.0) ? 1.0 : copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-									c = 1.0 / sqrt(1.0 + tt * tt);
+									const double tt = bj_tan(app, aqq, apq);
+									c = rsqrt(tt * tt + 1.0);
 									sn = tt * c;
 								}
 								sl.cs[2 * lane] = c;

@@ -7,11 +7,13 @@
 #include <cstring>
 int fh_emu_reverse = 0;
 int fh_emu_cross_only = 1;
+int fh_emu_fp32_angle = 1;
 long long fh_emu_count[4] = {0, 0, 0, 0};
 #include "../../fast-higashi_b200/csrc/fh_polar_block.cuh"
 
 extern "C" {
 void fh_emu_set_policy(int cross_only) { fh_emu_cross_only = cross_only; }
+void fh_emu_set_fp32_angle(int on) { fh_emu_fp32_angle = on; }
 void fh_emu_counters(long long* out, int reset) {
 	for (int i = 0; i < 4; ++i) { out[i] = fh_emu_count[i]; if (reset) fh_emu_count[i] = 0; }
 }
