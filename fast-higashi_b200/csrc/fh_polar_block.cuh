@@ -171,28 +171,29 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 							for (int v = 0; v < 2; ++v) sl.S[(4 * a + u) * 16 + 2 * bq + v] = acc[u][v];
 					}
 					FH_WARP_SYNC();
-					// does any entry still need a rotation? same rule as the scalar kernel: s_ij^2 > skip * min(d_i, d_j)^2
+					// does any entry still need a rotation (scalar kernel's rule: s_ij^2 > skip * min(d_i, d_j)^2), and is any of those
+					// above the stopping level s_ij^2 > 1e-11 d_i d_j? Two flags per row, no divisions.
 					const bool cross = kBJCrossOnly && step != 0;
 					FH_FOR_LANES(lane) {
 						if (lane < 16) {
 							const double di = sl.S[lane * 16 + lane];
-							double worst = 0.0;
+							int flags = 0;
 							for (int j = 0; j < 16; ++j) {
 								if (j == lane || (cross && ((j < 8) == (lane < 8)))) continue;
 								const double sij = sl.S[lane * 16 + j], dj = sl.S[j * 16 + j];
 								const double mn = fmin(di, dj), g2 = sij * sij;
-								if (g2 > skip_tol * mn * mn) worst = fmax(worst, g2 / (di * dj));
+								if (g2 > skip_tol * mn * mn) flags |= (g2 > 1e-11 * (di * dj)) ? 3 : 1;
 							}
-							sl.cs[lane] = worst;
+							sl.cs[lane] = (double)flags;
 						}
 					}
 					FH_WARP_SYNC();
 					FH_FOR_LANES(lane) {
 						if (lane == 0) {
-							double wmax = 0.0;
-							for (int i = 0; i < 16; ++i) wmax = fmax(wmax, sl.cs[i]);
-							sl.worst[0] = wmax;
-							sl.ctl[2] = wmax > 0.0;
+							int flags = 0;
+							for (int i = 0; i < 16; ++i) flags |= (int)sl.cs[i];
+							sl.worst[0] = (flags & 2) ? 1.0 : 0.0;  // 1: this visit met an off-diagonal above the stopping level
+							sl.ctl[2] = flags & 1;
 							sl.ctl[3] = nv; sl.ctl[4] = P; sl.ctl[5] = Q;
 						}
 					}
@@ -321,8 +322,8 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 			}
 			FH_CTA_SYNC();
 		}
-		// the largest scaled off-diagonal met in the sweep (CTA-uniform read): same stopping rule as the scalar kernel
-		if (*sw_cur <= 1e-11) { ++sweep; break; }
+		// no rotated pair of the whole sweep was above the stopping level (CTA-uniform read): same rule as the scalar kernel
+		if (*sw_cur < 0.5) { ++sweep; break; }
 	}
 	return sweep;
 }
