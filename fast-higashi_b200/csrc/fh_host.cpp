@@ -413,7 +413,7 @@ extern "C" int fh_host_pack_fetch(void* handle, int32_t* indices, float* values)
 		int64_t k = P->offset[(size_t)c];
 		for (const Entry& x : P->ent[(size_t)c]) {
 			row[k] = x.r; col[k] = x.c; cell[k] = (int32_t)c;
-			const float f = (float)std::log1p((double)(float)x.v);
+			const float f = std::log1p((float)x.v);  // fp32 log1p like numpy on the fp32 array (:353)
 			values[k] = f;
 			sum += (double)f;
 			++k;
