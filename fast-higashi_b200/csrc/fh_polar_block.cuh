@@ -121,59 +121,72 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 	for (; sweep < max_sweeps; ++sweep) {
 		double* sw_cur = sweep_worst + (sweep & 1);
 		for (int step = 0; step < mm; ++step) {
-			// ---------------- P1: Gram of every block pair of this step, one warp per pair ----------------
+			// ---------------- P1: Gram of every block pair of this step, two work items per pair over all warps ----------------
+			// item 2t    : rows of block P against the rows of P and Q (8 x 16 entries, a 2 x 2 tile per lane)
+			// item 2t + 1: rows of block Q against the rows of Q      (8 x 8 entries, 1 x 2 per lane)
+			// The Q x P block is the transpose of P x Q: the pair's warp mirrors it at the start of P2 (3/4 of the fp64 work of
+			// the full 16 x 16 product, spread over all warps instead of one warp per pair).
+			FH_FOR_WARPS(w, nw) {
+				for (int item = w; item < 2 * nslot; item += nw) {
+					const int t = item >> 1, half = item & 1;
+					BJSlot sl = bj_slot(scratch, t);
+					int P, Q;
+					bj_pair(t, step, mm, P, Q);
+					const bool hasQ = Q < nblk;  // false: the dummy player of an odd block count, P is alone
+					FH_FOR_LANES(lane) {
+						if (half == 0) {
+							const int a = lane >> 3, l = 2 * (lane & 7);
+							const double* pi = R + (size_t)(P * 8 + 2 * a) * ld;
+							const bool jv = l < 8 || hasQ;
+							const double* pj = R + (size_t)((l < 8) ? P * 8 + l : (hasQ ? Q * 8 + (l - 8) : 0)) * ld;
+							double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+							if (jv) {
+								for (int c = 0; c < ld; c += 2) {
+									const fh_d2 x0 = FH_LD2(pi + c), x1 = FH_LD2(pi + ld + c), y0 = FH_LD2(pj + c), y1 = FH_LD2(pj + ld + c);
+									a00 = fma(x0.x, y0.x, a00); a00 = fma(x0.y, y0.y, a00);
+									a01 = fma(x0.x, y1.x, a01); a01 = fma(x0.y, y1.y, a01);
+									a10 = fma(x1.x, y0.x, a10); a10 = fma(x1.y, y0.y, a10);
+									a11 = fma(x1.x, y1.x, a11); a11 = fma(x1.y, y1.y, a11);
+								}
+							}
+							sl.S[(2 * a) * 16 + l] = a00; sl.S[(2 * a) * 16 + l + 1] = a01;
+							sl.S[(2 * a + 1) * 16 + l] = a10; sl.S[(2 * a + 1) * 16 + l + 1] = a11;
+						} else {
+							const int i = lane >> 2, l = 2 * (lane & 3);
+							double a0 = 0.0, a1 = 0.0;
+							if (hasQ) {
+								const double* pi = R + (size_t)(Q * 8 + i) * ld;
+								const double* pj = R + (size_t)(Q * 8 + l) * ld;
+								for (int c = 0; c < ld; c += 2) {
+									const fh_d2 x = FH_LD2(pi + c), y0 = FH_LD2(pj + c), y1 = FH_LD2(pj + ld + c);
+									a0 = fma(x.x, y0.x, a0); a0 = fma(x.y, y0.y, a0);
+									a1 = fma(x.x, y1.x, a1); a1 = fma(x.y, y1.y, a1);
+								}
+							}
+							sl.S[(8 + i) * 16 + 8 + l] = a0; sl.S[(8 + i) * 16 + 8 + l + 1] = a1;
+						}
+					}
+				}
+			}
+			FH_CTA_SYNC();
+			// ---------------- P2: per pair: activity flags, then the rotations of S (two-sided cyclic Jacobi), one warp ----------------
 			FH_FOR_WARPS(w, nw) {
 				for (int t = w; t < nslot; t += nw) {
 					BJSlot sl = bj_slot(scratch, t);
 					int P, Q;
 					bj_pair(t, step, mm, P, Q);
-					const int nv = (Q < nblk) ? 16 : 8;  // the dummy player of an odd block count: P alone
-					FH_FOR_LANES(lane) {
-						const int a = lane >> 3, bq = lane & 7;  // rows 4a..4a+3 against rows 2bq, 2bq+1
-						const double* pi[4];
-						const double* pj[2];
+					const int nv = (Q < nblk) ? 16 : 8;
+					const bool cross = kBJCrossOnly && step != 0;
+					FH_FOR_LANES(lane) {  // Q x P block = (P x Q block)^T
 #pragma unroll
-						for (int u = 0; u < 4; ++u) {
-							const int l = 4 * a + u;
-							pi[u] = (l < nv) ? R + (size_t)((l < 8) ? P * 8 + l : Q * 8 + (l - 8)) * ld : nullptr;
+						for (int e = 0; e < 2; ++e) {
+							const int idx = lane * 2 + e, i = 8 + (idx >> 3), j = idx & 7;
+							sl.S[i * 16 + j] = sl.S[j * 16 + i];
 						}
-#pragma unroll
-						for (int v = 0; v < 2; ++v) {
-							const int l = 2 * bq + v;
-							pj[v] = (l < nv) ? R + (size_t)((l < 8) ? P * 8 + l : Q * 8 + (l - 8)) * ld : nullptr;
-						}
-						double acc[4][2];
-#pragma unroll
-						for (int u = 0; u < 4; ++u) { acc[u][0] = 0.0; acc[u][1] = 0.0; }
-						for (int c = 0; c < ld; c += 2) {
-							fh_d2 xi[4], xj[2];
-#pragma unroll
-							for (int u = 0; u < 4; ++u) {
-								if (pi[u]) xi[u] = FH_LD2(pi[u] + c);
-								else { xi[u].x = 0.0; xi[u].y = 0.0; }
-							}
-#pragma unroll
-							for (int v = 0; v < 2; ++v) {
-								if (pj[v]) xj[v] = FH_LD2(pj[v] + c);
-								else { xj[v].x = 0.0; xj[v].y = 0.0; }
-							}
-#pragma unroll
-							for (int u = 0; u < 4; ++u)
-#pragma unroll
-								for (int v = 0; v < 2; ++v) {
-									acc[u][v] = fma(xi[u].x, xj[v].x, acc[u][v]);
-									acc[u][v] = fma(xi[u].y, xj[v].y, acc[u][v]);
-								}
-						}
-#pragma unroll
-						for (int u = 0; u < 4; ++u)
-#pragma unroll
-							for (int v = 0; v < 2; ++v) sl.S[(4 * a + u) * 16 + 2 * bq + v] = acc[u][v];
 					}
 					FH_WARP_SYNC();
 					// does any entry still need a rotation (scalar kernel's rule: s_ij^2 > skip * min(d_i, d_j)^2), and is any of those
 					// above the stopping level s_ij^2 > 1e-11 d_i d_j? Two flags per row, no divisions.
-					const bool cross = kBJCrossOnly && step != 0;
 					FH_FOR_LANES(lane) {
 						if (lane < 16) {
 							const double di = sl.S[lane * 16 + lane];
@@ -198,13 +211,6 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 						}
 					}
 					FH_WARP_SYNC();
-				}
-			}
-			FH_CTA_SYNC();
-			// ---------------- P2: S = Z Lambda Z^T, two-sided cyclic Jacobi, one warp per active pair ----------------
-			FH_FOR_WARPS(w, nw) {
-				for (int t = w; t < nslot; t += nw) {
-					BJSlot sl = bj_slot(scratch, t);
 					if (sl.ctl[2] == 0) continue;
 					FH_EMU_COUNT(0);
 					FH_FOR_LANES(lane) {
@@ -213,7 +219,6 @@ FH_DEV int block_jacobi_sweeps(double* R, const int n, const int ld, double* scr
 					FH_WARP_SYNC();
 					// ONE cyclic sweep over the pair's rotations per visit (measured on the CPU: iterating the 16 x 16 problem to
 					// convergence triples the phases per visit and does not save a single outer sweep)
-					const bool cross = kBJCrossOnly && step != 0;
 					const int nsteps = cross ? 8 : 15;
 					for (int s = 0; s < nsteps; ++s) {
 						// J1: the 8 disjoint rotations of this step
