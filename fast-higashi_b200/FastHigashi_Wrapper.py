@@ -303,12 +303,27 @@ class FastHigashi:
 		new_x[self.reorder] = x
 		return new_x
 
-	def fetch_cell_embedding(self, final_dim=None, restore_order=False):
-		"""FastHigashi_Wrapper.py:750-789 (host numpy/sklearn post-processing, as in the reference)."""
+	def _reduce(self, embedding, dim, svd):
+		"""TruncatedSVD(n_components=dim).fit_transform(embedding): sklearn on the host (reference behaviour, :767,:872) or
+		the same randomized algorithm on the device (dist_svd.py; matters from ~100k cells on)."""
+		if svd == "host":
+			from sklearn.decomposition import TruncatedSVD
+			return TruncatedSVD(n_components=dim).fit_transform(embedding)
+		if svd != "device":
+			raise ValueError("svd must be 'host' or 'device'")
+		from .dist_svd import sharded_truncated_svd
+		dev = getattr(self, "device", "cpu")
+		emb, _, _ = sharded_truncated_svd(torch.as_tensor(embedding, dtype=torch.float64).to(dev), dim, n_iter=5,
+		                                  seed=int(np.random.randint(0, 2 ** 31 - 1)))
+		return emb.cpu().numpy()
+
+	def fetch_cell_embedding(self, final_dim=None, restore_order=False, svd="host"):
+		"""FastHigashi_Wrapper.py:750-789 (host numpy/sklearn post-processing, as in the reference; `svd="device"` runs the
+		two truncated SVDs on the GPU)."""
 		print("fetching embedding")
 		from sklearn.preprocessing import quantile_transform, normalize
-		from sklearn.decomposition import TruncatedSVD
 		final_dim = self.rank if final_dim is None else final_dim
+		self._embed_svd = svd
 		embedding_list = []
 		for p in self.D_list:
 			p = np.asarray(p)
@@ -316,7 +331,7 @@ class FastHigashi:
 			embedding_list.append(self.meta_embedding @ p)
 		embedding = np.concatenate(embedding_list, axis=1)
 		self.label_info["coverage_fh"] = quantile_transform(self.coverage_feats, n_quantiles=100)
-		embed = TruncatedSVD(n_components=final_dim).fit_transform(embedding)
+		embed = self._reduce(embedding, final_dim, svd)
 		if restore_order:
 			embedding = self.restore_order_fun(embedding)
 			embed = self.restore_order_fun(embed)
@@ -328,7 +343,6 @@ class FastHigashi:
 	def correct_batch_linear(self, var_to_regress_name, add_intercept_back=False):
 		"""FastHigashi_Wrapper.py:815-878."""
 		from sklearn.linear_model import LinearRegression
-		from sklearn.decomposition import TruncatedSVD
 		from sklearn.preprocessing import normalize
 		if self.embedding_storage is None:
 			print("Run fetch_cell_embedding() first!")
@@ -353,7 +367,7 @@ class FastHigashi:
 		embedding = embedding - model.fit(var, embedding).predict(var)
 		if add_intercept_back:
 			embedding = embedding + model.intercept_[None]
-		reduce = TruncatedSVD(n_components=self.embedding_storage["embed_raw"].shape[-1]).fit_transform(embedding)
+		reduce = self._reduce(embedding, self.embedding_storage["embed_raw"].shape[-1], getattr(self, "_embed_svd", "host"))
 		self.embedding_storage["embed_correct_%s" % key] = reduce
 		self.embedding_storage["embed_l2_norm_correct_%s" % key] = normalize(reduce)
 		return self.embedding_storage

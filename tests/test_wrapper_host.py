@@ -131,3 +131,28 @@ def test_only_partial_rwr_assembly_logic(tmp_path, monkeypatch):
 				assert np.array_equal(got[str(fh.reorder[sl.start + i])], m)        # fp32 on the device == float64-then-cast
 	with pytest.raises(ValueError):
 		fh.only_partial_rwr(out_format="csv")
+
+
+def test_fetch_cell_embedding_device_svd_option(tmp_path):
+	"""svd="device" (dist_svd randomized SVD instead of sklearn's): same subspace and singular directions as the reference
+	output up to sign for the well-separated leading components; here it runs on the CPU device."""
+	fh = host_only_wrapper(str(tmp_path), str(tmp_path))
+	fh.device = "cpu"
+	reorder = G["reorder"]
+	fh.rank = 8
+	fh.meta_embedding = G["emb_meta"]
+	fh.D_list = [G["emb_D0"], G["emb_D1"]]
+	fh.coverage_feats = G["readcount"][reorder].reshape(-1, 1)
+	fh.reorder = reorder
+	fh.label_info = pd.DataFrame({"batch": G["batch"]}).iloc[reorder].reset_index()
+	np.random.seed(0)
+	store = fh.fetch_cell_embedding(final_dim=6, restore_order=True, svd="device")
+	np.testing.assert_allclose(store["embed_all"], G["emb_out_embed_all"], rtol=1e-10, atol=1e-12)
+	a, b = store["embed_raw"], G["emb_out_embed_raw"]
+	assert a.shape == b.shape
+	# rank-8 input, 6 components, 5 power iterations: both randomized SVDs have converged to the exact one
+	sgn = np.sign(np.sum(a * b, axis=0))
+	np.testing.assert_allclose(a * sgn, b, rtol=1e-6, atol=1e-8)
+	assert "embed_correct_coverage_fh" in store and store["embed_correct_coverage_fh"].shape == b.shape
+	with pytest.raises(ValueError):
+		fh.fetch_cell_embedding(final_dim=6, svd="gpu")
