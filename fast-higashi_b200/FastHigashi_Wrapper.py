@@ -151,7 +151,7 @@ class FastHigashi:
 			packed = ingest.preprocess_contact_map(self.config, reorder, ours, self.off_diag, res,
 			                                       getattr(self, "batch_id", None) if "batch_id" in self.config else None,
 			                                       self._batch_norm)
-			return [Sparse(torch.as_tensor(idx.astype(np.int64)), torch.as_tensor(val), shape, copy=False) for idx, val, shape in packed]
+			return [Sparse(torch.as_tensor(idx), torch.as_tensor(val), shape, copy=False) for idx, val, shape in packed]  # int32 ids: no copy
 		raise RuntimeError("no input tensors: call set_tensors(), or provide %s/raw/{chrom}_sparse_adj.npy, or a cache file %s"
 		                   % (self.temp_dir, ours))
 

@@ -435,3 +435,172 @@ extern "C" int fh_host_pack_fetch(void* handle, int32_t* indices, float* values)
 }
 
 extern "C" void fh_host_pack_free(void* handle) { delete (Packed*)handle; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Block-CSR staging (include/fh_host.h): COO (row, col, cell) -> per bin-block CSR over (cell, local row) with
+// window-local int16 columns. Two linear passes with per-row atomic counters / cursors instead of a sort of
+// nnz 64-bit keys; the entries of a row are then put in ascending column order (rows are short, and already in
+// order when the input is the pack stage's), which makes the result independent of the thread schedule.
+namespace {
+
+struct StageError {
+	int kind = 0;          // 1 = outside window, 2 = index out of range, 3 = duplicate
+	int64_t at = -1;       // entry (kinds 1, 2) or flattened (block, row) id (kind 3)
+	void set(int k, int64_t where) {
+#pragma omp critical(fh_stage_error)
+		if (kind == 0 || where < at) { kind = k; at = where; }
+	}
+};
+
+int check_geom(const fh_host_block_geom* g) {
+	if (!g) return fail(FH_HOST_EINVAL, "geometry == NULL");
+	if (g->num_bin <= 0 || g->bs_bin <= 0 || g->num_cell <= 0 || g->num_block <= 0 || !g->nb || !g->col0 || !g->w)
+		return fail(FH_HOST_EINVAL, "bad block geometry (num_bin %d, bs_bin %d, blocks %d, cells %lld)", g->num_bin, g->bs_bin,
+		            g->num_block, (long long)g->num_cell);
+	if ((int64_t)g->num_block * g->bs_bin < g->num_bin) return fail(FH_HOST_EINVAL, "blocks do not cover the %d bins", g->num_bin);
+	for (int b = 0; b < g->num_block; ++b) {
+		if (g->nb[b] <= 0 || g->nb[b] > g->bs_bin || g->w[b] <= 0 || g->col0[b] < 0)
+			return fail(FH_HOST_EINVAL, "bad geometry of block %d", b);
+		if (g->w[b] > 32767) return fail(FH_HOST_EINVAL, "window of block %d is %d columns wide: int16 column ids hold 32767", b, g->w[b]);
+		if ((int64_t)g->num_cell * g->nb[b] + 1 > INT32_MAX) return fail(FH_HOST_EINVAL, "cells x rows of block %d exceeds int32", b);
+	}
+	return FH_HOST_OK;
+}
+
+}  // namespace
+
+extern "C" int fh_host_block_csr_count(const void* row, const void* col, const void* cell, int32_t index_type, int64_t nnz,
+                                       const fh_host_block_geom* g, int32_t* const* rowptr, int64_t* nnz_block,
+                                       int32_t num_threads) {
+	if (int rc = check_geom(g)) return rc;
+	if (index_type != FH_HOST_I32 && index_type != FH_HOST_I64) return fail(FH_HOST_EINVAL, "index_type must be I32 or I64");
+	if (nnz < 0 || (nnz > 0 && (!row || !col || !cell)) || !rowptr || !nnz_block) return fail(FH_HOST_EINVAL, "NULL argument");
+	const int threads = thread_count(num_threads);
+	Tracer trace;
+	const int B = g->num_block;
+	for (int b = 0; b < B; ++b) {
+		if (!rowptr[b]) return fail(FH_HOST_EINVAL, "rowptr[%d] == NULL", b);
+		const int64_t rows = g->num_cell * g->nb[b] + 1;
+		int32_t* rp = rowptr[b];
+#pragma omp parallel for num_threads(threads) schedule(static)
+		for (int64_t i = 0; i < rows; ++i) rp[i] = 0;
+	}
+	StageError err;
+#pragma omp parallel for num_threads(threads) schedule(static)
+	for (int64_t k = 0; k < nnz; ++k) {
+		const int64_t r = load_index(row, k, index_type), c = load_index(col, k, index_type), z = load_index(cell, k, index_type);
+		if (r < 0 || r >= g->num_bin || z < 0 || z >= g->num_cell || c < 0) { err.set(2, k); continue; }
+		const int b = (int)(r / g->bs_bin);
+		const int64_t lc = c - g->col0[b];
+		if (lc < 0 || lc >= g->w[b]) { err.set(1, k); continue; }
+		int32_t* slot = rowptr[b] + (z * g->nb[b] + (r - (int64_t)b * g->bs_bin)) + 1;
+		__atomic_fetch_add(slot, 1, __ATOMIC_RELAXED);
+	}
+	if (err.kind == 2) return fail(FH_HOST_EINVAL, "entry %lld: index outside the (%d, *, %lld) tensor", (long long)err.at, g->num_bin, (long long)g->num_cell);
+	if (err.kind == 1) return fail(FH_HOST_EWINDOW, "entry %lld lies outside the window of its bin block", (long long)err.at);
+	trace.mark("block-CSR count");
+	int bad_block = -1;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+	for (int b = 0; b < B; ++b) {
+		int32_t* rp = rowptr[b];
+		const int64_t rows = g->num_cell * g->nb[b];
+		int64_t run = 0;
+		for (int64_t i = 1; i <= rows; ++i) {
+			run += rp[i];
+			rp[i] = (int32_t)run;   // checked below: a block holds fewer than 2^31 entries
+		}
+		nnz_block[b] = run;
+		if (run > INT32_MAX) {
+#pragma omp critical(fh_stage_error)
+			bad_block = b;
+		}
+	}
+	if (bad_block >= 0) return fail(FH_HOST_EINVAL, "block %d holds %lld entries: exceeds int32", bad_block, (long long)nnz_block[bad_block]);
+	trace.mark("block-CSR prefix sums");
+	return FH_HOST_OK;
+}
+
+extern "C" int fh_host_block_csr_fill(const void* row, const void* col, const void* cell, int32_t index_type, const float* val,
+                                      int64_t nnz, const fh_host_block_geom* g, int32_t* const* rowptr, int16_t* const* col_out,
+                                      float* const* val_out, int32_t num_threads) {
+	if (int rc = check_geom(g)) return rc;
+	if (index_type != FH_HOST_I32 && index_type != FH_HOST_I64) return fail(FH_HOST_EINVAL, "index_type must be I32 or I64");
+	if (nnz < 0 || (nnz > 0 && (!row || !col || !cell || !val)) || !rowptr || !col_out || !val_out) return fail(FH_HOST_EINVAL, "NULL argument");
+	const int threads = thread_count(num_threads);
+	Tracer trace;
+	const int B = g->num_block;
+	for (int b = 0; b < B; ++b) {
+		const int64_t rows = g->num_cell * g->nb[b];
+		if (!rowptr[b]) return fail(FH_HOST_EINVAL, "rowptr[%d] == NULL", b);
+		if (rowptr[b][rows] > 0 && (!col_out[b] || !val_out[b])) return fail(FH_HOST_EINVAL, "NULL output of block %d", b);
+	}
+	// scatter: rowptr[b][i] is the cursor of row i; afterwards it equals the original rowptr[b][i + 1]
+	StageError err;
+#pragma omp parallel for num_threads(threads) schedule(static)
+	for (int64_t k = 0; k < nnz; ++k) {
+		const int64_t r = load_index(row, k, index_type), c = load_index(col, k, index_type), z = load_index(cell, k, index_type);
+		if (r < 0 || r >= g->num_bin || z < 0 || z >= g->num_cell) { err.set(2, k); continue; }
+		const int b = (int)(r / g->bs_bin);
+		const int64_t lc = c - g->col0[b];
+		if (lc < 0 || lc >= g->w[b]) { err.set(1, k); continue; }
+		const int64_t rid = z * g->nb[b] + (r - (int64_t)b * g->bs_bin);
+		const int32_t pos = __atomic_fetch_add(rowptr[b] + rid, 1, __ATOMIC_RELAXED);
+		// the last pointer of a block is never a cursor: it bounds every write even if the pointers are not this input's
+		if (pos < 0 || pos >= rowptr[b][g->num_cell * g->nb[b]]) { err.set(5, k); continue; }
+		col_out[b][pos] = (int16_t)lc;
+		val_out[b][pos] = val[k];
+	}
+	// restore the row pointers (cursor i ended at the start of row i + 1) and verify that every row was filled exactly
+	int mismatch = 0;
+	for (int b = 0; b < B; ++b) {
+		int32_t* rp = rowptr[b];
+		const int64_t rows = g->num_cell * g->nb[b];
+		const int32_t total = rp[rows];
+		// rp[rows] was never a cursor: total is intact. Shift right by one.
+		int32_t prev = 0;
+		for (int64_t i = 0; i < rows; ++i) {
+			const int32_t ended = rp[i];
+			rp[i] = prev;
+			prev = ended;
+		}
+		if (prev != total) mismatch = 1;
+	}
+	if (err.kind == 2) return fail(FH_HOST_EINVAL, "entry %lld: index outside the tensor", (long long)err.at);
+	if (err.kind == 1) return fail(FH_HOST_EWINDOW, "entry %lld lies outside the window of its bin block", (long long)err.at);
+	if (mismatch || err.kind == 5) return fail(FH_HOST_EINVAL, "row pointers do not match the entries (not the output of fh_host_block_csr_count for this input)");
+	trace.mark("block-CSR scatter");
+	// ascending columns inside every row; equal neighbours are duplicates of one (row, col, cell)
+	for (int b = 0; b < B; ++b) {
+		const int32_t* rp = rowptr[b];
+		const int64_t rows = g->num_cell * g->nb[b];
+		int16_t* cb = col_out[b];
+		float* vb = val_out[b];
+#pragma omp parallel for num_threads(threads) schedule(static, 4096)
+		for (int64_t i = 0; i < rows; ++i) {
+			const int32_t lo = rp[i], hi = rp[i + 1];
+			if (hi < lo) { err.set(4, i); continue; }
+			bool sorted = true;
+			for (int32_t p = lo + 1; p < hi; ++p)
+				if (cb[p] <= cb[p - 1]) { sorted = false; break; }
+			if (sorted) continue;
+			for (int32_t p = lo + 1; p < hi; ++p) {   // insertion sort: rows hold at most a window of entries
+				const int16_t c = cb[p];
+				const float v = vb[p];
+				int32_t q = p;
+				while (q > lo && cb[q - 1] > c) { cb[q] = cb[q - 1]; vb[q] = vb[q - 1]; --q; }
+				cb[q] = c; vb[q] = v;
+			}
+			for (int32_t p = lo + 1; p < hi; ++p)
+				if (cb[p] == cb[p - 1]) { err.set(3, (int64_t)b * ((int64_t)1 << 40) + i); break; }
+		}
+	}
+	if (err.kind == 4) return fail(FH_HOST_EINVAL, "row pointers are not monotone");
+	if (err.kind == 3) {
+		const int b = (int)(err.at >> 40);
+		const int64_t i = err.at & (((int64_t)1 << 40) - 1);
+		return fail(FH_HOST_EDUP, "duplicate (row, col, cell) entries: block %d, cell %lld, local row %lld", b, (long long)(i / g->nb[b]),
+		            (long long)(i % g->nb[b]));
+	}
+	trace.mark("block-CSR row order");
+	return FH_HOST_OK;
+}

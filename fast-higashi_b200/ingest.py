@@ -20,7 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfh_host.so")
 EXPORTS = ["fh_host_last_error", "fh_host_version", "fh_host_qc_chrom", "fh_host_pack_chrom", "fh_host_pack_fetch",
-           "fh_host_pack_free"]
+           "fh_host_pack_free", "fh_host_block_csr_count", "fh_host_block_csr_fill"]
 _I32, _I64, _F32, _F64 = 0, 1, 2, 3
 _DTYPES = {np.dtype(np.int32): _I32, np.dtype(np.int64): _I64, np.dtype(np.float32): _F32, np.dtype(np.float64): _F64}
 
@@ -32,6 +32,11 @@ class IngestError(RuntimeError):
 class _Cells(C.Structure):
 	_fields_ = [("num_cell", C.c_int64), ("n_row", C.c_int32), ("n_col", C.c_int32), ("indptr", C.c_void_p),
 	            ("indices", C.c_void_p), ("data", C.c_void_p), ("index_type", C.c_int32), ("data_type", C.c_int32)]
+
+
+class _BlockGeom(C.Structure):
+	_fields_ = [("num_bin", C.c_int32), ("bs_bin", C.c_int32), ("num_block", C.c_int32), ("nb", C.c_void_p), ("col0", C.c_void_p),
+	            ("w", C.c_void_p), ("num_cell", C.c_int64)]
 
 
 class _PackOpts(C.Structure):
@@ -55,13 +60,19 @@ def lib():
 		L.fh_host_pack_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 		L.fh_host_pack_free.argtypes = [C.c_void_p]
 		L.fh_host_pack_free.restype = None
+		L.fh_host_block_csr_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.POINTER(_BlockGeom),
+		                                      C.c_void_p, C.c_void_p, C.c_int32]
+		L.fh_host_block_csr_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+		                                     C.POINTER(_BlockGeom), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
 		_lib = L
 	return _lib
 
 
 def _check(rc):
 	if rc != 0:
-		raise IngestError("libfh_host: %s (code %d)" % (lib().fh_host_last_error().decode(), rc))
+		e = IngestError("libfh_host: %s (code %d)" % (lib().fh_host_last_error().decode(), rc))
+		e.code = rc
+		raise e
 
 
 def num_threads():
@@ -200,3 +211,43 @@ def preprocess_contact_map(config, reorder, path2input_cache, off_diag, res, bat
 		with open(path2input_cache, "wb") as f:
 			pickle.dump(out, f, protocol=4)
 	return out
+
+
+# ------------------------------------------------------------------------------------------------
+def block_csr(indices, values, num_bin, bs_bin, num_cell, nb, col0, w):
+	"""COO chromosome tensor -> the per-bin-block CSR arrays of `sparse_for_schic.Chrom_Dataset`
+	(replaces the reference's bin-block x cell-batch split, sparse_for_schic.py:440-499).
+	`indices`: (3, nnz) int32/int64 numpy [row, col, cell], any order; `values`: (nnz,) float32;
+	`nb`, `col0`, `w`: per-block rows, first window column, window width.
+	Returns ([rowptr int32], [col int16], [val float32]) as numpy arrays, one per block.
+	Raises IngestError; `.code` is the library's (FH_HOST_EWINDOW = -4, FH_HOST_EDUP = -5)."""
+	indices = np.asarray(indices)
+	if indices.ndim != 2 or indices.shape[0] != 3:
+		raise IngestError("indices must be (3, nnz)")
+	if indices.dtype not in (np.dtype(np.int32), np.dtype(np.int64)):
+		indices = indices.astype(np.int64)
+	rows = [np.ascontiguousarray(indices[i]) for i in range(3)]  # views when `indices` is C-contiguous
+	values = np.ascontiguousarray(values, dtype=np.float32)
+	nnz = int(values.shape[0])
+	if indices.shape[1] != nnz:
+		raise IngestError("indices must be (3, nnz)")
+	nb = np.ascontiguousarray(nb, dtype=np.int32)
+	col0 = np.ascontiguousarray(col0, dtype=np.int32)
+	w = np.ascontiguousarray(w, dtype=np.int32)
+	B = len(nb)
+	geom = _BlockGeom(int(num_bin), int(bs_bin), B, nb.ctypes.data, col0.ctypes.data, w.ctypes.data, int(num_cell))
+	itype = _DTYPES[indices.dtype]
+	L = lib()
+	rowptr = [np.empty(int(num_cell) * int(n) + 1, dtype=np.int32) for n in nb]
+	rp_tab = np.array([a.ctypes.data for a in rowptr], dtype=np.uintp)
+	nnz_block = np.zeros(B, dtype=np.int64)
+	ptrs = [a.ctypes.data if nnz else None for a in rows]
+	_check(L.fh_host_block_csr_count(ptrs[0], ptrs[1], ptrs[2], itype, nnz, C.byref(geom), rp_tab.ctypes.data,
+	                                 nnz_block.ctypes.data, num_threads()))
+	col = [np.empty(int(n), dtype=np.int16) for n in nnz_block]
+	val = [np.empty(int(n), dtype=np.float32) for n in nnz_block]
+	c_tab = np.array([a.ctypes.data for a in col], dtype=np.uintp)
+	v_tab = np.array([a.ctypes.data for a in val], dtype=np.uintp)
+	_check(L.fh_host_block_csr_fill(ptrs[0], ptrs[1], ptrs[2], itype, values.ctypes.data if nnz else None, nnz, C.byref(geom),
+	                                rp_tab.ctypes.data, c_tab.ctypes.data, v_tab.ctypes.data, num_threads()))
+	return rowptr, col, val

@@ -135,6 +135,13 @@ class Chrom_Dataset:
 		if not torch.is_tensor(idx): idx = torch.as_tensor(np.ascontiguousarray(idx))
 		if not torch.is_tensor(val): val = torch.as_tensor(np.ascontiguousarray(val))
 		dev = torch.device(device) if device is not None else idx.device
+		if idx.device.type == "cpu":
+			self._build_host(idx, val, dev)
+		else:
+			self._build_sort(idx, val, dev)
+
+	def _build_sort(self, idx, val, dev):
+		"""COO already on the device: one device sort of 64-bit keys."""
 		idx = idx.to(dev)
 		val = val.to(dev, torch.float32)
 		C = self.total_cell_num
@@ -168,6 +175,27 @@ class Chrom_Dataset:
 			self.rowptr.append(rp.int())
 			self.col.append(lcol[lo:hi].short())
 			self.val.append(val[lo:hi].clone())  # own allocation: the kernels need 16-byte aligned bases
+		self.device = dev
+
+	def _build_host(self, idx, val, dev):
+		"""COO in host memory: two counting passes in libfh_host.so (include/fh_host.h `fh_host_block_csr_*`, OpenMP),
+		then one upload per array. Same arrays, bit for bit, as the device-sort route of `_build`."""
+		from . import ingest
+		g = self.geoms
+		try:
+			rowptr, col, vals = ingest.block_csr(idx.numpy(), val.to(torch.float32).numpy(), self.num_bin, self.bs_bin,
+			                                     self.total_cell_num, [x.nb for x in g], [x.col0 for x in g], [x.w for x in g])
+		except ingest.IngestError as e:
+			code = getattr(e, "code", 0)
+			if code == -4:
+				raise ValueError("%s: contact outside the +-flank window (|col-row| > flank=%d); filter "
+				                 "with off_diag first (FastHigashi_Wrapper.py:265-269)" % (self.chrom, self.flank)) from e
+			if code == -5:
+				raise ValueError("%s: duplicate (row, col, cell) entries; sum duplicates first (%s)" % (self.chrom, e)) from e
+			raise
+		self.rowptr = [torch.from_numpy(a).to(dev) for a in rowptr]
+		self.col = [torch.from_numpy(a).to(dev) for a in col]
+		self.val = [torch.from_numpy(a).to(dev) for a in vals]
 		self.device = dev
 
 	@classmethod

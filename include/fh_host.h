@@ -7,6 +7,8 @@
  *   fh_host_pack_chrom  <- pack_training_data_one_process  :221-366 with
  *                          preprocessing.filter_bin :474-489, normalize_per_batch :232-292,
  *                          norm2 :195-215, normalize_by_coverage :137-142
+ *   fh_host_block_csr_* <- sparse_for_schic.py:356-510 (Chrom_Dataset.__init__: the bin-block x cell-batch
+ *                          split into Fake_Sparse objects, :322-353), producing the device layout instead
  * The reference walks a Python list of scipy matrices (one object per cell, about ten passes);
  * here one call handles a chromosome with the cells spread over the host threads.
  *
@@ -22,7 +24,7 @@
 extern "C" {
 #endif
 
-enum { FH_HOST_OK = 0, FH_HOST_EINVAL = -1, FH_HOST_ENOMEM = -2, FH_HOST_ENAN = -3 };
+enum { FH_HOST_OK = 0, FH_HOST_EINVAL = -1, FH_HOST_ENOMEM = -2, FH_HOST_ENAN = -3, FH_HOST_EWINDOW = -4, FH_HOST_EDUP = -5 };
 /* element types of the scipy arrays */
 enum { FH_HOST_I32 = 0, FH_HOST_I64 = 1, FH_HOST_F32 = 2, FH_HOST_F64 = 3 };
 
@@ -62,6 +64,31 @@ int fh_host_pack_chrom(const fh_host_cells* cells, const fh_host_pack_opts* opts
  * entries are cell-major, row-major inside a cell (the reference's order). */
 int fh_host_pack_fetch(void* handle, int32_t* indices, float* values);
 void fh_host_pack_free(void* handle);
+
+/* Block-CSR staging: the chromosome tensor as COO (row, col, cell; any order) -> for every bin block b ONE CSR over
+ * (cell, local row): rowptr int32 [num_cell * nb[b] + 1], window-local columns int16 (col - col0[b]), values fp32,
+ * columns ascending inside a row. This is the layout fh_rwr_batched / fh_densify read (include/fh_b200.h); the
+ * reference builds one pinned COO object per (bin block, cell batch) instead (sparse_for_schic.py:440-499). */
+typedef struct {
+	int32_t num_bin;                /* rows (= columns) of the chromosome tensor */
+	int32_t bs_bin;                 /* rows per bin block; block of row r = r / bs_bin */
+	int32_t num_block;
+	const int32_t* nb;              /* [num_block] rows of block b (bs_bin except the last) */
+	const int32_t* col0;            /* [num_block] first global column of the block's window */
+	const int32_t* w;               /* [num_block] window width (<= 32767) */
+	int64_t num_cell;               /* cells (good-QC first, then bad-QC: the caller's order is kept) */
+} fh_host_block_geom;
+
+/* pass 1: rowptr[b] (caller-allocated, [num_cell * nb[b] + 1]) and nnz_block[b]. index_type: FH_HOST_I32 | FH_HOST_I64.
+ * FH_HOST_EWINDOW when a contact lies outside its block's window (|col - row| > flank: filter with off_diag first). */
+int fh_host_block_csr_count(const void* row, const void* col, const void* cell, int32_t index_type, int64_t nnz,
+                            const fh_host_block_geom* geom, int32_t* const* rowptr, int64_t* nnz_block, int32_t num_threads);
+/* pass 2: col_out[b] int16 [nnz_block[b]], val_out[b] fp32 [nnz_block[b]] (caller-allocated). rowptr is pass 1's output
+ * for the same input; it is used as scratch during the call and restored. FH_HOST_EDUP when two entries share
+ * (row, col, cell). The result does not depend on the thread count or schedule. */
+int fh_host_block_csr_fill(const void* row, const void* col, const void* cell, int32_t index_type, const float* val,
+                           int64_t nnz, const fh_host_block_geom* geom, int32_t* const* rowptr, int16_t* const* col_out,
+                           float* const* val_out, int32_t num_threads);
 
 #ifdef __cplusplus
 }

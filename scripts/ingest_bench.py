@@ -50,7 +50,7 @@ def main():
 		idx, val, shape = ingest.pack_training_data_one_process(os.path.join(tmp, "raw"), "chr1", reorder, args.off_diag)
 		out["pack_s"] = time.perf_counter() - t
 		t = time.perf_counter()
-		ds = Chrom_Dataset(Sparse(idx.astype(np.int64), val, shape, copy=False), bs_bin=125, bs_cell=args.cells, compact=True,
+		ds = Chrom_Dataset(Sparse(idx, val, shape, copy=False), bs_bin=125, bs_cell=args.cells, compact=True,
 		                   flank=args.off_diag, chrom="chr1", resolution=500000, device="cpu")
 		out["block_csr_cpu_s"] = time.perf_counter() - t
 		out["nnz"] = int(len(val))

@@ -76,3 +76,67 @@ def test_geometry_matches_reference_at_full_baseline_sizes():
 			assert np.array_equal(mine, ref), (case, ci)
 			blocks += len(mine)
 	assert blocks == 348
+
+
+def _random_coo(rng, n, ncell, flank, density, dtype):
+	"""Unique (row, col, cell) entries inside the band |col - row| <= flank, in random order."""
+	r, c, z = np.meshgrid(np.arange(n), np.arange(n), np.arange(ncell), indexing="ij")
+	keep = (np.abs(r - c) <= flank) & (rng.random(r.shape) < density)
+	idx = np.stack([r[keep], c[keep], z[keep]]).astype(dtype)
+	perm = rng.permutation(idx.shape[1])
+	return idx[:, perm], rng.random(idx.shape[1]).astype(np.float32)
+
+
+def _sort_route(idx, val, shape, **kw):
+	"""The device-sort route of Chrom_Dataset (taken when the COO is already on the GPU), run on CPU tensors."""
+	ds = object.__new__(Chrom_Dataset)
+	ref = Chrom_Dataset(Sparse(np.zeros((3, 0), np.int64), np.zeros(0, np.float32), shape), **kw)
+	ds.__dict__.update(ref.__dict__)
+	ds._build_sort(torch.as_tensor(idx.astype(np.int64)), torch.as_tensor(val), torch.device("cpu"))
+	return ds
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64])
+@pytest.mark.parametrize("n,bs_bin,flank,compact", [(90, 32, 12, True), (50, 50, 100, True), (37, 8, 5, True), (40, 16, 40, False)])
+def test_native_block_csr_equals_sort_route(dtype, n, bs_bin, flank, compact, monkeypatch):
+	"""libfh_host's counting passes (host COO) and the 64-bit key sort (device COO) give the same arrays bit for bit, for
+	shuffled input, both index widths, empty cells/rows, and any host thread count."""
+	rng = np.random.default_rng(n + bs_bin)
+	ncell = 7
+	idx, val = _random_coo(rng, n, ncell, flank, 0.3, dtype)
+	idx = idx[:, idx[2] != 3]            # one cell without contacts
+	val = val[:idx.shape[1]]
+	kw = dict(bs_bin=bs_bin, bs_cell=4, good_qc_num=5, compact=compact, flank=flank)
+	want = _sort_route(idx, val, (n, n, ncell), **kw)
+	for threads in ("1", "3", "0"):
+		monkeypatch.setenv("FH_HOST_THREADS", threads)
+		got = Chrom_Dataset(Sparse(idx, val, (n, n, ncell), copy=False), **kw)
+		assert len(got.rowptr) == len(want.rowptr) == len(got.geoms)
+		for b in range(len(got.geoms)):
+			assert got.rowptr[b].dtype == torch.int32 and got.col[b].dtype == torch.int16 and got.val[b].dtype == torch.float32
+			assert torch.equal(got.rowptr[b], want.rowptr[b])
+			assert torch.equal(got.col[b], want.col[b])
+			assert torch.equal(got.val[b], want.val[b])
+		assert got.nnz() == idx.shape[1]
+
+
+def test_native_block_csr_empty_tensor_and_errors():
+	from fasthigashi_b200 import ingest
+	ds = Chrom_Dataset(Sparse(np.zeros((3, 0), np.int64), np.zeros(0, np.float32), (20, 20, 3)), 8, 3, compact=True, flank=4)
+	assert ds.nnz() == 0 and [len(r) for r in ds.rowptr] == [3 * 8 + 1, 3 * 8 + 1, 3 * 4 + 1]
+	# error codes of the C ABI (include/fh_host.h)
+	geom = dict(num_bin=20, bs_bin=8, num_cell=3, nb=[8, 8, 4], col0=[0, 4, 12], w=[12, 16, 8])
+	with pytest.raises(ingest.IngestError) as e:
+		ingest.block_csr(np.array([[9], [3], [0]]), np.ones(1, np.float32), **geom)       # column left of the window
+	assert e.value.code == -4
+	with pytest.raises(ingest.IngestError) as e:
+		ingest.block_csr(np.array([[9, 9], [5, 5], [1, 1]]), np.ones(2, np.float32), **geom)
+	assert e.value.code == -5 and "cell 1" in str(e.value)
+	with pytest.raises(ingest.IngestError) as e:
+		ingest.block_csr(np.array([[20], [19], [0]]), np.ones(1, np.float32), **geom)     # row outside the tensor
+	assert e.value.code == -1
+	with pytest.raises(ingest.IngestError) as e:
+		ingest.block_csr(np.array([[1], [1], [3]]), np.ones(1, np.float32), **geom)       # cell outside the tensor
+	assert e.value.code == -1
+	with pytest.raises(ingest.IngestError):
+		ingest.block_csr(np.zeros((3, 0), np.int64), np.zeros(0, np.float32), 20, 8, 3, [8, 8, 4], [0, 4, 12], [12, 40000, 8])
