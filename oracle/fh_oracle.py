@@ -180,6 +180,16 @@ class OracleCore:
 		for ds in schic:
 			r = min(int(ds.num_bin * size_ratio * ds.resolution / 1000000), self.rank)
 			self.chrom2size[ds.chrom] = min(self.chrom2size.get(ds.chrom, r), r)
+		# multi-resolution stacking (:581-592): the datasets of one chromosome (one per resolution) share B and D and
+		# their bins are stacked along mode 0 of that chromosome's projected tensor
+		self.chrom2id = {c: [] for c in self.chrom2size}
+		self.chrom2num_bin = {}
+		self.gslice = []
+		for ci, ds in enumerate(schic):
+			self.chrom2id[ds.chrom].append(ci)
+			start = self.chrom2num_bin.get(ds.chrom, 0)
+			self.gslice.append(slice(start, start + ds.num_bin))
+			self.chrom2num_bin[ds.chrom] = start + ds.num_bin
 
 	def _imputed(self, ds, ci, b, c0, c1, do_conv, do_rwr, do_col, bad=False, k=None):
 		g = ds.geoms[b]
@@ -310,18 +320,15 @@ class OracleCore:
 		V, _ = polar(svd_term.T, self.rank)
 		x_V = float((V * svd_term.T).sum())
 		self.meta_embedding = V
-		self.projected = {}
+		self.projected = {c: torch.zeros(self.chrom2num_bin[c], self.chrom2size[c], self.rank) for c in self.chrom2size}
 		for ci, ds in enumerate(schic):
-			Y = torch.zeros(ds.num_bin, self.chrom2size[ds.chrom], self.rank)
+			Y = self.projected[ds.chrom][self.gslice[ci]]   # this resolution's rows of the stacked tensor (:526-529)
 			for b, g in enumerate(ds.geoms):
 				acc = 0
 				for sl in ds.cell_slice_list[:ds.num_cell_batch]:
 					X = self._imputed(ds, ci, b, sl.start, sl.stop, do_conv, do_rwr, do_col).permute(1, 2, 0)
 					acc = acc + torch.einsum("ijk,km,ijl->ilm", X, V[sl], self.projection_list[ci][b])
 				Y[g.row0:g.row0 + g.nb] = acc
-			# multi-resolution stacking (global_slice_bin) is handled by the caller order: one
-			# dataset per chromosome here, as in every BASELINE config
-			self.projected[ds.chrom] = Y
 		return x_U, x_V, xnorm
 
 	def core_norms(self, schic):
@@ -348,10 +355,12 @@ class OracleCore:
 			self.loss_terms.append(dict(xnorm=xnorm.copy(), core=core.copy(), x_U=x_U.copy(), x_V=x_V))
 			err_U = xnorm + core - 2 * x_U
 			err_V = xnorm.sum() + core.sum() - 2 * x_V
-			for ci, ds in enumerate(schic):
-				fac, _, _ = cp_als(self.projected[ds.chrom], [self.A_list[ci], self.B_dict[ds.chrom], self.D_dict[ds.chrom]],
-				                   n_iter_parafac)
-				self.A_list[ci], self.B_dict[ds.chrom], self.D_dict[ds.chrom] = fac
+			for chrom, ids in self.chrom2id.items():   # one CP-ALS per chromosome over the stacked bins (:670-695)
+				fac, _, _ = cp_als(self.projected[chrom], [torch.cat([self.A_list[i] for i in ids], 0), self.B_dict[chrom],
+				                                           self.D_dict[chrom]], n_iter_parafac)
+				for i in ids:
+					self.A_list[i] = fac[0][self.gslice[i]].clone()
+				self.B_dict[chrom], self.D_dict[chrom] = fac[1], fac[2]
 			core = self.core_norms(schic)
 			self.re_trace.append(float(np.sqrt(err_V) / np.sqrt(xnorm.sum())))
 			per_chrom.append(np.sqrt(err_U) / np.sqrt(xnorm))

@@ -41,3 +41,19 @@ def load_small_dataset(good_qc_num=-1, bs_cell=None, bs_bin=None, device="cpu"):
 def rel_fro(a, b):
 	a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
 	return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def load_multires_dataset(device="cpu"):
+	"""tests/golden/core_multires.npz: the same chromosomes at two resolutions, resolution-major (the wrapper's order)."""
+	import fasthigashi_b200  # noqa: F401
+	from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset
+	g = np.load(os.path.join(GOLDEN, "core_multires.npz"))
+	ncell, off = int(g["ncell"]), int(g["off_diag"])
+	out = []
+	for li in range(int(g["nlevel"])):
+		for i, n in enumerate(g["bins%d" % li]):
+			ch = "chr%d" % (i + 1)
+			sp = Sparse(g["l%d_%s_idx" % (li, ch)].astype(np.int64), g["l%d_%s_val" % (li, ch)], (int(n), int(n), ncell))
+			out.append(Chrom_Dataset(sp, bs_bin=int(g["bs_bin"][li]), bs_cell=ncell, compact=True, flank=off, chrom=ch,
+			                         resolution=int(g["res"][li]), device=device))
+	return out, g

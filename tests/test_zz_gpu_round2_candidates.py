@@ -120,3 +120,37 @@ def test_polar_block_jacobi_on_device():
 	r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
 	                    "-k", "polar or lockstep", "-p", "no:cacheprovider"], env=e, cwd=root, capture_output=True, text=True, timeout=900)
 	assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_multi_resolution_run_matches_reference_fixture():
+	"""Two resolutions of the same chromosomes (parafac2_intergrative.py:581-592, 670-695: shared B / D per chromosome,
+	bins stacked along mode 0 of the projected tensor, one CP-ALS per chromosome) against the UNMODIFIED reference's
+	run (tests/golden/core_multires.npz, to which the oracle is pinned by tests/test_oracle_golden.py):
+	(a) lock-step from the reference's init state: loss of every sweep <= 1e-4 relative;
+	(b) the full run from the shared seeds (init included): n_i, loss trace, embeddings Pearson >= 0.999."""
+	from conftest import load_multires_dataset, rel_fro
+	from fasthigashi_b200.parafac2_intergrative import Fast_Higashi_core
+	ds, g = load_multires_dataset()
+	res_list = [int(r) for r in g["res"]]
+	nchrom, nsweep = len(g["chrom2size"]), int(g["nsweep"])
+	state = ([g["t0_A%d" % i] for i in range(len(ds))], [g["t0_B%d" % c] for c in range(nchrom)],
+	         [g["t0_D%d" % c] for c in range(nchrom)], g["t0_V"], [g["bin_cov%d" % i] for i in range(len(ds))], [0] * len(ds), g["n_i"])
+	core = Fast_Higashi_core(int(g["rank"]), int(g["off_diag"]), res_list).to("cuda:0")
+	core.fit(ds, 0.3, nsweep, 1, True, True, False, 0.0, verbose=False, state=state)
+	assert list(core.chrom2size.values()) == list(g["chrom2size"])
+	re = np.array(core.re_trace)
+	assert np.max(np.abs(re - g["re"]) / g["re"]) < 1e-4, (re, g["re"])
+	core = Fast_Higashi_core(int(g["rank"]), int(g["off_diag"]), res_list).to("cuda:0")
+	torch.manual_seed(0); np.random.seed(0)
+	ds2, _ = load_multires_dataset()
+	_, (A_list, B_list, D_list, V), _ = core.fit_transform(ds2, size_ratio=0.3, n_iter_max=nsweep, n_iter_parafac=1, do_conv=True,
+	                                                      do_rwr=True, do_col=False, tol=0.0, gpu_id=0, run_init=True)
+	assert list(core.n_i) == list(g["n_i"])
+	re = np.array(core.re_trace)
+	assert np.max(np.abs(re - g["re"]) / g["re"]) < 1e-4, (re, g["re"])
+	E = O.embed_all(np.asarray(V), [np.asarray(d) for d in D_list])
+	Eref = O.embed_all(g["final_V"], [g["final_D%d" % c] for c in range(nchrom)])
+	for j in range(E.shape[1]):
+		assert abs(np.corrcoef(E[:, j], Eref[:, j])[0, 1]) > 0.999
+	for i in range(len(ds)):
+		assert tuple(A_list[i].shape) == g["final_A%d" % i].shape
