@@ -5,7 +5,9 @@
   3xFP16   the same split into two binary16 values after a power-of-two scaling of each operand matrix; kind::f16
            MMAs run at twice the TF32 rate and the operands take half the shared-memory bytes
   3xBF16   hi/lo bf16 (16 mantissa bits in total): shown as the negative control
-  1xTF32   a single TF32 product
+  2xFP16   (a_hi + a_lo) * b_hi: only one operand split; 1xFP16: a_hi * b_hi (binary16 rounds to nearest, so the error of
+           non-negative operands - everything in the RWR chain is >= 0 - averages out instead of adding up)
+  1xTF32   a single TF32 product (the tensor core truncates: a coherent bias)
 
 Operands are split exactly as a kernel would; every product is then accumulated in fp64 here, so the numbers isolate the
 operand-representation error (the tensor core's truncating fp32 accumulation is a separate, measured effect).
@@ -66,6 +68,17 @@ def mm3(split, a, b):
 	return (ah @ bh + (ah @ bl + al @ bh)).astype(np.float32)
 
 
+def mm2_f16(a, b):
+	"""Two products: a (both halves) times the hi half of b only."""
+	ah, al = split_f16(a.astype(np.float32))
+	bh, _ = split_f16(b.astype(np.float32))
+	return (ah @ bh + al @ bh).astype(np.float32)
+
+
+def mm1_f16(a, b):
+	return (split_f16(a.astype(np.float32))[0] @ split_f16(b.astype(np.float32))[0]).astype(np.float32)
+
+
 def mm1(a, b):
 	return (split_tf32(a.astype(np.float32))[0] @ split_tf32(b.astype(np.float32))[0]).astype(np.float32)
 
@@ -93,7 +106,7 @@ def main():
 	idx, val = synth.synth_chrom(n, ncell, 0.05, off, 5, np.arange(ncell) % 4, 4)
 	ds = Chrom_Dataset(Sparse(idx, val, (n, n, ncell), copy=False), bs_bin=115, bs_cell=ncell, compact=True, flank=off)
 	schemes = {"3xTF32": lambda a, b: mm3(split_tf32, a, b), "3xFP16_scaled": lambda a, b: mm3(split_f16, a, b),
-	           "3xBF16": lambda a, b: mm3(split_bf16, a, b), "1xTF32": mm1, "fp32_numpy": lambda a, b: a @ b}
+	           "3xBF16": lambda a, b: mm3(split_bf16, a, b), "2xFP16_scaled": mm2_f16, "1xFP16_scaled": mm1_f16, "1xTF32": mm1, "fp32_numpy": lambda a, b: a @ b}
 	errs = {k: [] for k in schemes}
 	for b, g in enumerate(ds.geoms):
 		x = O.densify_block(ds, b, 0, ncell)
