@@ -81,6 +81,12 @@ def check(rc):
 		raise FHError("libfh_b200: %s (code %d)" % (lib().fh_last_error().decode(), rc))
 
 
+def require_cuda(device, what="fasthigashi_b200"):
+	"""The one place that enforces "no CPU path" for the core objects."""
+	if torch.device(device).type != "cuda":
+		raise FHError("%s runs on CUDA devices only (got %s); there is no CPU path" % (what, device))
+
+
 def stream_ptr():
 	return torch.cuda.current_stream().cuda_stream
 

@@ -59,8 +59,7 @@ class Fast_Higashi_core:
 
 	def to(self, device):
 		self.device = torch.device(device)
-		if self.device.type != "cuda":
-			raise _lib.FHError("fasthigashi_b200 runs on CUDA devices only; there is no CPU path")
+		_lib.require_cuda(self.device)
 		_lib.lib()
 		if self.use_tc is None:
 			self.use_tc = True  # tcgen05 3xTF32 for the large contractions (csrc/fh_gemm_tc.cu)
@@ -529,8 +528,7 @@ class Fast_Higashi_core:
 	            run_init=True, state=None):
 		"""Everything `fit` does before its sweep loop (:551-632)."""
 		dev, R = self.device, self.rank
-		if self.device.type != "cuda":
-			raise _lib.FHError("call .to('cuda') first; fasthigashi_b200 has no CPU path")
+		_lib.require_cuda(getattr(self, "device", "cpu"), "Fast_Higashi_core (call .to('cuda') first)")
 		self._setup(schic, size_ratio, size_list)
 		self._log("empty params initialized")
 		if state is not None:

@@ -1,0 +1,188 @@
+"""The product's Python orchestration (`Fast_Higashi_core`: operand layouts / strides handed to the C ABI, the order of
+the stages, what is all-reduced when cells are sharded) run on the CPU against tests/emu/fake_abi.py - a host-memory
+stand-in that evaluates the documented contract of every include/fh_b200.h entry point in fp64. The CUDA kernels are NOT
+exercised here (tests/test_gpu_parity.py does that on the B200); these tests pin everything between the reference-facing
+API and the C ABI to the reference's own runs (tests/golden/core_*.npz)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_small_dataset, load_multires_dataset, rel_fro
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import fake_abi  # noqa: E402
+from oracle import fh_oracle as O  # noqa: E402
+
+
+@pytest.fixture
+def fake():
+	f, undo = fake_abi.install()
+	try:
+		yield f
+	finally:
+		undo()
+
+
+def _core(rank, off_diag, res_list, **kw):
+	from fasthigashi_b200.parafac2_intergrative import Fast_Higashi_core
+	return Fast_Higashi_core(rank, off_diag, res_list, **kw).to("cpu")
+
+
+def _state(g, nds, nchrom):
+	return ([g["t0_A%d" % i] for i in range(nds)], [g["t0_B%d" % c] for c in range(nchrom)], [g["t0_D%d" % c] for c in range(nchrom)],
+	        g["t0_V"], [g["bin_cov%d" % i] for i in range(nds)],
+	        [g["bad_bin_cov%d" % i] if "bad_bin_cov%d" % i in g.files else 0 for i in range(nds)], g["n_i"])
+
+
+@pytest.mark.parametrize("tag", ["nocol", "col"])
+def test_full_run_matches_reference_fixture(fake, tag):
+	"""fit_transform from the shared seeds: init (auto-stop RWR counts, coverage, pooled features, host SVD), every sweep's
+	loss, transform incl. bad-QC cells, embeddings - against the unmodified reference's run."""
+	g = np.load(os.path.join(GOLDEN, "core_%s.npz" % tag))
+	good = int(g["good_qc_num"])
+	ds = load_small_dataset(good_qc_num=good if good < 48 else -1, bs_cell=int(g["bs_cell"]))
+	core = _core(int(g["rank"]), 12, [1000000])
+	torch.manual_seed(0); np.random.seed(0)
+	nsweep = int(g["nsweep"])
+	_, (A_list, B_list, D_list, V), proj = core.fit_transform(ds, size_ratio=0.3, n_iter_max=nsweep, n_iter_parafac=1, do_conv=True,
+	                                                         do_rwr=True, do_col=bool(g["do_col"]), tol=0.0, verbose=False)
+	assert list(core.n_i) == list(g["n_i"])
+	re = np.array(core.re_trace)
+	assert np.max(np.abs(re - g["re"]) / g["re"]) < 1e-4, (re, g["re"])
+	assert tuple(V.shape) == (48, int(g["rank"]))                      # good AND bad-QC cells
+	E = O.embed_all(V.numpy(), [d.numpy() for d in D_list])
+	Eref = O.embed_all(g["final_V"], [g["final_D%d" % i] for i in range(3)])
+	for j in range(E.shape[1]):
+		assert abs(np.corrcoef(E[:, j], Eref[:, j])[0, 1]) > 0.999
+	for i in range(3):
+		fin = np.isfinite(g["bin_cov%d" % i])
+		assert np.array_equal(np.isfinite(core.bin_cov_list[i].numpy()), fin)
+		assert rel_fro(core.bin_cov_list[i].numpy()[fin], g["bin_cov%d" % i][fin]) < 1e-5
+		for b, U in enumerate(proj[i]):
+			assert tuple(U.shape) == g["final_U%d_%d" % (i, b)].shape
+	assert fake.calls["rwr_batched"] > 0 and fake.calls["polar_isqrt_multi"] == nsweep and fake.calls["cp_als"] == 3 * nsweep
+
+
+def test_lockstep_from_reference_state_and_rwr_cache_modes(fake):
+	"""From the reference's init state: per-sweep loss terms and the projected tensors; cache='run' (one RWR pass per
+	run) gives the same numbers as cache='sweep' with a third of the RWR calls."""
+	g = np.load(os.path.join(GOLDEN, "core_nocol.npz"))
+	out = {}
+	for cache in ("sweep", "run"):
+		fake.calls.clear()
+		core = _core(int(g["rank"]), 12, [1000000], cache=cache)
+		core.fit(load_small_dataset(), 0.3, 3, 1, True, True, False, 0.0, verbose=False, state=_state(g, 3, 3))
+		out[cache] = (np.array(core.re_trace), fake.calls["rwr_batched"], core)
+	re, calls, core = out["sweep"]
+	assert np.max(np.abs(re - g["re"][:3]) / g["re"][:3]) < 1e-4
+	for t in range(3):
+		assert rel_fro(core.loss_terms[t]["x_U"], g["t%d_x_U" % t]) < 1e-4
+		assert abs(core.loss_terms[t]["x_V"] - float(g["t%d_x_V" % t])) / abs(float(g["t%d_x_V" % t])) < 1e-4
+	assert rel_fro(core.loss_terms[0]["xnorm"], g["xnorm"]) < 1e-5
+	assert np.allclose(out["run"][0], re, rtol=1e-6) and out["run"][1] * 3 == calls
+
+
+def test_multi_resolution_matches_reference_fixture(fake):
+	"""Two resolutions of the same chromosomes (shared B / D, bins stacked in the projected tensor, one CP-ALS per
+	chromosome): lock-step from the reference's state, then the full run from the seeds."""
+	ds, g = load_multires_dataset()
+	res_list = [int(r) for r in g["res"]]
+	nchrom, nsweep = len(g["chrom2size"]), int(g["nsweep"])
+	core = _core(int(g["rank"]), int(g["off_diag"]), res_list)
+	core.fit(ds, 0.3, 2, 1, True, True, False, 0.0, verbose=False, state=_state(g, len(ds), nchrom))
+	assert list(core.chrom2size.values()) == list(g["chrom2size"])
+	assert np.max(np.abs(np.array(core.re_trace) - g["re"][:2]) / g["re"][:2]) < 1e-4
+	for c, chrom in enumerate(core.chrom2size):
+		assert rel_fro(core.projected_tensor_list[chrom].numpy(), g["t1_Y%d" % c]) < 1e-3    # after sweep 2 = reference's t1 return
+	for i in range(len(ds)):
+		assert ds[i].global_slice_bin == slice(0 if i < nchrom else ds[i - nchrom].num_bin, (0 if i < nchrom else ds[i - nchrom].num_bin) + ds[i].num_bin)
+	core = _core(int(g["rank"]), int(g["off_diag"]), res_list)
+	torch.manual_seed(0); np.random.seed(0)
+	ds2, _ = load_multires_dataset()
+	_, (A_list, B_list, D_list, V), _ = core.fit_transform(ds2, size_ratio=0.3, n_iter_max=nsweep, n_iter_parafac=1, do_conv=True,
+	                                                      do_rwr=True, do_col=False, tol=0.0, verbose=False)
+	assert list(core.n_i) == list(g["n_i"])
+	re = np.array(core.re_trace)
+	assert np.max(np.abs(re - g["re"]) / g["re"]) < 1e-4, (re, g["re"])
+	E = O.embed_all(V.numpy(), [d.numpy() for d in D_list])
+	Eref = O.embed_all(g["final_V"], [g["final_D%d" % c] for c in range(nchrom)])
+	for j in range(E.shape[1]):
+		assert abs(np.corrcoef(E[:, j], Eref[:, j])[0, 1]) > 0.999
+
+
+def test_device_init_svd_reaches_the_host_init_loss(fake):
+	"""init_svd='device' (cell-sharded randomized SVD, no gather) is another random start: same loss level after a few sweeps."""
+	res = {}
+	for mode in ("host", "device"):
+		core = _core(16, 12, [1000000], init_svd=mode)
+		torch.manual_seed(0); np.random.seed(0)
+		core.fit(load_small_dataset(), 0.3, 6, 1, True, True, False, 0.0, verbose=False)
+		res[mode] = core.re_trace[-1]
+	assert abs(res["device"] - res["host"]) / res["host"] < 0.02, res
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _free_port():
+	s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _sharded_worker(rank, world, port, q, do_col, good, bs_cell):
+	import torch.distributed as dist
+	os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+	dist.init_process_group("gloo", rank=rank, world_size=world)
+	torch.set_num_threads(2)
+	fake_abi.install()
+	from fasthigashi_b200.sharding import shard_datasets, gather_cell_rows
+	from fasthigashi_b200.parafac2_intergrative import Fast_Higashi_core
+	mine = shard_datasets(load_small_dataset(good_qc_num=good, bs_cell=bs_cell), world, rank)
+	core = Fast_Higashi_core(16, 12, [1000000], group=dist.group.WORLD).to("cpu")
+	torch.manual_seed(0); np.random.seed(0)
+	_, (A_list, B_list, D_list, V), _ = core.fit_transform(mine, size_ratio=0.3, n_iter_max=4, n_iter_parafac=1, do_conv=True,
+	                                                      do_rwr=True, do_col=do_col, tol=0.0, verbose=False)
+	V_all = gather_cell_rows(V, mine[0].num_cell, dist.group.WORLD)
+	q.put((rank, list(core.n_i), list(core.re_trace), V_all.numpy(), [a.numpy() for a in A_list], [d.numpy() for d in D_list]))
+	dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("do_col,good,bs_cell", [(False, -1, 24), (True, 44, 22)])
+def test_two_rank_gloo_run_equals_single_process(do_col, good, bs_cell):
+	"""The whole cell-sharded run (init with features gathered to rank 0 and the MAX of the RWR step counts, all-reduced
+	T1 / Gram / Y, per-bin polar problems partitioned over the ranks, factor broadcast, transform with bad-QC cells) on two
+	gloo ranks against the same run in one process: same n_i, loss trace to 1e-6, identical factors on both ranks,
+	embeddings of all cells in the unsharded order. `bs_cell` is chosen so that the good-cell batches of the single process
+	are the two slabs: the reference's auto-stop in `init_params` is per CELL BATCH (partial_rwr.py:119-123), so the init
+	features - and with them the whole run - depend on the batch composition (1e-4 on the loss with other batch sizes)."""
+	import torch.multiprocessing as mp
+	f, undo = fake_abi.install()
+	try:
+		core = _core(16, 12, [1000000])
+		torch.manual_seed(0); np.random.seed(0)
+		ds = load_small_dataset(good_qc_num=good, bs_cell=bs_cell)
+		_, (A1, B1, D1, V1), _ = core.fit_transform(ds, size_ratio=0.3, n_iter_max=4, n_iter_parafac=1, do_conv=True, do_rwr=True,
+		                                            do_col=do_col, tol=0.0, verbose=False)
+		re1, n_i1 = list(core.re_trace), list(core.n_i)
+	finally:
+		undo()
+	ctx = mp.get_context("spawn")
+	q = ctx.Queue()
+	port = _free_port()
+	procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q, do_col, good, bs_cell)) for r in range(2)]
+	for p in procs: p.start()
+	res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r[0])
+	for p in procs: p.join(timeout=60)
+	for r in res:
+		assert r[1] == n_i1
+		assert np.allclose(r[2], re1, rtol=1e-6), (r[2], re1)
+	for a, b in zip(res[0][4] + res[0][5], res[1][4] + res[1][5]):
+		assert np.array_equal(a, b)                                      # replicas stay bit-identical
+	assert np.array_equal(res[0][3], res[1][3])
+	V2 = res[0][3]
+	assert V2.shape == tuple(V1.shape)
+	E1 = O.embed_all(V1.numpy(), [d.numpy() for d in D1])
+	E2 = O.embed_all(V2, res[0][5])
+	for j in range(E1.shape[1]):
+		assert abs(np.corrcoef(E1[:, j], E2[:, j])[0, 1]) > 0.9999
