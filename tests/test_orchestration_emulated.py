@@ -125,6 +125,35 @@ def test_device_init_svd_reaches_the_host_init_loss(fake):
 	assert abs(res["device"] - res["host"]) / res["host"] < 0.02, res
 
 
+def _cpu_wrapper(tmp_path, off, res, chroms):
+	"""A `FastHigashi` object bound to the host-memory stand-in: the real constructor (with the three torch.cuda probes it
+	makes answered for it), then device 'cpu'. Only valid while the `fake` fixture is installed."""
+	import json
+	from unittest import mock
+	from fasthigashi_b200.FastHigashi_Wrapper import FastHigashi
+	cfg = dict(chrom_list=chroms, temp_dir=str(tmp_path), data_dir=str(tmp_path), resolution=res, resolution_fh=[res])
+	json.dump(cfg, open(tmp_path / "config.JSON", "w"))
+	with mock.patch("torch.cuda.is_available", lambda: True), mock.patch("torch.cuda.current_device", lambda: 0), \
+	     mock.patch("torch.cuda.mem_get_info", lambda *a: (64 << 30, 180 << 30)):
+		w = FastHigashi(str(tmp_path / "config.JSON"), None, None, off, True, True, True, False, False)
+	w.device = "cpu"
+	return w
+
+
+def test_wrapper_only_partial_rwr(fake, tmp_path):
+	"""FastHigashi.only_partial_rwr (FastHigashi_Wrapper.py:569-655): block pasting, symmetrisation, original cell ids,
+	good and bad-QC batches - the same case the B200 runs (tests/wrapper_cases.py)."""
+	import wrapper_cases
+	wrapper_cases.case_only_partial_rwr_matches_oracle(_cpu_wrapper, tmp_path)
+
+
+def test_wrapper_from_raw_files(fake, tmp_path):
+	"""prep_dataset from raw/{chrom}_sparse_adj.npy (libfh_host.so ingest + block-CSR staging) -> run_model ->
+	fetch_cell_embedding, against the oracle fed with the REFERENCE's packed tensors of the same raw files."""
+	import wrapper_cases
+	wrapper_cases.case_wrapper_from_raw_files(_cpu_wrapper, tmp_path)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def _free_port():
 	s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p

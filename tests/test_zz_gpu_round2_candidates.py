@@ -1,7 +1,9 @@
-"""GPU tests for code written at the end of round 1 AFTER the round's GPU budget was spent
-(DESIGN.md "written without GPU access"): they have never run on a B200, so they are opt-in
-(`FH_RUN_UNVERIFIED=1`) until a GPU run has confirmed them. They only compose entry points the
-verified tests already exercise (`rwr_block_csr`, the `FastHigashi` wrapper)."""
+"""GPU tests for code written at the end of round 1 AFTER the round's GPU budget was spent (DESIGN.md "written without
+GPU access"): they have never run on a B200. Their Python orchestration is verified on the CPU against the host-memory
+stand-in of the C ABI (tests/test_orchestration_emulated.py runs the same cases, tests/wrapper_cases.py), and they only
+compose kernels the verified tests already exercise, so they run by default but are marked `xfail(strict=False)` until a
+B200 run has confirmed them (XPASS = confirmed; a failure does not hide the verified suite's result). The one test that
+runs NEW device code (the block Jacobi kernel) stays opt-in: `FH_RUN_UNVERIFIED=1`."""
 import json
 import os
 import numpy as np
@@ -9,9 +11,11 @@ import pytest
 import torch
 from conftest import GOLDEN
 from oracle import fh_oracle as O
+import wrapper_cases
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FH_RUN_UNVERIFIED", "0") != "1", reason="not yet confirmed on a GPU (set FH_RUN_UNVERIFIED=1)")]
+pytestmark = [pytest.mark.gpu]
+first_run = pytest.mark.xfail(strict=False, reason="composition of verified kernels, CPU-verified orchestration; not yet run on a B200")
+opt_in = pytest.mark.skipif(os.environ.get("FH_RUN_UNVERIFIED", "0") != "1", reason="new device code, not yet confirmed on a GPU (set FH_RUN_UNVERIFIED=1)")
 
 
 def _wrapper(tmp_path, off, res, chroms):
@@ -21,78 +25,20 @@ def _wrapper(tmp_path, off, res, chroms):
 	return FastHigashi(str(tmp_path / "config.JSON"), None, None, off, True, True, True, False, False)
 
 
+@first_run
 def test_only_partial_rwr_matches_oracle(tmp_path):
 	"""FastHigashi_Wrapper.py:569-655: per-cell imputed maps, symmetrised, keyed by the original cell id."""
-	d = np.load(os.path.join(GOLDEN, "data_small.npz"))
-	ncell, off, res = int(d["ncell"]), int(d["off_diag"]), int(d["res"])
-	chroms = ["chr1", "chr2", "chr3"]
-	tensors = {res: [(d[c + "_idx"].astype(np.int64), d[c + "_val"], (int(n), int(n), ncell)) for c, n in zip(chroms, d["bins"])]}
-	qc = np.ones(ncell); qc[[5, 17]] = 0
-	w = _wrapper(tmp_path, off, res, chroms)
-	w.set_tensors(tensors, qc=qc, readcount=np.linspace(8, 10, ncell))
-	w.prep_dataset()
-	files = w.only_partial_rwr(out_format="npz")
-	assert len(files) == 3
-	for ds, path in zip(w.all_matrix, files):
-		got = np.load(path)
-		assert list(got["shape"]) == [ds.num_bin, ds.num_bin]
-		cpu = ds.select_cells(0, ds.total_cell_num, good_qc_num=ds.num_cell).to("cpu")
-		n = ds.num_bin
-		seen = 0
-		for sl in ds.cell_slice_list:
-			nc = sl.stop - sl.start
-			full = np.zeros((nc, n, n))
-			for b, g in enumerate(cpu.geoms):
-				x, _ = O.partial_rwr(O.densify_block(cpu, b, sl.start, sl.stop), g.s, g.e, True, True, False, None, -1)
-				full[:, g.row0:g.row0 + g.nb, g.col0:g.col0 + g.w] = x.numpy()
-			full = full + full.transpose(0, 2, 1)
-			for i in range(nc):
-				m = full[i] - np.diag(np.diag(full[i]) / 2)
-				a = got[str(w.reorder[sl.start + i])]
-				assert a.dtype == np.float32 and a.shape == (n, n)
-				assert np.linalg.norm(a - m) <= 1e-5 * np.linalg.norm(m)
-				seen += 1
-		assert seen == ncell and len(got.files) == ncell + 1
+	wrapper_cases.case_only_partial_rwr_matches_oracle(_wrapper, tmp_path)
 
 
+@first_run
 def test_wrapper_from_raw_files(tmp_path):
 	"""prep_dataset straight from raw/{chrom}_sparse_adj.npy (ingest.py) -> run_model -> embeddings, against the
 	oracle fed with the reference's own packed tensors of the same raw files (tests/golden/ingest_cases.npz)."""
-	from scipy.sparse import csr_matrix
-	from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset
-	G = np.load(os.path.join(GOLDEN, "ingest_cases.npz"), allow_pickle=True)
-	chroms = [str(c) for c in G["chroms"]]
-	ncell, res = int(G["ncell"]), int(G["res"])
-	os.makedirs(tmp_path / "raw")
-	for ch in chroms:
-		n = int(G["raw_%s_n" % ch])
-		indptr = G["raw_%s_indptr" % ch].reshape(ncell, n + 1)
-		arr, offp = np.empty(ncell, dtype=object), 0
-		for c in range(ncell):
-			nnz = int(indptr[c, -1])
-			arr[c] = csr_matrix((G["raw_%s_data" % ch][offp:offp + nnz], G["raw_%s_indices" % ch][offp:offp + nnz], indptr[c]), shape=(n, n))
-			offp += nnz
-		np.save(tmp_path / "raw" / ("%s_sparse_adj.npy" % ch), arr, allow_pickle=True)
-	w = _wrapper(tmp_path, 12, res, chroms)
-	w.prep_dataset()
-	assert np.array_equal(w.reorder, G["reorder"]) and w.good_qc_num == int(G["qc"].sum())
-	torch.manual_seed(0); np.random.seed(0)
-	w.run_model(dim1=0.6, rank=8, n_iter_parafac=1, n_iter_max=4, tol=0.0)
-	emb = w.fetch_cell_embedding(final_dim=4)
-	ods = []
-	for ds, ch in zip(w.all_matrix, chroms):
-		sp = Sparse(G["plain_%s_idx" % ch].astype(np.int64), G["plain_%s_val" % ch], tuple(int(x) for x in G["plain_%s_shape" % ch]))
-		ods.append(Chrom_Dataset(sp, bs_bin=ds.bs_bin, bs_cell=ds.bs_cell, good_qc_num=ds.num_cell, compact=True, flank=12,
-		                         chrom=ch, resolution=res))
-	oc = O.OracleCore(8, 12, [res])
-	torch.manual_seed(0); np.random.seed(0)
-	oc.fit(ods, 0.6, 4, 1, True, True, w.final_do_col, 0.0)
-	Vo = oc.transform(ods, True, True, w.final_do_col)
-	Eo = O.embed_all(Vo.numpy(), [x.numpy() for x in oc.D_dict.values()])
-	pear = [abs(np.corrcoef(emb["embed_all"][:, j], Eo[:, j])[0, 1]) for j in range(Eo.shape[1])]
-	assert min(pear) > 0.999, min(pear)
+	wrapper_cases.case_wrapper_from_raw_files(_wrapper, tmp_path)
 
 
+@first_run
 def test_device_init_svd_reaches_the_host_init_loss():
 	"""init_svd="device" (cell-sharded randomized SVD, dist_svd.py) is a different random start than the
 	reference's sklearn SVD: after a few sweeps the reconstruction loss must be as good (within 1 %)."""
@@ -109,6 +55,7 @@ def test_device_init_svd_reaches_the_host_init_loss():
 	assert abs(losses["device"] - losses["host"]) <= 0.01 * losses["host"], losses
 
 
+@opt_in
 def test_polar_block_jacobi_on_device():
 	"""FH_POLAR_BLOCK=1 (csrc/fh_polar_block.cuh): the polar tests and one lock-step core run in a child process (the
 	switch is read once per process). The variant's logic is already checked on the host (tests/test_polar_block_emulation.py)."""
@@ -122,6 +69,7 @@ def test_polar_block_jacobi_on_device():
 	assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+@first_run
 def test_multi_resolution_run_matches_reference_fixture():
 	"""Two resolutions of the same chromosomes (parafac2_intergrative.py:581-592, 670-695: shared B / D per chromosome,
 	bins stacked along mode 0 of the projected tensor, one CP-ALS per chromosome) against the UNMODIFIED reference's
