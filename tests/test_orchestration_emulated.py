@@ -159,7 +159,7 @@ def _free_port():
 	s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _sharded_worker(rank, world, port, q, do_col, good, bs_cell):
+def _sharded_worker(rank, world, port, q, do_col, good, bs_cell, init_svd):
 	import torch.distributed as dist
 	os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
 	dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -168,7 +168,7 @@ def _sharded_worker(rank, world, port, q, do_col, good, bs_cell):
 	from fasthigashi_b200.sharding import shard_datasets, gather_cell_rows
 	from fasthigashi_b200.parafac2_intergrative import Fast_Higashi_core
 	mine = shard_datasets(load_small_dataset(good_qc_num=good, bs_cell=bs_cell), world, rank)
-	core = Fast_Higashi_core(16, 12, [1000000], group=dist.group.WORLD).to("cpu")
+	core = Fast_Higashi_core(16, 12, [1000000], group=dist.group.WORLD, init_svd=init_svd).to("cpu")
 	torch.manual_seed(0); np.random.seed(0)
 	_, (A_list, B_list, D_list, V), _ = core.fit_transform(mine, size_ratio=0.3, n_iter_max=4, n_iter_parafac=1, do_conv=True,
 	                                                      do_rwr=True, do_col=do_col, tol=0.0, verbose=False)
@@ -177,18 +177,19 @@ def _sharded_worker(rank, world, port, q, do_col, good, bs_cell):
 	dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("do_col,good,bs_cell", [(False, -1, 24), (True, 44, 22)])
-def test_two_rank_gloo_run_equals_single_process(do_col, good, bs_cell):
+@pytest.mark.parametrize("do_col,good,bs_cell,init_svd", [(False, -1, 24, "host"), (True, 44, 22, "host"), (False, -1, 24, "device")])
+def test_two_rank_gloo_run_equals_single_process(do_col, good, bs_cell, init_svd):
 	"""The whole cell-sharded run (init with features gathered to rank 0 and the MAX of the RWR step counts, all-reduced
 	T1 / Gram / Y, per-bin polar problems partitioned over the ranks, factor broadcast, transform with bad-QC cells) on two
 	gloo ranks against the same run in one process: same n_i, loss trace to 1e-6, identical factors on both ranks,
 	embeddings of all cells in the unsharded order. `bs_cell` is chosen so that the good-cell batches of the single process
 	are the two slabs: the reference's auto-stop in `init_params` is per CELL BATCH (partial_rwr.py:119-123), so the init
-	features - and with them the whole run - depend on the batch composition (1e-4 on the loss with other batch sizes)."""
+	features - and with them the whole run - depend on the batch composition (1e-4 on the loss with other batch sizes).
+	init_svd='device': the init SVDs stay cell-sharded (dist_svd.py: only sketches and k x k Grams are all-reduced)."""
 	import torch.multiprocessing as mp
 	f, undo = fake_abi.install()
 	try:
-		core = _core(16, 12, [1000000])
+		core = _core(16, 12, [1000000], init_svd=init_svd)
 		torch.manual_seed(0); np.random.seed(0)
 		ds = load_small_dataset(good_qc_num=good, bs_cell=bs_cell)
 		_, (A1, B1, D1, V1), _ = core.fit_transform(ds, size_ratio=0.3, n_iter_max=4, n_iter_parafac=1, do_conv=True, do_rwr=True,
@@ -199,7 +200,7 @@ def test_two_rank_gloo_run_equals_single_process(do_col, good, bs_cell):
 	ctx = mp.get_context("spawn")
 	q = ctx.Queue()
 	port = _free_port()
-	procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q, do_col, good, bs_cell)) for r in range(2)]
+	procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q, do_col, good, bs_cell, init_svd)) for r in range(2)]
 	for p in procs: p.start()
 	res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r[0])
 	for p in procs: p.join(timeout=60)
