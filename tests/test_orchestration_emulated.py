@@ -114,6 +114,23 @@ def test_multi_resolution_matches_reference_fixture(fake):
 		assert abs(np.corrcoef(E[:, j], Eref[:, j])[0, 1]) > 0.999
 
 
+def test_wide_windows_take_the_row_gram_route(fake):
+	"""r > window width (the last block of chr3: 8 rows x 20 columns against r = 36): temp_i is wide, the Gram is
+	T T^T and U = M T (the FH_GEMM_F64xF32_F32 call) - against the pinned oracle from the same seeds."""
+	core = _core(40, 12, [1000000])
+	torch.manual_seed(0); np.random.seed(0)
+	core.fit(load_small_dataset(), 0.9, 3, 1, True, True, False, 0.0, verbose=False)
+	assert core.chrom2size["chr3"] == 36 and core.schic[2].geoms[1].w == 20
+	oc = O.OracleCore(40, 12, [1000000])
+	torch.manual_seed(0); np.random.seed(0)
+	oc.fit(load_small_dataset(), 0.9, 3, 1, True, True, False, 0.0)
+	re, ro = np.array(core.re_trace), np.array(oc.re_trace)
+	assert np.max(np.abs(re - ro) / ro) < 1e-4, (re, ro)
+	U = core.projection_list[1][2]                       # chr2's last block, (6, 18, 40): wide too, and well conditioned
+	assert tuple(U.shape) == (6, 18, 40)
+	assert torch.allclose(U @ U.transpose(1, 2), torch.eye(18).expand(6, 18, 18), atol=1e-4)   # orthonormal ROWS when wide
+
+
 def test_device_init_svd_reaches_the_host_init_loss(fake):
 	"""init_svd='device' (cell-sharded randomized SVD, no gather) is another random start: same loss level after a few sweeps."""
 	res = {}
