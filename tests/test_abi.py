@@ -66,3 +66,39 @@ def test_product_never_imports_oracle():
 			src = open(os.path.join(pkg, f)).read()
 			assert "oracle" not in src.replace("no oracle", ""), f
 			assert "/root/reference" not in src, f
+
+
+def test_argument_validation_returns_codes_before_any_launch():
+	"""Error convention of the C ABI (include/fh_b200.h): bad descriptors come back as a non-zero status with the reason in
+	fh_last_error(), decided on the host before any CUDA call - so it can be checked without a GPU."""
+	import ctypes as C
+	from fasthigashi_b200 import _lib
+	L = _lib.lib()
+	d = _lib.GemmDesc()
+	d.M = d.N = d.K = 4; d.batch = 1; d.sa_m, d.sa_k, d.sb_k, d.sb_n, d.ldc, d.alpha = 2, 2, 4, 1, 4, 1.0
+	assert L.fh_gemm_batched(C.byref(d), 16, 16, 16, None) != 0 and b"unit stride" in L.fh_last_error()
+	d.sa_m, d.sa_k, d.dtype = 4, 1, 99
+	assert L.fh_gemm_batched(C.byref(d), 16, 16, 16, None) != 0 and b"dtype" in L.fh_last_error()
+	n = C.c_int(0)
+	r = _lib.rwr_desc(16, 30, 30, 0, 3, True, True, False, 0, 4, 0)             # ldw not a multiple of 4
+	assert L.fh_rwr_batched(C.byref(r), 16, 16, 16, None, 0, 16, 480, 16, 1 << 30, C.byref(n), None) != 0
+	assert b"ldw" in L.fh_last_error()
+	r = _lib.rwr_desc(16, 30, 32, 20, 3, True, True, False, 0, 4, 0)            # diagonal block sticks out of the window
+	assert L.fh_rwr_batched(C.byref(r), 16, 16, 16, None, 0, 16, 512, 16, 1 << 30, C.byref(n), None) != 0
+	assert b"outside window" in L.fh_last_error()
+	r = _lib.rwr_desc(115, 315, 316, 100, 4, True, True, False, 0, 64, 0)
+	need = L.fh_rwr_workspace_bytes(C.byref(r))
+	assert need > 0
+	assert L.fh_polar_batched(16, 16, 1, 8, 4, 4, 32, None, None, 0, 16, 0, None, None) != 0 and b"workspace" in L.fh_last_error()
+	assert L.fh_polar_workspace_bytes(1, 8, 4) > 0
+	assert L.fh_cp_als(16, 4, 2, 3, 16, 16, 16, 1, 16, 0, None, None) != 0 and b"workspace" in L.fh_last_error()
+	assert L.fh_cp_als_workspace_bytes(4, 2, 3) > 0
+	with pytest.raises(_lib.FHError, match="unit stride"):
+		_lib.check(L.fh_gemm_batched(C.byref(_bad_gemm()), 16, 16, 16, None))
+
+
+def _bad_gemm():
+	from fasthigashi_b200 import _lib
+	d = _lib.GemmDesc()
+	d.M = d.N = d.K = 4; d.batch = 1; d.sa_m, d.sa_k, d.sb_k, d.sb_n, d.ldc, d.alpha = 2, 2, 4, 1, 4, 1.0
+	return d
