@@ -233,3 +233,16 @@ def test_two_rank_gloo_run_equals_single_process(do_col, good, bs_cell, init_svd
 	E2 = O.embed_all(V2, res[0][5])
 	for j in range(E1.shape[1]):
 		assert abs(np.corrcoef(E1[:, j], E2[:, j])[0, 1]) > 0.9999
+
+
+def test_headline_job_script_runs_end_to_end(fake):
+	"""scripts/headline_run.py (init + S sweeps + transform on per-rank synthetic slabs, the north star's full job) at a toy
+	size: the JSON fields exist, the loss decreases, one RWR pass per sweep plus the one of transform's cache refresh."""
+	import argparse
+	sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+	import headline_run
+	args = argparse.Namespace(cells_total=24, sweeps=3, geometry="pfc", rank=8, cache="sweep", init_svd="device")
+	out = headline_run.run(args, "cpu", None, 0, 1, bins=[48, 36])
+	assert out["cells_per_gpu"] == 24 and out["embedding_rows_local"] == 24 and len(out["rwr_steps"]) == 2
+	assert out["re_last"][-1] < out["re_first"][1] and np.isfinite(out["job_s"])
+	assert out["rwr_passes"] == 3
