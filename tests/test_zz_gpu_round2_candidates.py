@@ -102,3 +102,34 @@ def test_multi_resolution_run_matches_reference_fixture():
 		assert abs(np.corrcoef(E[:, j], Eref[:, j])[0, 1]) > 0.999
 	for i in range(len(ds)):
 		assert tuple(A_list[i].shape) == g["final_A%d" % i].shape
+
+
+@first_run
+@pytest.mark.parametrize("use_tc", [True, False])
+def test_full_size_rwr_conserves_column_mass(use_tc):
+	"""Size-independent property at the full block size of BASELINE config 2 (chr1 of the PFC geometry: 457 bins at
+	500 kb, blocks of 115 rows with 215 / 315-column windows, density 0.05) where the oracle is too slow to be the
+	checker: the transition matrix P is column-stochastic, hence so is every Q_k = 1/2 Q_{k-1} P + 1/2 I, and the imputed
+	panel X = Q A has exactly the column sums of the convolved panel A (partial_rwr.py:84-138; 2e-7 on the oracle).
+	Also: X > 0, pad columns exactly 0, and a second call reproduces the first bit for bit."""
+	from fasthigashi_b200 import synth
+	from fasthigashi_b200.partial_rwr import rwr_block_csr, pad4
+	from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset
+	n, ncell, off = 457, 512, 100
+	cluster = np.arange(ncell) % 8
+	idx, val = synth.synth_chrom(n, ncell, 0.05, off, 77, cluster, 8, device="cuda:0", cell_chunk=256)
+	ds = Chrom_Dataset(Sparse(idx, val, (n, n, ncell), copy=False), bs_bin=115, bs_cell=ncell, compact=True, flank=off, device="cuda:0")
+	assert [(g.nb, g.w) for g in ds.geoms][:2] == [(115, 215), (115, 315)]
+	for b, g in enumerate(ds.geoms):
+		ldw = pad4(g.w)
+		A = torch.empty(ncell, g.nb * ldw, device="cuda:0")
+		X = torch.full((ncell, g.nb * ldw), float("nan"), device="cuda:0")
+		X2 = torch.empty_like(X)
+		rwr_block_csr(ds, b, 0, ncell, A, g.nb * ldw, 0, True, False, False, use_tc=use_tc)
+		rwr_block_csr(ds, b, 0, ncell, X, g.nb * ldw, 4, True, True, False, use_tc=use_tc)
+		rwr_block_csr(ds, b, 0, ncell, X2, g.nb * ldw, 4, True, True, False, use_tc=use_tc)
+		A, X = A.view(ncell, g.nb, ldw), X.view(ncell, g.nb, ldw)
+		assert torch.equal(X.reshape(ncell, -1), X2)
+		assert float(X[:, :, g.w:].abs().sum()) == 0.0 and bool((X[:, :, :g.w] > 0).all())
+		ca, cx = A.double().sum(1)[:, :g.w], X.double().sum(1)[:, :g.w]
+		assert float(((cx - ca).abs() / ca).max()) < 1e-5
