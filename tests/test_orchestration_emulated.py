@@ -246,3 +246,46 @@ def test_headline_job_script_runs_end_to_end(fake):
 	assert out["cells_per_gpu"] == 24 and out["embedding_rows_local"] == 24 and len(out["rwr_steps"]) == 2
 	assert out["re_last"][-1] < out["re_first"][1] and np.isfinite(out["job_s"])
 	assert out["rwr_passes"] == 3
+
+
+def _reference_datasets(**kw):
+	from oracle import ref_shims
+	from fasthigashi_b200 import synth
+	if not ref_shims.reference_available():
+		pytest.skip("the reference checkout is only present in the build container")
+	mods = ref_shims.import_reference()
+	# the generator call of tests/golden/make_golden.py: the tensors of data_small.npz
+	chroms, _ = synth.synth_dataset([90, 70, 40], 48, 0.12, off_diag=12, seed=3, num_cluster=4)
+	return ref_shims.build_reference_datasets(mods, chroms, off_diag=12, res=1000000, bs_bin=32, **kw)
+
+
+def test_restaging_reference_chrom_datasets_is_exact():
+	"""the reference's own `Chrom_Dataset` objects (pinned COO `Fake_Sparse` per bin block x cell
+	batch, +1-offset int16 indices, good-QC batches then bad-QC batches) re-staged by `Chrom_Dataset.from_reference` give
+	the same block-CSR, bit for bit, as building from the COO tensor directly."""
+	from fasthigashi_b200.sparse_for_schic import Chrom_Dataset
+	ref = _reference_datasets(bs_cell=20, good_qc_num=44)
+	mine = load_small_dataset(good_qc_num=44, bs_cell=20)
+	for r, m in zip(ref, mine):
+		got = Chrom_Dataset.from_reference(r)
+		assert (got.num_cell, got.total_cell_num, got.bs_bin, got.bs_cell, got.flank) == (44, 48, 32, 20, 12)
+		assert [tuple(g) for g in got.geoms] == [tuple(g) for g in m.geoms]
+		assert [(s.start, s.stop) for s in got.cell_slice_list] == [(s.start, s.stop) for s in m.cell_slice_list]
+		for b in range(len(m.geoms)):
+			assert torch.equal(got.rowptr[b], m.rowptr[b]) and torch.equal(got.col[b], m.col[b]) and torch.equal(got.val[b], m.val[b])
+
+
+def test_core_accepts_the_reference_datasets(fake):
+	"""The two-line patch of INTEGRATION.md section 2: `Fast_Higashi_core.fit_transform` fed with the REFERENCE's
+	List[Chrom_Dataset] reproduces the reference's own run (core_col.npz) and writes `global_slice_bin` on its objects."""
+	g = np.load(os.path.join(GOLDEN, "core_col.npz"))
+	ref = _reference_datasets(bs_cell=int(g["bs_cell"]), good_qc_num=int(g["good_qc_num"]))
+	core = _core(int(g["rank"]), 12, [1000000])
+	torch.manual_seed(0); np.random.seed(0)
+	nsweep = 4
+	_, (A_list, B_list, D_list, V), proj = core.fit_transform(ref, size_ratio=0.3, n_iter_max=nsweep, n_iter_parafac=1, do_conv=True,
+	                                                         do_rwr=True, do_col=True, tol=0.0, verbose=False)
+	assert list(core.n_i) == list(g["n_i"])
+	re = np.array(core.re_trace)
+	assert np.max(np.abs(re - g["re"][:nsweep]) / g["re"][:nsweep]) < 1e-4
+	assert tuple(V.shape) == (48, int(g["rank"])) and all(r.global_slice_bin == slice(0, r.num_bin) for r in ref)
