@@ -289,3 +289,49 @@ def test_core_accepts_the_reference_datasets(fake):
 	re = np.array(core.re_trace)
 	assert np.max(np.abs(re - g["re"][:nsweep]) / g["re"][:nsweep]) < 1e-4
 	assert tuple(V.shape) == (48, int(g["rank"])) and all(r.global_slice_bin == slice(0, r.num_bin) for r in ref)
+
+
+def test_reference_wrapper_with_the_core_swapped_in(fake, tmp_path, monkeypatch):
+	"""The literal two-line patch of INTEGRATION.md section 2 applied to the UNMODIFIED reference wrapper
+	(`FastHigashi_Wrapper.Fast_Higashi_core = ours`): its own prep_dataset (reference ingest, reference Chrom_Datasets) ->
+	run_model -> fetch_cell_embedding runs unchanged and gives the embeddings of the reference's own core (same seeds)."""
+	import importlib
+	import io
+	import json
+	import contextlib
+	import pickle
+	from oracle import ref_shims
+	import wrapper_cases
+	if not ref_shims.reference_available():
+		pytest.skip("the reference checkout is only present in the build container")
+	ref_shims.import_reference()
+	W = importlib.import_module("fasthigashi.FastHigashi_Wrapper")
+	from fasthigashi_b200.parafac2_intergrative import Fast_Higashi_core as Ours
+	G = np.load(os.path.join(GOLDEN, "ingest_cases.npz"), allow_pickle=True)
+	chroms = [str(c) for c in G["chroms"]]
+	wrapper_cases.write_raw_files(G, tmp_path)
+	pickle.dump({"batch": list(G["batch"])}, open(tmp_path / "label_info.pickle", "wb"))
+	cfg = dict(chrom_list=chroms, temp_dir=str(tmp_path), data_dir=str(tmp_path), resolution=int(G["res"]), resolution_fh=[int(G["res"])])
+	json.dump(cfg, open(tmp_path / "config.JSON", "w"))
+	monkeypatch.chdir(tmp_path)                      # the reference constructor writes ./tmp1 ./tmp2 (:58-59)
+	out = {}
+	for who in ("reference", "ours"):
+		(tmp_path / who).mkdir()
+		if who == "ours":
+			monkeypatch.setattr(W, "Fast_Higashi_core", Ours)
+		with contextlib.redirect_stdout(io.StringIO()):
+			w = W.FastHigashi(str(tmp_path / "config.JSON"), str(tmp_path / who), str(tmp_path / who), 12, True, True, True, False, False)
+			w.prep_dataset()
+			torch.manual_seed(0); np.random.seed(0)
+			w.run_model(dim1=0.6, rank=8, n_iter_parafac=1, n_iter_max=4, tol=0.0)
+			np.random.seed(1)
+			out[who] = (w.fetch_cell_embedding(final_dim=4), [np.asarray(a) for a in w.A_list], w.meta_embedding)
+		assert os.path.exists(tmp_path / who / ("results_all%s.pkl" % w.save_str))
+	assert fake.calls["rwr_batched"] > 0 and fake.calls["cp_als"] > 0     # the second run went through the C-ABI entry points
+	ea, eb = out["reference"][0]["embed_all"], out["ours"][0]["embed_all"]
+	assert ea.shape == eb.shape
+	for j in range(ea.shape[1]):
+		assert abs(np.corrcoef(ea[:, j], eb[:, j])[0, 1]) > 0.999
+	for a, b in zip(out["reference"][1], out["ours"][1]):
+		assert a.shape == b.shape
+	assert out["reference"][2].shape == out["ours"][2].shape

@@ -42,15 +42,12 @@ def case_only_partial_rwr_matches_oracle(make_wrapper, tmp_path):
 		assert seen == ncell and len(got.files) == ncell + 1
 
 
-def case_wrapper_from_raw_files(make_wrapper, tmp_path):
-	"""prep_dataset straight from raw/{chrom}_sparse_adj.npy (ingest.py) -> run_model -> embeddings, against the
-	oracle fed with the reference's own packed tensors of the same raw files (tests/golden/ingest_cases.npz)."""
+def write_raw_files(G, tmp_path):
+	"""raw/{chrom}_sparse_adj.npy (object arrays of per-cell scipy CSR) from tests/golden/ingest_cases.npz."""
 	from scipy.sparse import csr_matrix
-	from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset
-	G = np.load(os.path.join(GOLDEN, "ingest_cases.npz"), allow_pickle=True)
 	chroms = [str(c) for c in G["chroms"]]
-	ncell, res = int(G["ncell"]), int(G["res"])
-	os.makedirs(tmp_path / "raw")
+	ncell = int(G["ncell"])
+	os.makedirs(os.path.join(str(tmp_path), "raw"))
 	for ch in chroms:
 		n = int(G["raw_%s_n" % ch])
 		indptr = G["raw_%s_indptr" % ch].reshape(ncell, n + 1)
@@ -59,7 +56,18 @@ def case_wrapper_from_raw_files(make_wrapper, tmp_path):
 			nnz = int(indptr[c, -1])
 			arr[c] = csr_matrix((G["raw_%s_data" % ch][offp:offp + nnz], G["raw_%s_indices" % ch][offp:offp + nnz], indptr[c]), shape=(n, n))
 			offp += nnz
-		np.save(tmp_path / "raw" / ("%s_sparse_adj.npy" % ch), arr, allow_pickle=True)
+		np.save(os.path.join(str(tmp_path), "raw", "%s_sparse_adj.npy" % ch), arr, allow_pickle=True)
+
+
+def case_wrapper_from_raw_files(make_wrapper, tmp_path):
+	"""prep_dataset straight from raw/{chrom}_sparse_adj.npy (ingest.py) -> run_model -> embeddings, against the
+	oracle fed with the reference's own packed tensors of the same raw files (tests/golden/ingest_cases.npz)."""
+	from scipy.sparse import csr_matrix
+	from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset
+	G = np.load(os.path.join(GOLDEN, "ingest_cases.npz"), allow_pickle=True)
+	chroms = [str(c) for c in G["chroms"]]
+	ncell, res = int(G["ncell"]), int(G["res"])
+	write_raw_files(G, tmp_path)
 	w = make_wrapper(tmp_path, 12, res, chroms)
 	w.prep_dataset()
 	assert np.array_equal(w.reorder, G["reorder"]) and w.good_qc_num == int(G["qc"].sum())
