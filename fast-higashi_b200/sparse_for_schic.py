@@ -83,6 +83,88 @@ class Sparse:
 	def __len__(self):
 		return int(self.shape[0])
 
+	# -- the container operations of the reference class (sparse_for_schic.py:96-275), which its own `test()` (:634-661)
+	#    exercises; none of them is on the decomposition's path, they are here so that code written against the
+	#    reference's `Sparse` keeps working
+	def numel(self):
+		return int(np.prod(self.shape))
+
+	def _flat(self):
+		"""Row-major linear index of every entry."""
+		mult = torch.as_tensor(np.concatenate([np.cumprod(self.shape[::-1])[::-1][1:], [1]]).astype(np.int64))
+		return (self.indices.long() * mult[:, None]).sum(0)
+
+	def permute(self, *dims, inplace=False):
+		if tuple(sorted(dims)) != tuple(range(self.ndim)):
+			raise AssertionError("dims must be a permutation of range(ndim)")
+		d = list(dims)
+		indices, shape = self.indices[d], self.shape[d]
+		indptr = self.indptr if d[0] == 0 else None
+		if inplace:
+			self.indices, self.shape, self.indptr = indices, shape, indptr
+			return self
+		return Sparse(indices, self.values, shape, indptr=indptr)
+
+	def reshape(self, *dims, inplace=False):
+		dims = np.asarray(dims, dtype=np.int64).copy()
+		total = int(np.prod(self.shape))
+		if (dims == -1).sum() > 1:
+			raise AssertionError(dims)
+		if (dims == -1).any():
+			known = int(-np.prod(dims))
+			if known == 0 or total % known:
+				raise AssertionError(dims)
+			dims[dims == -1] = total // known
+		if int(np.prod(dims)) != total:
+			raise AssertionError((self.shape, dims))
+		flat = self._flat()
+		rows = []
+		for n in dims[::-1]:
+			rows.append(flat % int(n))
+			flat = torch.div(flat, int(n), rounding_mode="floor")
+		indices = torch.stack(rows[::-1]).to(self.indices.dtype if self.indices.dtype == torch.int64 else torch.int64)
+		if inplace:
+			self.indices, self.shape, self.ndim, self.indptr = indices, dims, len(dims), None
+			return self
+		return Sparse(indices, self.values, dims)
+
+	def slicing(self, idx, dim=0):
+		assert dim == 0 and isinstance(idx, slice) and idx.step in (None, 1)
+		indices, values, shape, start = self.get_slice_idx_value(idx)
+		indices = indices.clone()
+		indices[0] -= start
+		return Sparse(indices, values, shape)
+
+	def indexing(self, idx, dim=0):
+		assert dim == 0
+		self.sort_indices()
+		lo, hi = int(self.indptr[idx]), int(self.indptr[idx + 1])
+		return Sparse(self.indices[1:, lo:hi], self.values[lo:hi], tuple(self.shape[1:]))
+
+	def __getitem__(self, item):
+		if isinstance(item, (int, np.integer)):
+			return self.indexing(int(item))
+		if isinstance(item, slice):
+			return self.slicing(item)
+		raise NotImplementedError(type(item))
+
+	def filter_max_distance(self, max_distance=100):
+		keep = (self.indices[1].long() - self.indices[0].long()).abs() <= max_distance
+		self.indices, self.values, self.indptr = self.indices[:, keep], self.values[keep], None
+
+	def to_dense(self):
+		out = torch.zeros(tuple(int(x) for x in self.shape), dtype=self.values.dtype)
+		out.view(-1).index_put_((self._flat(),), self.values, accumulate=False)
+		return out
+
+	def to_scipy(self):
+		from scipy.sparse import coo_matrix
+		assert self.ndim == 2
+		return coo_matrix((self.values.numpy(), (self.indices[0].numpy(), self.indices[1].numpy())), tuple(int(x) for x in self.shape))
+
+	def to_csr(self):
+		return self.to_scipy().tocsr()
+
 
 class Chrom_Dataset:
 	"""One chromosome at one resolution as block-CSR (see module docstring).

@@ -140,3 +140,53 @@ def test_native_block_csr_empty_tensor_and_errors():
 	assert e.value.code == -1
 	with pytest.raises(ingest.IngestError):
 		ingest.block_csr(np.zeros((3, 0), np.int64), np.zeros(0, np.float32), 20, 8, 3, [8, 8, 4], [0, 4, 12], [12, 40000, 8])
+
+
+def test_sparse_container_known_answers_of_the_reference():
+	"""The reference's only test for this path, `sparse_for_schic.test()` (:634-661), restated on this package's `Sparse`:
+	sort, permute, reshape, slicing and their composition against dense numpy."""
+	def new_obj():
+		return Sparse([[0, 2, 1, 0], [0, 3, 2, 1]], [1, 2, 3, 4.], (3, 4))
+	dense = lambda o: np.asarray(o.to_scipy().todense())
+	base = dense(new_obj())
+	assert np.array_equal(base, np.array([[1, 4, 0, 0], [0, 0, 3, 0], [0, 0, 0, 2.]]))
+	o = new_obj(); o.sort_indices()
+	assert np.array_equal(dense(o), base) and list(o.indptr) == [0, 2, 3, 4]
+	assert np.array_equal(dense(new_obj().permute(0, 1)), base)
+	assert np.array_equal(dense(new_obj().permute(1, 0)), base.T)
+	assert np.array_equal(dense(new_obj().reshape(1, 12)), base.reshape(1, 12))
+	assert np.array_equal(dense(new_obj().reshape(4, 3)), base.reshape(4, 3))
+	assert np.array_equal(dense(new_obj().reshape(-1, 6)), base.reshape(2, 6))
+	for s in [slice(2), slice(10), slice(0, None), slice(2, None), slice(1, 3)]:
+		assert np.array_equal(dense(new_obj().slicing(s)), base[s])
+		assert np.array_equal(dense(new_obj()[s]), base[s])
+	o = new_obj().permute(1, 0).reshape(6, 2).slicing(slice(1, 3)).permute(1, 0)
+	assert np.array_equal(dense(o), base.T.reshape(6, 2)[1:3].T)
+	assert np.array_equal(new_obj().to_dense().numpy(), base) and new_obj().numel() == 12 and len(new_obj()) == 3
+	assert np.array_equal(new_obj()[0].to_dense().numpy(), base[0])
+	o = new_obj(); o.filter_max_distance(1)
+	assert np.array_equal(dense(o), np.triu(np.tril(base, 1), -1))
+	assert np.array_equal(np.asarray(new_obj().to_csr().todense()), base)
+
+
+def test_sparse_container_matches_reference_class_on_random_tensors():
+	from oracle import ref_shims
+	if not ref_shims.reference_available():
+		pytest.skip("the reference checkout is only present in the build container")
+	R = ref_shims.import_reference()["sparse_for_schic"].Sparse
+	rng = np.random.default_rng(4)
+	shape = (7, 5, 6)
+	flat = rng.choice(int(np.prod(shape)), size=60, replace=False)
+	idx = np.stack(np.unravel_index(flat, shape)).astype(np.int64)
+	val = rng.random(60).astype(np.float32)
+	ours, ref = Sparse(idx, val, shape), R(idx.copy(), val.copy(), np.asarray(shape))
+	assert np.array_equal(ours.to_dense().numpy(), ref.to_dense())
+	for perm in [(2, 0, 1), (1, 2, 0)]:
+		assert np.array_equal(ours.permute(*perm).to_dense().numpy(), ref.permute(*perm).to_dense())
+	for dims in [(35, 6), (7, 30), (5, -1, 3)]:
+		assert np.array_equal(ours.reshape(*dims).to_dense().numpy(), ref.reshape(*dims).to_dense())
+	for sl in [slice(1, 4), slice(3, None), slice(0, 20)]:
+		a, b = ours.get_slice_idx_value(sl), ref.get_slice_idx_value(sl)
+		assert a[2] == tuple(b[2]) and a[3] == b[3]
+		assert np.array_equal(ours[sl].to_dense().numpy(), ref[sl].to_dense())
+	assert np.array_equal(ours[2].to_dense().numpy(), ref[2].to_dense())
