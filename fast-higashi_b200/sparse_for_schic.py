@@ -324,6 +324,32 @@ class Chrom_Dataset:
 	def nnz(self):
 		return int(sum(v.numel() for v in self.val))
 
+	def fetch(self, bin_id, cell_id, save_context=None, transpose=False, good_qc=True, **kwargs):
+		"""Reference API (sparse_for_schic.py:588-613): the dense block of bin block `bin_id` and cell batch `cell_id`
+		(index into the good-QC batches, or into the bad-QC batches with good_qc=False), floor 1e-8, on the device:
+		(cells, nb, w) when `transpose` else the (nb, w, cells) view. Returns ((tensor, [seconds]), kind).
+		The decomposition itself never densifies separately (fh_rwr_batched reads the block-CSR)."""
+		import time
+		from .partial_rwr import densify_block
+		t = time.perf_counter()
+		sl = self.cell_slice_list[cell_id if good_qc else self.num_cell_batch + cell_id]
+		g = self.geoms[bin_id]
+		x = densify_block(self, bin_id, sl.start, sl.stop - sl.start)[:, :, :g.w]
+		if not transpose:
+			x = x.permute(1, 2, 0)
+		return (x, [time.perf_counter() - t]), self.kind
+
+	def fetch_bad(self, bin_id, cell_id, **kwargs):
+		return self.fetch(bin_id, cell_id, good_qc=False, **kwargs)
+
+	def norm(self):
+		"""Frobenius norm of all stored values (sparse_for_schic.py:615-620: good-QC cells only)."""
+		total = 0.0
+		for b, g in enumerate(self.geoms):
+			hi = int(self.rowptr[b][self.num_cell * g.nb])
+			total += float(self.val[b][:hi].double().square().sum())
+		return math.sqrt(total)
+
 	def cell_range_csr(self, b, cell_start, cell_stop):
 		"""CSR of cells [cell_start, cell_stop) of block b, rowptr rebased to 0 (host helper)."""
 		g = self.geoms[b]

@@ -335,3 +335,21 @@ def test_reference_wrapper_with_the_core_swapped_in(fake, tmp_path, monkeypatch)
 	for a, b in zip(out["reference"][1], out["ours"][1]):
 		assert a.shape == b.shape
 	assert out["reference"][2].shape == out["ours"][2].shape
+
+
+def test_chrom_dataset_fetch_matches_reference_fetch(fake):
+	"""`Chrom_Dataset.fetch` / `fetch_bad` / `norm` (sparse_for_schic.py:585-620) against the dense blocks the reference's
+	own fetch returned (tests/golden/rwr_cases.npz), bit for bit."""
+	g = np.load(os.path.join(GOLDEN, "rwr_cases.npz"))
+	ds = load_small_dataset(good_qc_num=44, bs_cell=20)
+	for c in range(int(g["ncase"])):
+		ci, b, cb, s, e = g["c%d_meta" % c]
+		(x, t), kind = ds[ci].fetch(int(b), int(cb), save_context=dict(device="cpu"), transpose=True, do_conv=False)
+		assert kind == "hic" and np.array_equal(x.numpy(), g["c%d_dense" % c])
+		(xt, _), _ = ds[ci].fetch(int(b), int(cb), save_context=dict(device="cpu"))
+		assert xt.shape == (x.shape[1], x.shape[2], x.shape[0]) and torch.equal(xt.permute(2, 0, 1), x)
+	(xb, _), _ = ds[0].fetch_bad(1, 0, save_context=dict(device="cpu"), transpose=True)
+	assert xb.shape[0] == 4 and torch.equal(xb, O.densify_block(ds[0], 1, 44, 48))
+	d = np.load(os.path.join(GOLDEN, "data_small.npz"))
+	good = d["chr1_idx"][2] < 44
+	assert abs(ds[0].norm() - float(np.sqrt(np.square(d["chr1_val"][good].astype(np.float64)).sum()))) < 1e-6

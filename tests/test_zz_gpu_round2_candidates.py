@@ -133,3 +133,19 @@ def test_full_size_rwr_conserves_column_mass(use_tc):
 		assert float(X[:, :, g.w:].abs().sum()) == 0.0 and bool((X[:, :, :g.w] > 0).all())
 		ca, cx = A.double().sum(1)[:, :g.w], X.double().sum(1)[:, :g.w]
 		assert float(((cx - ca).abs() / ca).max()) < 1e-5
+
+
+@first_run
+def test_chrom_dataset_fetch_api():
+	"""`Chrom_Dataset.fetch` / `fetch_bad` (sparse_for_schic.py:585-613) on the device against the reference's own fetch
+	outputs (tests/golden/rwr_cases.npz), bit for bit."""
+	from conftest import load_small_dataset
+	g = np.load(os.path.join(GOLDEN, "rwr_cases.npz"))
+	ds = load_small_dataset(good_qc_num=44, bs_cell=20, device="cuda:0")
+	for c in range(int(g["ncase"])):
+		ci, b, cb, s, e = g["c%d_meta" % c]
+		(x, t), kind = ds[ci].fetch(int(b), int(cb), save_context=dict(device="cuda:0"), transpose=True, do_conv=False)
+		assert kind == "hic" and x.is_cuda and np.array_equal(x.cpu().numpy(), g["c%d_dense" % c])
+	cpu = load_small_dataset(good_qc_num=44, bs_cell=20)
+	(xb, _), _ = ds[0].fetch_bad(1, 0, save_context=dict(device="cuda:0"), transpose=True)
+	assert torch.equal(xb.cpu(), O.densify_block(cpu[0], 1, 44, 48))
