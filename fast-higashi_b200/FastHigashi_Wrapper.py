@@ -129,6 +129,24 @@ class FastHigashi:
 			getattr(self, "batch_id", None) if "batch_id" in self.config else None, batch_norm,
 			ingest.load_blacklist(self.temp_dir), filename_pattern)
 
+	def preprocess_contact_map(self, config, reorder, path2input_cache, batch_norm, key_fn=lambda c: c, off_diag=None,
+	                           merge_fac_row=1, merge_fac_col=1, fac_size=1, is_sym=True, force_shift=False,
+	                           filename_pattern="%s_sparse_adj.npy", **kwargs):
+		"""Reference signature (FastHigashi_Wrapper.py:368-412): every chromosome of `config['chrom_list']` packed at the
+		coarsening `merge_fac_row` (= merge_fac_col), cached in `path2input_cache`, returned as a list of `Sparse` tensors
+		sorted on dim 0. The cache is this package's own format (plain arrays), not class pickles."""
+		if (fac_size not in (None, 1)) or not is_sym or force_shift or merge_fac_row != merge_fac_col:
+			raise NotImplementedError("fac_size != 1, is_sym=False, force_shift and unequal merge factors are never used by prep_dataset (:484-494)")
+		res = int(config["resolution"]) * int(merge_fac_row)
+		packed = ingest.preprocess_contact_map(config, reorder, path2input_cache, self.off_diag if off_diag is None else off_diag, res,
+		                                       getattr(self, "batch_id", None) if "batch_id" in self.config else None, batch_norm)
+		out = []
+		for idx, val, shape in packed:
+			m = Sparse(torch.as_tensor(idx), torch.as_tensor(val), shape, copy=False)
+			m.sort_indices()
+			out.append(m)
+		return out
+
 	def _load_tensors(self, res, reorder):
 		if self._tensors is not None:
 			out = []

@@ -156,3 +156,28 @@ def test_fetch_cell_embedding_device_svd_option(tmp_path):
 	assert "embed_correct_coverage_fh" in store and store["embed_correct_coverage_fh"].shape == b.shape
 	with pytest.raises(ValueError):
 		fh.fetch_cell_embedding(final_dim=6, svd="gpu")
+
+
+def test_preprocess_contact_map_method(raw_dir, tmp_path):  # noqa: F811
+	"""FastHigashi.preprocess_contact_map with the reference's call (FastHigashi_Wrapper.py:484-494): one dim-0-sorted
+	`Sparse` per chromosome, cached; coarsening through merge_fac_row/col (the reference's 'merge2' fixture)."""
+	fh = host_only_wrapper(raw_dir, str(tmp_path))
+	reorder = G["reorder"]
+	cache = os.path.join(str(tmp_path), "cache_intra_x.pkl")
+	mats = fh.preprocess_contact_map(fh.config, reorder=reorder, path2input_cache=cache, batch_norm=False, is_sym=True, off_diag=12,
+	                                 fac_size=1, merge_fac_row=1, merge_fac_col=1, filename_pattern="%s_sparse_adj.npy", force_shift=False)
+	assert os.path.exists(cache) and len(mats) == len(CHROMS)
+	for ch, m in zip(CHROMS, mats):
+		assert tuple(int(x) for x in m.shape) == tuple(int(x) for x in G["plain_%s_shape" % ch])
+		assert m.indptr is not None and bool((m.indices[0][1:] >= m.indices[0][:-1]).all())
+		ref = np.zeros(tuple(int(x) for x in m.shape), np.float32)
+		ri = G["plain_%s_idx" % ch]
+		ref[ri[0], ri[1], ri[2]] = G["plain_%s_val" % ch]
+		np.testing.assert_allclose(m.to_dense().numpy(), ref, rtol=2e-6, atol=1e-7)
+	again = fh.preprocess_contact_map(fh.config, reorder=reorder, path2input_cache=cache, batch_norm=False, off_diag=12)
+	assert all(np.array_equal(a.values.numpy(), b.values.numpy()) for a, b in zip(mats, again))
+	m2 = fh.preprocess_contact_map(fh.config, reorder=reorder, path2input_cache=None, batch_norm=False, off_diag=8, merge_fac_row=2, merge_fac_col=2)
+	for ch, m in zip(CHROMS, m2):
+		assert tuple(int(x) for x in m.shape) == tuple(int(x) for x in G["merge2_%s_shape" % ch])
+	with pytest.raises(NotImplementedError):
+		fh.preprocess_contact_map(fh.config, reorder=reorder, path2input_cache=None, batch_norm=False, fac_size=2)
