@@ -72,6 +72,22 @@ class FastHigashi:
 		self.avail_mem = torch.cuda.mem_get_info(self.gpu_id)[0]
 		self._tensors = None
 		self._meta = None
+		self.group = None
+
+	def distribute(self, group):
+		"""Cell-sharded mode, one process per GPU (not in the reference, which is single-GPU): call on every
+		rank of `group` (a torch.distributed process group) before `prep_dataset`. The ingest is partitioned by
+		CHROMOSOME (rank k packs chromosomes k, k + N, ... for all cells - the pooled normalisation is per chromosome, so
+		nothing is reduced), every chromosome's block-CSR is then scattered as cell slabs; `run_model` runs the sharded
+		core and gathers the embedding rows, so `fetch_cell_embedding` works unchanged on every rank; rank 0 writes files."""
+		self.group = group
+		return self
+
+	def _rank_world(self):
+		if getattr(self, "group", None) is None:
+			return 0, 1
+		import torch.distributed as dist
+		return dist.get_rank(self.group), dist.get_world_size(self.group)
 
 	# ------------------------------------------------------------------------------------------
 	def set_tensors(self, tensors, qc=None, readcount=None, label_info=None):
@@ -86,9 +102,18 @@ class FastHigashi:
 		"""FastHigashi_Wrapper.py:176-211: good-QC cells first; returns (label_info, reorder, readcount, qc)."""
 		import pandas as pd
 		qc, readcount, label_info = self._meta if self._meta is not None else (None, None, None)
-		if qc is None and os.path.isfile(os.path.join(self.path2input_cache, "qc.npy")):
+		rank, world = self._rank_world()
+		cached = qc is None and os.path.isfile(os.path.join(self.path2input_cache, "qc.npy"))
+		if world > 1:  # one decision for all ranks: get_qc is a collective there, and rank 0 (re)writes the cache below
+			import torch.distributed as dist
+			flag = [cached]
+			dist.broadcast_object_list(flag, src=dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0, group=self.group)
+			cached = flag[0]
+		if cached:
 			qc = np.load(os.path.join(self.path2input_cache, "qc.npy"))
 			readcount = np.load(os.path.join(self.path2input_cache, "read_count_all.npy"))
+		if world > 1:
+			dist.barrier(group=self.group)  # everybody has read the cache before rank 0 rewrites it
 		if qc is None:
 			qc, readcount = self.get_qc()
 		qc = np.asarray(qc)
@@ -102,11 +127,12 @@ class FastHigashi:
 		if len(label_info) == 0:
 			label_info = pd.DataFrame(np.ones(len(readcount)), columns=["placeholder"])
 		label_info = label_info.iloc[reorder].reset_index()
-		np.save(os.path.join(self.path2input_cache, "reorder.npy"), reorder)
 		if "batch_id" in self.config:
 			self.batch_id = np.asarray(label_info[self.config["batch_id"]])
-		np.save(os.path.join(self.path2input_cache, "qc.npy"), qc)  # :208-209
-		np.save(os.path.join(self.path2input_cache, "read_count_all.npy"), readcount)
+		if rank == 0:
+			np.save(os.path.join(self.path2input_cache, "reorder.npy"), reorder)
+			np.save(os.path.join(self.path2input_cache, "qc.npy"), qc)  # :208-209
+			np.save(os.path.join(self.path2input_cache, "read_count_all.npy"), readcount)
 		return label_info, reorder, readcount, qc
 
 	def get_qc(self):
@@ -115,7 +141,25 @@ class FastHigashi:
 		if not os.path.isdir(raw_dir):
 			raise RuntimeError("no QC information: pass qc/readcount to set_tensors(), provide qc.npy / read_count_all.npy in "
 			                   "path2input_cache, or the per-cell matrices under %s" % raw_dir)
-		return ingest.get_qc(raw_dir, self.chrom_list, self.config["resolution"])
+		rank, world = self._rank_world()
+		if world == 1:
+			return ingest.get_qc(raw_dir, self.chrom_list, self.config["resolution"])
+		# chromosome-partitioned: per-cell pass counts and read sums of disjoint chromosome subsets add up exactly
+		import torch.distributed as dist
+		mine = self.chrom_list[rank::world]
+		passed, reads, dtype = ingest.qc_partial(raw_dir, mine, self.config["resolution"]) if mine else (0, 0, np.float64)
+		ncell = [int(np.size(passed)) if mine else 0]
+		sizes = [None] * world
+		dist.all_gather_object(sizes, (ncell[0], np.dtype(dtype).str), group=self.group)
+		n = max(x[0] for x in sizes)
+		dtype = np.dtype(next(x[1] for x in sizes if x[0] > 0))
+		buf = torch.zeros(2, n, dtype=torch.float64)
+		if mine:
+			buf[0], buf[1] = torch.from_numpy(np.asarray(passed, dtype=np.float64)), torch.from_numpy(np.asarray(reads, dtype=np.float64))
+		buf = buf.to(self.device)
+		dist.all_reduce(buf, group=self.group)
+		buf = buf.cpu().numpy()
+		return ingest.qc_combine(buf[0], buf[1], len(self.chrom_list), dtype)
 
 	def pack_training_data_one_process(self, raw_dir, chrom, reorder, off_diag=None, fac_size=None, merge_fac_row=1,
 	                                   merge_fac_col=1, is_sym=True, filename_pattern="%s_sparse_adj.npy", force_shift=None,
@@ -184,21 +228,15 @@ class FastHigashi:
 			return
 		good_qc_num = int(np.sum(qc > 0))
 		print("total number of cells that pass qc check", good_qc_num, "bad", len(qc) - good_qc_num, "total:", len(qc))
+		if self._rank_world()[1] > 1:
+			return self._prep_dataset_distributed(reorder, good_qc_num, len(qc))
 		datasets = []
 		for res in self.fh_resolutions:
 			all_matrix = self._load_tensors(res, reorder)
 			num_cell = int(all_matrix[-1].shape[-1])
-			max_tensor_size = self.avail_mem / (4 * 12)
-			recommend_bs_bin = min(max(int(15000000 / res), 128), 256)
 			total_reads, total_possible = 0, 0
 			for i, m in enumerate(all_matrix):
-				size = int(m.shape[0])
-				n_batch = max(math.ceil(size / recommend_bs_bin), 1)
-				bs_bin_local = math.ceil(size / n_batch)
-				bs_cell = int(max_tensor_size / (bs_bin_local * (bs_bin_local + 2 * self.off_diag)))
-				ncell_eff = good_qc_num if self.filter else num_cell
-				n_cb = int(math.ceil(ncell_eff / max(bs_cell, 1)))
-				bs_cell = min(int(math.ceil(ncell_eff / n_cb)), ncell_eff)
+				bs_bin_local, bs_cell = self._batch_sizes(int(m.shape[0]), res, good_qc_num, num_cell)
 				total_reads += len(m.values)
 				total_possible += float(np.prod(np.asarray(m.shape, dtype=np.float64)))
 				datasets.append(Chrom_Dataset(tensor=m, bs_bin=bs_bin_local, bs_cell=bs_cell,
@@ -218,6 +256,72 @@ class FastHigashi:
 		self.good_qc_num = good_qc_num
 		self.all_matrix = datasets
 
+	def _batch_sizes(self, size, res, good_qc_num, num_cell):
+		"""bs_bin, bs_cell of one chromosome (FastHigashi_Wrapper.py:500-517)."""
+		max_tensor_size = self.avail_mem / (4 * 12)
+		recommend_bs_bin = min(max(int(15000000 / res), 128), 256)
+		n_batch = max(math.ceil(size / recommend_bs_bin), 1)
+		bs_bin_local = math.ceil(size / n_batch)
+		bs_cell = int(max_tensor_size / (bs_bin_local * (bs_bin_local + 2 * self.off_diag)))
+		ncell_eff = good_qc_num if self.filter else num_cell
+		n_cb = int(math.ceil(ncell_eff / max(bs_cell, 1)))
+		return bs_bin_local, min(int(math.ceil(ncell_eff / n_cb)), ncell_eff)
+
+	def _load_tensor_one(self, res, reorder, i):
+		"""The COO tensor of chromosome i at `res` (distributed mode: only the owner rank loads it)."""
+		if self._tensors is not None:
+			idx, val, shape = self._tensors[res][i]
+			inv = np.empty(len(reorder), dtype=np.int64)
+			inv[reorder] = np.arange(len(reorder))
+			idx = torch.as_tensor(np.asarray(idx)).long().clone()
+			idx[2] = torch.as_tensor(inv)[idx[2]]
+			return Sparse(idx, torch.as_tensor(np.asarray(val)).float(), shape, copy=False)
+		raw_dir = os.path.join(self.temp_dir, "raw")
+		if not os.path.isdir(raw_dir):
+			raise RuntimeError("distributed prep_dataset needs set_tensors() or the per-cell matrices under %s" % raw_dir)
+		fac = int(res / self.config["resolution"])
+		idx, val, shape = ingest.pack_training_data_one_process(
+			raw_dir, self.chrom_list[i], reorder, self.off_diag, fac, fac,
+			getattr(self, "batch_id", None) if "batch_id" in self.config else None, self._batch_norm, ingest.load_blacklist(self.temp_dir))
+		return Sparse(torch.as_tensor(idx), torch.as_tensor(val), shape, copy=False)
+
+	def _prep_dataset_distributed(self, reorder, good_qc_num, num_cell):
+		"""prep_dataset when `distribute(group)` was called: chromosome i is packed and staged (on the host) by rank
+		i mod N alone, then scattered as cell slabs; every rank ends with `shard_datasets(all cells, N, rank)`."""
+		from .sharding import scatter_dataset
+		rank, world = self._rank_world()
+		datasets = []
+		for res in self.fh_resolutions:
+			total_reads, total_possible = 0, 0.0
+			for i, chrom in enumerate(self.chrom_list):
+				owner = i % world
+				full = None
+				if rank == owner:
+					m = self._load_tensor_one(res, reorder, i)
+					bs_bin_local, bs_cell = self._batch_sizes(int(m.shape[0]), res, good_qc_num, num_cell)
+					full = Chrom_Dataset(tensor=m, bs_bin=bs_bin_local, bs_cell=bs_cell, good_qc_num=good_qc_num if self.filter else -1,
+					                     kind="hic", upper_sim=False, compact=True, flank=self.off_diag, chrom=chrom, resolution=res,
+					                     device="cpu")
+					del m
+				slab, meta = scatter_dataset(full, owner, self.group, self.device)
+				del full
+				total_reads += meta["nnz"]
+				total_possible += float(np.prod(np.asarray(meta["shape"], dtype=np.float64)))
+				datasets.append(slab)
+			sparsity = total_reads / total_possible
+			do_col = sparsity * (500000 / res) ** 2 <= 0.03 or self.do_col
+			if self.no_col:
+				do_col = False
+			if rank == 0:
+				print("sparsity", sparsity)
+				print("do_conv", self.do_conv, "do_rwr", self.do_rwr, "do_col", do_col)
+			self.final_do_col = do_col
+			if self.no_col and self.do_col:
+				print("choose one between do col or no col!")
+				raise EOFError
+		self.good_qc_num = good_qc_num
+		self.all_matrix = datasets
+
 	def only_partial_rwr(self, out_format=None):
 		"""FastHigashi_Wrapper.py:569-655: impute every cell (good and bad QC) with conv + auto-stopped RWR
 		(`force_rwr_epochs=-1`, `do_col=False`, one stop decision per (bin-block, cell batch) as in the
@@ -230,6 +334,8 @@ class FastHigashi:
 		symmetrisation in fp32 (x + y and 2x/2 are exact in fp32, so the result equals the reference's
 		float64-then-cast arithmetic bit for bit)."""
 		from .partial_rwr import rwr_block_csr, pad4
+		if self._rank_world()[1] > 1:
+			raise NotImplementedError("only_partial_rwr writes whole per-cell maps from one process; run it without distribute()")
 		if out_format is None:
 			try:
 				import h5py  # noqa: F401
@@ -289,21 +395,28 @@ class FastHigashi:
 		self.save_str = save_str
 		print(save_str)
 		start = time.time()
+		my_rank, world = self._rank_world()
 		if self.model is None:
-			self.model = Fast_Higashi_core(rank=rank, off_diag=self.off_diag, res_list=self.fh_resolutions).to(self.device)
+			self.model = Fast_Higashi_core(rank=rank, off_diag=self.off_diag, res_list=self.fh_resolutions,
+			                               group=self.group if world > 1 else None).to(self.device)
 		if n_iter_max is None:
 			n_iter_max = int(self.good_qc_num / 15)
 		result = self.model.fit_transform(self.all_matrix, size_ratio=dim1, n_iter_max=n_iter_max, n_iter_parafac=n_iter_parafac,
 		                                  do_conv=self.do_conv, do_rwr=self.do_rwr, do_col=self.final_do_col, tol=tol,
-		                                  gpu_id=self.gpu_id, run_init=run_init)
+		                                  gpu_id=self.gpu_id, run_init=run_init, verbose=my_rank == 0)
 		print("takes: %.2f s" % (time.time() - start))
 		_, factors_all, p_list = result
 		A_list, B_list, D_list, meta_embedding = factors_all
+		if world > 1:  # rows of this rank's good then bad cells -> all cells in the unsharded order, on every rank
+			from .sharding import gather_cell_rows
+			meta_embedding = gather_cell_rows(meta_embedding, self.all_matrix[0].num_cell, self.group)
 		self.meta_embedding = meta_embedding.detach().cpu().numpy()
 		self.A_list = [A.detach().cpu().numpy() for A in A_list]
 		self.B_list = [B.detach().cpu().numpy() for B in B_list]
 		self.D_list = [D.detach().cpu().numpy() for D in D_list]
 		self.p_list = [[p.detach().cpu().numpy() for p in temp] for temp in p_list]
+		if my_rank != 0:
+			return
 		pickle.dump([self.A_list, self.B_list, self.D_list, self.meta_embedding, self.p_list],
 		            open(os.path.join(self.path2result_dir, "results_all%s.pkl" % save_str), "wb"), protocol=4)
 		pickle.dump([self.meta_embedding, self.D_list],

@@ -124,12 +124,12 @@ def load_raw_chrom(raw_dir, chrom, reorder=None, filename_pattern="%s_sparse_adj
 
 
 # ------------------------------------------------------------------------------------------------
-def get_qc(raw_dir, chrom_list, resolution, filename_pattern="%s_sparse_adj.npy"):
-	"""FastHigashi_Wrapper.py:428-458 -> (kept float32 (cells,), log1p(total read count) (cells,)).
-	A cell is kept when, on every chromosome, its number of distinct contacts (nnz + positive
-	diagonal)/2 exceeds the number of well-covered bins (or the median, when fewer than half pass)."""
+def qc_partial(raw_dir, chrom_list, resolution, filename_pattern="%s_sparse_adj.npy"):
+	"""The per-chromosome part of get_qc for a SUBSET of the chromosomes: (number of chromosomes on which each cell
+	passes (cells,) float64, summed read counts (cells,) float64, dtype of the files). Partial results of disjoint
+	subsets add up (the counts are integers, so the sums are exact in any order)."""
 	scale = int(1000000 / resolution)
-	masks, read_all, dtype = [], 0, np.float64
+	passed, read_all, dtype = 0, 0, np.float64
 	L = lib()
 	for chrom in chrom_list:
 		cm = load_raw_chrom(raw_dir, chrom, None, filename_pattern)
@@ -139,13 +139,26 @@ def get_qc(raw_dir, chrom_list, resolution, filename_pattern="%s_sparse_adj.npy"
 		_check(L.fh_host_qc_chrom(C.byref(cm.desc), scale, contacts.ctypes.data, reads.ctypes.data, C.byref(n_bin), num_threads()))
 		n_bin = n_bin.value
 		if np.sum(contacts > n_bin) > 0.5 * len(contacts):
-			masks.append(contacts > n_bin)
+			mask = contacts > n_bin
 		else:
-			masks.append(contacts > np.quantile(contacts, 0.5))
+			mask = contacts > np.quantile(contacts, 0.5)
+		passed = passed + mask.astype(np.float64)
 		read_all = read_all + reads
 		dtype = cm.dtype if np.issubdtype(cm.dtype, np.floating) else np.float64
-	kept = (np.sum(np.array(masks).astype("float"), axis=0) >= len(chrom_list)).astype("float32")
-	return kept, np.log1p(read_all.astype(dtype))  # the reference sums in the files' dtype (fp32 files -> fp32 log1p)
+	return passed, read_all, dtype
+
+
+def qc_combine(passed, read_all, num_chrom, dtype=np.float64):
+	kept = (np.asarray(passed) >= num_chrom).astype("float32")
+	return kept, np.log1p(np.asarray(read_all).astype(dtype))  # the reference sums in the files' dtype (fp32 files -> fp32 log1p)
+
+
+def get_qc(raw_dir, chrom_list, resolution, filename_pattern="%s_sparse_adj.npy"):
+	"""FastHigashi_Wrapper.py:428-458 -> (kept float32 (cells,), log1p(total read count) (cells,)).
+	A cell is kept when, on every chromosome, its number of distinct contacts (nnz + positive
+	diagonal)/2 exceeds the number of well-covered bins (or the median, when fewer than half pass)."""
+	passed, read_all, dtype = qc_partial(raw_dir, chrom_list, resolution, filename_pattern)
+	return qc_combine(passed, read_all, len(chrom_list), dtype)
 
 
 def pack_training_data_one_process(raw_dir, chrom, reorder, off_diag, merge_fac_row=1, merge_fac_col=1,

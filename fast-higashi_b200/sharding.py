@@ -56,3 +56,21 @@ def polar_partition(sizes, world_size, rank):
 	sizes = np.asarray(sizes)
 	order = np.argsort(-sizes, kind="stable")
 	return order, order[int(rank)::int(world_size)]
+
+
+def scatter_dataset(ds, owner, group, device):
+	"""`ds` (a Chrom_Dataset holding ALL cells, on the host) lives on rank `owner` only (None elsewhere); every rank gets
+	its slab - exactly `shard_datasets([ds], world, rank)[0]` - on `device`. Used by the chromosome-partitioned ingest of
+	`FastHigashi.prep_dataset` in distributed mode. Returns (slab, meta) with meta = dict(nnz, shape) of the whole tensor."""
+	import torch.distributed as dist
+	from .sparse_for_schic import Chrom_Dataset
+	world, rank = dist.get_world_size(group), dist.get_rank(group)
+	src = dist.get_global_rank(group, owner) if hasattr(dist, "get_global_rank") else owner
+	payloads = None
+	if rank == owner:
+		meta = dict(nnz=ds.nnz(), shape=(ds.num_bin, ds.num_bin, ds.total_cell_num))
+		payloads = [(shard_datasets([ds], world, j)[0].to_payload(), meta) for j in range(world)]
+	got = [None]
+	dist.scatter_object_list(got, payloads, src=src, group=group)
+	payload, meta = got[0]
+	return Chrom_Dataset.from_payload(payload, device), meta

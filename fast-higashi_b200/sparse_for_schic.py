@@ -324,6 +324,21 @@ class Chrom_Dataset:
 	def nnz(self):
 		return int(sum(v.numel() for v in self.val))
 
+	def to_payload(self):
+		"""Everything needed to rebuild this dataset in another process: plain fields + the CSR arrays on the host."""
+		d = {k: v for k, v in self.__dict__.items() if k not in ("rowptr", "col", "val", "device")}
+		d["rowptr"] = [t.cpu() for t in self.rowptr]
+		d["col"] = [t.cpu() for t in self.col]
+		d["val"] = [t.cpu() for t in self.val]
+		return d
+
+	@classmethod
+	def from_payload(cls, payload, device="cpu"):
+		new = object.__new__(cls)
+		new.__dict__.update(payload)
+		new.device = torch.device("cpu")
+		return new.to(device)
+
 	def fetch(self, bin_id, cell_id, save_context=None, transpose=False, good_qc=True, **kwargs):
 		"""Reference API (sparse_for_schic.py:588-613): the dense block of bin block `bin_id` and cell batch `cell_id`
 		(index into the good-QC batches, or into the bad-QC batches with good_qc=False), floor 1e-8, on the device:

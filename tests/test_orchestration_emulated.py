@@ -149,10 +149,12 @@ def _cpu_wrapper(tmp_path, off, res, chroms):
 	from unittest import mock
 	from fasthigashi_b200.FastHigashi_Wrapper import FastHigashi
 	cfg = dict(chrom_list=chroms, temp_dir=str(tmp_path), data_dir=str(tmp_path), resolution=res, resolution_fh=[res])
-	json.dump(cfg, open(tmp_path / "config.JSON", "w"))
+	cfg_path = tmp_path / ("config_%d.JSON" % os.getpid())         # per process: the gloo workers share tmp_path
+	with open(cfg_path, "w") as f:
+		json.dump(cfg, f)
 	with mock.patch("torch.cuda.is_available", lambda: True), mock.patch("torch.cuda.current_device", lambda: 0), \
 	     mock.patch("torch.cuda.mem_get_info", lambda *a: (64 << 30, 180 << 30)):
-		w = FastHigashi(str(tmp_path / "config.JSON"), None, None, off, True, True, True, False, False)
+		w = FastHigashi(str(cfg_path), None, None, off, True, True, True, False, False)
 	w.device = "cpu"
 	return w
 
@@ -219,7 +221,7 @@ def test_two_rank_gloo_run_equals_single_process(do_col, good, bs_cell, init_svd
 	port = _free_port()
 	procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q, do_col, good, bs_cell, init_svd)) for r in range(2)]
 	for p in procs: p.start()
-	res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r[0])
+	res = sorted([q.get(timeout=180) for _ in procs], key=lambda r: r[0])
 	for p in procs: p.join(timeout=60)
 	for r in res:
 		assert r[1] == n_i1
@@ -353,3 +355,66 @@ def test_chrom_dataset_fetch_matches_reference_fetch(fake):
 	d = np.load(os.path.join(GOLDEN, "data_small.npz"))
 	good = d["chr1_idx"][2] < 44
 	assert abs(ds[0].norm() - float(np.sqrt(np.square(d["chr1_val"][good].astype(np.float64)).sum()))) < 1e-6
+
+
+def _dist_wrapper_worker(rank, world, port, q, tmp):
+	import pathlib
+	import torch.distributed as dist
+	os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+	dist.init_process_group("gloo", rank=rank, world_size=world)
+	torch.set_num_threads(2)
+	fake_abi.install()
+	G = np.load(os.path.join(GOLDEN, "ingest_cases.npz"), allow_pickle=True)
+	chroms = [str(c) for c in G["chroms"]]
+	w = _cpu_wrapper(pathlib.Path(tmp), 12, int(G["res"]), chroms).distribute(dist.group.WORLD)
+	w.prep_dataset()
+	torch.manual_seed(0); np.random.seed(0)
+	w.run_model(dim1=0.6, rank=8, n_iter_parafac=1, n_iter_max=4, tol=0.0)
+	np.random.seed(1)
+	emb = w.fetch_cell_embedding(final_dim=4)
+	csr = [[(ds.rowptr[b].numpy(), ds.col[b].numpy(), ds.val[b].numpy()) for b in range(len(ds.geoms))] for ds in w.all_matrix]
+	q.put((rank, w.reorder, w.good_qc_num, w.final_do_col, [(d.num_cell, d.total_cell_num, d.bs_bin, d.bs_cell) for d in w.all_matrix], csr,
+	       emb["embed_all"], w.meta_embedding, os.path.exists(os.path.join(tmp, "results_all%s.pkl" % w.save_str))))
+	dist.destroy_process_group()
+
+
+def test_distributed_wrapper_on_two_gloo_ranks(fake, tmp_path):
+	"""`FastHigashi.distribute(group)`: QC and ingest partitioned by chromosome (each raw file is read by ONE rank), the
+	block-CSR of every chromosome scattered as cell slabs (== shard_datasets of the single-process datasets, bit for
+	bit), sharded run_model with the embedding rows gathered in the unsharded order, files written by rank 0."""
+	import pickle
+	import torch.multiprocessing as mp
+	import wrapper_cases
+	from fasthigashi_b200.sharding import shard_datasets
+	G = np.load(os.path.join(GOLDEN, "ingest_cases.npz"), allow_pickle=True)
+	chroms = [str(c) for c in G["chroms"]]
+	wrapper_cases.write_raw_files(G, tmp_path)
+	single = _cpu_wrapper(tmp_path, 12, int(G["res"]), chroms)
+	single.path2input_cache = single.path2result_dir = str(tmp_path / "single")
+	os.makedirs(single.path2input_cache)
+	single.prep_dataset()
+	torch.manual_seed(0); np.random.seed(0)
+	single.run_model(dim1=0.6, rank=8, n_iter_parafac=1, n_iter_max=4, tol=0.0)
+	np.random.seed(1)
+	emb1 = single.fetch_cell_embedding(final_dim=4)
+	ctx = mp.get_context("spawn")
+	q = ctx.Queue()
+	port = _free_port()
+	procs = [ctx.Process(target=_dist_wrapper_worker, args=(r, 2, port, q, str(tmp_path))) for r in range(2)]
+	for p in procs: p.start()
+	res = sorted([q.get(timeout=180) for _ in procs], key=lambda r: r[0])
+	for p in procs: p.join(timeout=60)
+	for r in res:
+		rank = r[0]
+		assert np.array_equal(r[1], single.reorder) and r[2] == single.good_qc_num and r[3] == single.final_do_col
+		want = shard_datasets(single.all_matrix, 2, rank)
+		assert r[4] == [(d.num_cell, d.total_cell_num, d.bs_bin, d.bs_cell) for d in want]
+		for ds, got in zip(want, r[5]):
+			for b in range(len(ds.geoms)):
+				assert np.array_equal(got[b][0], ds.rowptr[b].numpy()) and np.array_equal(got[b][1], ds.col[b].numpy())
+				assert np.array_equal(got[b][2], ds.val[b].numpy())
+		assert r[6].shape == emb1["embed_all"].shape and r[7].shape == single.meta_embedding.shape
+		for j in range(r[6].shape[1]):
+			assert abs(np.corrcoef(r[6][:, j], emb1["embed_all"][:, j])[0, 1]) > 0.99
+	assert np.array_equal(res[0][6], res[1][6])        # every rank holds the embeddings of ALL cells
+	assert res[0][8]                                   # rank 0 wrote results_all*.pkl
