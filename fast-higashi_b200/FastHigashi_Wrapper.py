@@ -334,8 +334,8 @@ class FastHigashi:
 		symmetrisation in fp32 (x + y and 2x/2 are exact in fp32, so the result equals the reference's
 		float64-then-cast arithmetic bit for bit)."""
 		from .partial_rwr import rwr_block_csr, pad4
-		if self._rank_world()[1] > 1:
-			raise NotImplementedError("only_partial_rwr writes whole per-cell maps from one process; run it without distribute()")
+		my_rank, world = self._rank_world()
+		suffix = "" if world == 1 else "_rank%d" % my_rank  # distributed: every rank writes the maps of ITS cells
 		if out_format is None:
 			try:
 				import h5py  # noqa: F401
@@ -345,13 +345,23 @@ class FastHigashi:
 		h5 = None
 		if out_format == "hdf5":
 			import h5py
-			h5 = h5py.File(os.path.join(self.path2result_dir, "impute_prwr.hdf5"), "w")
+			h5 = h5py.File(os.path.join(self.path2result_dir, "impute_prwr%s.hdf5" % suffix), "w")
 		elif out_format != "npz":
 			raise ValueError("out_format must be 'hdf5' or 'npz'")
 		written = []
 		for ds in self.all_matrix:
 			n = ds.num_bin
 			maps = {"shape": np.asarray([n, n])}
+			# position of the dataset's cells in the unsharded (good first, then bad) order that `reorder` indexes
+			if world == 1:
+				cell_pos = np.arange(ds.total_cell_num)
+			else:
+				from .sharding import cell_slab
+				glo, ghi = cell_slab(self.good_qc_num if self.filter else len(self.reorder), world, my_rank)
+				nbad_all = len(self.reorder) - self.good_qc_num if self.filter else 0
+				blo, bhi = cell_slab(nbad_all, world, my_rank)
+				cell_pos = np.concatenate([np.arange(glo, ghi), self.good_qc_num + np.arange(blo, bhi)]) if self.filter else np.arange(glo, ghi)
+				assert len(cell_pos) == ds.total_cell_num
 			for sl in ds.cell_slice_list:
 				c0, nc = sl.start, sl.stop - sl.start
 				if nc <= 0:
@@ -373,19 +383,19 @@ class FastHigashi:
 					d.sub_(d / 2)
 					host = full.cpu().numpy()
 					for i in range(s1 - s0):
-						maps[str(self.reorder[c0 + s0 + i])] = host[i]
+						maps[str(self.reorder[cell_pos[c0 + s0 + i]])] = host[i]
 				del panels
 			if h5 is not None:
 				group = h5.create_group(ds.chrom)
 				for k, v in maps.items():
 					group.create_dataset(k, data=v)
 			else:
-				path = os.path.join(self.path2result_dir, "impute_prwr_%s.npz" % ds.chrom)
+				path = os.path.join(self.path2result_dir, "impute_prwr_%s%s.npz" % (ds.chrom, suffix))
 				np.savez(path, **maps)
 				written.append(path)
 		if h5 is not None:
 			h5.close()
-			return os.path.join(self.path2result_dir, "impute_prwr.hdf5")
+			return os.path.join(self.path2result_dir, "impute_prwr%s.hdf5" % suffix)
 		return written
 
 	def run_model(self, dim1=.6, rank=256, n_iter_parafac=1, n_iter_max=None, tol=2e-5, extra="", run_init=True):

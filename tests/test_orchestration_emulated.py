@@ -373,6 +373,9 @@ def _dist_wrapper_worker(rank, world, port, q, tmp):
 	np.random.seed(1)
 	emb = w.fetch_cell_embedding(final_dim=4)
 	csr = [[(ds.rowptr[b].numpy(), ds.col[b].numpy(), ds.val[b].numpy()) for b in range(len(ds.geoms))] for ds in w.all_matrix]
+	w.path2result_dir = tmp
+	files = w.only_partial_rwr(out_format="npz")
+	assert all(f.endswith("_rank%d.npz" % rank) for f in files)
 	q.put((rank, w.reorder, w.good_qc_num, w.final_do_col, [(d.num_cell, d.total_cell_num, d.bs_bin, d.bs_cell) for d in w.all_matrix], csr,
 	       emb["embed_all"], w.meta_embedding, os.path.exists(os.path.join(tmp, "results_all%s.pkl" % w.save_str))))
 	dist.destroy_process_group()
@@ -417,4 +420,16 @@ def test_distributed_wrapper_on_two_gloo_ranks(fake, tmp_path):
 		for j in range(r[6].shape[1]):
 			assert abs(np.corrcoef(r[6][:, j], emb1["embed_all"][:, j])[0, 1]) > 0.99
 	assert np.array_equal(res[0][6], res[1][6])        # every rank holds the embeddings of ALL cells
+	# only_partial_rwr in distributed mode: every rank wrote the maps of its own cells under their ORIGINAL ids
+	single.path2result_dir = str(tmp_path / "single")
+	ref_files = single.only_partial_rwr(out_format="npz")
+	for ch, ref_file in zip(chroms, ref_files):
+		ref = np.load(ref_file)
+		parts = [np.load(os.path.join(str(tmp_path), "impute_prwr_%s_rank%d.npz" % (ch, r))) for r in range(2)]
+		keys = [set(p.files) - {"shape"} for p in parts]
+		assert not (keys[0] & keys[1]) and (keys[0] | keys[1]) == set(ref.files) - {"shape"}
+		for p in parts:
+			for k in set(p.files) - {"shape"}:
+				# the auto-stop is per cell batch, so a slab may stop one step earlier or later than the full batch
+				assert np.linalg.norm(p[k] - ref[k]) <= 0.05 * np.linalg.norm(ref[k])
 	assert res[0][8]                                   # rank 0 wrote results_all*.pkl
