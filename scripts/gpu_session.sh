@@ -4,7 +4,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/gpu_session.sh'
 # 1. pytest -m gpu (verified tests), then the opt-in tests of code never run on a GPU (FH_RUN_UNVERIFIED=1)
 # 2. smoke()
-# 3. bench.py default line, reference arm
+# 3. bench.py default line, reference arm, scripts/headline_run.py (the whole job) at N = 1
 # 4. ncu launch list of a short bench (kernel shares) and one --set full capture of the fused RWR kernel
 set -u
 OUT=gpurun_out
@@ -15,6 +15,9 @@ TAG=${1:-r02}
 ( timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -5 ) > $OUT/${TAG}_smoke.txt
 ( timeout 900 python bench.py 2>$OUT/${TAG}_bench_n1.err | tail -1 ) > $OUT/${TAG}_bench_n1.json
 ( timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 ) > $OUT/${TAG}_bench_reference_arm.json
+# the whole job (init + sweeps + transform) of config 2 on this GPU, host and device init SVDs
+( timeout 600 python scripts/headline_run.py --cells-total 4238 --sweeps 10 --geometry pfc --init-svd device 2>/dev/null | tail -1 ) > $OUT/${TAG}_job_n1_device_init.json
+( timeout 600 python scripts/headline_run.py --cells-total 4238 --sweeps 10 --geometry pfc --init-svd host 2>/dev/null | tail -1 ) > $OUT/${TAG}_job_n1_host_init.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'densify|rwr_chain|gemm_|chol_jacobi|transition|khatri|mode|balance|hadamard|scale_cols|sqnorm|ns_' \
 	-c 2200 --csv --log-file $OUT/${TAG}_launches_512cells.csv python bench.py --cells 512 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_launches_bench.log 2>&1
 python scripts/agg_launches.py $OUT/${TAG}_launches_512cells.csv > $OUT/${TAG}_launches_summary_512cells.txt 2>&1
