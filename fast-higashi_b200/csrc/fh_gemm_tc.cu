@@ -36,7 +36,10 @@ constexpr int EPI_BYTES = 8 * 32 * 32 * 4;       // epilogue transposes: 8 drain
 constexpr uint32_t TM_A = 2 * BN;                // TMEM: accumulators [0, 2 BN), then per stage A_hi (32 cols) | A_lo (32 cols)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NTHREADS = 512;
-constexpr int CHUNK_KB = 4;                      // k-blocks accumulated in TMEM before a drain (K = 128)
+#ifndef FH_GEMM_CHUNK_KB
+#define FH_GEMM_CHUNK_KB 4                       // compile-time knob for A/B builds (FH_NVCC_EXTRA, scripts/gpu_session.sh)
+#endif
+constexpr int CHUNK_KB = FH_GEMM_CHUNK_KB;       // k-blocks accumulated in TMEM before a drain (K = 128 at the default 4)
 
 struct TcP {
 	int M, N, K, batch;

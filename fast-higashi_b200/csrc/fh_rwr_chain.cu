@@ -37,7 +37,10 @@ constexpr int SLOT_BYTES = 2 * TILE_BYTES;      // hi (raw fp32 as landed), lo
 constexpr int EPI_BYTES = 8 * 32 * 32 * 4;      // 8 drain warps x (32 x 32 floats, XOR-swizzled)
 constexpr int XCH_FLOATS = 4 * 128 + 2 * 128 + 4 * 128;  // PANEL: column partials [4][128], row sums [2][128], cs1/w1/w2/flag [128]
 constexpr int NTHREADS = 512;
-constexpr int CHUNK_KB = 4;                     // S2: k-blocks accumulated in TMEM before a drain (as fh_gemm_tc.cu)
+#ifndef FH_CHAIN_CHUNK_KB
+#define FH_CHAIN_CHUNK_KB 4                     // compile-time knob for A/B builds (FH_NVCC_EXTRA, scripts/gpu_session.sh)
+#endif
+constexpr int CHUNK_KB = FH_CHAIN_CHUNK_KB;     // S2: k-blocks accumulated in TMEM before a drain (as fh_gemm_tc.cu)
 constexpr float EPS = 1e-15f;                   // partial_rwr.py:88-97
 template <bool PANEL> struct Cfg {
 	static constexpr int SLOTS = PANEL ? 5 : 6;

@@ -26,10 +26,11 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:rwr_
 	python bench.py --cells 2072 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_ncu_full.log 2>&1
 ncu -i $OUT/${TAG}_ncu_full_rwr_chain.ncu-rep --page details > $OUT/${TAG}_ncu_full_rwr_chain_kernel.txt 2>&1
 # A/B of compile-time variants (nvcc is on the box): rebuild with the flag, parity test of the kernel, bench line; then restore
-for V in FH_CHAIN_PROLOGUE_ROLLED; do
+# (the chunk sizes change the summation order of the TF32 accumulations: the parity tests in front of the bench decide)
+for V in FH_CHAIN_PROLOGUE_ROLLED FH_CHAIN_CHUNK_KB=5 FH_GEMM_CHUNK_KB=8; do
 	( FH_NVCC_EXTRA="-D$V" timeout 600 python -c "import __graft_entry__ as g; g.build()" \
-	  && timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "rwr" 2>&1 | tail -3 \
-	  && FH_NVCC_EXTRA="-D$V" timeout 600 python bench.py --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 ) > $OUT/${TAG}_variant_$V.txt 2>&1
+	  && timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "rwr or tcgen05 or lockstep or midsize" 2>&1 | tail -3 \
+	  && FH_NVCC_EXTRA="-D$V" timeout 600 python bench.py --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 ) > $OUT/${TAG}_variant_${V%%=*}.txt 2>&1
 done
 timeout 600 python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
 tail -3 $OUT/${TAG}_pytest_gpu.txt $OUT/${TAG}_pytest_unverified.txt $OUT/${TAG}_smoke.txt
