@@ -25,6 +25,8 @@ gzip -f $OUT/${TAG}_launches_512cells.csv
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:rwr_chain_kernel -s 4 -c 1 -o $OUT/${TAG}_ncu_full_rwr_chain \
 	python bench.py --cells 2072 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_ncu_full.log 2>&1
 ncu -i $OUT/${TAG}_ncu_full_rwr_chain.ncu-rep --page details > $OUT/${TAG}_ncu_full_rwr_chain_kernel.txt 2>&1
+# the opt-in block Jacobi of the per-bin polar step, timed next to the default line (only meaningful if its test above passed)
+( FH_POLAR_BLOCK=1 timeout 600 python bench.py --no-cpu-baseline --no-e2e 2>$OUT/${TAG}_bench_polar_block.err | tail -1 ) > $OUT/${TAG}_bench_polar_block.json
 # A/B of compile-time variants (nvcc is on the box): rebuild with the flag, parity test of the kernel, bench line; then restore
 # (the chunk sizes change the summation order of the TF32 accumulations: the parity tests in front of the bench decide)
 for V in FH_CHAIN_PROLOGUE_ROLLED FH_CHAIN_CHUNK_KB=5 FH_GEMM_CHUNK_KB=8; do
