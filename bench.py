@@ -146,25 +146,47 @@ def algorithmic_work(datasets, rank_R):
 
 
 # --------------------------------------------------------------------------------------------
-def time_oracle(datasets_dev, rank_R, n_i, sample_cells, steps, warmup):
-	"""The reference algorithm on the host cores (oracle/fh_oracle.py = CPU restatement pinned to the
-	reference's outputs; the reference itself is not on the GPU box) on a cell sample of the same
-	geometry. Returns per-step seconds split into the part linear in cells and the fixed part."""
+def oracle_rwr_steps(cpu_ds, sample=8):
+	"""The auto-stop step count of init_params (parafac2_intergrative.py:131-140,265) evaluated by the ORACLE on a few cells
+	per block (host only: the reference arm must not touch the product's CUDA library)."""
+	from oracle import fh_oracle as O
+	n_i = []
+	for ds in cpu_ds:
+		worst = 0
+		nc = min(sample, ds.num_cell)
+		for b, g in enumerate(ds.geoms):
+			worst = max(worst, O.partial_rwr(O.densify_block(ds, b, 0, nc), g.s, g.e, True, True, False, None, -1)[1])
+		n_i.append(worst)
+	return n_i
+
+
+def time_oracle(datasets, rank_R, n_i, sample_cells, steps, warmup, device="cpu"):
+	"""The reference algorithm (oracle/fh_oracle.py = stock-torch restatement pinned to the reference's outputs; the reference
+	itself is not on the GPU box) on a cell sample of the same geometry. One step = one iteration of the reference's outer loop
+	(parafac2_intergrative.py:635-737): projections with TWO RWR passes (one cell batch, as the reference's batching rule gives
+	on a 180 GB device, FastHigashi_Wrapper.py:500-517), V update, projected tensor, CP-ALS per chromosome, core norms.
+	device="cpu": host cores (cpu_baseline / --impl reference); device="cuda": the same stock torch ops (cuBLAS / cuSOLVER) on
+	the GPU - the same-box stock-PyTorch baseline of BASELINE.md 3.5. Returns measured seconds per step."""
 	from oracle import fh_oracle as O
 	ncpu = os.cpu_count() or 1
-	torch.set_num_threads(ncpu)
-	cpu_ds = [ds.select_cells(0, sample_cells).to("cpu") for ds in datasets_dev]
-	core = O.OracleCore(rank_R, OFF_DIAG, [RES])
-	state = random_state(cpu_ds, rank_R, 7, n_i=n_i)
-	core.set_sizes(cpu_ds, DIM1)
+	if device == "cpu":
+		torch.set_num_threads(ncpu)
+	sample_cells = min(sample_cells, datasets[0].num_cell)
+	ods = [ds.select_cells(0, sample_cells).to(device) for ds in datasets]
+	core = O.OracleCore(rank_R, OFF_DIAG, [RES], device=device)
+	state = random_state(ods, rank_R, 7, n_i=n_i)
+	core.set_sizes(ods, DIM1)
 	core.load_state(*state)
 	fixed = [0.0]
 	orig_polar, orig_cp = O.polar, O.cp_als
+	sync = torch.cuda.synchronize if device != "cpu" else (lambda: None)
 
 	def timed(fn):
 		def w(*a, **k):
+			sync()
 			t = time.perf_counter()
 			r = fn(*a, **k)
+			sync()
 			fixed[0] += time.perf_counter() - t
 			return r
 		return w
@@ -173,20 +195,36 @@ def time_oracle(datasets_dev, rank_R, n_i, sample_cells, steps, warmup):
 	try:
 		for it in range(warmup + steps):
 			fixed[0] = 0.0
+			sync()
 			t = time.perf_counter()
-			core.sweep(cpu_ds, True, True, False, want_norm=(it == 0))
-			for ci, ds in enumerate(cpu_ds):
+			core.sweep(ods, True, True, False, want_norm=(it == 0))
+			for ci, ds in enumerate(ods):
 				fac, _, _ = O.cp_als(core.projected[ds.chrom], [core.A_list[ci], core.B_dict[ds.chrom], core.D_dict[ds.chrom]], 1)
 				core.A_list[ci], core.B_dict[ds.chrom], core.D_dict[ds.chrom] = fac
-			core.core_norms(cpu_ds)
+			core.core_norms(ods)
+			sync()
 			total = time.perf_counter() - t
 			if it >= warmup:
 				rec.append((total, fixed[0]))
 	finally:
 		O.polar, O.cp_als = orig_polar, orig_cp
-	total = float(np.median([r[0] for r in rec]))
+	tot = [r[0] for r in rec]
 	fx = float(np.median([r[1] for r in rec]))
-	return dict(total=total, fixed=fx, per_cell=(total - fx) / sample_cells, cores=ncpu, sample_cells=sample_cells)
+	med = float(np.median(tot))
+	return dict(total=med, sum=float(np.sum(tot)), fixed=fx, per_cell=(med - fx) / sample_cells, cores=ncpu, sample_cells=sample_cells)
+
+
+def baseline_record(t, full_cells, kind, where):
+	"""cells/s MEASURED on the sample (value) + the labelled linear extrapolation to the full cell count (not the headline)."""
+	sec_full = t["fixed"] + full_cells * t["per_cell"]
+	return {"value": t["sample_cells"] / t["total"], "unit": "cells/s", "cores": t["cores"] if where == "cpu" else 0, "kind": kind,
+	        "sample": "%s: %d-cell sample of the same geometry (all 22 chromosomes, every bin block), measured %.2f s per sweep "
+	                  "(2 RWR passes per sweep as the reference; cell-independent part - per-bin polar + CP-ALS - %.2f s of it)" % (
+		                  where, t["sample_cells"], t["total"], t["fixed"]),
+	        "seconds_per_sweep_sample": t["total"],
+	        "extrapolated_full_workload": {"cells": full_cells, "seconds_per_sweep": sec_full, "cells_per_s": full_cells / sec_full,
+	                                       "model": "fixed + cells x per_cell (cost linear in cells except the cell-independent part); "
+	                                                "NOT the value above"}}
 
 
 def main():
@@ -198,7 +236,8 @@ def main():
 	ap.add_argument("--cells", type=int, default=4238)
 	ap.add_argument("--geometry", default="pfc", help="pfc (configs[1]) | hg19")
 	ap.add_argument("--cache", default="sweep", help="sweep: RWR recomputed every sweep (metric); run: once per run")
-	ap.add_argument("--cpu-sample-cells", type=int, default=32)
+	ap.add_argument("--cpu-sample-cells", type=int, default=0, help="cells of the CPU baseline sample (0: 512 for --impl reference, 64 for the cpu_baseline leg)")
+	ap.add_argument("--torch-gpu-sample-cells", type=int, default=512, help="cells of the same-box stock-PyTorch (cuBLAS/cuSOLVER) baseline; 0: skip")
 	ap.add_argument("--no-cpu-baseline", action="store_true")
 	ap.add_argument("--no-e2e", action="store_true")
 	ap.add_argument("--tc", type=int, default=-1, help="1: tcgen05 3xTF32 GEMMs, 0: CUDA-core fp32 (default: library default)")
@@ -217,30 +256,32 @@ def main():
 	          "sharding": "cells x%d" % world}
 
 	if args.impl == "reference":
-		# the reference's own CPU implementation of the path, host cores only; rank 0 alone
+		# The reference's own algorithm on the box's host cores: the pinned stock-torch port (the reference is pure Python and
+		# cannot travel; oracle/fh_oracle.py restates it and is pinned to its outputs). Host only - this arm neither imports
+		# __graft_entry__ / _lib nor maps libfh_b200.so. Rank 0 alone; every step is one MEASURED sweep over a bounded cell
+		# sample (>= 512 cells) of the same geometry; value = sample cells / measured seconds (no extrapolation).
 		if rank != 0:
 			return
-		if not torch.cuda.is_available():
-			ds = make_datasets(args.cpu_sample_cells, 1000, "cpu", bins)
-			n_i = [4] * len(ds)
-		else:
-			torch.cuda.set_device(local_rank)
-			ds = make_datasets(max(args.cpu_sample_cells, 128), 1000, "cuda", bins)
-			import __graft_entry__ as ge
-			ge.build()
-			n_i = probe_rwr_steps(ds)
-		w_eff = min(args.warmup, 1)
-		t = time_oracle(ds, RANK, n_i, args.cpu_sample_cells, args.steps, w_eff)
-		sec = t["fixed"] + args.cells * t["per_cell"]
-		val = args.cells / sec
-		cb = {"value": val, "unit": "cells/s", "cores": t["cores"], "kind": "port",
-		      "sample": "%d-cell sample of the same geometry per step; per-sweep cost = fixed (polar+CP-ALS, %.2fs) + cells x %.4fs, "
-		                "extrapolated to %d cells" % (t["sample_cells"], t["fixed"], t["per_cell"], args.cells)}
-		print(json.dumps({"impl": "reference", "metric": "cells/s per PARAFAC2 ALS sweep (incl. RWR)", "value": val, "unit": "cells/s",
-		                  "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "warmup_effective": w_eff,
-		                  "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-		                  "data": "synthetic", "config": config, "cpu_baseline": cb,
-		                  "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+		sample = args.cpu_sample_cells or 512
+		ds = make_datasets(sample, 1000, "cpu", bins)
+		n_i = oracle_rwr_steps(ds)
+		# wall-clock guard ("the whole --steps K --warmup W run ends within a few minutes"): one probe sweep on the full sample;
+		# if K + W such sweeps would not fit FH_REF_BUDGET_S (default 240 s) the sample is cut (never below 128 cells) and said so
+		budget = float(os.environ.get("FH_REF_BUDGET_S", "240"))
+		probe = time_oracle(ds, RANK, n_i, sample, 1, 0, "cpu")
+		n_sweeps = args.steps + max(args.warmup - 1, 0)  # the probe is the first warm-up sweep
+		if probe["total"] * n_sweeps > budget:
+			per_cell = max(probe["per_cell"], 1e-9)
+			fit = int((budget / n_sweeps - probe["fixed"]) / per_cell)
+			sample = int(min(sample, max(128, fit)))
+		t = time_oracle(ds, RANK, n_i, sample, args.steps, max(args.warmup - 1, 0) if sample == probe["sample_cells"] else max(args.warmup, 1), "cpu")
+		cb = baseline_record(t, args.cells, "port", "cpu")
+		config = dict(config, rwr="2 passes per sweep (the reference re-imputes for the projected tensor)", cells_per_step=sample)
+		print(json.dumps({"impl": "reference", "metric": "cells/s per PARAFAC2 ALS sweep (incl. RWR)", "value": cb["value"], "unit": "cells/s",
+		                  "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+		                  "ms_per_step": t["total"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+		                  "data": "synthetic", "config": config, "cpu_baseline": cb, "rwr_steps": n_i,
+		                  "e2e": {"value": cb["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 		return
 
 	# ---------------------------------------------------------------------------- b200 arm
@@ -419,12 +460,19 @@ def main():
 	       "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
 	       "stages_ms_per_sweep": per, "roofline_all": roof_all, "rwr_steps": n_i, "re_trace_tail": core.re_trace[-3:]}
 	if not args.no_cpu_baseline and world == 1:
-		t = time_oracle(datasets, RANK, n_i, args.cpu_sample_cells, 1, 0)
-		sec = t["fixed"] + args.cells * t["per_cell"]
-		out["cpu_baseline"] = {"value": args.cells / sec, "unit": "cells/s", "cores": t["cores"], "kind": "port",
-		                       "sample": "one oracle sweep on a %d-cell sample of the same geometry: fixed part (polar+CP-ALS) %.2fs + "
-		                                 "cells x %.4fs, extrapolated to %d cells (%.1fs per sweep)" % (
-			                       t["sample_cells"], t["fixed"], t["per_cell"], args.cells, sec)}
+		# reported baselines, not targets: (1) the reference algorithm on the host cores, (2) the same stock torch ops on this
+		# GPU (cuBLAS / cuSOLVER driven as the reference drives them: one cell batch on a 180 GB device, gesvda polar) - the
+		# same-box number BASELINE.md 3.5 names. Both on bounded cell samples of the same geometry, measured, not extrapolated.
+		core.release()
+		torch.cuda.empty_cache()
+		t = time_oracle(datasets, RANK, n_i, args.cpu_sample_cells or 256, 1, 0, "cpu")
+		out["cpu_baseline"] = baseline_record(t, args.cells, "port", "cpu")
+		if args.torch_gpu_sample_cells > 0:
+			try:
+				t = time_oracle(datasets, RANK, n_i, args.torch_gpu_sample_cells, 1, 1, str(dev))
+				out["torch_gpu_baseline"] = baseline_record(t, args.cells, "port on cuda (stock torch: cuBLAS bmm/einsum, cuSOLVER gesvda/getrf)", "cuda")
+			except Exception as e:  # a baseline must not take the product's line down
+				out["torch_gpu_baseline"] = {"unavailable": repr(e)[:200]}
 	print(json.dumps(out))
 
 

@@ -51,6 +51,7 @@ __device__ __forceinline__ double jacobi_tan(double al, double be, double ga) {
 }
 
 #include "fh_polar_block.cuh"  // block one-sided Jacobi, opt-in (FH_POLAR_BLOCK=1); uses jacobi_tan
+#include "fh_polar_rb.cuh"     // register-blocked one-sided Jacobi (default)
 
 // One-sided Jacobi sweeps over the rows of R (n x ld, ld a multiple of 16, pad columns zero).
 // A half-warp (G = 16 lanes) owns one row pair and keeps row p in registers (PL = ld / 16 elements per
@@ -324,6 +325,130 @@ chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// Default kernel: same pipeline (pivoted Cholesky -> one-sided Jacobi on the factor's rows -> scaled eigenvector
+// rows), the Jacobi phase register-blocked (fh_polar_rb.cuh). One instantiation per row length class PL = ceil(n / 32)
+// so that each gets its own register budget and CTA count per SM.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pivoted_cholesky_upper(double* __restrict__ R, const int n, const int ld, int* __restrict__ perm) {
+	__shared__ int s_piv;
+	__shared__ double s_val;
+	const int JT = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	double dmax0 = 0.0;
+	for (int k = 0; k < n; ++k) {
+		if (warp == 0) {  // pivot = largest remaining diagonal
+			double best = -1.0; int bi = k;
+			for (int i = k + lane; i < n; i += 32) {
+				double v = R[i * ld + i];
+				if (v > best) { best = v; bi = i; }
+			}
+			for (int o = 16; o > 0; o >>= 1) {
+				double ov = __shfl_xor_sync(0xffffffffu, best, o);
+				int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+				if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+			}
+			if (lane == 0) { s_piv = bi; s_val = best; }
+		}
+		__syncthreads();
+		const int pv = s_piv;
+		const double pval = s_val;
+		if (k == 0) dmax0 = pval;
+		// rank-revealing stop (see chol_jacobi_kernel): the trailing block is noise, replaced by thr * I
+		if (pval <= dmax0 * 1e-14 || !(pval > 0.0)) {
+			const double rt = sqrt(fmax(dmax0 * 1e-14, 1e-300));
+			const int rem0 = n - k;
+			__syncthreads();
+			for (int t = tid; t < rem0 * rem0; t += JT) {
+				int i = k + t / rem0, j = k + t % rem0;
+				R[i * ld + j] = (i == j) ? rt : 0.0;
+			}
+			__syncthreads();
+			break;
+		}
+		if (pv != k) {  // symmetric swap k <-> pv: rows, then columns (earlier factor rows included)
+			for (int j = tid; j < n; j += JT) { double t = R[k * ld + j]; R[k * ld + j] = R[pv * ld + j]; R[pv * ld + j] = t; }
+			__syncthreads();
+			for (int i = tid; i < n; i += JT) { double t = R[i * ld + k]; R[i * ld + k] = R[i * ld + pv]; R[i * ld + pv] = t; }
+			if (tid == 0) { int t = perm[k]; perm[k] = perm[pv]; perm[pv] = t; }
+			__syncthreads();
+		}
+		const double rkk = sqrt(R[k * ld + k]);
+		const double rinv = 1.0 / rkk;
+		__syncthreads();
+		for (int j = k + tid; j < n; j += JT) R[k * ld + j] = (j == k) ? rkk : R[k * ld + j] * rinv;
+		__syncthreads();
+		// trailing update, a warp per row (full square keeps the swaps simple): G[i][j] -= R[k][i] R[k][j]
+		const int nwp = JT >> 5;
+		for (int i = k + 1 + warp; i < n; i += nwp) {
+			const double rki = R[k * ld + i];
+			for (int j = k + 1 + lane; j < n; j += 32) R[i * ld + j] = fma(-rki, R[k * ld + j], R[i * ld + j]);
+		}
+		__syncthreads();
+	}
+	for (int t = tid; t < n * n; t += JT) {  // strict lower triangle of R is not part of the factor
+		int i = t / n, j = t % n;
+		if (j < i) R[i * ld + j] = 0.0;
+	}
+	__syncthreads();
+}
+
+template <int PL>
+__global__ void __launch_bounds__(PL == 5 ? 640 : PL * 128, PL == 5 ? 1 : (PL == 4 ? 1 : (PL == 3 ? 2 : (PL == 2 ? 4 : 8))))
+chol_jacobi_rb_kernel(const double* __restrict__ Gall, const int* __restrict__ prob_n, const long long* __restrict__ prob_off,
+                      const int* __restrict__ prob_slot, int uniform_n, int max_sweeps, double skip_tol,
+                      double* __restrict__ WTall, double* __restrict__ sigma_all, double* __restrict__ sigma_sum,
+                      int* __restrict__ nsweep_out) {
+	extern __shared__ __align__(16) double sm[];
+	const int b = blockIdx.x;
+	const int n = prob_n ? prob_n[b] : uniform_n;
+	const long long off = prob_off ? prob_off[b] : (long long)b * n * n;
+	const int slot = prob_slot ? prob_slot[b] : b;
+	const int ld = PL * 32 + 1, nrow = rb_rows(n);
+	double* R = sm;                          // nrow x ld
+	double* red = R + (size_t)nrow * ld;     // 64 doubles scratch
+	double* nrm = red + 64;                  // nrow squared norms
+	int* perm = (int*)(nrm + nrow);          // n
+	const int JT = blockDim.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = JT >> 5;
+	const double* Gg = Gall + off;
+	for (int r = warp; r < nrow; r += nw)
+		for (int c = lane; c < ld; c += 32) R[r * ld + c] = (c < n && r < n) ? Gg[r * n + c] : 0.0;
+	for (int i = tid; i < n; i += JT) perm[i] = i;
+	__syncthreads();
+	pivoted_cholesky_upper(R, n, ld, perm);
+	const int sweep = (PL > 4) ? jacobi_sweeps_rb_half<PL>(R, n, ld, nrm, red, max_sweeps, skip_tol)
+	                           : jacobi_sweeps_rb<PL>(R, n, ld, nrm, red, max_sweeps, skip_tol);
+	if (tid == 0 && nsweep_out) nsweep_out[slot] = sweep;
+	// ---------------- lambda_j = |w_j|^2, outputs (as chol_jacobi_kernel) ----------------
+	__shared__ double s_lmax, s_ssum;
+	if (tid == 0) { s_lmax = 0.0; s_ssum = 0.0; }
+	__syncthreads();
+	double* lamv = sigma_all ? sigma_all + (long long)b * n : nullptr;
+	for (int j = warp; j < n; j += nw) {
+		double s2 = 0.0;
+		for (int i = lane; i < n; i += 32) { double v = R[j * ld + i]; s2 += v * v; }
+		s2 = fh_warp_sum(s2);
+		if (lane == 0) {
+			nrm[j] = s2;
+			atomicMax((unsigned long long*)&s_lmax, (unsigned long long)__double_as_longlong(s2));  // s2 >= 0: order preserved
+			if (lamv) lamv[j] = sqrt(s2);
+		}
+	}
+	__syncthreads();
+	if (tid == 0 && sigma_sum) {  // fixed summation order: the value feeds the loss
+		double t = 0.0;
+		for (int j = 0; j < n; ++j) t += sqrt(nrm[j]);
+		sigma_sum[slot] = t;
+	}
+	const double floor_l = fmax(s_lmax * 1e-17, 1e-300);
+	double* WT = WTall + off;
+	for (int j = warp; j < n; j += nw) {
+		const double l = fmax(nrm[j], floor_l);
+		const double f = rsqrt(l) * rsqrt(sqrt(l));  // lambda^{-3/4}
+		for (int i = lane; i < n; i += 32) WT[(size_t)j * n + perm[i]] = R[j * ld + i] * f;
+	}
+}
+
 int gemm(int dtype, int M, int N, int K, int batch, const void* A, long long sa_m, long long sa_k, long long ba,
          const void* B, long long sb_k, long long sb_n, long long bb, void* C, long long ldc, long long bc,
          void* stream) {
@@ -364,18 +489,44 @@ int polar_block_mode() {
 	return mode;
 }
 
+// FH_POLAR_RB=0: the scalar round-robin kernel of round 1 instead of the register-blocked one (A/B timing only).
+int polar_rb_mode() {
+	static int mode = -1;
+	if (mode < 0) { const char* e = getenv("FH_POLAR_RB"); mode = (e && e[0] == '0') ? 0 : 1; }
+	return (mode && !polar_block_mode()) ? 1 : 0;
+}
+
 int jacobi_threads(int n) {
+	if (polar_rb_mode()) return rb_threads(n);
 	const int t = n > 83 ? 1024 : (n > 58 ? 512 : 256);
 	return (polar_block_mode() && t > 512) ? 512 : t;  // chol_jacobi_kernel<true> is built for <= 512 threads
 }
 
+template <int PL>
+int launch_rb(int grid, int nmax, size_t smem, cudaStream_t st, const double* G, const int* pn, const long long* po, const int* ps,
+              int uniform_n, int max_sweeps, double skip, double* WT, double* sigma, double* sigma_sum, int* nsweep) {
+	FH_CUDA(cudaFuncSetAttribute(chol_jacobi_rb_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	chol_jacobi_rb_kernel<PL><<<grid, rb_threads(nmax), smem, st>>>(G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
+	FH_LAUNCH_CHECK();
+	return FH_OK;
+}
+
 int launch_jacobi(int grid, int nmax, size_t smem, cudaStream_t st, const double* G, const int* pn, const long long* po,
                   const int* ps, int uniform_n, int max_sweeps, double* WT, double* sigma, double* sigma_sum, int* nsweep) {
+	static double skip = -1.0;
+	if (skip < 0.0) { const char* e = getenv("FH_JACOBI_SKIP"); skip = e ? atof(e) : 1e-17; }
+	if (polar_rb_mode()) {
+		switch (rb_pl(nmax)) {
+			case 1: return launch_rb<1>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
+			case 2: return launch_rb<2>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
+			case 3: return launch_rb<3>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
+			case 4: return launch_rb<4>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
+			default: return launch_rb<5>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
+		}
+	}
 	const bool blkmode = polar_block_mode() != 0;
 	if (blkmode) FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	else FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	static double skip = -1.0;
-	if (skip < 0.0) { const char* e = getenv("FH_JACOBI_SKIP"); skip = e ? atof(e) : 1e-17; }
 	if (blkmode)
 		chol_jacobi_kernel<true><<<grid, jacobi_threads(nmax), smem, st>>>(G, pn, po, ps, nullptr, uniform_n, max_sweeps, skip,
 		                                                                  WT, sigma, sigma_sum, nsweep);
@@ -386,9 +537,9 @@ int launch_jacobi(int grid, int nmax, size_t smem, cudaStream_t st, const double
 	return FH_OK;
 }
 
-// A launch covers problems of side <= n with one shared-memory size: the scalar layout of the largest, and in
-// block mode also the block layout of the largest side that uses it.
+// A launch covers problems of side <= n with one shared-memory size: the layout of the largest.
 size_t jacobi_smem(int n) {
+	if (polar_rb_mode()) return ((size_t)rb_rows(n) * rb_ld(n) + 64 + rb_rows(n) + (n + 1) / 2) * 8 + 16;
 	size_t scalar = ((size_t)n * jacobi_ld(n, jacobi_threads(n)) + 64 + (n + 1) / 2 + n) * 8 + 16;
 	if (!polar_block_mode()) return scalar;
 	const int nb = n < kBJMaxSide ? n : kBJMaxSide;
@@ -457,14 +608,17 @@ extern "C" int fh_polar_isqrt_multi(const double* G_all, double* WT_all, const i
 	             "fh_polar_isqrt_multi: null argument");
 	if (max_sweeps <= 0 || max_sweeps > kMaxSweeps) max_sweeps = kMaxSweeps;
 	cudaStream_t st = (cudaStream_t)stream;
-	const int bounds[4] = {117, 83, 58, 0};  // class lower bounds (exclusive): (117,160], (83,117], (58,83], (0,58]
+	// class lower bounds (exclusive). Register-blocked kernel: one class per row-length template (32 columns per lane
+	// element); scalar kernel: (117,160], (83,117], (58,83], (0,58]
+	const int rb_bounds[5] = {128, 96, 64, 32, 0}, sc_bounds[5] = {117, 83, 58, 0, 0};
+	const int* bounds = polar_rb_mode() ? rb_bounds : sc_bounds;
 	int i = 0;
 	while (i < count) {
 		const int nmax = host_prob_n[i];
 		FH_CHECK_ARG(nmax > 0 && jacobi_smem(nmax) <= 227 * 1024 && nmax <= kMaxGram,
 		             "fh_polar_isqrt_multi: Gram side %d does not fit shared memory (max 160)", nmax);
 		int lb = 0;
-		for (int c = 0; c < 4; ++c)
+		for (int c = 0; c < 5; ++c)
 			if (nmax > bounds[c]) { lb = bounds[c]; break; }
 		int j = i;
 		while (j < count && host_prob_n[j] > lb) {
@@ -552,6 +706,10 @@ extern "C" int fh_inv_sqrt_spd(const double* G, double* out, int n, void* ws, si
 		FH_CUDA(cudaMemcpyAsync(Z, tmp, nn * 8, cudaMemcpyDeviceToDevice, st));
 	}
 	if (host_iters) *host_iters = it;
+	if (it >= 200) {  // singular / numerically rank-deficient Gram: the null directions of Z grow ~1.5x per step - never hand that back
+		fh_set_error("fh_inv_sqrt_spd: Newton-Schulz did not converge in 200 iterations (Gram matrix singular: fewer rows than columns, or a rank-deficient input)");
+		return FH_ERR_ARG;
+	}
 	ns_final_kernel<<<fh_cdiv(nn, 256), 256, 0, st>>>(Z, n, scal, out);
 	FH_LAUNCH_CHECK();
 	return FH_OK;

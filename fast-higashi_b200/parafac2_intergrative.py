@@ -18,6 +18,7 @@ PyTorch is used for memory, streams and torch.distributed only; all arithmetic o
 goes through libfh_b200.so (fast-higashi_b200/_lib.py).
 """
 import math
+import os
 import sys
 import time
 import numpy as np
@@ -272,6 +273,10 @@ class Fast_Higashi_core:
 		for ci, ds in enumerate(self.schic):
 			good = self.bin_cov_list[ci]
 			bad = self.bad_bin_cov_list[ci]
+			if not torch.is_tensor(bad) and ds.total_cell_num > ds.num_cell:
+				# bad-QC cells without a coverage table (the reference stores 0 for "none"): rows of inf, i.e. a 1/bin_cov column
+				# scale of 0, instead of reading past the end of the good cells' table in a do_col transform
+				bad = torch.full((ds.total_cell_num - ds.num_cell, good.shape[1]), float("inf"), dtype=torch.float32, device=dev)
 			self._cov_all[ci] = torch.cat([good, bad], 0).contiguous() if torch.is_tensor(bad) else good
 			self.bin_cov_list[ci] = self._cov_all[ci][:ds.num_cell]
 		self.n_i = np.asarray(n_i)
@@ -288,6 +293,10 @@ class Fast_Higashi_core:
 			X = torch.zeros(ds.num_cell, g.nb * ldw, dtype=torch.float32, device=self.device)
 			self._X[key] = X
 			self._X_valid = getattr(self, "_X_valid", set())
+		flags = (bool(do_conv), bool(do_rwr), bool(do_col))
+		if getattr(self, "_X_flags", flags) != flags:  # transform() called with other flags than fit(): never reuse the old maps
+			self.invalidate_cache()
+		self._X_flags = flags
 		if key not in self._X_valid:
 			ev = getattr(self, "input_events", None)
 			if ev is not None and ev.get(ci) is not None:  # block-CSR of this chromosome still in flight (H2D on another stream)
@@ -373,6 +382,12 @@ class Fast_Higashi_core:
 
 	def invalidate_cache(self):
 		self._X_valid = set()
+
+	def release(self):
+		"""Drop the resident imputed tensor and the scratch buffers (the factors stay)."""
+		self._X = {}
+		self.invalidate_cache()
+		_lib.free_workspaces()
 
 	# P1-P5: parafac2_intergrative.py:304-540
 	@torch.no_grad()
@@ -571,7 +586,8 @@ class Fast_Higashi_core:
 		acc = torch.zeros(nch, dtype=torch.float64, device=self.device)
 		main = torch.cuda.current_stream()
 		if getattr(self, "_cp_streams", None) is None:
-			self._cp_streams = [torch.cuda.Stream(device=self.device) for _ in range(11)]
+			n_st = int(os.environ.get("FH_CP_STREAMS", "11"))  # 0: everything on the caller's stream
+			self._cp_streams = [torch.cuda.Stream(device=self.device) for _ in range(n_st)] if n_st > 0 else [main]
 		ready = torch.cuda.Event()
 		ready.record(main)
 		for k, (chrom, ids) in enumerate(self.chrom2id.items()):

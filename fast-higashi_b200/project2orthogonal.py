@@ -50,6 +50,15 @@ def polar_tall(M, group=None):
 	"""Polar factor of one tall (rows x R) fp32 matrix whose rows may be sharded over `group`
 	(torch.distributed): V = M (M^T M)^{-1/2}, Gram in fp64 and all-reduced."""
 	rows, R = M.shape
+	if group is None and rows < R:
+		# fewer rows than columns (fewer cells than the rank; the reference's SVD route handles it, project2orthogonal.py:6-29):
+		# the R x R Gram is singular, the polar factor is (M M^T)^{-1/2} M through the rows x rows Gram
+		G = torch.empty(rows, rows, dtype=torch.float64, device=M.device)
+		_lib.gemm(M, M, G, rows, rows, R, (M.stride(0), 1), (1, M.stride(0)), rows, dtype=_lib.GEMM_F32_ACC64)
+		Gi = inv_sqrt_spd(G)
+		V = torch.empty(rows, R, dtype=torch.float32, device=M.device)
+		_lib.gemm(Gi, M, V, rows, R, rows, (rows, 1), (M.stride(0), 1), R, dtype=_lib.GEMM_F64xF32_F32)
+		return V
 	G = torch.empty(R, R, dtype=torch.float64, device=M.device)
 	_lib.gemm(M, M, G, R, R, rows, (1, M.stride(0)), (M.stride(0), 1), R, dtype=_lib.GEMM_F32_ACC64)
 	if group is not None:

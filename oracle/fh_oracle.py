@@ -26,15 +26,16 @@ RWR_TOL = 0.01  # partial_rwr.py:122
 # ----------------------------------------------------------------------------------------------
 # S4: densify            sparse_for_schic.py:279-320 (transpose=True, do_conv=False branch)
 # ----------------------------------------------------------------------------------------------
-def densify_block(ds, b, c0, c1):
+def densify_block(ds, b, c0, c1, device="cpu"):
 	"""(c, nb, w) dense fp32 block of cells [c0, c1) from the block-CSR container; zeros filled,
-	values scattered (no accumulation), floor 1e-8."""
+	values scattered (no accumulation), floor 1e-8. `device`: where the stock-torch ops run ("cpu" for the
+	checker; "cuda" only for bench.py's same-box stock-PyTorch baseline)."""
 	g = ds.geoms[b]
 	rp, col, val = ds.cell_range_csr(b, c0, c1)
-	rp, col, val = rp.cpu().long(), col.cpu().long(), val.cpu()
+	rp, col, val = rp.to(device).long(), col.to(device).long(), val.to(device)
 	c = c1 - c0
-	dense = torch.zeros(c * g.nb, g.w, dtype=torch.float32)
-	rows = torch.repeat_interleave(torch.arange(c * g.nb), rp[1:] - rp[:-1])
+	dense = torch.zeros(c * g.nb, g.w, dtype=torch.float32, device=device)
+	rows = torch.repeat_interleave(torch.arange(c * g.nb, device=device), rp[1:] - rp[:-1])
 	dense[rows, col] = val
 	return dense.view(c, g.nb, g.w).clamp_(min=FLOOR)
 
@@ -69,7 +70,7 @@ def rwr_iterate(P, force_rwr_epochs):
 	(k < 0): up to 60 steps; the step is applied, THEN the loop breaks if the largest per-cell
 	Frobenius change is < 0.01; the returned count excludes the breaking step."""
 	c, n, _ = P.shape
-	eye = torch.eye(n, dtype=P.dtype)
+	eye = torch.eye(n, dtype=P.dtype, device=P.device)
 	Q = eye[None].repeat(c, 1, 1)
 	auto = force_rwr_epochs < 0
 	steps = MAX_RWR if auto else int(force_rwr_epochs)
@@ -117,7 +118,16 @@ def polar(matrix, rank=None):
 	"""U Vh of the thin SVD and the leading singular values."""
 	if rank is None:
 		rank = min(matrix.shape[-2:])
-	U, S, Vh = torch.linalg.svd(matrix, full_matrices=False)
+	if matrix.is_cuda and matrix.shape[-2] / matrix.shape[-1] >= 0.5:
+		# project2orthogonal.py:9-19 - the reference's GPU route: gesvda when tall enough, default driver on NaN / failure
+		try:
+			U, S, Vh = torch.linalg.svd(matrix, full_matrices=False, driver="gesvda")
+			if not (torch.isfinite(U).all() and torch.isfinite(Vh).all()):
+				raise RuntimeError("gesvda: non-finite")
+		except Exception:
+			U, S, Vh = torch.linalg.svd(matrix, full_matrices=False)
+	else:
+		U, S, Vh = torch.linalg.svd(matrix, full_matrices=False)
 	return U[..., :rank] @ Vh[..., :rank, :], S[..., :rank]
 
 
@@ -171,8 +181,9 @@ def core_sqnorm(A, B, D):
 class OracleCore:
 	"""Restatement of Fast_Higashi_core on the block-CSR container (CPU, fp32)."""
 
-	def __init__(self, rank, off_diag, res_list):
+	def __init__(self, rank, off_diag, res_list, device="cpu"):
 		self.rank, self.off_diag, self.res_list = rank, off_diag, res_list
+		self.device = torch.device(device)  # "cuda": the same stock-torch ops on the GPU (bench.py's torch_gpu_baseline only)
 
 	# parafac2_intergrative.py:558-567
 	def set_sizes(self, schic, size_ratio):
@@ -194,7 +205,7 @@ class OracleCore:
 	def _imputed(self, ds, ci, b, c0, c1, do_conv, do_rwr, do_col, bad=False, k=None):
 		g = ds.geoms[b]
 		off = ds.num_cell if bad else 0
-		x = densify_block(ds, b, off + c0, off + c1)
+		x = densify_block(ds, b, off + c0, off + c1, self.device)
 		cov = None
 		if do_col:
 			src = self.bad_bin_cov_list[ci] if bad else self.bin_cov_list[ci]
@@ -274,19 +285,20 @@ class OracleCore:
 
 	def load_state(self, A_list, B_list, D_list, meta_embedding, bin_cov_list, bad_bin_cov_list, n_i):
 		chroms = list(self.chrom2size)
-		self.A_list = [torch.as_tensor(a).clone().float() for a in A_list]
-		self.B_dict = {c: torch.as_tensor(b).clone().float() for c, b in zip(chroms, B_list)}
-		self.D_dict = {c: torch.as_tensor(d).clone().float() for c, d in zip(chroms, D_list)}
-		self.meta_embedding = torch.as_tensor(meta_embedding).clone().float()
-		self.bin_cov_list = [torch.as_tensor(b).float() for b in bin_cov_list]
-		self.bad_bin_cov_list = [torch.as_tensor(b).float() if not np.isscalar(b) else 0 for b in bad_bin_cov_list]
+		dev = self.device
+		self.A_list = [torch.as_tensor(a).clone().float().to(dev) for a in A_list]
+		self.B_dict = {c: torch.as_tensor(b).clone().float().to(dev) for c, b in zip(chroms, B_list)}
+		self.D_dict = {c: torch.as_tensor(d).clone().float().to(dev) for c, d in zip(chroms, D_list)}
+		self.meta_embedding = torch.as_tensor(meta_embedding).clone().float().to(dev)
+		self.bin_cov_list = [torch.as_tensor(b).float().to(dev) for b in bin_cov_list]
+		self.bad_bin_cov_list = [torch.as_tensor(b).float().to(dev) if not np.isscalar(b) else 0 for b in bad_bin_cov_list]
 		self.n_i = np.asarray(n_i)
 
 	# parafac2_intergrative.py:304-540
 	def sweep_projections(self, schic, do_conv, do_rwr, do_col, want_norm):
 		V = self.meta_embedding
 		R = self.rank
-		svd_term = torch.zeros(R, V.shape[0])
+		svd_term = torch.zeros(R, V.shape[0], device=self.device)
 		x_U = np.zeros(len(schic)); xnorm = np.zeros(len(schic))
 		self.projection_list = []
 		for ci, ds in enumerate(schic):
@@ -320,7 +332,7 @@ class OracleCore:
 		V, _ = polar(svd_term.T, self.rank)
 		x_V = float((V * svd_term.T).sum())
 		self.meta_embedding = V
-		self.projected = {c: torch.zeros(self.chrom2num_bin[c], self.chrom2size[c], self.rank) for c in self.chrom2size}
+		self.projected = {c: torch.zeros(self.chrom2num_bin[c], self.chrom2size[c], self.rank, device=self.device) for c in self.chrom2size}
 		for ci, ds in enumerate(schic):
 			Y = self.projected[ds.chrom][self.gslice[ci]]   # this resolution's rows of the stacked tensor (:526-529)
 			for b, g in enumerate(ds.geoms):
@@ -374,7 +386,7 @@ class OracleCore:
 	# parafac2_intergrative.py:742-834
 	def transform(self, schic, do_conv, do_rwr, do_col):
 		R = self.rank
-		svd_term = torch.zeros(R, schic[0].total_cell_num)
+		svd_term = torch.zeros(R, schic[0].total_cell_num, device=self.device)
 		for ci, ds in enumerate(schic):
 			A, B, D = self.A_list[ci], self.B_dict[ds.chrom], self.D_dict[ds.chrom]
 			for b, g in enumerate(ds.geoms):

@@ -1,8 +1,18 @@
-"""Aggregates an ncu --csv launch list (gpu__time_duration.sum) by kernel: count, total ms, share."""
+"""Aggregates an ncu --csv launch list (gpu__time_duration.sum) by kernel: count, total ms, share.
+agg_launches.py launches.csv [bench.log]: with the bench's own output (its JSON line holds gpu_launches of the timed steps) only
+the LAST gpu_launches rows - the timed sweeps - are aggregated."""
 import csv, re, sys, collections
 path = sys.argv[1]
 lines = [l for l in open(path) if not l.startswith('==')]
 rows = list(csv.DictReader(lines))
+if len(sys.argv) > 2:
+	import json
+	for l in open(sys.argv[2]):
+		if l.startswith('{') and '"gpu_launches"' in l:
+			n = int(json.loads(l)["gpu_launches"])
+			print('timed region: last %d of %d launches' % (n, len(rows)))
+			ours = [r for r in rows if 'at::' not in r['Kernel Name']]  # gpu_launches counts this library's kernels only
+			rows = ours[-n:]
 agg = collections.defaultdict(lambda: [0, 0.0])
 def short(n):
 	n = n.replace('(anonymous namespace)::', '').replace('void ', '')

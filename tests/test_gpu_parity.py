@@ -138,7 +138,9 @@ def test_polar_realistic_shapes_graded_spectra():
 	the singular values and the Jacobi sweep count of the Cholesky-preconditioned solver."""
 	from fasthigashi_b200.project2orthogonal import polar_batched
 	g = torch.Generator().manual_seed(0)
-	for (batch, rows, cols) in [(6, 316, 137), (9, 72, 21), (3, 152, 150), (4, 12, 20), (2, 1, 1)]:
+	# Gram sides in every row-length class of the register-blocked Jacobi kernel (32 columns per lane element)
+	for (batch, rows, cols) in [(6, 316, 137), (9, 72, 21), (3, 152, 150), (4, 12, 20), (2, 1, 1), (5, 200, 60), (4, 216, 90),
+	                            (3, 300, 120), (3, 300, 128), (2, 200, 129), (2, 170, 160), (3, 40, 33), (3, 9, 5)]:
 		for logk in [2.0, 5.5, 6.5]:
 			n = min(rows, cols)
 			Uq, _ = torch.linalg.qr(torch.randn(batch, max(rows, cols), n, generator=g, dtype=torch.float64))
@@ -287,7 +289,7 @@ def test_core_init_params_matches_reference():
 		got = core.bin_cov_list[i].cpu().numpy()
 		assert np.array_equal(np.isfinite(ref), np.isfinite(got))
 		assert rel_fro(got[np.isfinite(ref)], ref[np.isfinite(ref)]) < 1e-5
-	assert np.max(np.abs(np.array(core.re_trace) - g["re"][:3]) / g["re"][:3]) < 2e-4
+	assert np.max(np.abs(np.array(core.re_trace) - g["re"][:3]) / g["re"][:3]) < 1e-4
 
 
 @pytest.mark.parametrize("layout", ["nn", "tn", "nt", "tt"])
@@ -445,3 +447,80 @@ def test_rwr_alternative_paths(env):
 	                   timeout=600)
 	assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 	assert "1 passed" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("nb", [147, 150, 250])
+def test_rwr_wide_bin_blocks(nb):
+	"""Bin blocks wider than one 128-row tile (the reference's block rule gives nb = 147 at 100 kb, up to 256 at coarser
+	resolutions; FastHigashi_Wrapper.py:500-517): do_col on / off, forced and auto-stop step counts, against the oracle."""
+	from fasthigashi_b200 import synth
+	from fasthigashi_b200.partial_rwr import rwr_block_csr, pad4
+	from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset
+	n, ncell, off = 2 * nb, 20, 100
+	cluster = np.arange(ncell) % 4
+	idx, val = synth.synth_chrom(n, ncell, 0.08, off, 5 + nb, cluster, 4, device="cpu", cell_chunk=ncell)
+	mk = lambda device: Chrom_Dataset(Sparse(idx, val, (n, n, ncell)), bs_bin=nb, bs_cell=ncell, compact=True, flank=off, device=device)
+	ds_c, ds_g = mk("cpu"), mk(DEV)
+	assert [g.nb for g in ds_c.geoms] == [nb, nb]
+	gen = torch.Generator().manual_seed(nb)
+	cov = torch.rand(ncell, n, generator=gen) + 0.5
+	for use_tc in (True, False):
+		for (do_col, k) in [(False, 3), (True, 3), (False, -1), (True, -1), (True, 1)]:
+			for b, g in enumerate(ds_c.geoms):
+				ldw = pad4(g.w)
+				out = torch.full((ncell, g.nb * ldw), float("nan"), device=DEV)
+				n_it = rwr_block_csr(ds_g, b, 0, ncell, out, g.nb * ldw, k, True, True, do_col, bin_cov=cov.to(DEV), use_tc=use_tc)
+				ref, n_ref = O.partial_rwr(O.densify_block(ds_c, b, 0, ncell), g.s, g.e, True, True, do_col, cov[:, g.col0:g.col0 + g.w], k)
+				got = out.view(ncell, g.nb, ldw).cpu()
+				assert n_it == n_ref, (use_tc, do_col, k, b)
+				assert rel_fro(got[:, :, :g.w].numpy(), ref.numpy()) < 1e-5, (use_tc, do_col, k, b)
+				assert float(got[:, :, g.w:].abs().sum()) == 0.0
+
+
+def test_config2_geometry_lockstep_vs_oracle():
+	"""BASELINE config 2's geometry at full width - 22 chromosomes of the PFC-shaped genome at 500 kb (5,432 bins, blocks of
+	<= 128 rows with windows up to 328 columns), off_diag 100, rank 256, dim1 0.6 (per-chromosome rank up to 144) - on 256 cells:
+	three sweeps in lock-step with the oracle from the same state. Loss of every sweep <= 1e-4 relative (same ||X||^2 on both
+	sides: the oracle, like the reference, sums it in fp32; it is compared separately), embeddings Pearson >= 0.999."""
+	import bench
+	from fasthigashi_b200 import synth
+	from fasthigashi_b200.parafac2_intergrative import Fast_Higashi_core
+	bins = synth.chrom_bins("pfc", bench.RES)
+	ncell, R, nsweep = 256, bench.RANK, 3
+	gds = bench.make_datasets(ncell, 1000, DEV, bins)
+	ods = [d.select_cells(0, ncell).to("cpu") for d in gds]  # .to() moves in place: copy first
+	state = bench.random_state(ods, R, 7, n_i=[3] * len(ods))
+	ocore = O.OracleCore(R, bench.OFF_DIAG, [bench.RES])
+	ocore.fit(ods, bench.DIM1, nsweep, 1, True, True, False, 0.0, state=state)
+	Vo = ocore.transform(ods, True, True, False)
+	core = Fast_Higashi_core(R, bench.OFF_DIAG, [bench.RES]).to(DEV)
+	res = core.fit_transform(gds, bench.DIM1, nsweep, 1, True, True, False, 0.0, verbose=False, state=state)
+	assert max(core.chrom2size.values()) > 128  # the Gram sides of chr1 / chr2 are in the largest polar class
+	for tg, to in zip(core.loss_terms, ocore.loss_terms):
+		assert np.max(np.abs(tg["xnorm"] - to["xnorm"]) / to["xnorm"]) < 1e-3
+		assert np.max(np.abs(tg["x_U"] - to["x_U"]) / to["x_U"]) < 5e-5
+		assert abs(tg["x_V"] - to["x_V"]) / to["x_V"] < 5e-5
+		assert np.max(np.abs(tg["core"] - to["core"]) / to["core"]) < 1e-4
+		xn = to["xnorm"].sum()
+		re_g = np.sqrt(xn + tg["core"].sum() - 2 * tg["x_V"]) / np.sqrt(xn)
+		re_o = np.sqrt(xn + to["core"].sum() - 2 * to["x_V"]) / np.sqrt(xn)
+		assert abs(re_g - re_o) / re_o < 1e-4, (re_g, re_o)
+	E = O.embed_all(res[1][3].cpu().numpy(), [d.cpu().numpy() for d in res[1][2]])
+	Eo = O.embed_all(Vo.numpy(), [d.numpy() for d in ocore.D_dict.values()])
+	pear = [abs(np.corrcoef(E[:, j], Eo[:, j])[0, 1]) for j in range(E.shape[1])]
+	assert min(pear) > 0.999, min(pear)
+
+
+def test_polar_tall_fewer_rows_than_columns_and_singular_gram():
+	"""Fewer cells than the rank (the reference's SVD route handles it, project2orthogonal.py:6-29): the polar factor comes
+	from the rows x rows Gram; a singular Gram handed to the Newton-Schulz inverse square root is an error, never garbage."""
+	from fasthigashi_b200.project2orthogonal import polar_tall, inv_sqrt_spd
+	g = torch.Generator().manual_seed(4)
+	M = torch.randn(40, 64, generator=g)
+	V = polar_tall(M.to(DEV)).cpu()
+	truth = O.polar(M.double(), 40)[0]
+	assert rel_fro(V.numpy(), truth.numpy()) < 2e-6
+	assert _ortho_err(V.double()) < 2e-6
+	B = torch.randn(64, 20, generator=g, dtype=torch.float64)
+	with pytest.raises(_lib().FHError):
+		inv_sqrt_spd((B @ B.T).to(DEV))  # rank 20 of 64
