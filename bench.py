@@ -227,6 +227,83 @@ def baseline_record(t, full_cells, kind, where):
 	                                                "NOT the value above"}}
 
 
+def build_roofline(per, kt, work, datasets, n_i, pk, dev, top):
+	"""`roofline` of the dominant kernel + `roofline_all` for the three stage groups SURVEY.md 8d names.
+	RWR: HBM bound per 8d (algorithmic bytes = block-CSR read + imputed panel written once), the tensor-pipe figure beside it
+	(the stage is compute bound at fp32 parity: ~170 flop per algorithmic byte, 3 TF32 MMAs per product).
+	Contractions: tensor pipe (useful fp32-equivalent flops counted once; 3xTF32 executes 3x that).
+	Per-bin polar: fp64 pipe, against a DGEMM peak measured in this run.
+	achieved = algorithmic work per launch / average launch duration from CUDA events on the launching stream (kt);
+	traffic = dram__bytes_read + write per launch of that kernel from the committed ncu --set full capture (profiles/), or null."""
+	roof_all = {}
+	rwr_flops = 0.0
+	for ds, k in zip(datasets, n_i):
+		for g_ in ds.geoms:
+			rwr_flops += ds.num_cell * (4.0 * g_.nb * g_.nb * g_.w + 2.0 * max(k - 1, 0) * g_.nb ** 3)
+	traffic = {}
+	tp = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+	if os.path.exists(tp):
+		traffic = json.load(open(tp))
+
+	def per_launch(name, work_total, unit_scale):
+		k = kt.get(name)
+		if not k or not k["launches_per_sweep"] or k["ms_per_sweep"] <= 0:
+			return None
+		return work_total / k["launches_per_sweep"] / (k["ms_per_sweep"] / k["launches_per_sweep"] / 1e3) / unit_scale
+
+	if "rwr" in per:
+		stage = work["rwr_bytes"] / (per["rwr"] / 1e3) / 1e9
+		chain = per_launch("rwr_chain_kernel", work["rwr_bytes"], 1e9)
+		t_stage = rwr_flops / (per["rwr"] / 1e3) / 1e12
+		t_chain = per_launch("rwr_chain_kernel", rwr_flops, 1e12)
+		roof_all["rwr"] = {"bound": "hbm", "kernel": "rwr_chain_kernel (tcgen05 3xTF32 + TMA: A A^T, transition matrix, RWR steps with Q in TMEM, Q A)",
+		                   "achieved": chain if chain is not None else stage, "peak": pk["hbm"], "unit": "GB/s",
+		                   "frac": (chain if chain is not None else stage) / pk["hbm"], "stage_achieved": stage, "stage_frac": stage / pk["hbm"],
+		                   "stage": "densify_conv_kernel + rwr_chain_kernel",
+		                   "tensor_side": {"achieved": t_chain if t_chain is not None else t_stage, "stage_achieved": t_stage, "peak": pk["tensor"],
+		                                   "unit": "TFLOP/s", "frac": (t_chain if t_chain is not None else t_stage) / pk["tensor"],
+		                                   "note": "algorithmic fp32 flops (2 nb^2 w for A A^T, 2 nb^3 per step, 2 nb^2 w for Q A) against the measured dense "
+		                                           "bf16 peak; fp32-parity maths executes 3 TF32 MMAs per product on 128-padded tiles (~3.5x the algorithmic "
+		                                           "flops), which is why this stage is bound by the tensor pipe and not by HBM"}}
+	gem = sum(per.get(k, 0.0) for k in ("p1_mttkrp", "p3_project", "p5_tensor"))
+	if gem > 0:
+		a = work["contraction_flops"] / (gem / 1e3) / 1e12
+		ak = per_launch("gemm_tc_kernel", work["contraction_flops"], 1e12)
+		roof_all["contractions"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 3xTF32, TMA, A operand in TMEM)", "achieved": a, "peak": pk["tensor"],
+		                            "unit": "TFLOP/s", "frac": a / pk["tensor"], "kernel_only_achieved": ak,
+		                            "note": "useful fp32-equivalent flops over the P1+P3+P5 stage times; fp32-parity maths: 3xTF32 ceiling is ~peak_tf32/3 = ~peak_bf16/6. "
+		                                    "kernel_only_achieved divides by the gemm_tc_kernel launches alone (they also serve the small per-bin products)"}
+	if "polar_bins" in per:
+		# measured fp64 peak of this GPU: cuBLAS DGEMM (library call used ONLY as the yardstick, never on the path)
+		a64 = torch.randn(4096, 4096, device=dev, dtype=torch.float64)
+		torch.matmul(a64, a64)
+		torch.cuda.synchronize()
+		g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		g0.record()
+		for _ in range(3):
+			torch.matmul(a64, a64)
+		g1.record()
+		torch.cuda.synchronize()
+		pk64 = 3 * 2.0 * 4096 ** 3 / (g0.elapsed_time(g1) / 1e3) / 1e12
+		del a64
+		a = work["polar_flops"] / (per["polar_bins"] / 1e3) / 1e12
+		roof_all["polar_bins"] = {"bound": "fp64", "kernel": "chol_jacobi_rb_kernel (pivoted Cholesky + register-blocked one-sided Jacobi) + fp64 Gram / factor GEMMs",
+		                          "achieved": a, "unit": "TFLOP/s fp64", "peak": pk64, "frac": a / pk64, "peak_source": "cuBLAS DGEMM 4096^3 timed in this run",
+		                          "problems_per_s": work["polar_problems"] / (per["polar_bins"] / 1e3),
+		                          "jacobi_kernel_ms_per_sweep": kt.get("chol_jacobi_rb_kernel", {}).get("ms_per_sweep")}
+	# the dominant kernel: the largest of the per-kernel totals of one sweep
+	kname = max(kt, key=lambda k: kt[k]["ms_per_sweep"]) if kt else "rwr_chain_kernel"
+	dom = {"rwr_chain_kernel": "rwr", "densify_conv_kernel": "rwr", "gemm_tc_kernel": "contractions", "chol_jacobi_rb_kernel": "polar_bins"}[kname]
+	roofline = dict(roof_all.get(dom, {}))
+	roofline["dominant_kernel"] = kname
+	roofline["dominant_stage"] = top
+	tr = traffic.get(kname)
+	roofline["traffic"] = tr["dram_bytes_per_launch"] if tr else None
+	roofline["traffic_source"] = tr["source"] if tr else None
+	roofline["peak_source"] = pk["src"]
+	return roofline, roof_all
+
+
 def main():
 	ap = argparse.ArgumentParser()
 	ap.add_argument("--gpus", type=int, default=1)
@@ -388,6 +465,17 @@ def main():
 		       "d2h_bytes_per_step": int((2 * len(datasets) + 1) * 8 + len(datasets) * 8), "ms_per_step": ms_e, "steps": n_e2e}
 		del host
 
+	# one more sweep with the library's per-kernel CUDA-event timing on (events on the launching stream around every
+	# launch of the four hot kernels): average launch durations for the roofline, outside the timed region above
+	kt = {}
+	_lib.kernel_timing(True)
+	core.sweep_once(1)
+	torch.cuda.synchronize()
+	for name, kind in (("densify_conv_kernel", _lib.TIME_DENSIFY), ("rwr_chain_kernel", _lib.TIME_RWR_CHAIN),
+	                   ("gemm_tc_kernel", _lib.TIME_GEMM_TC), ("chol_jacobi_rb_kernel", _lib.TIME_POLAR_JACOBI)):
+		ms_k, n_k = _lib.kernel_time(kind)
+		kt[name] = {"ms_per_sweep": ms_k, "launches_per_sweep": n_k}
+	_lib.kernel_timing(False)
 	if world > 1:
 		dist.barrier()
 		dist.destroy_process_group()
@@ -396,69 +484,12 @@ def main():
 	pk = peaks()
 	per = {k: v / args.steps for k, v in stages.items()}
 	top = max(per, key=per.get) if per else None
-	roof_all = {}
-	if "rwr" in per:
-		a = work["rwr_bytes"] / (per["rwr"] / 1e3) / 1e9
-		roof_all["rwr"] = {"bound": "hbm", "achieved": a, "peak": pk["hbm"], "unit": "GB/s", "frac": a / pk["hbm"]}
-	gem = sum(per.get(k, 0.0) for k in ("p1_mttkrp", "p3_project", "p5_tensor"))
-	if gem > 0:
-		a = work["contraction_flops"] / (gem / 1e3) / 1e12
-		roof_all["contractions"] = {"bound": "tensor", "achieved": a, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": a / pk["tensor"],
-		                            "note": "fp32-parity maths: 3xTF32 ceiling is ~peak_tf32/3 = ~peak_bf16/6"}
-	if "polar_bins" in per:
-		a = work["polar_flops"] / (per["polar_bins"] / 1e3) / 1e12
-		roof_all["polar_bins"] = {"bound": "fp64 CUDA cores (no tensor path at fp64)", "achieved": a, "unit": "TFLOP/s fp64",
-		                          "problems_per_s": work["polar_problems"] / (per["polar_bins"] / 1e3)}
-	# `roofline` is the north-star kernel group with the larger share: the RWR pass (densify_conv_kernel +
-	# the fused tcgen05 rwr_chain_kernel) or the cell-mode contractions (gemm_tc_kernel). The per-bin polar step
-	# (chol_jacobi_kernel, fp64 CUDA cores: neither an HBM nor a tensor-core roofline) is reported beside it in
-	# roofline_all with a measured fp64 peak, and `dominant_stage` names the largest stage whatever its kind.
-	rwr_flops = 0.0
-	for ds, k in zip(datasets, n_i):
-		for g_ in ds.geoms:
-			rwr_flops += ds.num_cell * (4.0 * g_.nb * g_.nb * g_.w + 2.0 * max(k - 1, 0) * g_.nb ** 3)
-	if "rwr" in per:
-		t = rwr_flops / (per["rwr"] / 1e3) / 1e12
-		hb = roof_all["rwr"]
-		roof_all["rwr"] = {"bound": "tensor", "achieved": t, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": t / pk["tensor"],
-		                   "note": "algorithmic fp32 flops (2 nb^2 w for A A^T, 2 nb^3 per step, 2 nb^2 w for Q A) over the whole RWR stage "
-		                           "(densify included) against the measured dense bf16 peak; fp32-parity maths runs 3 TF32 MMAs per product on "
-		                           "128-padded tiles, so the executed tensor work is ~3.5x this (ncu: tensor pipe 39 % active in rwr_chain_kernel)",
-		                   "hbm_side": {"achieved": hb["achieved"], "peak": hb["peak"], "unit": "GB/s", "frac": hb["frac"]}}
-	if "polar_bins" in per:
-		# measured fp64 peak of this GPU: cuBLAS DGEMM (library call used ONLY as the yardstick, never on the path)
-		a64 = torch.randn(4096, 4096, device=dev, dtype=torch.float64)
-		torch.matmul(a64, a64)
-		torch.cuda.synchronize()
-		g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-		g0.record()
-		for _ in range(3):
-			torch.matmul(a64, a64)
-		g1.record()
-		torch.cuda.synchronize()
-		pk64 = 3 * 2.0 * 4096 ** 3 / (g0.elapsed_time(g1) / 1e3) / 1e12
-		del a64
-		pb = roof_all["polar_bins"]
-		pb.update({"bound": "fp64", "peak": pk64, "frac": pb["achieved"] / pk64, "peak_source": "cuBLAS DGEMM 4096^3 timed in this run"})
-	cand = {k: v for k, v in (("rwr", per.get("rwr", 0.0)), ("contractions", gem)) if v > 0}
-	dom = max(cand, key=cand.get) if cand else "rwr"
-	roofline = dict(roof_all.get(dom, {}))
-	roofline["kernel_stage"] = dom
-	roofline["dominant_stage"] = top
-	roofline["kernels"] = {"rwr": "fh_rwr_batched = densify_conv_kernel (block-CSR -> conv'd panel) + rwr_chain_kernel<PANEL> (tcgen05 3xTF32, "
-	                              "TMA: A A^T, transition matrix, RWR steps with Q resident in TMEM, Q A, TMA stores)",
-	                       "contractions": "gemm_tc_kernel (tcgen05 3xTF32, TMA) + small batched gemm_simt_kernel"}[dom]
-	# DRAM traffic of the RWR stage from the ncu captures committed under profiles/ (chr1 bin block, 2048 cells:
-	# densify 0.277 GB + rwr_chain_kernel 0.646 GB moved for 0.331 GB of algorithmic bytes), scaled to this run
-	roofline["traffic"] = work["rwr_bytes"] * (0.923 / 0.331) if dom == "rwr" else None
-	roofline["traffic_source"] = ("profiles/r01_ncu_full_rwr_chain_kernel.txt + r01_micro_kernels_metrics.csv "
-	                              "(ncu dram__bytes_read+write.sum), scaled") if dom == "rwr" else None
-	roofline["peak_source"] = pk["src"]
+	roofline, roof_all = build_roofline(per, kt, work, datasets, n_i, pk, dev, top)
 	out = {"metric": "cells/s per PARAFAC2 ALS sweep (incl. RWR)", "value": value, "unit": "cells/s", "n_gpus": world,
 	       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
 	       "vs_baseline": None, "dtype": "f32 (fp64 inside the polar step)", "data": "synthetic", "config": config,
 	       "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
-	       "stages_ms_per_sweep": per, "roofline_all": roof_all, "rwr_steps": n_i, "re_trace_tail": core.re_trace[-3:]}
+	       "stages_ms_per_sweep": per, "kernels_ms_per_sweep": kt, "roofline_all": roof_all, "rwr_steps": n_i, "re_trace_tail": core.re_trace[-3:]}
 	if not args.no_cpu_baseline and world == 1:
 		# reported baselines, not targets: (1) the reference algorithm on the host cores, (2) the same stock torch ops on this
 		# GPU (cuBLAS / cuSOLVER driven as the reference drives them: one cell batch on a 180 GB device, gesvda polar) - the

@@ -33,7 +33,7 @@ class RwrDesc(C.Structure):
 EXPORTS = ["fh_last_error", "fh_version", "fh_launch_count", "fh_tc_fallback_count", "fh_gemm_batched", "fh_rwr_workspace_bytes",
            "fh_rwr_batched", "fh_densify", "fh_rwr_dense", "fh_colsum_accum", "fh_avgpool", "fh_sqnorm_accum",
            "fh_dot_accum", "fh_polar_workspace_bytes", "fh_polar_batched", "fh_polar_isqrt_multi", "fh_inv_sqrt_spd",
-           "fh_cp_als_workspace_bytes", "fh_cp_als", "fh_cp_core_sqnorm", "fh_scale_cols_batched"]
+           "fh_cp_als_workspace_bytes", "fh_cp_als", "fh_cp_core_sqnorm", "fh_scale_cols_batched", "fh_timing_enable", "fh_timing_read"]
 
 _lib = None
 
@@ -72,6 +72,9 @@ def lib():
 		L.fh_cp_als.argtypes = [vp, ci, ci, ci, vp, vp, vp, ci, vp, sz, C.POINTER(C.c_double), vp]
 		L.fh_scale_cols_batched.argtypes = [vp, ci, ci, ll, vp, ci, ci, vp, vp]
 		L.fh_cp_core_sqnorm.argtypes = [vp, ci, vp, vp, ci, ci, vp, vp, vp]
+		L.fh_timing_enable.argtypes = [ci]
+		L.fh_timing_enable.restype = None
+		L.fh_timing_read.argtypes = [ci, C.POINTER(C.c_double), C.POINTER(ll)]
 		_lib = L
 	return _lib
 
@@ -93,6 +96,21 @@ def stream_ptr():
 
 def launch_count():
 	return int(lib().fh_launch_count())
+
+
+TIME_DENSIFY, TIME_RWR_CHAIN, TIME_GEMM_TC, TIME_POLAR_JACOBI = 0, 1, 2, 3
+
+
+def kernel_timing(on):
+	"""Per-kernel CUDA-event timing inside the library (bench.py's roofline denominators): on / off, clears the records."""
+	lib().fh_timing_enable(1 if on else 0)
+
+
+def kernel_time(kind):
+	"""(total ms, launches) of one kernel kind since kernel_timing(True); synchronises on the recorded events."""
+	t, n = C.c_double(0.0), C.c_longlong(0)
+	check(lib().fh_timing_read(int(kind), C.byref(t), C.byref(n)))
+	return t.value, n.value
 
 
 def _ptr(t):

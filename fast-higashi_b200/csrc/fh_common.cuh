@@ -36,6 +36,10 @@ extern "C" void fh_count_launch(int n);
 		FH_CUDA(cudaGetLastError()); \
 	} while (0)
 
+// optional CUDA-event timing of a kernel launch (fh_api.cu; ids = FH_TIME_* of include/fh_b200.h)
+extern "C" int fh_time_begin(int id, void* stream);
+extern "C" void fh_time_end(int idx, void* stream);
+
 static inline int fh_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float fh_warp_sum(float v) {

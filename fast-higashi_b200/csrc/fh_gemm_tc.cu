@@ -411,11 +411,13 @@ int fh_gemm_tc(const fh_gemm_desc* d, const float* A, const float* B, float* C, 
 		FH_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
 		gemm_tc_kernel<AM, BMN><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, p, C);                                    \
 	} while (0)
+	const int tmr = fh_time_begin(FH_TIME_GEMM_TC, st);
 	if (a_mn && b_mn) FH_TC_LAUNCH(true, true);
 	else if (a_mn) FH_TC_LAUNCH(true, false);
 	else if (b_mn) FH_TC_LAUNCH(false, true);
 	else FH_TC_LAUNCH(false, false);
 #undef FH_TC_LAUNCH
+	fh_time_end(tmr, st);
 	FH_LAUNCH_CHECK();
 	return FH_OK;
 }

@@ -503,6 +503,7 @@ int launch_densify(const fh_rwr_desc* d, bool from_dense, const int32_t* rowptr,
                    long long out_cs, cudaStream_t st) {
 	size_t smem = (size_t)((RT + 2) * (d->w + 2) + RT + 4) * 4;
 	dim3 grid(fh_cdiv(d->nb, RT), d->ncell);
+	const int tmr = fh_time_begin(FH_TIME_DENSIFY, st);
 	if (from_dense) {
 		if (smem > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(densify_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		densify_conv_kernel<true><<<grid, 256, smem, st>>>(nullptr, nullptr, nullptr, 0, dense_in, in_cs, 0, d->nb, d->w,
@@ -512,6 +513,7 @@ int launch_densify(const fh_rwr_desc* d, bool from_dense, const int32_t* rowptr,
 		densify_conv_kernel<false><<<grid, 256, smem, st>>>(rowptr, col, val, d->nnz, nullptr, 0, d->cell0, d->nb, d->w,
 		                                                   d->ldw, do_conv, out, out_cs);
 	}
+	fh_time_end(tmr, st);
 	FH_LAUNCH_CHECK();
 	return FH_OK;
 }

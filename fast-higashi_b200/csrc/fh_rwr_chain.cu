@@ -644,13 +644,12 @@ int fh_rwr_chain(const float* P, const float* A, float* out, int nb, int w, int 
 		FH_CUDA(cudaMalloc(&p.trace, 32 * sizeof(long long)));
 		FH_CUDA(cudaMemsetAsync(p.trace, 0, 32 * sizeof(long long), st));
 	}
-	if (panel) {
-		FH_CUDA(cudaFuncSetAttribute(rwr_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
-		rwr_chain_kernel<true><<<grid, NTHREADS, Cfg<true>::SMEM_BYTES, st>>>(tp, ta, tk, to, ts, p);
-	} else {
-		FH_CUDA(cudaFuncSetAttribute(rwr_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
-		rwr_chain_kernel<false><<<grid, NTHREADS, Cfg<false>::SMEM_BYTES, st>>>(tp, ta, tk, to, ts, p);
-	}
+	if (panel) FH_CUDA(cudaFuncSetAttribute(rwr_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM_BYTES));
+	else FH_CUDA(cudaFuncSetAttribute(rwr_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM_BYTES));
+	const int tmr = fh_time_begin(FH_TIME_RWR_CHAIN, st);
+	if (panel) rwr_chain_kernel<true><<<grid, NTHREADS, Cfg<true>::SMEM_BYTES, st>>>(tp, ta, tk, to, ts, p);
+	else rwr_chain_kernel<false><<<grid, NTHREADS, Cfg<false>::SMEM_BYTES, st>>>(tp, ta, tk, to, ts, p);
+	fh_time_end(tmr, st);
 	FH_LAUNCH_CHECK();
 	if (trace_on) {  // debug only: synchronises and prints the phase stamps (SM clocks relative to stamp 0 / 8)
 		long long h[32];

@@ -57,6 +57,7 @@ class Fast_Higashi_core:
 		self.n_rwr_passes = 0
 		self._X = {}
 		self._eig = {}
+		self._scratch = {}
 
 	def to(self, device):
 		self.device = torch.device(device)
@@ -356,8 +357,8 @@ class Fast_Higashi_core:
 		rp = pad4(r)
 		if rp == r:
 			return B, D
-		Bp = torch.zeros(r, rp, dtype=torch.float32, device=B.device); Bp[:, :r] = B
-		Dp = torch.zeros(D.shape[0], rp, dtype=torch.float32, device=B.device); Dp[:, :r] = D
+		Bp = self._buf(("Bp", chrom), r, rp); Bp[:, :r].copy_(B)
+		Dp = self._buf(("Dp", chrom), D.shape[0], rp); Dp[:, :r].copy_(D)
 		return Bp, Dp
 
 	def _build_W(self, ci, b):
@@ -372,13 +373,25 @@ class Fast_Higashi_core:
 		Bp, Dp = self._padded_factors(ds.chrom)
 		U = self.projection_dev[ci][b]
 		Arows = self.A_dev[ci][g.row0:g.row0 + g.nb]
-		UB = torch.zeros(P, rp, dtype=torch.float32, device=dev)
+		UB = self._buf("UB", P, rp)
 		_lib.gemm(U, Bp, UB, P, r, r, (rp, 1), (rp, 1), rp, dtype=gd)
-		Dsc = torch.empty(g.nb, R, rp, dtype=torch.float32, device=dev)
+		Dsc = self._buf("Dsc", g.nb, R, rp)
 		_lib.scale_cols_batched(Dp, R, r, rp, Arows, g.nb, rp, Dsc)
-		W = torch.empty(P, R, dtype=torch.float32, device=dev)
+		W = self._buf("W", P, R)
 		_lib.gemm(UB, Dsc, W, ldw, R, r, (rp, 1), (1, rp), R, batch=g.nb, batch_strides=(ldw * rp, R * rp, ldw * R), dtype=gd)
 		return W
+
+	def _buf(self, key, *shape, dtype=torch.float32):
+		"""Scratch buffer of the sweep, allocated (and zero-filled) ONCE per (key, shape): the timed sweep makes no allocator
+		calls and no per-block zero-fills. Pad columns (row pitch round_up(r, 4) > r) are never written by the GEMMs (their
+		stores stop at N), so they keep the zeros of the first fill. Buffers of equal key and shape are shared by successive
+		blocks - safe because every use is ordered on the caller's stream."""
+		k = (key, shape, dtype)
+		t = self._scratch.get(k)
+		if t is None:
+			t = torch.zeros(*shape, dtype=dtype, device=self.device)
+			self._scratch[k] = t
+		return t
 
 	def invalidate_cache(self):
 		self._X_valid = set()
@@ -386,6 +399,7 @@ class Fast_Higashi_core:
 	def release(self):
 		"""Drop the resident imputed tensor and the scratch buffers (the factors stay)."""
 		self._X = {}
+		self._scratch = {}
 		self.invalidate_cache()
 		_lib.free_workspaces()
 
@@ -401,8 +415,8 @@ class Fast_Higashi_core:
 		if self.cache == "sweep" or not hasattr(self, "_X_valid"):
 			self.invalidate_cache()
 			self.n_rwr_passes += 1
-		MT = torch.zeros(Cn, R, dtype=torch.float32, device=dev)  # SVD_term^T
-		stats = torch.zeros(2 * nch + 1, dtype=torch.float64, device=dev)  # x_U | ||X||^2 | x_V
+		MT = self._buf("MT", Cn, R).zero_()  # SVD_term^T (accumulated block by block)
+		stats = self._buf("stats", 2 * nch + 1, dtype=torch.float64).zero_()  # x_U | ||X||^2 | x_V
 		tab = self._polar_table()
 		G_all, WT_all = tab["G"], tab["WT"]
 		temps = {}
@@ -414,7 +428,7 @@ class Fast_Higashi_core:
 			rp = pad4(r)
 			A = self.A_dev[ci]
 			Bp, Dp = self._padded_factors(ds.chrom)
-			Cc = torch.zeros(Cn, rp, dtype=torch.float32, device=dev)
+			Cc = self._buf("Cc", Cn, rp)
 			_lib.gemm(V, Dp, Cc, Cn, r, R, (R, 1), (rp, 1), rp, dtype=gd)  # C = V D  (:336)
 			for b, g in enumerate(ds.geoms):
 				ldw = pad4(g.w)
@@ -427,15 +441,13 @@ class Fast_Higashi_core:
 					                                      _lib.stream_ptr()))
 				# P1: T1 = X^T C ; temp_i = T1_i (B diag(A_i))^T
 				t = self._tic()
-				T1 = torch.empty(P, rp, dtype=torch.float32, device=dev)
+				T1 = self._buf("T1", P, rp)
 				_lib.gemm(X, Cc, T1, P, r, Cn, (1, P), (rp, 1), rp, dtype=gd)
-				if rp > r:
-					T1[:, r:].zero_()
 				self._allreduce(T1)
 				Arows = A[g.row0:g.row0 + g.nb]
-				Bsc = torch.empty(g.nb, r, rp, dtype=torch.float32, device=dev)
+				Bsc = self._buf("Bsc", g.nb, r, rp)
 				_lib.scale_cols_batched(Bp, r, r, rp, Arows, g.nb, rp, Bsc)
-				temp = torch.zeros(g.nb, ldw, rp, dtype=torch.float32, device=dev)
+				temp = self._buf(("temp", ci, b), g.nb, ldw, rp)
 				_lib.gemm(T1, Bsc, temp, ldw, r, r, (rp, 1), (1, rp), rp, batch=g.nb, batch_strides=(ldw * rp, r * rp, ldw * rp), dtype=gd)
 				temps[(ci, b)] = temp
 				self._toc("p1_mttkrp", t)
@@ -450,7 +462,6 @@ class Fast_Higashi_core:
 					_lib.gemm(temp, temp, Gb, ns, ns, r, (rp, 1), (1, rp), ns, batch=g.nb, batch_strides=(ldw * rp, ldw * rp, ns * ns),
 					          dtype=_lib.GEMM_F32_ACC64)
 				self._toc("polar_bins", t)
-				del T1, Bsc
 		# ---- phase B: G^{-1/2} of all bins of all chromosomes at once (P2b)
 		t = self._tic()
 		if tab["world"] > 1:
@@ -491,7 +502,6 @@ class Fast_Higashi_core:
 				W = self._build_W(ci, b)
 				_lib.gemm(X, W, MT, Cn, R, P, (P, 1), (R, 1), R, beta=1.0, dtype=gd)
 				self._toc("p3_project", t)
-				del W, temp
 		# P4: V = polar(SVD_term^T) (:483-486)
 		self.last_svd_term_T = MT
 		t = self._tic()
@@ -510,13 +520,12 @@ class Fast_Higashi_core:
 				P = g.nb * ldw
 				X = self._impute_good(ci, b, do_conv, do_rwr, do_col)
 				t = self._tic()
-				Z = torch.empty(P, R, dtype=torch.float32, device=dev)
+				Z = self._buf("Z", P, R)
 				_lib.gemm(X, Vn, Z, P, R, Cn, (1, P), (R, 1), R, dtype=gd)
 				U = self.projection_dev[ci][b]
 				Yb = Y[ds.global_slice_bin.start + g.row0: ds.global_slice_bin.start + g.row0 + g.nb]
 				_lib.gemm(U, Z, Yb, r, R, ldw, (1, rp), (R, 1), R, batch=g.nb, batch_strides=(ldw * rp, ldw * R, r * R), dtype=gd)
 				self._toc("p5_tensor", t)
-				del Z
 		for chrom in self.chrom2size:
 			self._allreduce(self.projected_dev[chrom])
 		if self._dist() is not None:
@@ -555,7 +564,7 @@ class Fast_Higashi_core:
 		                        for g in ds.geoms] for ds in self.schic]
 		self.projected_dev = {c: torch.zeros(self.chrom2num_bin[c], self.chrom2size[c], R, dtype=torch.float32, device=dev)
 		                      for c in self.chrom2size}
-		self._X, self._eig, self._ptab = {}, {}, None
+		self._X, self._eig, self._ptab, self._scratch = {}, {}, None, {}
 		self.invalidate_cache()
 		self.n_rwr_passes = 0
 		self._core_norm = self._core_norms()

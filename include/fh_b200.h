@@ -25,6 +25,12 @@ int fh_version(void);
 long long fh_launch_count(void);
 /* FH_GEMM_TF32X3 calls that ran on the CUDA-core fp32 kernel because TMA could not describe them */
 long long fh_tc_fallback_count(void);
+/* Optional per-kernel timing for the bench's roofline: while enabled, every launch of the kernels below is bracketed by
+ * CUDA events on its own stream; fh_timing_read synchronises on them and returns the summed duration and the launch count.
+ * fh_timing_enable(0 or 1) also discards what was recorded before. */
+enum { FH_TIME_DENSIFY = 0, FH_TIME_RWR_CHAIN = 1, FH_TIME_GEMM_TC = 2, FH_TIME_POLAR_JACOBI = 3 };
+void fh_timing_enable(int on);
+int fh_timing_read(int id, double* host_total_ms, long long* host_launches);
 
 /* ---------------------------------------------------------------------------------------------
  * Generic batched strided GEMM.  C[b](m,n) = alpha * sum_k A[b](m,k)*kscale[b][k]*B[b](k,n)

