@@ -637,39 +637,125 @@ extern "C" int fh_polar_isqrt_multi(const double* G_all, double* WT_all, const i
 }
 
 // ---------------------------------------------------------------------------------------------
-// G^{-1/2} of one SPD matrix by the coupled Newton-Schulz iteration (cells x R polar).
+// G^{-1/2} of one SPD matrix by the coupled Newton-Schulz iteration (cells x R polar):
+//   Y_0 = G / tr G, Z_0 = I;  T = Z Y;  Y <- Y (3 I - T) / 2,  Z <- (3 I - T) Z / 2;  Z -> (G / tr G)^{-1/2}.
+// ONE cooperative kernel runs the whole iteration (grid-wide barriers between the product phases, 32 x 32 fp64 tiles
+// spread over the SMs, the residual ||I - Z Y||_F^2 summed from per-CTA partials in a fixed order so that every CTA takes
+// the same stopping decision). Round 1 drove it from the host: three 256^3 GEMM launches (16 CTAs each), a residual
+// kernel and two copies per step, a stream synchronisation every fourth step, and a stopping rule that never fired on
+// the sweep's Gram matrices (all 200 steps ran): 6.4 ms per sweep for 2.5 GFLOP.
 // ---------------------------------------------------------------------------------------------
+#include <cooperative_groups.h>
 namespace {
-__global__ void ns_init_kernel(const double* __restrict__ G, int n, double* __restrict__ Y, double* __restrict__ Z,
-                               double* __restrict__ scal) {
+namespace cg = cooperative_groups;
+
+constexpr int NS_T = 32, NS_K = 16;  // output tile, k-block
+
+// c[i][j] = sum_k A[m0 + 2 ty + i][k] B[k][n0 + 2 tx + j] for row-major n x n matrices; 256 threads as 16 x 16
+__device__ __forceinline__ void ns_tile_mm(const double* __restrict__ A, const double* __restrict__ B, const int n, const int m0,
+                                           const int n0, double (&c)[2][2], double (*As)[NS_T + 1], double (*Bs)[NS_T + 1]) {
+	const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+	c[0][0] = c[0][1] = c[1][0] = c[1][1] = 0.0;
+	for (int k0 = 0; k0 < n; k0 += NS_K) {
+#pragma unroll
+		for (int it = 0; it < 2; ++it) {
+			const int idx = tid + 256 * it;
+			{
+				const int mm = idx >> 4, kk = idx & 15;
+				const int m = m0 + mm, k = k0 + kk;
+				As[kk][mm] = (m < n && k < n) ? A[(size_t)m * n + k] : 0.0;
+			}
+			{
+				const int kk = idx >> 5, nn = idx & 31;
+				const int k = k0 + kk, nc = n0 + nn;
+				Bs[kk][nn] = (k < n && nc < n) ? B[(size_t)k * n + nc] : 0.0;
+			}
+		}
+		__syncthreads();
+#pragma unroll
+		for (int kk = 0; kk < NS_K; ++kk) {
+			const double a0 = As[kk][2 * ty], a1 = As[kk][2 * ty + 1], b0 = Bs[kk][2 * tx], b1 = Bs[kk][2 * tx + 1];
+			c[0][0] = fma(a0, b0, c[0][0]); c[0][1] = fma(a0, b1, c[0][1]);
+			c[1][0] = fma(a1, b0, c[1][0]); c[1][1] = fma(a1, b1, c[1][1]);
+		}
+		__syncthreads();
+	}
+}
+
+// scal: [0] trace, [1] last residual, [2] steps taken, [3] 1 = converged / 0 = not / -1 = NaN
+__global__ void __launch_bounds__(256)
+ns_fused_kernel(const double* __restrict__ G, const int n, double* Ya, double* Za, double* Yb, double* Zb, double* T,
+                double* part, double* scal, double* __restrict__ out, const int max_it) {
+	cg::grid_group grid = cg::this_grid();
+	__shared__ double As[NS_K][NS_T + 1], Bs[NS_K][NS_T + 1];
 	__shared__ double red[32];
-	double tr = 0.0;
-	for (int i = threadIdx.x; i < n; i += blockDim.x) tr += G[(size_t)i * n + i];
+	const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+	const int nt = (n + NS_T - 1) / NS_T, ntile = nt * nt;
+	const size_t nn = (size_t)n * n;
+	double tr = 0.0;  // every CTA sums the trace itself (same order: same value everywhere)
+	for (int i = tid; i < n; i += 256) tr += G[(size_t)i * n + i];
 	tr = fh_block_sum(tr, red);
-	if (threadIdx.x == 0) scal[0] = tr;
-	for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
-		Y[i] = G[i] / tr;
-		Z[i] = (i / n == i % n) ? 1.0 : 0.0;
+	for (size_t i = (size_t)blockIdx.x * 256 + tid; i < nn; i += (size_t)gridDim.x * 256) {
+		Ya[i] = G[i] / tr;
+		Za[i] = (i / n == i % n) ? 1.0 : 0.0;
 	}
-}
-// T = 0.5 * (3 I - T);  scal[1] = ||I - ZY||_F^2 (T holds ZY on entry)
-__global__ void ns_mid_kernel(double* __restrict__ T, int n, double* __restrict__ scal) {
-	__shared__ double red[32];
-	double r = 0.0;
-	for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
-		double eye = (i / n == i % n) ? 1.0 : 0.0;
-		double zy = T[i];
-		double d = eye - zy;
-		r += d * d;
-		T[i] = 0.5 * (3.0 * eye - zy);
+	grid.sync();
+	// converged below `tol`, or once the residual has stopped shrinking at the fp64 rounding level of the product
+	const double tol = 1e-26 * (double)n * (double)n, stall = 1e-18 * (double)n * (double)n;
+	double *Y = Ya, *Z = Za, *Yn = Yb, *Zn = Zb;
+	double hres = 1.0, prev = 1e300;
+	int it = 0, status = 0;
+	for (; it < max_it; ++it) {
+		// T = Z Y and this CTA's share of ||I - Z Y||_F^2
+		double r = 0.0;
+		for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+			const int m0 = (tile / nt) * NS_T, n0 = (tile % nt) * NS_T;
+			double c[2][2];
+			ns_tile_mm(Z, Y, n, m0, n0, c, As, Bs);
+#pragma unroll
+			for (int i = 0; i < 2; ++i)
+#pragma unroll
+				for (int j = 0; j < 2; ++j) {
+					const int m = m0 + 2 * ty + i, nc = n0 + 2 * tx + j;
+					if (m < n && nc < n) {
+						T[(size_t)m * n + nc] = c[i][j];
+						const double d = (m == nc ? 1.0 : 0.0) - c[i][j];
+						r = fma(d, d, r);
+					}
+				}
+		}
+		r = fh_block_sum(r, red);
+		if (tid == 0) part[blockIdx.x] = r;
+		grid.sync();
+		hres = 0.0;
+		for (int i = 0; i < (int)gridDim.x; ++i) hres += part[i];  // fixed order: identical in every thread of the grid
+		if (!(hres == hres)) { status = -1; break; }
+		if (hres < tol || (hres < stall && hres > 0.25 * prev)) { status = 1; break; }
+		prev = hres;
+		// Yn = (3 Y - Y T) / 2,  Zn = (3 Z - T Z) / 2
+		for (int w = blockIdx.x; w < 2 * ntile; w += gridDim.x) {
+			const bool zpart = w >= ntile;
+			const int tile = zpart ? w - ntile : w;
+			const int m0 = (tile / nt) * NS_T, n0 = (tile % nt) * NS_T;
+			double c[2][2];
+			if (zpart) ns_tile_mm(T, Z, n, m0, n0, c, As, Bs); else ns_tile_mm(Y, T, n, m0, n0, c, As, Bs);
+			const double* src = zpart ? Z : Y;
+			double* dst = zpart ? Zn : Yn;
+#pragma unroll
+			for (int i = 0; i < 2; ++i)
+#pragma unroll
+				for (int j = 0; j < 2; ++j) {
+					const int m = m0 + 2 * ty + i, nc = n0 + 2 * tx + j;
+					if (m < n && nc < n) dst[(size_t)m * n + nc] = 1.5 * src[(size_t)m * n + nc] - 0.5 * c[i][j];
+				}
+		}
+		grid.sync();
+		double* t_ = Y; Y = Yn; Yn = t_;
+		t_ = Z; Z = Zn; Zn = t_;
 	}
-	r = fh_block_sum(r, red);
-	if (threadIdx.x == 0) scal[1] = r;
-}
-__global__ void ns_final_kernel(const double* __restrict__ Z, int n, const double* __restrict__ scal,
-                                double* __restrict__ out) {
-	double f = rsqrt(scal[0]);
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * n; i += gridDim.x * blockDim.x) out[i] = Z[i] * f;
+	const double f = rsqrt(tr);
+	for (size_t i = (size_t)blockIdx.x * 256 + tid; i < nn; i += (size_t)gridDim.x * 256) out[i] = Z[i] * f;
+	if (blockIdx.x == 0 && tid == 0) { scal[0] = tr; scal[1] = hres; scal[2] = (double)it; scal[3] = (double)status; }
 }
 }  // namespace
 
@@ -677,50 +763,40 @@ extern "C" int fh_inv_sqrt_spd(const double* G, double* out, int n, void* ws, si
                                void* stream) {
 	FH_CHECK_ARG(n > 0, "fh_inv_sqrt_spd: n <= 0");
 	const size_t nn = (size_t)n * n;
-	FH_CHECK_ARG(ws && ws_bytes >= (4 * nn + 8) * 8, "fh_inv_sqrt_spd: workspace too small");
+	FH_CHECK_ARG(ws && ws_bytes >= (5 * nn + 512) * 8, "fh_inv_sqrt_spd: workspace too small (need (5 n^2 + 512) doubles)");
 	cudaStream_t st = (cudaStream_t)stream;
-	double* Y = (double*)ws;
-	double* Z = Y + nn;
-	double* T = Z + nn;
-	double* tmp = T + nn;
-	double* scal = tmp + nn;
-	ns_init_kernel<<<1, 1024, 0, st>>>(G, n, Y, Z, scal);
-	FH_LAUNCH_CHECK();
-	int it = 0, rc;
-	double hres = 1.0, prev = 1e300;
-	// ||I - ZY||_F^2: converged below `tol`, or once it has stopped shrinking at the fp64 rounding level of the product
-	// (~ (n eps kappa(G)^(1/2))^2; on the sweep's R x R Gram matrices the residual stalls above `tol`: the old rule never
-	// fired and the loop ran all 200 steps - 6.5 ms per sweep). Still large after the loop = singular input = error.
-	const double tol = 1e-26 * (double)n * (double)n, stall = 1e-18 * (double)n * (double)n, bad = 1e-12 * (double)n * (double)n;
-	bool ok = false;
-	for (; it < 200; ++it) {
-		rc = gemm(FH_GEMM_F64, n, n, n, 1, Z, n, 1, 0, Y, n, 1, 0, T, n, 0, stream);  // T = Z Y
-		if (rc) return rc;
-		ns_mid_kernel<<<1, 1024, 0, st>>>(T, n, scal);
-		FH_LAUNCH_CHECK();
-		if ((it & 3) == 3 || it > 24) {
-			FH_CUDA(cudaMemcpyAsync(&hres, scal + 1, 8, cudaMemcpyDeviceToHost, st));
-			FH_CUDA(cudaStreamSynchronize(st));
-			if (!(hres == hres)) { fh_set_error("fh_inv_sqrt_spd: NaN (matrix not SPD?)"); return FH_ERR_ARG; }
-			if (hres < tol || (hres < stall && hres > 0.25 * prev)) { ok = true; break; }
-			prev = hres;
-		}
-		rc = gemm(FH_GEMM_F64, n, n, n, 1, Y, n, 1, 0, T, n, 1, 0, tmp, n, 0, stream);  // Y = Y T
-		if (rc) return rc;
-		FH_CUDA(cudaMemcpyAsync(Y, tmp, nn * 8, cudaMemcpyDeviceToDevice, st));
-		rc = gemm(FH_GEMM_F64, n, n, n, 1, T, n, 1, 0, Z, n, 1, 0, tmp, n, 0, stream);  // Z = T Z
-		if (rc) return rc;
-		FH_CUDA(cudaMemcpyAsync(Z, tmp, nn * 8, cudaMemcpyDeviceToDevice, st));
+	double* Ya = (double*)ws;
+	double *Za = Ya + nn, *Yb = Za + nn, *Zb = Yb + nn, *T = Zb + nn, *part = T + nn, *scal = part + 504;
+	static int num_sms = 0, per_sm = 0;
+	if (!num_sms) {
+		int dev = 0;
+		FH_CUDA(cudaGetDevice(&dev));
+		FH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+		FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ns_fused_kernel, 256, 0));
+		FH_CHECK_ARG(per_sm >= 1, "fh_inv_sqrt_spd: the cooperative kernel does not fit an SM");
 	}
-	if (host_iters) *host_iters = it;
+	const int nt = (n + NS_T - 1) / NS_T;
+	int grid = 2 * nt * nt;                    // the two-product phase has 2 nt^2 tiles
+	if (grid > num_sms) grid = num_sms;        // one CTA per SM at most: all CTAs must be co-resident (grid barrier)
+	if (grid > 500) grid = 500;
+	int max_it = 200;
+	int n_ = n;
+	void* args[] = {(void*)&G, (void*)&n_, (void*)&Ya, (void*)&Za, (void*)&Yb, (void*)&Zb, (void*)&T, (void*)&part, (void*)&scal, (void*)&out, (void*)&max_it};
+	FH_CUDA(cudaLaunchCooperativeKernel((void*)ns_fused_kernel, dim3(grid), dim3(256), args, 0, st));
+	fh_count_launch(1);
+	double h[4] = {0, 0, 0, 0};  // one read-back per call: the error status must reach the caller
+	FH_CUDA(cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, st));
+	FH_CUDA(cudaStreamSynchronize(st));
+	if (host_iters) *host_iters = (int)h[2];
 	static int ns_dbg = -1;
 	if (ns_dbg < 0) { const char* e = getenv("FH_NS_DEBUG"); ns_dbg = (e && e[0] == '1') ? 1 : 0; }
-	if (ns_dbg) fprintf(stderr, "fh_inv_sqrt_spd: n %d iterations %d residual^2 %.3e converged %d\n", n, it, hres, (int)ok);
-	if (!ok && !(hres < bad)) {  // singular / numerically rank-deficient Gram: the null directions of Z grow ~1.5x per step - never hand that back
-		fh_set_error("fh_inv_sqrt_spd: Newton-Schulz did not converge in 200 iterations, ||I - ZY||_F^2 = %.3g (Gram matrix singular: fewer rows than columns, or a rank-deficient input)", hres);
+	if (ns_dbg) fprintf(stderr, "fh_inv_sqrt_spd: n %d iterations %d residual^2 %.3e status %d grid %d\n", n, (int)h[2], h[1], (int)h[3], grid);
+	if (h[3] < 0.0) { fh_set_error("fh_inv_sqrt_spd: NaN (matrix not SPD?)"); return FH_ERR_ARG; }
+	// not converged and the residual still large: singular / numerically rank-deficient Gram (the null directions of Z grow
+	// ~1.5x per step) - never hand that back
+	if (h[3] < 1.0 && !(h[1] < 1e-12 * (double)n * (double)n)) {
+		fh_set_error("fh_inv_sqrt_spd: Newton-Schulz did not converge in 200 iterations, ||I - ZY||_F^2 = %.3g (Gram matrix singular: fewer rows than columns, or a rank-deficient input)", h[1]);
 		return FH_ERR_ARG;
 	}
-	ns_final_kernel<<<fh_cdiv(nn, 256), 256, 0, st>>>(Z, n, scal, out);
-	FH_LAUNCH_CHECK();
 	return FH_OK;
 }

@@ -29,7 +29,7 @@ from .partial_rwr import rwr_block_csr, pad4, cells_per_chunk
 from .project2orthogonal import polar_batched, polar_tall
 from .parafac_integrative import cp_als_, core_sqnorm_accum
 from .sparse_for_schic import Chrom_Dataset
-from .sharding import polar_partition
+from .sharding import polar_bin_range
 from .dist_svd import sharded_truncated_svd, sharded_svd_gram
 
 
@@ -79,6 +79,14 @@ class Fast_Higashi_core:
 		if d is not None:
 			d.all_reduce(t, op=op or d.ReduceOp.SUM, group=self.group)
 		return t
+
+	def _allreduce_async(self, t):
+		"""Start an all-reduce (SUM) of t on the communicator's own stream; returns a handle whose .wait() makes the current
+		stream wait for it (None when not sharded). Lets the next block's RWR / GEMMs run under the transfer."""
+		d = self._dist()
+		if d is None:
+			return None
+		return d.all_reduce(t, op=d.ReduceOp.SUM, group=self.group, async_op=True)
 
 	def _log(self, *a):
 		if self.verbose and (self.group is None or self._dist().get_rank(self.group) == 0):
@@ -308,46 +316,44 @@ class Fast_Higashi_core:
 		return X
 
 	def _polar_table(self):
-		"""Problem table of the per-bin polar step (one Gram matrix per bin, all chromosomes): offsets
-		into one fp64 buffer, sorted by decreasing size for fh_polar_isqrt_multi. Built once."""
+		"""Problem table of the per-bin polar step (one Gram matrix per bin, all chromosomes): offsets into one fp64
+		buffer, sorted by decreasing size for fh_polar_isqrt_multi. Built once. Multi-GPU: the bins are independent
+		problems that depend only on the all-reduced T1, so rank k takes a contiguous share [lo, hi) of the bins of EVERY
+		block (sharding.polar_bin_range) - its Gram matrices, eigen-problems and G^{-1/2} products - and the inverse
+		square roots are exchanged with ONE all-reduce over the zero-initialised buffer (x + 0 is exact: every rank ends
+		with identical bits)."""
 		if getattr(self, "_ptab", None) is not None:
 			return self._ptab
 		dev = self.device
-		block, n_list, off_list, lengths = {}, [], [], []
-		off = 0
+		d = self._dist()
+		world = d.get_world_size(self.group) if d is not None else 1
+		rank = d.get_rank(self.group) if d is not None else 0
+		block, own, n_list, off_list, slot_list, lengths = {}, {}, [], [], [], []
+		off = slot = 0
 		for ci, ds in enumerate(self.schic):
 			r = self.chrom2size[ds.chrom]
 			cnt = 0
 			for b, g in enumerate(ds.geoms):
 				ns = min(pad4(g.w), r)
 				block[(ci, b)] = (off, ns)
-				for i in range(g.nb):
-					n_list.append(ns); off_list.append(off + i * ns * ns)
+				lo, hi = polar_bin_range(g.nb, world, rank)
+				own[(ci, b)] = (lo, hi)
+				for i in range(lo, hi):
+					n_list.append(ns); off_list.append(off + i * ns * ns); slot_list.append(slot + i)
 				off += g.nb * ns * ns
+				slot += g.nb
 				cnt += g.nb
 			lengths.append(cnt)
 		n_arr = np.asarray(n_list, dtype=np.int32)
-		d = self._dist()
-		world = d.get_world_size(self.group) if d is not None else 1
-		order, sub = polar_partition(n_arr, world, d.get_rank(self.group) if d is not None else 0)
-		self._ptab = dict(block=block, count=len(n_list), n_host=np.ascontiguousarray(n_arr[order]),
+		order = np.argsort(-n_arr, kind="stable")
+		self._ptab = dict(block=block, own=own, world=world, count=len(n_list), n_host=np.ascontiguousarray(n_arr[order]),
 		                  n_dev=torch.from_numpy(np.ascontiguousarray(n_arr[order])).to(dev),
 		                  off_dev=torch.from_numpy(np.asarray(off_list, dtype=np.int64)[order].copy()).to(dev),
-		                  slot_dev=torch.from_numpy(order.astype(np.int32)).to(dev),
-		                  ssum=torch.zeros(len(n_list), dtype=torch.float64, device=dev),
-		                  nsweep=torch.zeros(len(n_list), dtype=torch.int32, device=dev),  # Jacobi sweeps per bin (diagnostics)
+		                  slot_dev=torch.from_numpy(np.asarray(slot_list, dtype=np.int32)[order].copy()).to(dev),
+		                  ssum=torch.zeros(slot, dtype=torch.float64, device=dev),
+		                  nsweep=torch.zeros(slot, dtype=torch.int32, device=dev),  # Jacobi sweeps per bin (diagnostics)
 		                  chrom_lengths=torch.tensor(lengths, device=dev),
-		                  G=torch.empty(off, dtype=torch.float64, device=dev), WT=torch.empty(off, dtype=torch.float64, device=dev))
-		# Multi-GPU: the bins are independent problems and every rank holds every (all-reduced) Gram matrix, so
-		# rank k factorises problems k, k + world, ... of the size-sorted list (balanced by construction); the
-		# factors are exchanged with ONE all-reduce over the zero-initialised WT buffer (x + 0 is exact, every
-		# rank ends with identical bits).
-		self._ptab["world"] = world
-		if world > 1:
-			self._ptab.update(count=len(sub), n_host=np.ascontiguousarray(n_arr[sub]),
-			                  n_dev=torch.from_numpy(np.ascontiguousarray(n_arr[sub])).to(dev),
-			                  off_dev=torch.from_numpy(np.asarray(off_list, dtype=np.int64)[sub].copy()).to(dev),
-			                  slot_dev=torch.from_numpy(sub.astype(np.int32)).to(dev))
+		                  G=torch.zeros(off, dtype=torch.float64, device=dev), WT=torch.empty(off, dtype=torch.float64, device=dev))
 		return self._ptab
 
 	def _padded_factors(self, chrom):
@@ -419,16 +425,49 @@ class Fast_Higashi_core:
 		stats = self._buf("stats", 2 * nch + 1, dtype=torch.float64).zero_()  # x_U | ||X||^2 | x_V
 		tab = self._polar_table()
 		G_all, WT_all = tab["G"], tab["WT"]
+		if tab["world"] > 1:
+			G_all.zero_()  # the other ranks' slots must be exact zeros for the exchange by all-reduce
 		temps = {}
 		# Every r-wide operand lives at a row pitch rp = round_up(r, 4) (zero pad columns) so that TMA can
 		# describe it and all GEMMs below except the fp64 ones run on the tcgen05 kernel.
-		# ---- phase A: impute, P1, Gram of every temp_i
+		# ---- phase A: impute, P1, Gram of every temp_i. Sharded: the all-reduce of a block's T1 runs on the communicator's
+		# stream under the NEXT block's RWR and P1 GEMM (software pipeline of depth one, two T1 buffers)
+		def finish_block(pend):
+			work, ci, b, T1, Bp = pend
+			ds = self.schic[ci]
+			g = ds.geoms[b]
+			r = self.chrom2size[ds.chrom]
+			rp, ldw = pad4(r), pad4(g.w)
+			if work is not None:
+				work.wait()
+			t = self._tic()
+			Arows = self.A_dev[ci][g.row0:g.row0 + g.nb]
+			Bsc = self._buf("Bsc", g.nb, r, rp)
+			_lib.scale_cols_batched(Bp, r, r, rp, Arows, g.nb, rp, Bsc)
+			temp = self._buf(("temp", ci, b), g.nb, ldw, rp)
+			_lib.gemm(T1, Bsc, temp, ldw, r, r, (rp, 1), (1, rp), rp, batch=g.nb, batch_strides=(ldw * rp, r * rp, ldw * rp), dtype=gd)
+			temps[(ci, b)] = temp
+			self._toc("p1_mttkrp", t)
+			# P2a: Gram of every temp_i of this rank's bins in fp64 (tall: T^T T, wide: T T^T)
+			t = self._tic()
+			off, ns = tab["block"][(ci, b)]
+			lo, hi = tab["own"][(ci, b)]
+			if hi > lo:
+				Gb = G_all[off + lo * ns * ns:off + hi * ns * ns]
+				if ldw >= r:
+					_lib.gemm(temp[lo:hi], temp[lo:hi], Gb, ns, ns, ldw, (1, rp), (rp, 1), ns, batch=hi - lo,
+					          batch_strides=(ldw * rp, ldw * rp, ns * ns), dtype=_lib.GEMM_F32_ACC64)
+				else:
+					_lib.gemm(temp[lo:hi], temp[lo:hi], Gb, ns, ns, r, (rp, 1), (1, rp), ns, batch=hi - lo,
+					          batch_strides=(ldw * rp, ldw * rp, ns * ns), dtype=_lib.GEMM_F32_ACC64)
+			self._toc("polar_bins", t)
+
+		pending, nblk = None, 0
 		for ci, ds in enumerate(self.schic):
 			r = self.chrom2size[ds.chrom]
 			rp = pad4(r)
-			A = self.A_dev[ci]
 			Bp, Dp = self._padded_factors(ds.chrom)
-			Cc = self._buf("Cc", Cn, rp)
+			Cc = self._buf(("Cc", ci & 1), Cn, rp)
 			_lib.gemm(V, Dp, Cc, Cn, r, R, (R, 1), (rp, 1), rp, dtype=gd)  # C = V D  (:336)
 			for b, g in enumerate(ds.geoms):
 				ldw = pad4(g.w)
@@ -441,37 +480,35 @@ class Fast_Higashi_core:
 					                                      _lib.stream_ptr()))
 				# P1: T1 = X^T C ; temp_i = T1_i (B diag(A_i))^T
 				t = self._tic()
-				T1 = self._buf("T1", P, rp)
+				T1 = self._buf(("T1", nblk & 1), P, rp)
+				nblk += 1
 				_lib.gemm(X, Cc, T1, P, r, Cn, (1, P), (rp, 1), rp, dtype=gd)
-				self._allreduce(T1)
-				Arows = A[g.row0:g.row0 + g.nb]
-				Bsc = self._buf("Bsc", g.nb, r, rp)
-				_lib.scale_cols_batched(Bp, r, r, rp, Arows, g.nb, rp, Bsc)
-				temp = self._buf(("temp", ci, b), g.nb, ldw, rp)
-				_lib.gemm(T1, Bsc, temp, ldw, r, r, (rp, 1), (1, rp), rp, batch=g.nb, batch_strides=(ldw * rp, r * rp, ldw * rp), dtype=gd)
-				temps[(ci, b)] = temp
 				self._toc("p1_mttkrp", t)
-				# P2a: Gram of every temp_i in fp64 (tall: T^T T, wide: T T^T)
-				t = self._tic()
-				off, ns = tab["block"][(ci, b)]
-				Gb = G_all[off:off + g.nb * ns * ns]
-				if ldw >= r:
-					_lib.gemm(temp, temp, Gb, ns, ns, ldw, (1, rp), (rp, 1), ns, batch=g.nb, batch_strides=(ldw * rp, ldw * rp, ns * ns),
-					          dtype=_lib.GEMM_F32_ACC64)
-				else:
-					_lib.gemm(temp, temp, Gb, ns, ns, r, (rp, 1), (1, rp), ns, batch=g.nb, batch_strides=(ldw * rp, ldw * rp, ns * ns),
-					          dtype=_lib.GEMM_F32_ACC64)
-				self._toc("polar_bins", t)
+				work = self._allreduce_async(T1)
+				if pending is not None:
+					finish_block(pending)
+				pending = (work, ci, b, T1, Bp)
+		if pending is not None:
+			finish_block(pending)
 		# ---- phase B: G^{-1/2} of all bins of all chromosomes at once (P2b)
 		t = self._tic()
 		if tab["world"] > 1:
-			WT_all.zero_(); tab["ssum"].zero_()
+			tab["ssum"].zero_()
 		_lib.check(_lib.lib().fh_polar_isqrt_multi(G_all.data_ptr(), WT_all.data_ptr(), tab["n_dev"].data_ptr(),
 		                                           tab["off_dev"].data_ptr(), tab["slot_dev"].data_ptr(),
 		                                           tab["n_host"].ctypes.data, tab["count"], tab["ssum"].data_ptr(), 0,
 		                                           tab["nsweep"].data_ptr(), _lib.stream_ptr()))
+		# M = G^{-1/2} = WT^T WT of this rank's bins, over the Gram matrices (the other ranks' slots of G_all stay zero)
+		for ci, ds in enumerate(self.schic):
+			for b, g in enumerate(ds.geoms):
+				off, ns = tab["block"][(ci, b)]
+				lo, hi = tab["own"][(ci, b)]
+				if hi > lo:
+					nn = ns * ns
+					WTb, Mb = WT_all[off + lo * nn:off + hi * nn], G_all[off + lo * nn:off + hi * nn]
+					_lib.gemm(WTb, WTb, Mb, ns, ns, ns, (1, ns), (ns, 1), ns, batch=hi - lo, batch_strides=(nn, nn, nn), dtype=_lib.GEMM_F64)
 		if tab["world"] > 1:
-			self._allreduce(WT_all)
+			self._allreduce(G_all)
 			self._allreduce(tab["ssum"])
 		stats[:nch] = torch.segment_reduce(tab["ssum"], "sum", lengths=tab["chrom_lengths"])
 		self._toc("polar_bins", t)
@@ -487,8 +524,7 @@ class Fast_Higashi_core:
 				t = self._tic()
 				off, ns = tab["block"][(ci, b)]
 				nn = ns * ns
-				WTb, Mb = WT_all[off:off + g.nb * nn], G_all[off:off + g.nb * nn]
-				_lib.gemm(WTb, WTb, Mb, ns, ns, ns, (1, ns), (ns, 1), ns, batch=g.nb, batch_strides=(nn, nn, nn), dtype=_lib.GEMM_F64)
+				Mb = G_all[off:off + g.nb * nn]
 				U = self.projection_dev[ci][b]
 				if ldw >= r:
 					_lib.gemm(temp, Mb, U, ldw, r, r, (rp, 1), (ns, 1), rp, batch=g.nb, batch_strides=(ldw * rp, nn, ldw * rp),
@@ -511,6 +547,7 @@ class Fast_Higashi_core:
 		self._toc("polar_cells", t)
 		self.meta_embedding = Vn
 		# P5: Y_i = U_i^T X_i V (:488-529)
+		y_works = []
 		for ci, ds in enumerate(self.schic):
 			r = self.chrom2size[ds.chrom]
 			rp = pad4(r)
@@ -526,8 +563,11 @@ class Fast_Higashi_core:
 				Yb = Y[ds.global_slice_bin.start + g.row0: ds.global_slice_bin.start + g.row0 + g.nb]
 				_lib.gemm(U, Z, Yb, r, R, ldw, (1, rp), (R, 1), R, batch=g.nb, batch_strides=(ldw * rp, ldw * R, r * R), dtype=gd)
 				self._toc("p5_tensor", t)
-		for chrom in self.chrom2size:
-			self._allreduce(self.projected_dev[chrom])
+			if ci == self.chrom2id[ds.chrom][-1]:  # every dataset of this chromosome has added its bins: reduce Y under the next one's GEMMs
+				y_works.append(self._allreduce_async(Y))
+		for w in y_works:
+			if w is not None:
+				w.wait()
 		if self._dist() is not None:
 			loc = stats[nch:].clone()
 			self._allreduce(loc)

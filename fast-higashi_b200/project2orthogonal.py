@@ -39,7 +39,7 @@ def inv_sqrt_spd(G):
 	"""G^{-1/2} of one SPD fp64 matrix on device."""
 	n = G.shape[0]
 	out = torch.empty_like(G)
-	ws = _lib.workspace((4 * n * n + 8) * 8, G.device, "ns")
+	ws = _lib.workspace((5 * n * n + 512) * 8, G.device, "ns")
 	it = C.c_int(0)
 	_lib.check(_lib.lib().fh_inv_sqrt_spd(G.data_ptr(), out.data_ptr(), n, ws.data_ptr(), ws.numel(), C.byref(it),
 	                                      _lib.stream_ptr()))

@@ -1,7 +1,7 @@
 """Cell-slab sharding for one-process-per-GPU runs: rank g owns a contiguous
 slab of cells for ALL chromosomes; A, B, D, U, Y are replicated; T1, Y, the R x R Gram of
 SVD_term^T and two scalars are all-reduced every sweep; the per-bin polar problems (which depend only
-on all-reduced data) are partitioned across ranks."""
+on all-reduced data) are partitioned across ranks and their inverse square roots exchanged."""
 import numpy as np
 
 
@@ -48,14 +48,12 @@ def gather_cell_rows(local, num_good_local, group=None):
 	return torch.cat(good + bad, 0)
 
 
-def polar_partition(sizes, world_size, rank):
-	"""Problems of the per-bin polar step owned by `rank`. `sizes`: Gram side of every bin (any order).
-	Returns (order, mine): `order` = all problem indices sorted by decreasing size (stable), `mine` = the
-	indices this rank factorises, i.e. entries rank, rank + world, ... of `order` - still sorted, and
-	balanced to within one problem per size class because neighbours in `order` have (nearly) equal cost."""
-	sizes = np.asarray(sizes)
-	order = np.argsort(-sizes, kind="stable")
-	return order, order[int(rank)::int(world_size)]
+def polar_bin_range(num_bins_in_block, world_size, rank):
+	"""Bins [lo, hi) of one bin block whose per-bin polar problems `rank` solves. All bins of a block have the same problem
+	size, so a contiguous even split of every block balances the ranks AND keeps each rank's share of a block one
+	contiguous batch for the Gram / factor GEMMs around the eigen-solver (the whole stage is partitioned, not only the
+	Jacobi kernel)."""
+	return cell_slab(num_bins_in_block, world_size, rank)
 
 
 def scatter_dataset(ds, owner, group, device):

@@ -30,7 +30,7 @@ for n, logk in ((64, 3.6), (256, 3.6), (256, 4.5)):
 	M = ((Uq * torch.logspace(0, -logk, n, dtype=torch.float64)) @ Vq.T)
 	G = (M.T @ M).cuda()
 	out = torch.empty_like(G)
-	ws = _lib.workspace((4 * n * n + 8) * 8, G.device, "ns")
+	ws = _lib.workspace((5 * n * n + 512) * 8, G.device, "ns")
 	it = C.c_int(0)
 	rc = _lib.lib().fh_inv_sqrt_spd(G.data_ptr(), out.data_ptr(), n, ws.data_ptr(), ws.numel(), C.byref(it), _lib.stream_ptr())
 	res = float(((out @ G @ out) - torch.eye(n, dtype=torch.float64, device="cuda")).norm() ** 2)

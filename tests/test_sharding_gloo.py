@@ -78,20 +78,30 @@ def test_two_rank_gloo_sharding():
 	assert all(r[6] == [24, 24, 24] for r in res)
 
 
-def test_polar_partition_is_a_balanced_cover():
-	"""Per-bin polar problems across ranks: every problem exactly once, each rank's list sorted by decreasing size,
-	Jacobi cost (~n^3) balanced to a few per cent at the PFC problem mix."""
-	from fasthigashi_b200.sharding import polar_partition
+def test_polar_bin_ranges_are_a_balanced_cover():
+	"""Per-bin polar problems across ranks: every bin of every block exactly once, contiguous per block (one GEMM batch per
+	rank and block), Jacobi cost (~n^3) balanced to a few per cent at the PFC problem mix (blocks of <= 128 rows)."""
+	import math
+	from fasthigashi_b200.sharding import polar_bin_range
 	from fasthigashi_b200 import synth
-	sizes = np.concatenate([np.full(nb, min(316, int(nb * 0.3))) for nb in synth.PFC_VALID_BINS])
+	blocks = []  # (rows, problem size) of every bin block: the wrapper's block rule at 500 kb, dim1 0.6
+	for n in synth.PFC_VALID_BINS:
+		nblk = max(math.ceil(n / 128), 1)
+		bs = math.ceil(n / nblk)
+		r = min(int(n * 0.6 * 0.5), 256)
+		blocks += [(min(bs, n - i * bs), r) for i in range(nblk)]
 	for world in (1, 2, 3, 8):
-		seen, cost = [], []
+		cost = []
 		for rank in range(world):
-			order, mine = polar_partition(sizes, world, rank)
-			assert sorted(order.tolist()) == list(range(len(sizes)))
-			s = sizes[mine]
-			assert np.all(s[:-1] >= s[1:])
-			seen += mine.tolist()
-			cost.append(float((s.astype(np.float64) ** 3).sum()))
-		assert sorted(seen) == list(range(len(sizes)))
-		assert max(cost) / min(cost) < 1.05
+			c = 0.0
+			for nb, r in blocks:
+				lo, hi = polar_bin_range(nb, world, rank)
+				assert 0 <= lo <= hi <= nb
+				if rank + 1 < world:
+					assert polar_bin_range(nb, world, rank + 1)[0] == hi
+				else:
+					assert hi == nb
+				c += (hi - lo) * float(r) ** 3
+			cost.append(c)
+		assert polar_bin_range(blocks[0][0], world, 0)[0] == 0
+		assert max(cost) / min(cost) < 1.08
