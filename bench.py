@@ -314,7 +314,7 @@ def main():
 	ap.add_argument("--geometry", default="pfc", help="pfc (configs[1]) | hg19")
 	ap.add_argument("--cache", default="sweep", help="sweep: RWR recomputed every sweep (metric); run: once per run")
 	ap.add_argument("--cpu-sample-cells", type=int, default=0, help="cells of the CPU baseline sample (0: 512 for --impl reference, 64 for the cpu_baseline leg)")
-	ap.add_argument("--torch-gpu-sample-cells", type=int, default=512, help="cells of the same-box stock-PyTorch (cuBLAS/cuSOLVER) baseline; 0: skip")
+	ap.add_argument("--torch-gpu-sample-cells", type=int, default=-1, help="cells of the same-box stock-PyTorch (cuBLAS/cuSOLVER) baseline; -1: the full workload, 0: skip")
 	ap.add_argument("--no-cpu-baseline", action="store_true")
 	ap.add_argument("--no-e2e", action="store_true")
 	ap.add_argument("--tc", type=int, default=-1, help="1: tcgen05 3xTF32 GEMMs, 0: CUDA-core fp32 (default: library default)")
@@ -498,9 +498,9 @@ def main():
 		torch.cuda.empty_cache()
 		t = time_oracle(datasets, RANK, n_i, args.cpu_sample_cells or 256, 1, 0, "cpu")
 		out["cpu_baseline"] = baseline_record(t, args.cells, "port", "cpu")
-		if args.torch_gpu_sample_cells > 0:
+		if args.torch_gpu_sample_cells != 0:
 			try:
-				t = time_oracle(datasets, RANK, n_i, args.torch_gpu_sample_cells, 1, 1, str(dev))
+				t = time_oracle(datasets, RANK, n_i, args.cells if args.torch_gpu_sample_cells < 0 else args.torch_gpu_sample_cells, 1, 1, str(dev))
 				out["torch_gpu_baseline"] = baseline_record(t, args.cells, "port on cuda (stock torch: cuBLAS bmm/einsum, cuSOLVER gesvda/getrf)", "cuda")
 			except Exception as e:  # a baseline must not take the product's line down
 				out["torch_gpu_baseline"] = {"unavailable": repr(e)[:200]}
