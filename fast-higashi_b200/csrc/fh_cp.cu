@@ -64,7 +64,8 @@ col_norms_kernel(const float* __restrict__ A, int n, const float* __restrict__ B
 
 // balance_norm (parafac_integrative.py:19-26): unit columns; product of the norms into D
 __global__ void balance_kernel(float* __restrict__ A, int n, float* __restrict__ B, float* __restrict__ D,
-                               int R, int r, const float* __restrict__ norms) {
+                               int R, int r, const float* __restrict__ norms, const int* __restrict__ stopped) {
+	if (stopped && *stopped) return;  // the reference leaves its loop before this step once the loss has stalled
 	const long long total = (long long)(n + r + R) * r;
 	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
 	     i += (long long)gridDim.x * blockDim.x) {
@@ -79,6 +80,28 @@ __global__ void balance_kernel(float* __restrict__ A, int n, float* __restrict__
 			D[j] = (D[j] / (nd + 1e-15f)) * (prod + 1e-15f);
 		}
 	}
+}
+
+// Early stop without a host round trip (parafac_integrative.py:98-110: break once the relative loss change is < 1e-5).
+// Every factor update is computed into a scratch buffer and COMMITTED only while the device-side flag is clear; the
+// flag is raised by cp_stop_kernel after the commits of the stopping iteration, so the factors end exactly where the
+// reference's loop leaves them and the later (speculative) iterations change nothing. Round 1 read the loss back
+// after every iteration: with n_iter_parafac > 1 that serialised the chromosomes' streams on the host (headline job:
+// 173 ms of a 447 ms sweep at six inner iterations).
+__global__ void cp_commit_kernel(float* __restrict__ dst, const float* __restrict__ src, long long count,
+                                 const int* __restrict__ stopped) {
+	if (*stopped) return;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+// scal: [0] ||Y||^2, [1] <Y, Xhat>, [2] ||Xhat||^2, [3] previous loss, [6] != 0 once [3] is valid (and was >= 0, as the
+// reference's `prev_loss >= 0` guard), [4] / [5] the pair reported to the caller
+__global__ void cp_stop_kernel(double* __restrict__ scal, int* __restrict__ stopped) {
+	if (*stopped) return;
+	const double loss = scal[0] - 2.0 * scal[1] + scal[2];
+	scal[4] = scal[2]; scal[5] = scal[1];
+	if (scal[6] != 0.0 && (scal[3] - loss) / scal[3] < 1e-5) *stopped = 1;
+	scal[3] = loss;
+	scal[6] = loss >= 0.0 ? 1.0 : 0.0;
 }
 
 // M0[i,p] = sum_j Z[(i*r+j), p] * B[j,p]
@@ -156,7 +179,7 @@ __global__ void scale_cols_batched_kernel(const float* __restrict__ F, int rows,
 
 size_t al(size_t x) { return (x + 255) / 256 * 256; }
 struct CpWs {
-	float *Z, *M, *norms;
+	float *Z, *M, *Tm, *norms;
 	double *Ga, *Gb, *Gd, *Hinv, *scal;
 	size_t bytes;
 };
@@ -166,6 +189,7 @@ CpWs carve(int n, int r, int R, void* ws) {
 	c.Z = (float*)b; b += al((size_t)n * r * r * 4);
 	int mx = n > R ? n : R; mx = mx > r ? mx : r;
 	c.M = (float*)b; b += al((size_t)mx * r * 4);
+	c.Tm = (float*)b; b += al((size_t)mx * r * 4);  // factor update before its commit
 	c.norms = (float*)b; b += al((size_t)3 * r * 4);
 	c.Ga = (double*)b; b += al((size_t)r * r * 8);
 	c.Gb = (double*)b; b += al((size_t)r * r * 8);
@@ -176,25 +200,30 @@ CpWs carve(int n, int r, int R, void* ws) {
 	return c;
 }
 
-int balance(float* A, int n, float* B, float* D, int R, int r, float* norms, cudaStream_t st) {
+int balance(float* A, int n, float* B, float* D, int R, int r, float* norms, const int* stopped, cudaStream_t st) {
 	col_norms_kernel<<<3, 256, 0, st>>>(A, n, B, D, R, r, norms);
 	FH_LAUNCH_CHECK();
 	long long total = (long long)(n + r + R) * r;
-	balance_kernel<<<fh_cdiv(total, 256), 256, 0, st>>>(A, n, B, D, R, r, norms);
+	balance_kernel<<<fh_cdiv(total, 256), 256, 0, st>>>(A, n, B, D, R, r, norms, stopped);
 	FH_LAUNCH_CHECK();
 	return FH_OK;
 }
 
 // F = M * (G1 * G2 + ridge I)^{-1}
-int solve_update(const float* M, int rows, const double* G1, const double* G2, int r, double* Hinv, float* out,
-                 cudaStream_t st) {
+int solve_update(const float* M, int rows, const double* G1, const double* G2, int r, double* Hinv, float* tmp, float* out,
+                 const int* stopped, cudaStream_t st) {
 	size_t smem = ((size_t)r * (r | 1) + r) * 8;
 	FH_CHECK_ARG(smem <= 227 * 1024, "fh_cp_als: r=%d too large for the shared-memory SPD inverse", r);
 	FH_CUDA(cudaFuncSetAttribute(hadamard_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int threads = r * r >= 1024 ? 1024 : ((r * r + 31) / 32 * 32);
 	hadamard_inverse_kernel<<<1, threads, smem, st>>>(G1, G2, r, 1e-10, Hinv);
 	FH_LAUNCH_CHECK();
-	return gemm(FH_GEMM_F32xF64_F32, rows, r, r, M, r, 1, Hinv, r, 1, out, r, (void*)st);
+	int rc = gemm(FH_GEMM_F32xF64_F32, rows, r, r, M, r, 1, Hinv, r, 1, tmp, r, (void*)st);
+	if (rc) return rc;
+	const long long count = (long long)rows * r;
+	cp_commit_kernel<<<fh_cdiv(count, 256) > 592 ? 592 : fh_cdiv(count, 256), 256, 0, st>>>(out, tmp, count, stopped);
+	FH_LAUNCH_CHECK();
+	return FH_OK;
 }
 
 }  // namespace
@@ -209,12 +238,12 @@ extern "C" int fh_cp_als(const float* Y, int n, int r, int R, float* A, float* B
 	CpWs w = carve(n, r, R, workspace);
 	int rc;
 	if (host_out) host_out[0] = host_out[1] = 0.0;
-	rc = balance(A, n, B, D, R, r, w.norms, st);
+	rc = balance(A, n, B, D, R, r, w.norms, nullptr, st);
 	if (rc) return rc;
-	double prev_loss = -1.0, ynorm = 0.0;
 	const bool need_loss = n_iter_max > 1;
+	int* stopped = (int*)(w.scal + 8);
+	FH_CUDA(cudaMemsetAsync(w.scal, 0, 128, st));
 	if (need_loss) {
-		FH_CUDA(cudaMemsetAsync(w.scal, 0, 64, st));
 		rc = fh_sqnorm_accum(Y, 1, (long long)n * r * R, (long long)n * r * R, w.scal, stream);
 		if (rc) return rc;
 	}
@@ -227,42 +256,37 @@ extern "C" int fh_cp_als(const float* Y, int n, int r, int R, float* A, float* B
 		if ((rc = gram(D, R, r, w.Gd, stream))) return rc;
 		mode0_reduce_kernel<<<n, 128, 0, st>>>(w.Z, B, n, r, w.M);
 		FH_LAUNCH_CHECK();
-		if ((rc = solve_update(w.M, n, w.Gb, w.Gd, r, w.Hinv, A, st))) return rc;
+		if ((rc = solve_update(w.M, n, w.Gb, w.Gd, r, w.Hinv, w.Tm, A, stopped, st))) return rc;
 		// mode 1: B = M1 ((A^T A) * (D^T D))^{-1}
 		if ((rc = gram(A, n, r, w.Ga, stream))) return rc;
 		mode1_reduce_kernel<<<r, 128, 0, st>>>(w.Z, A, n, r, w.M);
 		FH_LAUNCH_CHECK();
-		if ((rc = solve_update(w.M, r, w.Ga, w.Gd, r, w.Hinv, B, st))) return rc;
+		if ((rc = solve_update(w.M, r, w.Ga, w.Gd, r, w.Hinv, w.Tm, B, stopped, st))) return rc;
 		// mode 2: D = M2 ((A^T A) * (B^T B))^{-1},  M2 = Y_(R x n r) KhatriRao(A, B)
 		if ((rc = gram(B, r, r, w.Gb, stream))) return rc;
 		khatri_rao_kernel<<<fh_cdiv((long long)n * r * r, 256) > 4096 ? 4096 : fh_cdiv((long long)n * r * r, 256), 256, 0, st>>>(A, B, n, r, w.Z);
 		FH_LAUNCH_CHECK();
 		rc = gemm(FH_GEMM_F32, R, r, n * r, Y, 1, R, w.Z, r, 1, w.M, r, stream);
 		if (rc) return rc;
-		if ((rc = solve_update(w.M, R, w.Ga, w.Gb, r, w.Hinv, D, st))) return rc;
+		if ((rc = solve_update(w.M, R, w.Ga, w.Gb, r, w.Hinv, w.Tm, D, stopped, st))) return rc;
 		if (need_loss) {
-			// loss = ||Y||^2 - 2 <Y, Xhat> + ||Xhat||^2 ; <Y, Xhat> = <M2, D>
+			// loss = ||Y||^2 - 2 <Y, Xhat> + ||Xhat||^2 ; <Y, Xhat> = <M2, D>; decided on the device (cp_stop_kernel)
 			FH_CUDA(cudaMemsetAsync(w.scal + 1, 0, 16, st));
 			if ((rc = fh_dot_accum(w.M, D, R, r, r, r, w.scal + 1, stream))) return rc;
 			if ((rc = gram(D, R, r, w.Gd, stream))) return rc;
 			triple_hadamard_sum_kernel<<<1, 1024, 0, st>>>(w.Ga, w.Gb, w.Gd, r * r, w.scal + 2);
 			FH_LAUNCH_CHECK();
-			double h[3];
-			FH_CUDA(cudaMemcpyAsync(h, w.scal, 24, cudaMemcpyDeviceToHost, st));
-			FH_CUDA(cudaStreamSynchronize(st));
-			ynorm = h[0];
-			double loss = ynorm - 2.0 * h[1] + h[2];
-			if (host_out) { host_out[0] = h[2]; host_out[1] = h[1]; }
-			bool stop = false;
-			if (prev_loss >= 0.0) {
-				double wdiff = (prev_loss - loss) / prev_loss;
-				stop = wdiff < 1e-5;
-			}
-			prev_loss = loss;
-			if (stop) break;
+			cp_stop_kernel<<<1, 1, 0, st>>>(w.scal, stopped);
+			FH_LAUNCH_CHECK();
 		}
-		rc = balance(A, n, B, D, R, r, w.norms, st);
+		rc = balance(A, n, B, D, R, r, w.norms, stopped, st);
 		if (rc) return rc;
+	}
+	if (host_out && need_loss) {  // only the API-compatible `parafac` entry asks for these: one read-back at the end
+		double h[2];
+		FH_CUDA(cudaMemcpyAsync(h, w.scal + 4, 16, cudaMemcpyDeviceToHost, st));
+		FH_CUDA(cudaStreamSynchronize(st));
+		host_out[0] = h[0]; host_out[1] = h[1];
 	}
 	return FH_OK;
 }

@@ -4,16 +4,17 @@ import torch
 from . import _lib
 
 
-def cp_als_(Y, A, B, D, n_iter_max, tag="cp"):
-	"""In-place device CP-ALS: Y (n, r, R) fp32 contiguous; A (n,r), B (r,r), D (R,r) fp32 contiguous.
-	Returns (||Xhat||^2, <Xhat, Y>) (zeros unless n_iter_max > 1, see include/fh_b200.h)."""
+def cp_als_(Y, A, B, D, n_iter_max, tag="cp", want_norms=False):
+	"""In-place device CP-ALS: Y (n, r, R) fp32 contiguous; A (n,r), B (r,r), D (R,r) fp32 contiguous. The reference's early
+	stop (relative loss change < 1e-5) is decided on the device; nothing is read back unless `want_norms`, which returns
+	(||Xhat||^2, <Xhat, Y>) of the last committed iteration (zeros unless n_iter_max > 1) and synchronises the stream."""
 	n, r, R = Y.shape
 	lib = _lib.lib()
 	ws = _lib.workspace(lib.fh_cp_als_workspace_bytes(n, r, R), Y.device, tag)
-	out = (C.c_double * 2)()
+	out = (C.c_double * 2)() if want_norms else None
 	_lib.check(lib.fh_cp_als(Y.data_ptr(), n, r, R, A.data_ptr(), B.data_ptr(), D.data_ptr(), int(n_iter_max),
 	                         ws.data_ptr(), ws.numel(), out, _lib.stream_ptr()))
-	return out[0], out[1]
+	return (out[0], out[1]) if want_norms else (0.0, 0.0)
 
 
 def core_sqnorm_accum(A, B, D, acc, tag="core"):
@@ -32,5 +33,5 @@ def parafac(X, rank, n_iter_max=100, init=None, verbose=False, common_factor=Non
 		raise _lib.FHError("parafac: CUDA tensor required (no CPU path in fasthigashi_b200)")
 	Y = X.contiguous().float()
 	A, B, D = [f.to(Y.device, torch.float32).contiguous().clone() for f in init]
-	norm_hat, inner = cp_als_(Y, A, B, D, n_iter_max)
+	norm_hat, inner = cp_als_(Y, A, B, D, n_iter_max, want_norms=True)
 	return [A, B, D], norm_hat, inner

@@ -142,8 +142,9 @@ int fh_polar_isqrt_multi(const double* G_all, double* WT_all, const int* dev_pro
 
 /* Inverse square root of ONE symmetric positive definite n x n fp64 matrix by the coupled
  * Newton-Schulz iteration (tall cells x R polar, parafac2_intergrative.py:483,831: V = M G^{-1/2}
- * with G = M^T M all-reduced across ranks). Synchronises the stream to test convergence.
- * ws: >= 4*n*n doubles. */
+ * with G = M^T M all-reduced across ranks). One cooperative kernel runs the whole iteration; the stream is synchronised
+ * once at the end to return the iteration count and the error status (singular input = error).
+ * ws: >= 5*n*n + 512 doubles. */
 int fh_inv_sqrt_spd(const double* G, double* out, int n, void* ws, size_t ws_bytes, int* host_iters,
                     void* stream);
 
@@ -155,7 +156,8 @@ int fh_inv_sqrt_spd(const double* G, double* out, int n, void* ws, size_t ws_byt
  * (fp64) and the factor is the MTTKRP times that inverse; balance_norm is fused in the same call.
  * host_out[0] = ||Xhat||^2, host_out[1] = <Xhat, Y> of the last iteration (both only computed when
  * n_iter_max > 1, where the reference's early-stop test needs them; otherwise 0).
- * Synchronises the stream only when n_iter_max > 1.
+ * The early stop is decided on the device (no read-back per iteration); the stream is synchronised only when
+ * host_out is given AND n_iter_max > 1 (one read of the two scalars at the end).
  * ------------------------------------------------------------------------------------------- */
 size_t fh_cp_als_workspace_bytes(int n, int r, int R);
 int fh_cp_als(const float* Y, int n, int r, int R, float* A, float* B, float* D, int n_iter_max,
