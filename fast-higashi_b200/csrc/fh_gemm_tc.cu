@@ -137,7 +137,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 		if (lane == 0) {
 			// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b_format TF32 [7,10)/[10,13)=2,
 			// a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
-			const uint32_t idesc = make_idesc_tf32(false, B_MN, BN, BM);  // A comes from TMEM (always "K-major")
+			// A comes from TMEM (always "K-major"). N of the instruction = the tile's useful columns rounded up to 32 (a whole
+			// 32-column group of the MN-major B layout): the last column tile of a contraction whose N is just above a multiple
+			// of 128 (P1: N = r = 137..149 -> tiles of 128 + 32) no longer pays 128 columns of tensor-pipe time. The columns
+			// beyond it keep stale accumulator contents; the epilogue never stores columns >= N.
+			const uint32_t idesc_full = make_idesc_tf32(false, B_MN, BN, BM);
 			// K-major B tile (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO); a K=8 step = +32 B.
 			// MN-major B tile (SWIZZLE_128B_BASE32B): k rows of 128 B (32 N elements), 4-row atoms 512 B apart
 			// (SBO), 32-element N groups BK*128 B apart (LBO); a K=8 step = 8 rows = +1024 B.
@@ -146,6 +150,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 			for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 				const int ksm = (int)(tile % p.ksplit);
 				const int nkb_t = min(nkb, (ksm + 1) * p.kb_per_split) - ksm * p.kb_per_split;
+				const int n0t = (int)((tile / p.ksplit) % tiles_n) * BN;
+				const int n_eff = min(BN, (p.N - n0t + 31) & ~31);
+				const uint32_t idesc = n_eff == BN ? idesc_full : make_idesc_tf32(false, B_MN, n_eff, BM);
 				for (int kb = 0; kb < nkb_t; ++kb, ++it) {
 					const int s = (int)(it % STAGES);
 					const uint32_t ph = (uint32_t)((it / STAGES) & 1);
@@ -391,9 +398,20 @@ int fh_gemm_tc(const fh_gemm_desc* d, const float* A, const float* B, float* C, 
 	p.dbg = dbg;
 	const int nkb_h = fh_cdiv(d->K, BK);
 	p.ksplit = 1; p.kb_per_split = nkb_h;
-	if (total_tiles * 2 <= num_sms + 12 && nkb_h >= 64 && !d->cscale && d->epilogue == FH_EPI_NONE && (d->beta == 0.0 || d->beta == 1.0)) {
-		int ks = (int)(num_sms / total_tiles);
-		if (ks > nkb_h / 32) ks = nkb_h / 32;
+	// ... and, for any long-K problem, so that the work items fill whole waves of the persistent grid: 196 output tiles
+	// on 148 SMs (P3 at 12,500 cells) are two waves of which the second is a third full; split 3 ways they are four full ones
+	if (nkb_h >= 64 && !d->cscale && d->epilogue == FH_EPI_NONE && (d->beta == 0.0 || d->beta == 1.0)) {
+		int ks = 1;
+		double best = (double)fh_cdiv(total_tiles, num_sms);  // waves, in units of one unsplit tile
+		for (int c = 2; c <= 8 && nkb_h / c >= 32; ++c) {
+			const double cost = (double)fh_cdiv(total_tiles * c, num_sms) / c;
+			if (cost < best * 0.93) { best = cost; ks = c; }  // atomics + the zero-fill must be paid for
+		}
+		if (total_tiles * 2 <= num_sms + 12) {  // few tiles: as before, one work item per SM at least
+			int k2 = (int)(num_sms / total_tiles);
+			if (k2 > nkb_h / 32) k2 = nkb_h / 32;
+			if (k2 > ks) ks = k2;
+		}
 		if (ks > 1) {
 			p.kb_per_split = (fh_cdiv(nkb_h, ks) + CHUNK_KB - 1) / CHUNK_KB * CHUNK_KB;
 			p.ksplit = fh_cdiv(nkb_h, p.kb_per_split);

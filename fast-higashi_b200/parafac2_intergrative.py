@@ -639,7 +639,16 @@ class Fast_Higashi_core:
 			self._cp_streams = [torch.cuda.Stream(device=self.device) for _ in range(n_st)] if n_st > 0 else [main]
 		ready = torch.cuda.Event()
 		ready.record(main)
+		# Sharded: the inner CP-ALS is cell independent (it only sees the all-reduced Y), so the chromosomes are dealt to the
+		# ranks (largest first, round-robin) and the updated factors exchanged with ONE all-reduce over a packed buffer that
+		# is zero where a rank does not own the chromosome (x + 0 is exact: replicas stay bit-identical)
+		world = dist.get_world_size(self.group) if dist is not None else 1
+		myrank = dist.get_rank(self.group) if dist is not None else 0
+		by_cost = sorted(self.chrom2id, key=lambda c: -self.chrom2num_bin[c] * self.chrom2size[c] ** 2)
+		owner = {c: i % world for i, c in enumerate(by_cost)}
 		for k, (chrom, ids) in enumerate(self.chrom2id.items()):
+			if owner[chrom] != myrank:
+				continue
 			st = self._cp_streams[k % len(self._cp_streams)]
 			st.wait_event(ready)
 			with torch.cuda.stream(st):
@@ -657,13 +666,14 @@ class Fast_Higashi_core:
 						core_sqnorm_accum(self.A_dev[i], self.B_dict[chrom], self.D_dict[chrom], acc[i:], tag=tag)
 		for st in self._cp_streams:
 			main.wait_stream(st)
-		if dist is not None:  # keep replicas bit-identical (split-K atomics are unordered): ONE packed broadcast
-			src = dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0
-			parts = []
+		if dist is not None:
+			parts, mine = [], []
 			for chrom, ids in self.chrom2id.items():
-				parts += [self.A_dev[i] for i in ids] + [self.B_dict[chrom], self.D_dict[chrom]]
-			flat = torch.cat([p_.reshape(-1) for p_ in parts])
-			dist.broadcast(flat, src=src, group=self.group)
+				p_ = [self.A_dev[i] for i in ids] + [self.B_dict[chrom], self.D_dict[chrom]]
+				parts += p_
+				mine += [owner[chrom] == myrank] * len(p_)
+			flat = torch.cat([p_.reshape(-1) if m else torch.zeros(p_.numel(), dtype=p_.dtype, device=p_.device) for p_, m in zip(parts, mine)])
+			self._allreduce(flat)
 			off = 0
 			for p_ in parts:
 				p_.copy_(flat[off:off + p_.numel()].view_as(p_))
