@@ -6,9 +6,8 @@
 // DESIGN.md "polar"). Pipeline, batched over the bins of one block, all fp64:
 //   G = T^T T                          fp64 accumulate      (fh_gemm_batched, FH_GEMM_F32_ACC64)
 //   G = P L L^T P^T                    diagonally pivoted Cholesky, G resident in shared memory
-//   L V = W, columns of W orthogonal   one-sided (Hestenes) Jacobi on the columns of L, parallel
-//                                      round-robin ordering (pair t of step s: (s+t, s-t) mod m-1, player m-1
-//                                      fixed), a half-warp per column pair.
+//   L V = W, columns of W orthogonal   one-sided (Hestenes) Jacobi on the columns of L, register-blocked
+//                                      (fh_polar_rb.cuh: a warp per pair of 4-row blocks, odd-even block ordering).
 //                                      (Veselic-Hari: L^T L is far closer to diagonal than L L^T, so
 //                                      the strongly graded spectra converge in <= 9 sweeps where Jacobi
 //                                      on G itself needed 14-24, measured.) lambda_j = |w_j|^2.
@@ -20,315 +19,18 @@
 
 namespace {
 
-__host__ __device__ inline int even_up(int n) { return (n + 1) & ~1; }
+constexpr int kMaxGram = 160;   // shared memory: 160 x 161 fp64 = 206 KB
 
-constexpr int kMaxGram = 160;   // shared memory: 160 x 160 fp64 = 200 KB
+#include "fh_polar_rb.cuh"     // register-blocked one-sided Jacobi
 
-template <int G>
-__device__ __forceinline__ double group_sum(double v, unsigned mask) {
-#pragma unroll
-	for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
-	return v;
-}
-
-// tan(theta) of the rotation that annihilates gamma = <w_p, w_q> given alpha = |w_p|^2, beta = |w_q|^2:
-// t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (beta - alpha) / (2 gamma). Evaluated in fp32
-// with approximate div/sqrt (an fp32-accurate angle only leaves a 1e-7 relative residual, removed
-// quadratically by the next sweep); cos = rsqrt(1 + t^2) in fp64 keeps the rotation orthogonal to
-// fp64 rounding.
-__device__ __forceinline__ double jacobi_tan(double al, double be, double ga) {
-	const double d = be - al;
-	const double big = fmax(fabs(d), fabs(ga));  // common power-of-two scale: no fp32 over/underflow
-	const int ex = (__double2hiint(big) >> 20) & 0x7ff;
-	const double scale = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023 - ex)
-	const float ds = (float)(fabs(d) * scale), gs = (float)(2.0 * fabs(ga) * scale);
-	const float z = __fdividef(ds, gs);          // gs == 0 -> inf -> t = 0
-	float sq;
-	asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(fmaf(z, z, 1.f)));
-	float tf = (z > 1e18f) ? __fdividef(0.5f, z) : __fdividef(1.f, z + sq);
-	if (!(tf <= 1.f)) tf = 1.f;                  // nan guard: 45 degrees
-	return ((d >= 0.0) == (ga >= 0.0)) ? (double)tf : -(double)tf;
-}
-
-#include "fh_polar_block.cuh"  // block one-sided Jacobi, opt-in (FH_POLAR_BLOCK=1); uses jacobi_tan
-#include "fh_polar_rb.cuh"     // register-blocked one-sided Jacobi (default)
-
-// One-sided Jacobi sweeps over the rows of R (n x ld, ld a multiple of 16, pad columns zero).
-// A half-warp (G = 16 lanes) owns one row pair and keeps row p in registers (PL = ld / 16 elements per
-// lane). Measured and rejected: quarter-warp groups streaming both rows (one round per step for
-// n > 128, but 4 rows per warp request collide on the same banks: 73 vs 62 ms). Returns the sweep count.
-template <int PL, int G>
-__device__ __forceinline__ int jacobi_sweeps(double* __restrict__ R, const int n, const int ld, double* __restrict__ nrm,
-                                             double* __restrict__ red, const int max_sweeps, const double skip_tol) {
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-	const int m = even_up(n), half = m >> 1, mm = m - 1;
-	// Rotation threshold. With W^T W = Lambda + E the polar factor U = T W Lambda^{-3/2} W^T has
-	// U^T U - I ~ cos(w_a, w_b) sqrt(lambda_big / lambda_small), i.e. |gamma| / min(alpha, beta): a pair is left
-	// alone once gamma^2 <= kSkip min(alpha, beta)^2 (its contribution 3e-9, fp32 output). For equal norms that
-	// is far looser than a cosine test at fp64 rounding, for strongly graded pairs it is stricter - and it
-	// removes most rotations of the last sweeps (FH_JACOBI_SKIP overrides kSkip for experiments).
-	const double tol2 = skip_tol;
-	constexpr int GPW = 32 / G;                  // groups per warp
-	const int hw = lane / G, hl = lane % G;
-	const unsigned hmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (hw * G));
-	const int nslot = nw * GPW;
-	int sweep = 0;
-	for (; sweep < max_sweeps; ++sweep) {
-		for (int j = warp; j < n; j += nw) {        // refresh the tracked norms
-			double s2 = 0.0;
-			for (int i = lane; i < ld; i += 32) { double v = R[j * ld + i]; s2 += v * v; }
-			s2 = fh_warp_sum(s2);
-			if (lane == 0) nrm[j] = s2;
-		}
-		__syncthreads();
-		double worst = 0.0;                        // largest gamma^2/(alpha beta) met in this sweep
-		for (int step = 0; step < mm; ++step) {
-			for (int t = warp * GPW + hw; t < half; t += nslot) {
-				int p, q;
-				if (t == 0) { p = mm; q = step; }
-				else {
-					p = step + t; if (p >= mm) p -= mm;
-					q = step - t + mm; if (q >= mm) q -= mm;
-				}
-				if (p >= n || q >= n) continue;      // the padding player of an odd n
-				if (p > q) { int x = p; p = q; q = x; }
-				double* rp = R + p * ld + hl;
-				double* rq = R + q * ld + hl;
-				double ga = 0.0, gb = 0.0;
-				double a[PL > 0 ? PL : 1];
-				if (PL > 0) {  // row p in registers
-#pragma unroll
-					for (int e = 0; e < PL; ++e) {
-						a[e] = rp[G * e];
-						if (e & 1) gb += a[e] * rq[G * e]; else ga += a[e] * rq[G * e];
-					}
-				} else {       // streamed (quarter-warp groups: the register tile would not fit 64 registers)
-					int i = 0;
-#pragma unroll 4
-					for (; i + G < ld; i += 2 * G) {
-						ga += rp[i] * rq[i];
-						gb += rp[i + G] * rq[i + G];
-					}
-					if (i < ld) ga += rp[i] * rq[i];
-				}
-				ga = group_sum<G>(ga + gb, hmask);
-				const double al = nrm[p], be = nrm[q];
-				const double g2 = ga * ga, ab = al * be;
-				const double mn = fmin(al, be);
-				if (g2 > tol2 * mn * mn && ga != 0.0) {
-					worst = fmax(worst, g2 / ab);
-					const double tt = jacobi_tan(al, be, ga);
-					const double cs = rsqrt(tt * tt + 1.0), sn = tt * cs;
-					if (PL > 0) {
-#pragma unroll
-						for (int e = 0; e < PL; ++e) {
-							const double c = rq[G * e];
-							rp[G * e] = cs * a[e] - sn * c;
-							rq[G * e] = sn * a[e] + cs * c;
-						}
-					} else {
-#pragma unroll 4
-						for (int i = 0; i < ld; i += G) {
-							const double x = rp[i], c = rq[i];
-							rp[i] = cs * x - sn * c;
-							rq[i] = sn * x + cs * c;
-						}
-					}
-					if (hl == 0) {  // |w_p|^2, |w_q|^2 after the rotation
-						nrm[p] = fmax(al - tt * ga, 0.0);
-						nrm[q] = be + tt * ga;
-					}
-				}
-			}
-			__syncthreads();
-		}
-		// block max of `worst`
-#pragma unroll
-		for (int o = 16; o >= G; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
-		if (lane == 0) red[warp] = worst;
-		__syncthreads();
-		double wmax = 0.0;
-		for (int i = 0; i < nw; ++i) wmax = fmax(wmax, red[i]);
-		__syncthreads();
-		// convergence: the largest scaled off-diagonal met in the sweep was <= 3e-6, its rotations leave
-		// ~1e-11 behind (quadratic convergence), far below the fp32 output rounding - no confirming sweep
-		if (wmax <= 1e-11) { ++sweep; break; }
-	}
-	return sweep;
-}
-
-// Row pitch (doubles), pad columns zero. Half-warp groups: n rounded up to 16 (no predicates in the element
-// loops). Quarter-warp groups (a step has more pairs than the CTA has half-warps: one round per step instead
-// of a second, nearly empty one): an ODD multiple of 8, so that the four rows a warp touches per request
-// fall on both 64-byte halves of the banks (with a multiple of 16 every request is a 4-way conflict:
-// measured 73 vs 62 ms).
-__host__ __device__ inline bool jacobi_quarter(int n, int nthreads) { return (even_up(n) >> 1) > (nthreads >> 5) * 2; }
-__host__ __device__ inline int jacobi_ld(int n, int nthreads) {
-	if (!jacobi_quarter(n, nthreads)) return (n + 15) & ~15;
-	const int l = (n + 7) & ~7;
-	return (l & 8) ? l : l + 8;
-}
-
-// One CTA per matrix (problem b: size prob_n[b], data at prob_off[b] doubles into Gall / WTall).
-// Shared memory holds R (n x ld, row-major, ld = n rounded up to 16 with zero pad columns): first the
-// symmetric G, then its pivoted Cholesky factor as the UPPER triangle R = L^T (row j of R = column j
-// of L), then the rows are orthogonalised in place. Output WT (n x n): row j = w_j * lambda_j^{-3/4}
-// in the ORIGINAL index order; sigma[prob_sig[b] + j] = sqrt(lambda_j);
-// sigma_sum[prob_slot[b]] = sum_j sqrt(lambda_j).
-// BLK: the block one-sided Jacobi of fh_polar_block.cuh instead of the scalar sweeps (a separate instantiation, so
-// the default kernel's code generation is untouched by the opt-in variant).
-template <bool BLK>
-__global__ void __launch_bounds__(BLK ? 512 : 1024)  // the block variant wants 128 registers (Gram tiles, 16-row columns)
-chol_jacobi_kernel(const double* __restrict__ Gall, const int* __restrict__ prob_n, const long long* __restrict__ prob_off,
-                   const int* __restrict__ prob_slot, const long long* __restrict__ prob_sig, int uniform_n,
-                   int max_sweeps, double skip_tol, double* __restrict__ WTall, double* __restrict__ sigma_all,
-                   double* __restrict__ sigma_sum, int* __restrict__ nsweep_out) {
-	extern __shared__ __align__(16) double sm[];
-	const int b = blockIdx.x;
-	const int n = prob_n ? prob_n[b] : uniform_n;
-	const long long off = prob_off ? prob_off[b] : (long long)b * n * n;
-	const int slot = prob_slot ? prob_slot[b] : b;
-	const long long sig_off = prob_sig ? prob_sig[b] : (long long)b * n;
-	// block mode (fh_polar_block.cuh): rows padded to a multiple of 8 with zero rows, even pitch
-	const bool blk = BLK && n <= kBJMaxSide;
-	const int ld = blk ? bj_ld(n) : jacobi_ld(n, blockDim.x);
-	const int nrow = blk ? bj_rows(n) : n;
-	double* R = sm;                          // nrow x ld
-	double* red = R + (size_t)nrow * ld;     // 64 doubles scratch
-	int* perm = (int*)(red + 64);            // n
-	__shared__ int s_piv;
-	__shared__ double s_val;
-	const int JT = blockDim.x;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = JT >> 5;
-	const double* Gg = Gall + off;
-	for (int i = tid; i < nrow * ld; i += JT) {
-		const int r = i / ld, c = i - r * ld;
-		R[i] = (c < n && (!BLK || r < n)) ? Gg[r * n + c] : 0.0;
-	}
-	for (int i = tid; i < n; i += JT) perm[i] = i;
-	__syncthreads();
-	// ---------------- diagonally pivoted Cholesky, upper factor in place ----------------
-	double dmax0 = 0.0;
-	for (int k = 0; k < n; ++k) {
-		if (warp == 0) {  // pivot = largest remaining diagonal
-			double best = -1.0; int bi = k;
-			for (int i = k + lane; i < n; i += 32) {
-				double v = R[i * ld + i];
-				if (v > best) { best = v; bi = i; }
-			}
-			for (int o = 16; o > 0; o >>= 1) {
-				double ov = __shfl_xor_sync(0xffffffffu, best, o);
-				int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-				if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-			}
-			if (lane == 0) { s_piv = bi; s_val = best; }
-		}
-		__syncthreads();
-		const int pv = s_piv;
-		if (k == 0) dmax0 = s_val;
-		// rank-revealing stop: once the largest remaining diagonal is below the rounding level of the
-		// fp64 Gram (~n eps lambda_max) the trailing block is noise. It is replaced by thr * I, i.e.
-		// singular values ~1e-7 sigma_max in directions T has no resolvable energy in.
-		if (s_val <= dmax0 * 1e-14 || !(s_val > 0.0)) {
-			const double rt = sqrt(fmax(dmax0 * 1e-14, 1e-300));
-			const int rem0 = n - k;
-			__syncthreads();
-			for (int t = tid; t < rem0 * rem0; t += JT) {
-				int i = k + t / rem0, j = k + t % rem0;
-				R[i * ld + j] = (i == j) ? rt : 0.0;
-			}
-			__syncthreads();
-			break;
-		}
-		if (pv != k) {  // symmetric swap k <-> pv: rows, then columns (earlier factor rows included)
-			for (int j = tid; j < n; j += JT) { double t = R[k * ld + j]; R[k * ld + j] = R[pv * ld + j]; R[pv * ld + j] = t; }
-			__syncthreads();
-			for (int i = tid; i < n; i += JT) { double t = R[i * ld + k]; R[i * ld + k] = R[i * ld + pv]; R[i * ld + pv] = t; }
-			if (tid == 0) { int t = perm[k]; perm[k] = perm[pv]; perm[pv] = t; }
-			__syncthreads();
-		}
-		const double rkk = sqrt(R[k * ld + k]);
-		const double rinv = 1.0 / rkk;
-		__syncthreads();
-		for (int j = k + tid; j < n; j += JT) R[k * ld + j] = (j == k) ? rkk : R[k * ld + j] * rinv;
-		__syncthreads();
-		// trailing update (full square keeps the swaps simple): G[i][j] -= R[k][i] R[k][j]
-		const int rem = n - k - 1;
-		for (int t = tid; t < rem * rem; t += JT) {
-			int i = k + 1 + t / rem, j = k + 1 + t % rem;
-			R[i * ld + j] -= R[k * ld + i] * R[k * ld + j];
-		}
-		__syncthreads();
-	}
-	for (int t = tid; t < n * n; t += JT) {  // strict lower triangle of R is not part of the factor
-		int i = t / n, j = t % n;
-		if (j < i) R[i * ld + j] = 0.0;
-	}
-	__syncthreads();
-	// ---------------- one-sided Jacobi on the rows of R (columns of L) ----------------
-	// ncu: instruction-issue bound (32 warps x ~300 issue slots per pair). So: a half-warp per pair
-	// (two pairs share every instruction), squared norms tracked incrementally (one dot product per
-	// pair, refreshed every sweep), fp32 angle with approximate div/sqrt, rows padded to 16 so the
-	// element loops carry no predicates.
-	double* nrm = red + 64 + ((n + 1) >> 1);     // n squared norms, after perm (ints) in the scratch area
-	int sweep = 0;
-	bool done = false;
-	if constexpr (BLK) {
-		if (blk) {
-			// scratch behind the norms, on a 16-byte boundary (red starts on one: nrow * ld is even)
-			double* bjs = nrm + n + ((64 + ((n + 1) >> 1) + n) & 1);
-			sweep = block_jacobi_sweeps(R, n, ld, bjs, blockDim.x, max_sweeps, skip_tol);
-			done = true;
-		}
-	}
-	if (done) {}
-	else if (jacobi_quarter(n, blockDim.x)) sweep = jacobi_sweeps<0, 8>(R, n, ld, nrm, red, max_sweeps, skip_tol);
-	else switch (ld >> 4) {
-		case 1: sweep = jacobi_sweeps<1, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
-		case 2: sweep = jacobi_sweeps<2, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
-		case 3: sweep = jacobi_sweeps<3, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
-		case 4: sweep = jacobi_sweeps<4, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
-		case 5: sweep = jacobi_sweeps<5, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
-		case 6: sweep = jacobi_sweeps<6, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
-		case 7: sweep = jacobi_sweeps<7, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
-		case 8: sweep = jacobi_sweeps<8, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
-		case 9: sweep = jacobi_sweeps<9, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
-		default: sweep = jacobi_sweeps<10, 16>(R, n, ld, nrm, red, max_sweeps, skip_tol); break;
-	}
-	if (tid == 0 && nsweep_out) nsweep_out[slot] = sweep;
-	// ---------------- lambda_j = |w_j|^2, outputs ----------------
-	__shared__ double s_lmax, s_ssum;
-	if (tid == 0) { s_lmax = 0.0; s_ssum = 0.0; }
-	__syncthreads();
-	double* lamv = sigma_all ? sigma_all + sig_off : nullptr;
-	for (int j = warp; j < n; j += nw) {
-		double s2 = 0.0;
-		for (int i = lane; i < n; i += 32) { double v = R[j * ld + i]; s2 += v * v; }
-		s2 = fh_warp_sum(s2);
-		if (lane == 0) {
-			atomicMax((unsigned long long*)&s_lmax, (unsigned long long)__double_as_longlong(s2));  // s2 >= 0: order preserved
-			atomicAdd(&s_ssum, sqrt(s2));
-			if (lamv) lamv[j] = sqrt(s2);
-		}
-	}
-	__syncthreads();
-	const double floor_l = fmax(s_lmax * 1e-17, 1e-300);
-	if (tid == 0 && sigma_sum) sigma_sum[slot] = s_ssum;
-	double* WT = WTall + off;
-	for (int j = warp; j < n; j += nw) {
-		double s2 = 0.0;
-		for (int i = lane; i < n; i += 32) { double v = R[j * ld + i]; s2 += v * v; }
-		s2 = fh_warp_sum(s2);
-		const double l = fmax(s2, floor_l);
-		const double f = rsqrt(l) * rsqrt(sqrt(l));  // lambda^{-3/4}
-		for (int i = lane; i < n; i += 32) WT[(size_t)j * n + perm[i]] = R[j * ld + i] * f;
-	}
-}
 
 // ---------------------------------------------------------------------------------------------
-// Default kernel: same pipeline (pivoted Cholesky -> one-sided Jacobi on the factor's rows -> scaled eigenvector
-// rows), the Jacobi phase register-blocked (fh_polar_rb.cuh). One instantiation per row length class PL = ceil(n / 32)
-// so that each gets its own register budget and CTA count per SM.
+// One CTA per matrix (problem b: size prob_n[b], data at prob_off[b] doubles into Gall / WTall). Shared memory holds R
+// (rb_rows(n) x ld, row-major, pad rows / columns zero): first the symmetric G, then its pivoted Cholesky factor as the
+// UPPER triangle R = L^T (row j of R = column j of L), then the rows are orthogonalised in place (fh_polar_rb.cuh).
+// Output WT (n x n): row j = w_j * lambda_j^{-3/4} in the ORIGINAL index order; sigma_all[b n + j] = sqrt(lambda_j);
+// sigma_sum[prob_slot[b]] = sum_j sqrt(lambda_j). One instantiation per row length class PL = ceil(n / 32) so that each
+// gets its own register budget and CTA count per SM.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pivoted_cholesky_upper(double* __restrict__ R, const int n, const int ld, int* __restrict__ perm) {
 	__shared__ int s_piv;
@@ -353,7 +55,9 @@ __device__ __forceinline__ void pivoted_cholesky_upper(double* __restrict__ R, c
 		const int pv = s_piv;
 		const double pval = s_val;
 		if (k == 0) dmax0 = pval;
-		// rank-revealing stop (see chol_jacobi_kernel): the trailing block is noise, replaced by thr * I
+		// rank-revealing stop: once the largest remaining diagonal is below the rounding level of the fp64 Gram
+		// (~n eps lambda_max) the trailing block is noise. It is replaced by thr * I, i.e. singular values
+		// ~1e-7 sigma_max in directions T has no resolvable energy in.
 		if (pval <= dmax0 * 1e-14 || !(pval > 0.0)) {
 			const double rt = sqrt(fmax(dmax0 * 1e-14, 1e-300));
 			const int rem0 = n - k;
@@ -419,7 +123,7 @@ chol_jacobi_rb_kernel(const double* __restrict__ Gall, const int* __restrict__ p
 	const int sweep = (PL > 4) ? jacobi_sweeps_rb_half<PL>(R, n, ld, nrm, red, max_sweeps, skip_tol)
 	                           : jacobi_sweeps_rb<PL>(R, n, ld, nrm, red, max_sweeps, skip_tol);
 	if (tid == 0 && nsweep_out) nsweep_out[slot] = sweep;
-	// ---------------- lambda_j = |w_j|^2, outputs (as chol_jacobi_kernel) ----------------
+	// ---------------- lambda_j = |w_j|^2, outputs ----------------
 	__shared__ double s_lmax, s_ssum;
 	if (tid == 0) { s_lmax = 0.0; s_ssum = 0.0; }
 	__syncthreads();
@@ -481,27 +185,6 @@ PolarWs carve(int batch, int n, void* ws) {
 
 constexpr int kMaxSweeps = 30;
 
-// FH_POLAR_BLOCK=1: block one-sided Jacobi (fh_polar_block.cuh) for Gram sides <= kBJMaxSide. Default off: the
-// variant was written and checked through its host emulation after the round's GPU time was spent.
-int polar_block_mode() {
-	static int mode = -1;
-	if (mode < 0) { const char* e = getenv("FH_POLAR_BLOCK"); mode = (e && e[0] == '1') ? 1 : 0; }
-	return mode;
-}
-
-// FH_POLAR_RB=0: the scalar round-robin kernel of round 1 instead of the register-blocked one (A/B timing only).
-int polar_rb_mode() {
-	static int mode = -1;
-	if (mode < 0) { const char* e = getenv("FH_POLAR_RB"); mode = (e && e[0] == '0') ? 0 : 1; }
-	return (mode && !polar_block_mode()) ? 1 : 0;
-}
-
-int jacobi_threads(int n) {
-	if (polar_rb_mode()) return rb_threads(n);
-	const int t = n > 83 ? 1024 : (n > 58 ? 512 : 256);
-	return (polar_block_mode() && t > 512) ? 512 : t;  // chol_jacobi_kernel<true> is built for <= 512 threads
-}
-
 template <int PL>
 int launch_rb(int grid, int nmax, size_t smem, cudaStream_t st, const double* G, const int* pn, const long long* po, const int* ps,
               int uniform_n, int max_sweeps, double skip, double* WT, double* sigma, double* sigma_sum, int* nsweep) {
@@ -517,37 +200,17 @@ int launch_jacobi(int grid, int nmax, size_t smem, cudaStream_t st, const double
                   const int* ps, int uniform_n, int max_sweeps, double* WT, double* sigma, double* sigma_sum, int* nsweep) {
 	static double skip = -1.0;
 	if (skip < 0.0) { const char* e = getenv("FH_JACOBI_SKIP"); skip = e ? atof(e) : 1e-17; }
-	if (polar_rb_mode()) {
-		switch (rb_pl(nmax)) {
-			case 1: return launch_rb<1>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
-			case 2: return launch_rb<2>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
-			case 3: return launch_rb<3>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
-			case 4: return launch_rb<4>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
-			default: return launch_rb<5>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
-		}
+	switch (rb_pl(nmax)) {
+		case 1: return launch_rb<1>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
+		case 2: return launch_rb<2>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
+		case 3: return launch_rb<3>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
+		case 4: return launch_rb<4>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
+		default: return launch_rb<5>(grid, nmax, smem, st, G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
 	}
-	const bool blkmode = polar_block_mode() != 0;
-	if (blkmode) FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	else FH_CUDA(cudaFuncSetAttribute(chol_jacobi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	if (blkmode)
-		chol_jacobi_kernel<true><<<grid, jacobi_threads(nmax), smem, st>>>(G, pn, po, ps, nullptr, uniform_n, max_sweeps, skip,
-		                                                                  WT, sigma, sigma_sum, nsweep);
-	else
-		chol_jacobi_kernel<false><<<grid, jacobi_threads(nmax), smem, st>>>(G, pn, po, ps, nullptr, uniform_n, max_sweeps, skip,
-		                                                                   WT, sigma, sigma_sum, nsweep);
-	FH_LAUNCH_CHECK();
-	return FH_OK;
 }
 
 // A launch covers problems of side <= n with one shared-memory size: the layout of the largest.
-size_t jacobi_smem(int n) {
-	if (polar_rb_mode()) return ((size_t)rb_rows(n) * rb_ld(n) + 64 + rb_rows(n) + (n + 1) / 2) * 8 + 16;
-	size_t scalar = ((size_t)n * jacobi_ld(n, jacobi_threads(n)) + 64 + (n + 1) / 2 + n) * 8 + 16;
-	if (!polar_block_mode()) return scalar;
-	const int nb = n < kBJMaxSide ? n : kBJMaxSide;
-	size_t block = ((size_t)bj_rows(nb) * bj_ld(nb) + 64 + (nb + 1) / 2 + nb + 1 + bj_scratch_doubles(nb)) * 8 + 16;
-	return block > scalar ? block : scalar;
-}
+size_t jacobi_smem(int n) { return ((size_t)rb_rows(n) * rb_ld(n) + 64 + rb_rows(n) + (n + 1) / 2) * 8 + 16; }
 
 }  // namespace
 
@@ -610,10 +273,8 @@ extern "C" int fh_polar_isqrt_multi(const double* G_all, double* WT_all, const i
 	             "fh_polar_isqrt_multi: null argument");
 	if (max_sweeps <= 0 || max_sweeps > kMaxSweeps) max_sweeps = kMaxSweeps;
 	cudaStream_t st = (cudaStream_t)stream;
-	// class lower bounds (exclusive). Register-blocked kernel: one class per row-length template (32 columns per lane
-	// element); scalar kernel: (117,160], (83,117], (58,83], (0,58]
-	const int rb_bounds[5] = {128, 96, 64, 32, 0}, sc_bounds[5] = {117, 83, 58, 0, 0};
-	const int* bounds = polar_rb_mode() ? rb_bounds : sc_bounds;
+	// class lower bounds (exclusive): one class per row-length template (32 columns per lane element)
+	const int bounds[5] = {128, 96, 64, 32, 0};
 	int i = 0;
 	while (i < count) {
 		const int nmax = host_prob_n[i];

@@ -1,4 +1,4 @@
-// Register-blocked one-sided Jacobi for the per-bin polar step (included by fh_polar.cu; uses jacobi_tan).
+// Register-blocked one-sided Jacobi for the per-bin polar step (included by fh_polar.cu inside its anonymous namespace).
 //
 // Why: the scalar kernel of round 1 (a quarter-warp per row pair, rows streamed from shared memory) was shared-memory
 // bound - every row crossed shared memory ~2.5 times per round-robin step, n - 1 steps per sweep (ncu: fp64 pipe 21 %,

@@ -8,7 +8,6 @@ import fasthigashi_b200  # noqa
 from fasthigashi_b200 import _lib
 from fasthigashi_b200.project2orthogonal import polar_batched
 g = torch.Generator().manual_seed(0)
-print("FH_POLAR_RB", os.environ.get("FH_POLAR_RB"))
 for n in [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "4,8,9,12,16,20,32,33,40,64,65,96,100,128,129,137,144,150,160".split(","))]:
 	for logk in (1.0, 5.0):
 		rows, batch = 2 * n + 3, 3

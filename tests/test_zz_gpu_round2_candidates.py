@@ -12,7 +12,6 @@ from oracle import fh_oracle as O
 import wrapper_cases
 
 pytestmark = [pytest.mark.gpu]
-opt_in = pytest.mark.skipif(os.environ.get("FH_RUN_UNVERIFIED", "0") != "1", reason="measured slower than the default kernel on a B200 (108 vs 59 ms per sweep); kept opt-in")
 
 
 def _wrapper(tmp_path, off, res, chroms):
@@ -47,20 +46,6 @@ def test_device_init_svd_reaches_the_host_init_loss():
 		losses[mode] = core.re_trace[-1]
 		assert np.all(np.diff(core.re_trace[1:]) <= 1e-6)
 	assert abs(losses["device"] - losses["host"]) <= 0.01 * losses["host"], losses
-
-
-@opt_in
-def test_polar_block_jacobi_on_device():
-	"""FH_POLAR_BLOCK=1 (csrc/fh_polar_block.cuh): the polar tests and one lock-step core run in a child process (the
-	switch is read once per process). The variant's logic is already checked on the host (tests/test_polar_block_emulation.py)."""
-	import subprocess
-	import sys
-	e = dict(os.environ)
-	e.update({"FH_POLAR_BLOCK": "1"})
-	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-	r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
-	                    "-k", "polar or lockstep", "-p", "no:cacheprovider"], env=e, cwd=root, capture_output=True, text=True, timeout=900)
-	assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_multi_resolution_run_matches_reference_fixture():
