@@ -398,8 +398,10 @@ class FastHigashi:
 			return os.path.join(self.path2result_dir, "impute_prwr%s.hdf5" % suffix)
 		return written
 
-	def run_model(self, dim1=.6, rank=256, n_iter_parafac=1, n_iter_max=None, tol=2e-5, extra="", run_init=True):
-		"""FastHigashi_Wrapper.py:657-701."""
+	def run_model(self, dim1=.6, rank=256, n_iter_parafac=1, n_iter_max=None, tol=2e-5, extra="", run_init=True, init_svd="auto"):
+		"""FastHigashi_Wrapper.py:657-701. `init_svd` (not in the reference): "host" = the reference's sklearn SVD of the pooled
+		features (reproduces its start from a shared seed), "device" = cell-sharded randomized SVD, "auto" = host for a single
+		process up to 20,000 cells, device otherwise (Fast_Higashi_core)."""
 		self.rank = rank
 		save_str = "dim1_%.1f_rank_%d_niterp_%d_%s" % (dim1, rank, n_iter_parafac, extra)
 		self.save_str = save_str
@@ -408,7 +410,7 @@ class FastHigashi:
 		my_rank, world = self._rank_world()
 		if self.model is None:
 			self.model = Fast_Higashi_core(rank=rank, off_diag=self.off_diag, res_list=self.fh_resolutions,
-			                               group=self.group if world > 1 else None).to(self.device)
+			                               group=self.group if world > 1 else None, init_svd=init_svd).to(self.device)
 		if n_iter_max is None:
 			n_iter_max = int(self.good_qc_num / 15)
 		result = self.model.fit_transform(self.all_matrix, size_ratio=dim1, n_iter_max=n_iter_max, n_iter_parafac=n_iter_parafac,

@@ -97,7 +97,7 @@ __device__ __forceinline__ void pivoted_cholesky_upper(double* __restrict__ R, c
 }
 
 template <int PL>
-__global__ void __launch_bounds__(PL == 5 ? 640 : PL * 128, PL >= 3 ? 1 : (PL == 2 ? 2 : 4))
+__global__ void __launch_bounds__(PL == 5 ? 640 : PL * 128, PL >= 3 ? 1 : (PL == 2 ? 3 : 6))
 chol_jacobi_rb_kernel(const double* __restrict__ Gall, const int* __restrict__ prob_n, const long long* __restrict__ prob_off,
                       const int* __restrict__ prob_slot, int uniform_n, int max_sweeps, double skip_tol,
                       double* __restrict__ WTall, double* __restrict__ sigma_all, double* __restrict__ sigma_sum,
@@ -189,7 +189,7 @@ template <int PL>
 int launch_rb(int grid, int nmax, size_t smem, cudaStream_t st, const double* G, const int* pn, const long long* po, const int* ps,
               int uniform_n, int max_sweeps, double skip, double* WT, double* sigma, double* sigma_sum, int* nsweep) {
 	FH_CUDA(cudaFuncSetAttribute(chol_jacobi_rb_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	const int tmr = fh_time_begin(FH_TIME_POLAR_JACOBI, st);
+	const int tmr = pn ? -1 : fh_time_begin(FH_TIME_POLAR_JACOBI, st);  // table-driven launches overlap on side streams: timed as one group by the caller
 	chol_jacobi_rb_kernel<PL><<<grid, rb_threads(nmax), smem, st>>>(G, pn, po, ps, uniform_n, max_sweeps, skip, WT, sigma, sigma_sum, nsweep);
 	fh_time_end(tmr, st);
 	FH_LAUNCH_CHECK();
@@ -273,9 +273,22 @@ extern "C" int fh_polar_isqrt_multi(const double* G_all, double* WT_all, const i
 	             "fh_polar_isqrt_multi: null argument");
 	if (max_sweeps <= 0 || max_sweeps > kMaxSweeps) max_sweeps = kMaxSweeps;
 	cudaStream_t st = (cudaStream_t)stream;
-	// class lower bounds (exclusive): one class per row-length template (32 columns per lane element)
+	// class lower bounds (exclusive): one class per row-length template (32 columns per lane element). The classes are
+	// independent, so every launch after the first goes to its own side stream: the last, partly filled wave of a class
+	// (938 problems of the largest class on 148 SMs = 6.3 waves) shares the GPU with the next class instead of idling it.
 	const int bounds[5] = {128, 96, 64, 32, 0};
-	int i = 0;
+	static cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+	static cudaEvent_t fork_ev = nullptr, join_ev[4];
+	if (!fork_ev) {
+		FH_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+		for (int c = 0; c < 4; ++c) {
+			FH_CUDA(cudaStreamCreateWithFlags(&side[c], cudaStreamNonBlocking));
+			FH_CUDA(cudaEventCreateWithFlags(&join_ev[c], cudaEventDisableTiming));
+		}
+	}
+	const int tmr = fh_time_begin(FH_TIME_POLAR_JACOBI, st);  // one record for the whole group of overlapping launches
+	FH_CUDA(cudaEventRecord(fork_ev, st));
+	int i = 0, launch = 0;
 	while (i < count) {
 		const int nmax = host_prob_n[i];
 		FH_CHECK_ARG(nmax > 0 && jacobi_smem(nmax) <= 227 * 1024 && nmax <= kMaxGram,
@@ -289,11 +302,22 @@ extern "C" int fh_polar_isqrt_multi(const double* G_all, double* WT_all, const i
 			++j;
 		}
 		const size_t smem = jacobi_smem(nmax);
-		int rc = launch_jacobi(j - i, nmax, smem, st, G_all, dev_prob_n + i, dev_prob_off + i, dev_prob_slot + i, 0, max_sweeps,
+		cudaStream_t ls = st;
+		if (launch > 0 && launch <= 4) {
+			ls = side[launch - 1];
+			FH_CUDA(cudaStreamWaitEvent(ls, fork_ev, 0));
+		}
+		int rc = launch_jacobi(j - i, nmax, smem, ls, G_all, dev_prob_n + i, dev_prob_off + i, dev_prob_slot + i, 0, max_sweeps,
 		                       WT_all, nullptr, sigma_sum, dev_nsweep);
 		if (rc) return rc;
+		if (ls != st) {
+			FH_CUDA(cudaEventRecord(join_ev[launch - 1], ls));
+			FH_CUDA(cudaStreamWaitEvent(st, join_ev[launch - 1], 0));
+		}
+		++launch;
 		i = j;
 	}
+	fh_time_end(tmr, st);
 	return FH_OK;
 }
 

@@ -15,8 +15,13 @@ constexpr int RT = 32;  // output rows per CTA in densify/conv
 
 // ---------------------------------------------------------------------------------------------
 // K1+K2: CSR -> dense (floor 1e-8) [-> 3x3 mean, zero padding counted, floor 1e-8]
-// grid (ceil(nb/RT), ncell), 256 threads, smem (RT+2) x (w+2) floats + rowptr slice
+// grid (ceil(nb/RT), ncell), 256 threads, smem (RT+2) x (ldw+8) floats + rowptr slice.
+// Tile layout: window column c of tile row tr lives at tile[tr * tp + c + 4] (tp = ldw + 8, a multiple of 4), so that a
+// group of four columns starting at a multiple of 4 is one aligned 128-bit shared load; index 3 is the left zero-padding
+// column, indices >= w + 4 the right one.
 // ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t densify_smem_bytes(int ldw) { return (size_t)((RT + 2) * (ldw + 8) + RT + 4) * 4; }
+
 template <bool FROM_DENSE>
 __global__ void __launch_bounds__(256)
 densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restrict__ col,
@@ -24,24 +29,32 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
                     const float* __restrict__ dense_in, long long in_cell_stride,
                     int cell0, int nb, int w, int ldw, int do_conv,
                     float* __restrict__ out, long long out_cell_stride) {
-	extern __shared__ float smem[];
-	const int tw = w + 2;
-	float* tile = smem;                                   // (RT+2) x tw
-	int* rp = (int*)(smem + (RT + 2) * tw);               // RT+3 row pointers
+	extern __shared__ __align__(16) float smem[];
+	const int tp = ldw + 8;
+	float* tile = smem;                                   // (RT+2) x tp
+	int* rp = (int*)(smem + (RT + 2) * tp);               // RT+3 row pointers
 	const int cell = blockIdx.y;
 	const int r0 = blockIdx.x * RT;
 	const int halo = do_conv ? 1 : 0;
 	const int ra = max(r0 - halo, 0), rb = min(r0 + RT + halo, nb);  // staged global rows [ra, rb)
 	const int tid = threadIdx.x;
 
-	// 1. background: floor inside the block, 0 in the zero padding ring (warp per tile row: no integer
-	// division in any per-element loop of this kernel - they dominated its instruction count)
+	// 1. background: floor inside the block, 0 in the zero padding ring and the pad columns (128-bit stores; no integer
+	// division in any per-element loop of this kernel - they dominated the first version's instruction count)
 	const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
 	for (int tr = warp; tr < RT + 2; tr += nwarp) {
 		const int gr = r0 - 1 + tr;
 		const bool rin = gr >= 0 && gr < nb;
-		float* trow = tile + tr * tw;
-		for (int tc = lane; tc < tw; tc += 32) trow[tc] = (rin && tc >= 1 && tc <= w) ? FH_FLOOR : 0.f;
+		float4* trow = reinterpret_cast<float4*>(tile + tr * tp);
+		for (int q = lane; q < (tp >> 2); q += 32) {
+			const int c = 4 * q - 4;  // window column of the first element
+			float4 v;
+			v.x = (rin && c >= 0 && c < w) ? FH_FLOOR : 0.f;
+			v.y = (rin && c + 1 >= 0 && c + 1 < w) ? FH_FLOOR : 0.f;
+			v.z = (rin && c + 2 >= 0 && c + 2 < w) ? FH_FLOOR : 0.f;
+			v.w = (rin && c + 3 >= 0 && c + 3 < w) ? FH_FLOOR : 0.f;
+			trow[q] = v;
+		}
 	}
 	if (!FROM_DENSE) {
 		const long long base = (long long)(cell0 + cell) * nb;
@@ -51,7 +64,7 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 	if (FROM_DENSE) {
 		const float* src = dense_in + (long long)cell * in_cell_stride;
 		for (int gr = ra + warp; gr < rb; gr += nwarp) {
-			float* trow = tile + (gr - r0 + 1) * tw + 1;
+			float* trow = tile + (gr - r0 + 1) * tp + 4;
 			const float* srow = src + (long long)gr * ldw;
 			for (int c = lane; c < w; c += 32) trow[c] = fmaxf(srow[c], FH_FLOOR);
 		}
@@ -93,38 +106,57 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 				if (idx < lo || idx >= hi) continue;
 				while (rp[r + 1] <= idx) ++r;
 				int gr = ra + r;
-				tile[(gr - r0 + 1) * tw + (int)c8[e] + 1] = fmaxf(v8[e], FH_FLOOR);
+				tile[(gr - r0 + 1) * tp + (int)c8[e] + 4] = fmaxf(v8[e], FH_FLOOR);
 			}
 		}
 	}
 	__syncthreads();
-	// 3. stencil + write; pad columns [w, ldw) are written as 0. One work unit = one column x 8 rows:
-	// the 3x3 window slides down the column on per-row triple sums (3 shared loads per output instead
-	// of 9); consecutive threads own consecutive columns, so shared reads are conflict free and every
-	// global store instruction writes a contiguous row segment.
+	// 3. stencil + write; pad columns [w, ldw) are written as 0. One work unit = FOUR columns x 8 rows: per tile row one
+	// 128-bit shared load + the two neighbours, seven adds for the four horizontal triple sums, the 3x3 window slides down
+	// the columns on them, one 128-bit global store per output row (ncu on the one-column version: issue slots 87 % busy,
+	// ALU the busiest pipe - the kernel was instruction bound at 2.2 TB/s, not memory bound).
 	float* dst = out + (long long)cell * out_cell_stride;
 	const int rows = min(RT, nb - r0);
+	const int ngrp = ldw >> 2;
 	if (do_conv) {
 		const int nstrip = (rows + 7) >> 3;            // <= 4 strips of 8 rows
 		const int per = nwarp / 4 > 0 ? nwarp / 4 : 1;  // warps per strip
 		for (int strip = warp & 3; strip < nstrip; strip += 4) {
 			const int tr0 = strip * 8;
 			const int nr = min(8, rows - tr0);
-			for (int c = (warp >> 2) * 32 + lane; c < ldw; c += 32 * per) {
+			for (int q = (warp >> 2) * 32 + lane; q < ngrp; q += 32 * per) {
+				const int c = 4 * q;
 				float* drow = dst + (long long)(r0 + tr0) * ldw + c;
-				if (c >= w) {
-					for (int k = 0; k < nr; ++k) drow[(long long)k * ldw] = 0.f;
-					continue;
+				const float* t = tile + tr0 * tp + c + 4;  // tile row tr0 = global row r0 + tr0 - 1
+				float4 h0, h1;
+				{
+					const float4 a = *reinterpret_cast<const float4*>(t);
+					const float l = t[-1], r_ = t[4];
+					const float s01 = a.x + a.y, s23 = a.z + a.w;
+					h0.x = l + s01; h0.y = s01 + a.z; h0.z = a.y + s23; h0.w = s23 + r_;
 				}
-				const float* t = tile + tr0 * tw + (c + 1);  // tile row tr0 = global row r0 + tr0 - 1
-				float h0 = (t[-1] + t[0]) + t[1];
-				float h1 = (t[tw - 1] + t[tw]) + t[tw + 1];
+				{
+					const float4 a = *reinterpret_cast<const float4*>(t + tp);
+					const float l = t[tp - 1], r_ = t[tp + 4];
+					const float s01 = a.x + a.y, s23 = a.z + a.w;
+					h1.x = l + s01; h1.y = s01 + a.z; h1.z = a.y + s23; h1.w = s23 + r_;
+				}
+				const bool m0 = c < w, m1 = c + 1 < w, m2 = c + 2 < w, m3 = c + 3 < w;
 #pragma unroll
 				for (int k = 0; k < 8; ++k) {
 					if (k < nr) {
-						const float* tn = t + (k + 2) * tw;
-						const float h2 = (tn[-1] + tn[0]) + tn[1];
-						drow[(long long)k * ldw] = fmaxf(((h0 + h1) + h2) * (1.0f / 9.0f), FH_FLOOR);  // 1 ulp from sum / 9: an IEEE division is ~9 instructions of the ~22 per output
+						const float* tn = t + (k + 2) * tp;
+						const float4 a = *reinterpret_cast<const float4*>(tn);
+						const float l = tn[-1], r_ = tn[4];
+						const float s01 = a.x + a.y, s23 = a.z + a.w;
+						float4 h2;
+						h2.x = l + s01; h2.y = s01 + a.z; h2.z = a.y + s23; h2.w = s23 + r_;
+						float4 o;  // 1 ulp from sum / 9: an IEEE division would be ~9 instructions per output
+						o.x = m0 ? fmaxf(((h0.x + h1.x) + h2.x) * (1.0f / 9.0f), FH_FLOOR) : 0.f;
+						o.y = m1 ? fmaxf(((h0.y + h1.y) + h2.y) * (1.0f / 9.0f), FH_FLOOR) : 0.f;
+						o.z = m2 ? fmaxf(((h0.z + h1.z) + h2.z) * (1.0f / 9.0f), FH_FLOOR) : 0.f;
+						o.w = m3 ? fmaxf(((h0.w + h1.w) + h2.w) * (1.0f / 9.0f), FH_FLOOR) : 0.f;
+						*reinterpret_cast<float4*>(drow + (long long)k * ldw) = o;
 						h0 = h1; h1 = h2;
 					}
 				}
@@ -132,9 +164,9 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 		}
 	} else {
 		for (int tr = warp; tr < rows; tr += nwarp) {
-			float* drow = dst + (long long)(r0 + tr) * ldw;
-			const float* trow = tile + (tr + 1) * tw + 1;
-			for (int c = lane; c < ldw; c += 32) drow[c] = (c < w) ? trow[c] : 0.f;
+			float4* drow = reinterpret_cast<float4*>(dst + (long long)(r0 + tr) * ldw);
+			const float4* trow = reinterpret_cast<const float4*>(tile + (tr + 1) * tp + 4);
+			for (int q = lane; q < ngrp; q += 32) drow[q] = trow[q];  // pad columns hold the background's zeros
 		}
 	}
 }
@@ -494,14 +526,15 @@ int check_desc(const fh_rwr_desc* d) {
 	FH_CHECK_ARG(d->ldw >= d->w && d->ldw % 4 == 0, "fh_rwr: ldw=%d must be >= w=%d and a multiple of 4", d->ldw, d->w);
 	FH_CHECK_ARG(d->s >= 0 && d->s + d->nb <= d->w, "fh_rwr: diagonal block [%d,%d) outside window %d", d->s, d->s + d->nb, d->w);
 	FH_CHECK_ARG(d->ncell <= 65535, "fh_rwr: ncell %d > 65535 per call", d->ncell);
-	FH_CHECK_ARG((size_t)((RT + 2) * (d->w + 2) + RT + 4) * 4 <= 200 * 1024, "fh_rwr: window %d too wide", d->w);
+	FH_CHECK_ARG(densify_smem_bytes(d->ldw) <= 200 * 1024, "fh_rwr: window %d too wide", d->w);
 	return FH_OK;
 }
 
 int launch_densify(const fh_rwr_desc* d, bool from_dense, const int32_t* rowptr, const int16_t* col,
                    const float* val, const float* dense_in, long long in_cs, int do_conv, float* out,
                    long long out_cs, cudaStream_t st) {
-	size_t smem = (size_t)((RT + 2) * (d->w + 2) + RT + 4) * 4;
+	size_t smem = densify_smem_bytes(d->ldw);
+	FH_CHECK_ARG(((uintptr_t)out & 15) == 0 && (out_cs & 3) == 0, "fh_rwr: output panels must be 16-byte aligned with a cell stride that is a multiple of 4 floats");
 	dim3 grid(fh_cdiv(d->nb, RT), d->ncell);
 	const int tmr = fh_time_begin(FH_TIME_DENSIFY, st);
 	if (from_dense) {

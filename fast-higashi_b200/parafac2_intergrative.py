@@ -42,7 +42,9 @@ def _as_block_csr(ds, device):
 
 
 class Fast_Higashi_core:
-	def __init__(self, rank, off_diag, res_list, cache="sweep", use_tc=None, group=None, init_svd="host"):
+	HOST_INIT_MAX_CELLS = 20000  # init_svd="auto": above this (or when cell-sharded) the init SVDs stay on the device
+
+	def __init__(self, rank, off_diag, res_list, cache="sweep", use_tc=None, group=None, init_svd="auto"):
 		self.rank = rank
 		self.off_diag = off_diag
 		self.res_list = res_list
@@ -50,9 +52,13 @@ class Fast_Higashi_core:
 		self.cache = cache            # "sweep": one RWR pass per ALS sweep; "run": one per run
 		self.use_tc = use_tc          # None -> decided in .to()
 		self.group = group            # torch.distributed process group when cell-sharded
-		if init_svd not in ("host", "device"):
-			raise ValueError("init_svd must be 'host' (the reference's sklearn SVD, features gathered to rank 0) or 'device'")
-		self.init_svd = init_svd      # "device": cell-sharded randomized SVD (dist_svd.py), nothing gathered
+		if init_svd not in ("auto", "host", "device"):
+			raise ValueError("init_svd must be 'auto', 'host' (the reference's sklearn SVD, features gathered to rank 0) or 'device'")
+		# "host": the reference's own route (sklearn TruncatedSVD with the numpy global RNG: a shared seed reproduces the
+		# reference's start). "device": cell-sharded randomized SVD (dist_svd.py), nothing gathered - measured 4.0 s for the
+		# whole init of 100k cells on 8 GPUs, where the host route would gather ~50 GB of fp64 features per chromosome to
+		# rank 0. "auto" (default): host for a single process with <= HOST_INIT_MAX_CELLS cells, device otherwise.
+		self.init_svd = init_svd
 		self.verbose = True
 		self.n_rwr_passes = 0
 		self._X = {}
@@ -145,6 +151,8 @@ class Fast_Higashi_core:
 		cum = np.concatenate([[0], np.cumsum(uniq)])
 		dist = self._dist()
 		rank0 = dist is None or dist.get_rank(self.group) == 0
+		if self.init_svd == "auto":
+			self.init_svd = "host" if (dist is None and self.schic[0].num_cell <= self.HOST_INIT_MAX_CELLS) else "device"
 		C = None
 		cstart = 0
 		self.bin_cov_list, self.bad_bin_cov_list, n_i_all = [], [], []

@@ -369,7 +369,7 @@ def _dist_wrapper_worker(rank, world, port, q, tmp):
 	w = _cpu_wrapper(pathlib.Path(tmp), 12, int(G["res"]), chroms).distribute(dist.group.WORLD)
 	w.prep_dataset()
 	torch.manual_seed(0); np.random.seed(0)
-	w.run_model(dim1=0.6, rank=8, n_iter_parafac=1, n_iter_max=4, tol=0.0)
+	w.run_model(dim1=0.6, rank=8, n_iter_parafac=1, n_iter_max=4, tol=0.0, init_svd="host")  # same start as the single process
 	np.random.seed(1)
 	emb = w.fetch_cell_embedding(final_dim=4)
 	csr = [[(ds.rowptr[b].numpy(), ds.col[b].numpy(), ds.val[b].numpy()) for b in range(len(ds.geoms))] for ds in w.all_matrix]
