@@ -64,6 +64,7 @@ class Fast_Higashi_core:
 		self._X = {}
 		self._eig = {}
 		self._scratch = {}
+		self._Z_valid = set()
 
 	def to(self, device):
 		self.device = torch.device(device)
@@ -297,6 +298,7 @@ class Fast_Higashi_core:
 			self._cov_all[ci] = torch.cat([good, bad], 0).contiguous() if torch.is_tensor(bad) else good
 			self.bin_cov_list[ci] = self._cov_all[ci][:ds.num_cell]
 		self.n_i = np.asarray(n_i)
+		self._Z_valid = set()
 
 	# ------------------------------------------------------------------------------------------
 	def _impute_good(self, ci, b, do_conv, do_rwr, do_col):
@@ -313,6 +315,7 @@ class Fast_Higashi_core:
 		flags = (bool(do_conv), bool(do_rwr), bool(do_col))
 		if getattr(self, "_X_flags", flags) != flags:  # transform() called with other flags than fit(): never reuse the old maps
 			self.invalidate_cache()
+			self._invalidate_Z()
 		self._X_flags = flags
 		if key not in self._X_valid:
 			ev = getattr(self, "input_events", None)
@@ -410,11 +413,16 @@ class Fast_Higashi_core:
 	def invalidate_cache(self):
 		self._X_valid = set()
 
+	def _invalidate_Z(self):
+		"""Z = X^T V of the last P5 is only reusable while X (flags, step counts) and V are the ones it was formed from."""
+		self._Z_valid = set()
+
 	def release(self):
 		"""Drop the resident imputed tensor and the scratch buffers (the factors stay)."""
 		self._X = {}
 		self._scratch = {}
 		self.invalidate_cache()
+		self._invalidate_Z()
 		_lib.free_workspaces()
 
 	# P1-P5: parafac2_intergrative.py:304-540
@@ -476,7 +484,8 @@ class Fast_Higashi_core:
 			rp = pad4(r)
 			Bp, Dp = self._padded_factors(ds.chrom)
 			Cc = self._buf(("Cc", ci & 1), Cn, rp)
-			_lib.gemm(V, Dp, Cc, Cn, r, R, (R, 1), (rp, 1), rp, dtype=gd)  # C = V D  (:336)
+			if any((ci, b) not in self._Z_valid for b in range(len(ds.geoms))):
+				_lib.gemm(V, Dp, Cc, Cn, r, R, (R, 1), (rp, 1), rp, dtype=gd)  # C = V D  (:336)
 			for b, g in enumerate(ds.geoms):
 				ldw = pad4(g.w)
 				P = g.nb * ldw
@@ -486,11 +495,17 @@ class Fast_Higashi_core:
 				if first_iter:
 					_lib.check(_lib.lib().fh_sqnorm_accum(X.data_ptr(), 1, Cn * P, Cn * P, stats[nch + ci:].data_ptr(),
 					                                      _lib.stream_ptr()))
-				# P1: T1 = X^T C ; temp_i = T1_i (B diag(A_i))^T
+				# P1: T1 = X^T C ; temp_i = T1_i (B diag(A_i))^T. C = V D with the V of the previous sweep's update, and the
+				# previous sweep's P5 already formed Z = X^T V for exactly that V (X is re-imputed every sweep but is the same
+				# deterministic function of the input), so T1 = Z D: a (P x R)(R x r) product instead of a third pass over X.
+				# Only the first sweep (no Z yet) contracts X with C directly.
 				t = self._tic()
 				T1 = self._buf(("T1", nblk & 1), P, rp)
 				nblk += 1
-				_lib.gemm(X, Cc, T1, P, r, Cn, (1, P), (rp, 1), rp, dtype=gd)
+				if (ci, b) in self._Z_valid:
+					_lib.gemm(self._buf(("Z", ci, b), P, R), Dp, T1, P, r, R, (R, 1), (rp, 1), rp, dtype=gd)
+				else:
+					_lib.gemm(X, Cc, T1, P, r, Cn, (1, P), (rp, 1), rp, dtype=gd)
 				self._toc("p1_mttkrp", t)
 				work = self._allreduce_async(T1)
 				if pending is not None:
@@ -565,8 +580,9 @@ class Fast_Higashi_core:
 				P = g.nb * ldw
 				X = self._impute_good(ci, b, do_conv, do_rwr, do_col)
 				t = self._tic()
-				Z = self._buf("Z", P, R)
+				Z = self._buf(("Z", ci, b), P, R)  # kept: the next sweep's T1 = Z D
 				_lib.gemm(X, Vn, Z, P, R, Cn, (1, P), (R, 1), R, dtype=gd)
+				self._Z_valid.add((ci, b))
 				U = self.projection_dev[ci][b]
 				Yb = Y[ds.global_slice_bin.start + g.row0: ds.global_slice_bin.start + g.row0 + g.nb]
 				_lib.gemm(U, Z, Yb, r, R, ldw, (1, rp), (R, 1), R, batch=g.nb, batch_strides=(ldw * rp, ldw * R, r * R), dtype=gd)
@@ -614,6 +630,7 @@ class Fast_Higashi_core:
 		                      for c in self.chrom2size}
 		self._X, self._eig, self._ptab, self._scratch = {}, {}, None, {}
 		self.invalidate_cache()
+		self._invalidate_Z()
 		self.n_rwr_passes = 0
 		self._core_norm = self._core_norms()
 		self._xnorm = None
