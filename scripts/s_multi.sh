@@ -2,7 +2,7 @@
 # round-2 multi-GPU session (one 8-GPU box): N-GPU == 1-GPU parity record, the headline job (config 4), the weak-scaling
 # bench line at N = 8, and the strong-scaling curve of config 3 (N = 8, then 4 / 2 / 1 side by side on disjoint GPUs)
 set -u
-OUT=gpurun_out; mkdir -p $OUT; T=r02m1
+OUT=gpurun_out; mkdir -p $OUT; T=r02m2
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 ( NCCL_DEBUG=INFO timeout 300 $TR --nproc-per-node 8 --master-port 29501 scripts/multigpu_check.py 2>&1 | grep -E "rank |MULTIGPU|NVLS|Error|error|Traceback" | head -60 ) > $OUT/${T}_multigpu_check_n8.txt
 tail -3 $OUT/${T}_multigpu_check_n8.txt
