@@ -124,8 +124,8 @@ __global__ void mode1_reduce_kernel(const float* __restrict__ Z, const float* __
 		M1[(size_t)j * r + p] = (float)s;
 	}
 }
-// KR[(i*r + j), p] = A[i,p] * B[j,p]
-__global__ void khatri_rao_kernel(const float* __restrict__ A, const float* __restrict__ B, int n, int r,
+// KR[(i*r + j), p] = A[i,p] * B[j,p]; KR rows at pitch ldk (a multiple of 4 floats: the tcgen05 GEMM reads them through TMA)
+__global__ void khatri_rao_kernel(const float* __restrict__ A, const float* __restrict__ B, int n, int r, int ldk,
                                   float* __restrict__ KR) {
 	const long long total = (long long)n * r * r;
 	for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -134,7 +134,15 @@ __global__ void khatri_rao_kernel(const float* __restrict__ A, const float* __re
 		long long ij = t / r;
 		int j = (int)(ij % r);
 		long long i = ij / r;
-		KR[t] = A[i * r + p] * B[j * r + p];
+		KR[ij * ldk + p] = A[i * r + p] * B[j * r + p];
+	}
+}
+// dst (rows x ldd) = src (rows x r), pad columns zero
+__global__ void pad_rows_kernel(const float* __restrict__ src, int rows, int r, int ldd, float* __restrict__ dst) {
+	const long long total = (long long)rows * ldd;
+	for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+		const int p = (int)(t % ldd);
+		dst[t] = p < r ? src[(t / ldd) * r + p] : 0.f;
 	}
 }
 // acc += sum(G1 * G2 * G3)
@@ -179,14 +187,16 @@ __global__ void scale_cols_batched_kernel(const float* __restrict__ F, int rows,
 
 size_t al(size_t x) { return (x + 255) / 256 * 256; }
 struct CpWs {
-	float *Z, *M, *Tm, *norms;
+	float *Z, *M, *Tm, *Dp, *norms;
 	double *Ga, *Gb, *Gd, *Hinv, *scal;
 	size_t bytes;
 };
 CpWs carve(int n, int r, int R, void* ws) {
 	CpWs c;
 	char* b = (char*)ws;
-	c.Z = (float*)b; b += al((size_t)n * r * r * 4);
+	const int rp = (r + 3) & ~3;
+	c.Z = (float*)b; b += al((size_t)n * r * rp * 4);  // Y D (pitch r), then KhatriRao(A, B) (pitch rp)
+	c.Dp = (float*)b; b += al((size_t)R * rp * 4);     // D at a TMA-describable pitch
 	int mx = n > R ? n : R; mx = mx > r ? mx : r;
 	c.M = (float*)b; b += al((size_t)mx * r * 4);
 	c.Tm = (float*)b; b += al((size_t)mx * r * 4);  // factor update before its commit
@@ -236,6 +246,7 @@ extern "C" int fh_cp_als(const float* Y, int n, int r, int R, float* A, float* B
 	FH_CHECK_ARG(workspace && workspace_bytes >= fh_cp_als_workspace_bytes(n, r, R), "fh_cp_als: workspace too small");
 	cudaStream_t st = (cudaStream_t)stream;
 	CpWs w = carve(n, r, R, workspace);
+	const int rp = (r + 3) & ~3;
 	int rc;
 	if (host_out) host_out[0] = host_out[1] = 0.0;
 	rc = balance(A, n, B, D, R, r, w.norms, nullptr, st);
@@ -248,8 +259,12 @@ extern "C" int fh_cp_als(const float* Y, int n, int r, int R, float* A, float* B
 		if (rc) return rc;
 	}
 	for (int it = 0; it < n_iter_max; ++it) {
-		// Z = Y_(n r x R) D : shared by the A and B updates (D is unchanged between them)
-		rc = gemm(FH_GEMM_F32, n * r, r, R, Y, R, 1, D, r, 1, w.Z, r, stream);
+		// Z = Y_(n r x R) D : shared by the A and B updates (D is unchanged between them). Both MTTKRP products run on the
+		// tcgen05 3xTF32 kernel (round 1: CUDA-core fp32, 18 of the CP-ALS stage's launch time): D and the Khatri-Rao
+		// matrix are read at the padded pitch rp; operands TMA cannot describe (R not a multiple of 4) fall back by themselves.
+		pad_rows_kernel<<<fh_cdiv((long long)R * rp, 256), 256, 0, st>>>(D, R, r, rp, w.Dp);
+		FH_LAUNCH_CHECK();
+		rc = gemm(FH_GEMM_TF32X3, n * r, r, R, Y, R, 1, w.Dp, rp, 1, w.Z, r, stream);
 		if (rc) return rc;
 		// mode 0: A = M0 ((B^T B) * (D^T D))^{-1}
 		if ((rc = gram(B, r, r, w.Gb, stream))) return rc;
@@ -264,9 +279,9 @@ extern "C" int fh_cp_als(const float* Y, int n, int r, int R, float* A, float* B
 		if ((rc = solve_update(w.M, r, w.Ga, w.Gd, r, w.Hinv, w.Tm, B, stopped, st))) return rc;
 		// mode 2: D = M2 ((A^T A) * (B^T B))^{-1},  M2 = Y_(R x n r) KhatriRao(A, B)
 		if ((rc = gram(B, r, r, w.Gb, stream))) return rc;
-		khatri_rao_kernel<<<fh_cdiv((long long)n * r * r, 256) > 4096 ? 4096 : fh_cdiv((long long)n * r * r, 256), 256, 0, st>>>(A, B, n, r, w.Z);
+		khatri_rao_kernel<<<fh_cdiv((long long)n * r * r, 256) > 4096 ? 4096 : fh_cdiv((long long)n * r * r, 256), 256, 0, st>>>(A, B, n, r, rp, w.Z);
 		FH_LAUNCH_CHECK();
-		rc = gemm(FH_GEMM_F32, R, r, n * r, Y, 1, R, w.Z, r, 1, w.M, r, stream);
+		rc = gemm(FH_GEMM_TF32X3, R, r, n * r, Y, 1, R, w.Z, rp, 1, w.M, r, stream);
 		if (rc) return rc;
 		if ((rc = solve_update(w.M, R, w.Ga, w.Gb, r, w.Hinv, w.Tm, D, stopped, st))) return rc;
 		if (need_loss) {
