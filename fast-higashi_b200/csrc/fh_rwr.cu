@@ -3,6 +3,7 @@
 // loads, staged through shared memory, and the imputed dense nb x w panel of every cell is written
 // once; everything in between (conv'd panel A, A A^T, transition matrix P, the Q iterates) lives in
 // an L2-sized workspace that is reused chunk after chunk.
+#include <cuda_fp16.h>
 #include "fh_common.cuh"
 #include "../../include/fh_b200.h"
 
@@ -22,13 +23,31 @@ constexpr int RT = 32;  // output rows per CTA in densify/conv
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t densify_smem_bytes(int ldw) { return (size_t)((RT + 2) * (ldw + 8) + RT + 4) * 4; }
 
-template <bool FROM_DENSE>
+// OUT16: the panel leaves as two binary16 planes (hi = rn16(s x), lo = rn16(s x - hi); rows of ld16 halves, the lo plane
+// lo_plane halves after the hi plane) for the 3xFP16 kernel (fh_rwr_chain16.cu); s is the power of two that brings *amax
+// (the largest floored CSR value of the block: an upper bound of every panel entry) into [2^13, 2^14).
+__device__ __forceinline__ void split_pair16(float a, float b, unsigned& hi, unsigned& lo) {
+	asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+	float fa, fb;
+	asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}\n" : "=f"(fa), "=f"(fb) : "r"(hi));
+	asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - fb), "f"(a - fa));
+}
+__device__ __forceinline__ void store4_16(__half* hi_row, long long lo_plane, float4 o, float sa) {
+	uint2 vh, vl;
+	split_pair16(o.x * sa, o.y * sa, vh.x, vl.x);
+	split_pair16(o.z * sa, o.w * sa, vh.y, vl.y);
+	*reinterpret_cast<uint2*>(hi_row) = vh;
+	*reinterpret_cast<uint2*>(hi_row + lo_plane) = vl;
+}
+
+template <bool FROM_DENSE, bool OUT16>
 __global__ void __launch_bounds__(256)
 densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restrict__ col,
                     const float* __restrict__ val, long long nnz_total,
                     const float* __restrict__ dense_in, long long in_cell_stride,
                     int cell0, int nb, int w, int ldw, int do_conv,
-                    float* __restrict__ out, long long out_cell_stride) {
+                    float* __restrict__ out, long long out_cell_stride,
+                    int ld16, long long lo_plane, const unsigned* __restrict__ amax) {
 	extern __shared__ __align__(16) float smem[];
 	const int tp = ldw + 8;
 	float* tile = smem;                                   // (RT+2) x tp
@@ -116,6 +135,12 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 	// the columns on them, one 128-bit global store per output row (ncu on the one-column version: issue slots 87 % busy,
 	// ALU the busiest pipe - the kernel was instruction bound at 2.2 TB/s, not memory bound).
 	float* dst = out + (long long)cell * out_cell_stride;
+	__half* dst16 = reinterpret_cast<__half*>(out) + (long long)cell * out_cell_stride;  // OUT16: strides in halves
+	float sa = 1.f;
+	if (OUT16) {
+		const unsigned abits = max(*amax, __float_as_uint(FH_FLOOR));
+		sa = __uint_as_float((267u - (abits >> 23)) << 23);
+	}
 	const int rows = min(RT, nb - r0);
 	const int ngrp = ldw >> 2;
 	if (do_conv) {
@@ -127,6 +152,7 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 			for (int q = (warp >> 2) * 32 + lane; q < ngrp; q += 32 * per) {
 				const int c = 4 * q;
 				float* drow = dst + (long long)(r0 + tr0) * ldw + c;
+				__half* drow16 = dst16 + (long long)(r0 + tr0) * ld16 + c;
 				const float* t = tile + tr0 * tp + c + 4;  // tile row tr0 = global row r0 + tr0 - 1
 				float4 h0, h1;
 				{
@@ -156,7 +182,8 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 						o.y = m1 ? fmaxf(((h0.y + h1.y) + h2.y) * (1.0f / 9.0f), FH_FLOOR) : 0.f;
 						o.z = m2 ? fmaxf(((h0.z + h1.z) + h2.z) * (1.0f / 9.0f), FH_FLOOR) : 0.f;
 						o.w = m3 ? fmaxf(((h0.w + h1.w) + h2.w) * (1.0f / 9.0f), FH_FLOOR) : 0.f;
-						*reinterpret_cast<float4*>(drow + (long long)k * ldw) = o;
+						if (OUT16) store4_16(drow16 + (long long)k * ld16, lo_plane, o, sa);
+						else *reinterpret_cast<float4*>(drow + (long long)k * ldw) = o;
 						h0 = h1; h1 = h2;
 					}
 				}
@@ -165,8 +192,12 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 	} else {
 		for (int tr = warp; tr < rows; tr += nwarp) {
 			float4* drow = reinterpret_cast<float4*>(dst + (long long)(r0 + tr) * ldw);
+			__half* drow16 = dst16 + (long long)(r0 + tr) * ld16;
 			const float4* trow = reinterpret_cast<const float4*>(tile + (tr + 1) * tp + 4);
-			for (int q = lane; q < ngrp; q += 32) drow[q] = trow[q];  // pad columns hold the background's zeros
+			for (int q = lane; q < ngrp; q += 32) {  // pad columns hold the background's zeros
+				if (OUT16) store4_16(drow16 + 4 * q, lo_plane, trow[q], sa);
+				else drow[q] = trow[q];
+			}
 		}
 	}
 }
@@ -346,9 +377,32 @@ sqnorm_kernel(const float* __restrict__ x, const float* __restrict__ y, long lon
 	if (threadIdx.x == 0) atomicAdd(acc, a);
 }
 
+// largest floored value of the CSR rows [row0, row1) -> *amax (bits of a non-negative float: integer order = float order)
+__global__ void __launch_bounds__(256)
+csr_absmax_kernel(const int32_t* __restrict__ rowptr, const float* __restrict__ val, long long row0, long long row1,
+                  unsigned* __restrict__ amax) {
+	__shared__ float red[8];
+	const long long lo = rowptr[row0], hi = rowptr[row1];
+	float m = 0.f;
+	for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x)
+		m = fmaxf(m, __ldg(val + i));
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+	__syncthreads();
+	if (threadIdx.x < 8) {
+		m = red[threadIdx.x];
+#pragma unroll
+		for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+		if (threadIdx.x == 0 && m > 0.f) atomicMax(amax, __float_as_uint(fmaxf(m, FH_FLOOR)));
+	}
+}
+
 }  // namespace
 extern "C" void fh_count_tc_fallback(void);
 size_t fh_rwr_chain_scratch_bytes();
+int fh_rwr_chain16(const void* Ahi, const unsigned* amax, float* out, int nb, int w, int ldw, int ld16, int s, int k,
+                   int ncell, long long a_cell_stride, long long out_cell_stride, void* stream);
 int fh_rwr_chain(const float* P, const float* A, float* out, int nb, int w, int ldw, int ldp, int s, int k, int ncell,
                  long long p_cell_stride, long long a_cell_stride, long long out_cell_stride, float* scratch,
                  void* stream);
@@ -358,13 +412,15 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct RwrWs {
 	float *A, *P, *Q0, *Q1, *delta, *scratch;
+	unsigned* amax;
 	size_t bytes;
 };
 
 RwrWs carve(const fh_rwr_desc* d, void* ws) {
 	RwrWs r;
 	const int ldp = (d->nb + 3) & ~3;
-	size_t a = align_up((size_t)d->ncell * d->nb * d->ldw * 4, 256);
+	// the conv'd panel: fp32 rows of ldw floats, or two binary16 planes with rows of round_up(w, 8) halves
+	size_t a = align_up((size_t)d->ncell * d->nb * ((d->ldw + 7) & ~7) * 4, 256);
 	size_t p = align_up((size_t)d->ncell * d->nb * ldp * 4, 256);
 	char* b = (char*)ws;
 	r.A = (float*)b; b += a;
@@ -373,6 +429,7 @@ RwrWs carve(const fh_rwr_desc* d, void* ws) {
 	r.Q1 = (float*)b; b += p;
 	r.delta = (float*)b; b += align_up((size_t)d->ncell * 4, 256);
 	r.scratch = (float*)b; b += align_up(fh_rwr_chain_scratch_bytes(), 256);
+	r.amax = (unsigned*)b; b += 256;
 	r.bytes = (size_t)(b - (char*)ws);
 	return r;
 }
@@ -405,6 +462,14 @@ int gemm_f32(int use_tc, int M, int N, int K, int batch, const float* A, long lo
 int rwr_fused_level() {
 	static int v = -1;
 	if (v < 0) { const char* e = getenv("FH_RWR_FUSED"); v = e ? atoi(e) : 2; }
+	return v;
+}
+
+// FH_RWR_F16: 1 (default) the fused kernel works on binary16 operand pairs (3xFP16, fh_rwr_chain16.cu: the panel is
+// densified straight into two binary16 planes); 0 the 3xTF32 kernel (fh_rwr_chain.cu)
+int rwr_f16_enabled() {
+	static int v = -1;
+	if (v < 0) { const char* e = getenv("FH_RWR_F16"); v = e ? atoi(e) : 1; }
 	return v;
 }
 
@@ -538,13 +603,13 @@ int launch_densify(const fh_rwr_desc* d, bool from_dense, const int32_t* rowptr,
 	dim3 grid(fh_cdiv(d->nb, RT), d->ncell);
 	const int tmr = fh_time_begin(FH_TIME_DENSIFY, st);
 	if (from_dense) {
-		if (smem > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(densify_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		densify_conv_kernel<true><<<grid, 256, smem, st>>>(nullptr, nullptr, nullptr, 0, dense_in, in_cs, 0, d->nb, d->w,
-		                                                  d->ldw, do_conv, out, out_cs);
+		if (smem > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(densify_conv_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		densify_conv_kernel<true, false><<<grid, 256, smem, st>>>(nullptr, nullptr, nullptr, 0, dense_in, in_cs, 0, d->nb, d->w,
+		                                                         d->ldw, do_conv, out, out_cs, 0, 0, nullptr);
 	} else {
-		if (smem > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(densify_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		densify_conv_kernel<false><<<grid, 256, smem, st>>>(rowptr, col, val, d->nnz, nullptr, 0, d->cell0, d->nb, d->w,
-		                                                   d->ldw, do_conv, out, out_cs);
+		if (smem > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(densify_conv_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		densify_conv_kernel<false, false><<<grid, 256, smem, st>>>(rowptr, col, val, d->nnz, nullptr, 0, d->cell0, d->nb, d->w,
+		                                                          d->ldw, do_conv, out, out_cs, 0, 0, nullptr);
 	}
 	fh_time_end(tmr, st);
 	FH_LAUNCH_CHECK();
@@ -581,6 +646,30 @@ extern "C" int fh_rwr_batched(const fh_rwr_desc* d, const int32_t* rowptr, const
 	             "fh_rwr_batched: workspace too small (%zu < %zu)", workspace_bytes, fh_rwr_workspace_bytes(d));
 	FH_CHECK_ARG(!d->do_col || bin_cov != nullptr, "fh_rwr_batched: do_col needs bin_cov");
 	RwrWs ws = carve(d, workspace);
+	// forced step count without do_col on the tensor cores (every call of the ALS sweep): 3xFP16 fused kernel
+	if (d->use_tensor_cores && d->k >= 1 && !d->do_col && d->nb <= 128 && rwr_fused_level() >= 2 && rwr_f16_enabled() &&
+	    ((uintptr_t)out & 15) == 0 && (out_cell_stride & 3) == 0) {
+		const int ld16 = (d->ldw + 7) & ~7;
+		const long long acs16 = (long long)d->nb * ld16;
+		FH_CUDA(cudaMemsetAsync(ws.amax, 0, 4, st));
+		csr_absmax_kernel<<<296, 256, 0, st>>>(rowptr, val, (long long)d->cell0 * d->nb, (long long)(d->cell0 + d->ncell) * d->nb, ws.amax);
+		FH_LAUNCH_CHECK();
+		const size_t smem = densify_smem_bytes(d->ldw);
+		if (smem > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(densify_conv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		dim3 grid(fh_cdiv(d->nb, RT), d->ncell);
+		const int tmr = fh_time_begin(FH_TIME_DENSIFY, st);
+		densify_conv_kernel<false, true><<<grid, 256, smem, st>>>(rowptr, col, val, d->nnz, nullptr, 0, d->cell0, d->nb, d->w, d->ldw,
+		                                                         conv, ws.A, acs16, ld16, (long long)d->ncell * acs16, ws.amax);
+		fh_time_end(tmr, st);
+		FH_LAUNCH_CHECK();
+		rc = fh_rwr_chain16(ws.A, ws.amax, out, d->nb, d->w, d->ldw, ld16, d->s, d->k, d->ncell, acs16, out_cell_stride, st);
+		if (rc == FH_OK) {
+			if (host_n_iter) *host_n_iter = d->k;
+			return FH_OK;
+		}
+		if (rc != FH_ERR_UNSUPPORTED) return rc;
+		fh_count_tc_fallback();
+	}
 	rc = launch_densify(d, false, rowptr, col, val, nullptr, 0, conv, ws.A, (long long)d->nb * d->ldw, st);
 	if (rc) return rc;
 	return rwr_from_panel(d, ws, bin_cov, bin_cov_ld, out, out_cell_stride, host_n_iter, st);

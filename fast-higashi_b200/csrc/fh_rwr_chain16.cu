@@ -1,0 +1,552 @@
+// Fused RWR imputation of one bin block from the conv'd panel A (reference: partial_rwr.py:80-126, :138), 3xFP16 variant:
+//   S2 = A A^T;  P = colnorm(3/4 colnorm(A_diag_block) + 1/4 colnorm(S2 - diag))
+//   Q_1 = 0.5 P + 0.5 I,   Q_{t+1} = 0.5 Q_t P + 0.5 I  (t = 1 .. k-1),   X = Q_k A
+// for every cell of the chunk in ONE persistent tcgen05 kernel, like fh_rwr_chain.cu, but every operand is a pair of
+// binary16 values (hi = rn16(s x), lo = rn16(s x - hi), s a power of two: 22 significand bits, the same as the two TF32
+// halves) and the three products hi hi + hi lo + lo hi run as kind::f16 MMAs: twice the tensor-pipe rate of kind::tf32 and
+// half the shared-memory bytes per operand (scripts/split_precision_study.py: operand error 1.2e-7 on the RWR chain).
+// What that changes in the data flow:
+//   * the conv'd panel arrives ALREADY SPLIT: densify_conv_kernel<.., true> (fh_rwr.cu) writes it as two binary16 planes
+//     (same bytes as fp32), scaled by the power of two that brings the block's largest CSR value into [2^13, 2^14)
+//     (device word `amax`); TMA lands the tiles in the layouts the MMAs read (K-major SWIZZLE_128B for S2, MN-major
+//     SWIZZLE_128B for X = Q A) - there are no splitter warps and no generic-proxy pass over the ring;
+//   * P never leaves the SM: the drain warps write its hi / lo tiles (scaled by 2^14) straight into a dedicated
+//     shared-memory operand (MN-major SWIZZLE_128B, conflict-free 16-byte stores) - no global scratch round trip;
+//   * Q (scaled by 2^14) lives in TENSOR MEMORY as packed halves (two per 32-bit column) and is the A operand of every
+//     MMA of the chain and of X = Q A.
+// TMEM (512 columns): Q_hi [0,64) | Q_lo [64,128) | parked first-order block [128,256) | accumulators [256,384) [384,512)
+// Roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 drain.
+// Accumulation control as in fh_gemm_tc.cu: S2 chunks of K = 128 alternate between the two accumulators and are summed in
+// registers with round-to-nearest adds; the chain's and X's products have K = nb <= 128.
+#include <cuda_fp16.h>
+#include "fh_tc.cuh"
+#include "../../include/fh_b200.h"
+
+namespace {
+using namespace fh_tc;
+
+constexpr int BM = 128, BN = 128, BK = 64;      // k-block: 64 halves = one 128-byte swizzled row
+constexpr int PLANE_BYTES = BK * BN * 2;        // 16 KB: the hi (or lo) tile of a slot
+constexpr int SLOT_BYTES = 2 * PLANE_BYTES;     // hi | lo
+constexpr int SLOTS = 3;
+constexpr int P_PLANE = 128 * 128 * 2;          // P hi (or lo): [n group (2)][k row (128)][128 B]
+constexpr int EPI_BYTES = 8 * 32 * 32 * 4;      // 8 drain warps x (32 x 32 floats)
+constexpr int XCH_FLOATS = 10 * 128;            // column partials [4][128], row sums [2][128], cs1 / w1 / w2 / flag [128]
+constexpr int NTHREADS = 384;
+constexpr int SMEM_BYTES = SLOTS * SLOT_BYTES + 2 * P_PLANE + EPI_BYTES + XCH_FLOATS * 4 + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int CHUNK_KB = 2;                     // S2: k-blocks (K = 128) accumulated in TMEM before a drain
+constexpr float EPS = 1e-15f;                   // partial_rwr.py:88-97
+constexpr uint32_t TM_QHI = 0, TM_QLO = 64, TM_PARK = 128, TM_ACC = 256;
+constexpr float QS = 16384.f;                   // scale of Q and P (entries in [0, 1])
+constexpr float QS_INV2 = 1.f / (16384.f * 16384.f);
+
+struct Chain16P {
+	int nb, w, ldw, ld16, k, ncell;
+	long long a_cell_stride, out_cell_stride;  // halves / floats
+	const __half* Ahi;     // planes: hi at Ahi, lo at Ahi + ncell * a_cell_stride
+	const unsigned* amax;  // bits of the largest (floored) CSR value of the block: fixes the panel's scale
+	int s;
+	float* out;
+	long long* trace;      // FH_CHAIN_TRACE=1: clock64 stamps of CTA 0's 4th cell (debug)
+};
+#define FH_TRACE(slot)                                                         \
+	do {                                                                       \
+		if (p.trace && blockIdx.x == 0 && cell == 3 * (int)gridDim.x) p.trace[slot] = clock64(); \
+	} while (0)
+
+// tmK: the planes as K-major boxes of 64 window columns x 128 rows (S2); tmA: as MN-major boxes of 64 window columns x
+// 64 bin rows (B tiles of X = Q A); plane / cell folded: z = cell (hi), ncell + cell (lo); tmO: X as 32 x 32 store boxes
+__global__ void __launch_bounds__(NTHREADS, 1)
+rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmA,
+                   const __grid_constant__ CUtensorMap tmO, Chain16P p) {
+	extern __shared__ uint8_t smem_raw[];
+	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	uint8_t* pbuf = smem + SLOTS * SLOT_BYTES;                 // P hi | P lo
+	uint8_t* stagebuf = pbuf + 2 * P_PLANE;
+	float* xch = (float*)(stagebuf + EPI_BYTES);
+	uint64_t* bars = (uint64_t*)(stagebuf + EPI_BYTES + XCH_FLOATS * 4);
+	uint64_t* full = bars;                        // TMA landed                  (count 1 + tx)
+	uint64_t* empty = bars + SLOTS;               // MMAs reading the slot done  (tcgen05.commit)
+	uint64_t* acc_full = bars + 2 * SLOTS;        // [2] accumulator complete    (tcgen05.commit)
+	uint64_t* acc_empty = bars + 2 * SLOTS + 2;   // [2] accumulator drained     (count 8: drain warps)
+	uint64_t* q_ready = bars + 2 * SLOTS + 4;     // Q hi / lo stored in TMEM    (count 8: drain warps)
+	uint64_t* p_written = bars + 2 * SLOTS + 5;   // P of the current cell is in shared memory (count 1)
+	uint32_t* tmem_holder = (uint32_t*)(bars + 2 * SLOTS + 6);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int nkb = (p.nb + BK - 1) / BK;         // k-blocks of the bin dimension (K of X = Q A)
+	const int NT = (p.ldw + BN - 1) / BN;         // 128-column tiles of the window
+	const int nkw = (p.w + BK - 1) / BK;          // k-blocks of the window (K of S2)
+	const int n_last = (p.ldw - (NT - 1) * BN + 15) & ~15;  // MMA width of the last window tile (multiple of 16)
+	const int box_last = (n_last + 63) / 64;                // its 64-column TMA boxes
+	const int n_step = (p.nb + 15) & ~15;                   // MMA width / K extent of the chain's products
+	const bool chain = p.k > 1;
+
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < SLOTS; ++s) {
+			mbar_init(&full[s], 1);
+			mbar_init(&empty[s], 1);
+		}
+		mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+		mbar_init(&acc_empty[0], 8); mbar_init(&acc_empty[1], 8);
+		mbar_init(q_ready, 8);
+		mbar_init(p_written, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 0 && lane == 0) {
+		asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmK) : "memory");
+		asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+		asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmO) : "memory");
+	}
+	if (warp == 2) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t tmem = *tmem_holder;
+
+	if (warp == 0) {
+		// ------------------------------------------------------------------ TMA producer
+		if (lane == 0) {
+			long long it = 0;
+			for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x) {
+				const int nslots = nkw + NT * nkb;
+				for (int j = 0; j < nslots; ++j, ++it) {
+					const int s = (int)(it % SLOTS);
+					mbar_wait(&empty[s], (uint32_t)(((it / SLOTS) & 1) ^ 1));
+					uint8_t* dst = smem + s * SLOT_BYTES;
+					if (j < nkw) {  // S2: one K-major box of 128 rows x 64 window columns per plane
+						if (j == 0) FH_TRACE(0);
+						mbar_expect_tx(&full[s], SLOT_BYTES);
+						tma_load_3d(dst, &tmK, &full[s], j * BK, 0, cell);
+						tma_load_3d(dst + PLANE_BYTES, &tmK, &full[s], j * BK, 0, p.ncell + cell);
+						if (j == nkw - 1) {
+							FH_TRACE(1);
+							// next cell's panel -> L2 while this cell's transition and step chain keep the TMA unit idle
+							if (cell + (int)gridDim.x < p.ncell)
+								for (int jj = 0; jj < nkw; ++jj) {
+									tma_prefetch_3d(&tmK, jj * BK, 0, cell + gridDim.x);
+									tma_prefetch_3d(&tmK, jj * BK, 0, p.ncell + cell + gridDim.x);
+								}
+						}
+						continue;
+					}
+					const int t = j - nkw, nt = t / nkb, kb = t % nkb;
+					const int nbox = (nt == NT - 1) ? box_last : BN / 64;  // the last window tile may be narrower
+					mbar_expect_tx(&full[s], 2 * nbox * (BK * 128));
+					for (int g = 0; g < nbox; ++g) {
+						tma_load_3d(dst + g * (BK * 128), &tmA, &full[s], nt * BN + 64 * g, kb * BK, cell);
+						tma_load_3d(dst + PLANE_BYTES + g * (BK * 128), &tmA, &full[s], nt * BN + 64 * g, kb * BK, p.ncell + cell);
+					}
+					if (j == nslots - 1) FH_TRACE(3);
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ------------------------------------------------------------------ MMA issuer
+		if (lane == 0) {
+			const uint32_t idesc_kk = make_idesc_f16(false, false, BN, BM);        // S2: both operands K-major
+			const uint32_t idesc_st = make_idesc_f16(false, true, n_step, BM);     // chain: B = P, MN-major
+			const uint32_t idesc_x = make_idesc_f16(false, true, BN, BM);          // X: B = panel tile, MN-major
+			const uint32_t idesc_xl = make_idesc_f16(false, true, n_last, BM);
+			const uint32_t p_hi = smem_u32(pbuf), p_lo = p_hi + P_PLANE;
+			long long it = 0, ch = 0, qn = 0, ncell_done = 0;
+			for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x, ++ncell_done) {
+				FH_TRACE(8);
+				// S2 = A A^T: the landed K-major tiles (SWIZZLE_128B: 128-byte rows, 8-row groups 1024 B apart, a K = 16
+				// step = +32 B) are both operands; accumulator chunks of CHUNK_KB k-blocks alternate buffers
+				for (int kb = 0; kb < nkw; ++kb, ++it) {
+					const int cb = (int)(ch & 1);
+					const long long tw2 = p.trace ? clock64() : 0;
+					if (kb % CHUNK_KB == 0) {
+						mbar_wait(&acc_empty[cb], (uint32_t)(((ch >> 1) & 1) ^ 1));
+						asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					}
+					const long long tw3 = p.trace ? clock64() : 0;
+					const uint32_t acc = tmem + TM_ACC + (uint32_t)(cb * BN);
+					const int s = (int)(it % SLOTS);
+					mbar_wait(&full[s], (uint32_t)((it / SLOTS) & 1));
+					if (p.trace && blockIdx.x == 0 && cell == 3 * (int)gridDim.x) { p.trace[6] += tw3 - tw2; p.trace[5] += clock64() - tw3; }
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					const uint32_t hi = smem_u32(smem + s * SLOT_BYTES), lo = hi + PLANE_BYTES;
+					const int nk = min(BK, p.w - kb * BK);
+					const int nk4 = (nk + 15) >> 4;
+					for (int k4 = 0; k4 < nk4; ++k4) {
+						const uint64_t dh = make_desc(hi + k4 * 32, 16, 1024, 2), dl = make_desc(lo + k4 * 32, 16, 1024, 2);
+						umma_f16(acc, dl, dh, idesc_kk, ((kb % CHUNK_KB) | k4) ? 1u : 0u);  // small terms first
+						umma_f16(acc, dh, dl, idesc_kk, 1u);
+						umma_f16(acc, dh, dh, idesc_kk, 1u);
+					}
+					umma_commit(&empty[s]);
+					if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkw - 1) {
+						umma_commit(&acc_full[cb]);
+						++ch;
+					}
+				}
+				FH_TRACE(9);
+				if (chain) {
+					// Q_{t+1} = 0.5 Q_t P + 0.5 I: A = Q from TMEM (K = 16 step = +8 columns), B = P in shared memory (MN-major:
+					// 64-wide n groups 16 KB apart, 8-row k groups 1024 B apart, a K = 16 step = +2048 B)
+					mbar_wait(p_written, (uint32_t)(ncell_done & 1));
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					const int nks = n_step >> 4;
+					for (int step = 1; step < p.k; ++step) {
+						mbar_wait(q_ready, (uint32_t)(qn & 1)); ++qn;
+						if (step == 2) FH_TRACE(30);
+						const int cb = (int)(ch & 1);
+						mbar_wait(&acc_empty[cb], (uint32_t)(((ch >> 1) & 1) ^ 1));
+						asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+						const uint32_t acc = tmem + TM_ACC + (uint32_t)(cb * BN);
+						for (int ks = 0; ks < nks; ++ks) {
+							const uint32_t a_hi = tmem + TM_QHI + (uint32_t)(8 * ks), a_lo = tmem + TM_QLO + (uint32_t)(8 * ks);
+							const uint64_t dbh = make_desc(p_hi + ks * 2048, 128 * 128, 1024, 2);
+							const uint64_t dbl = make_desc(p_lo + ks * 2048, 128 * 128, 1024, 2);
+							umma_f16_ts(acc, a_lo, dbh, idesc_st, ks ? 1u : 0u);  // small terms first
+							umma_f16_ts(acc, a_hi, dbl, idesc_st, 1u);
+							umma_f16_ts(acc, a_hi, dbh, idesc_st, 1u);
+						}
+						umma_commit(&acc_full[cb]);
+						++ch;
+						if (step == 1) FH_TRACE(29);
+					}
+				}
+				FH_TRACE(10);
+				mbar_wait(q_ready, (uint32_t)(qn & 1)); ++qn;   // Q_k
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				FH_TRACE(11);
+				for (int nt = 0; nt < NT; ++nt) {
+					const int cb = (int)(ch & 1);
+					const long long tw1 = p.trace ? clock64() : 0;
+					mbar_wait(&acc_empty[cb], (uint32_t)(((ch >> 1) & 1) ^ 1));
+					if (p.trace && blockIdx.x == 0 && cell == 3 * (int)gridDim.x) p.trace[14] += clock64() - tw1;
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					const uint32_t acc = tmem + TM_ACC + (uint32_t)(cb * BN);
+					const uint32_t idesc = nt == NT - 1 ? idesc_xl : idesc_x;
+					for (int kb = 0; kb < nkb; ++kb, ++it) {
+						const int s = (int)(it % SLOTS);
+						const long long tw0 = p.trace ? clock64() : 0;
+						mbar_wait(&full[s], (uint32_t)((it / SLOTS) & 1));
+						if (p.trace && blockIdx.x == 0 && cell == 3 * (int)gridDim.x) p.trace[13] += clock64() - tw0;
+						asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+						const uint32_t hi = smem_u32(smem + s * SLOT_BYTES), lo = hi + PLANE_BYTES;
+						const int nk4 = (min(BK, n_step - kb * BK) + 15) >> 4;
+						for (int k4 = 0; k4 < nk4; ++k4) {
+							const uint32_t qc = (uint32_t)(kb * (BK / 2) + 8 * k4);
+							const uint64_t dbh = make_desc(hi + k4 * 2048, BK * 128, 1024, 2);
+							const uint64_t dbl = make_desc(lo + k4 * 2048, BK * 128, 1024, 2);
+							umma_f16_ts(acc, tmem + TM_QLO + qc, dbh, idesc, (kb | k4) ? 1u : 0u);  // small terms first
+							umma_f16_ts(acc, tmem + TM_QHI + qc, dbl, idesc, 1u);
+							umma_f16_ts(acc, tmem + TM_QHI + qc, dbh, idesc, 1u);
+						}
+						umma_commit(&empty[s]);
+					}
+					umma_commit(&acc_full[cb]);
+					++ch;
+				}
+				FH_TRACE(12);
+			}
+		}
+	} else if (warp >= 4) {
+		// ------------------------------------------------------------------ drain: accumulator -> P, Q / X
+		const int q = warp & 3;             // TMEM lane quarter of this warp (rows 32q .. 32q+31)
+		const int h = (warp - 4) >> 2;      // column half (64 columns)
+		const int m = q * 32 + lane;        // this thread's row
+		const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+		float* tile_s = (float*)(stagebuf + (warp - 4) * (32 * 32 * 4));
+		// the panel's scale: amax * sa in [2^13, 2^14)
+		const unsigned abits = max(*p.amax, __float_as_uint(1e-8f));
+		const float sa_inv = __uint_as_float(((abits >> 23) - 13u) << 23);
+		const float s2_scale = sa_inv * sa_inv, x_scale = sa_inv * (1.f / QS);
+		// 32 values of Q (this thread's row, columns 64h + 32c ..) -> TMEM hi / lo halves, scaled by 2^14
+		auto store_q_chunk = [&](int c, const float (&qv)[32]) {
+			uint32_t hi[16], lo[16];
+#pragma unroll
+			for (int j = 0; j < 16; ++j) f16_split2(qv[2 * j] * QS, qv[2 * j + 1] * QS, hi[j], lo[j]);
+			tmem_st16(tmem + lane_addr + TM_QHI + (uint32_t)(h * 32 + c * 16), hi);
+			tmem_st16(tmem + lane_addr + TM_QLO + (uint32_t)(h * 32 + c * 16), lo);
+		};
+		auto publish_q = [&]() {
+			tmem_st_wait();
+			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+			__syncwarp();
+			if (lane == 0) mbar_arrive(q_ready);
+		};
+		auto drain_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };  // the 8 drain warps
+		float* colpart = xch;                  // [4][128] per-row-quarter column sums
+		float* rowsum = xch + 4 * 128;         // [2][128] S2 row sums of the two column halves
+		float* cs1raw = xch + 6 * 128;         // column sums of the first-order block
+		float* w1 = xch + 7 * 128;             // per-column weights of the first / second order parts of P
+		float* w2 = xch + 8 * 128;
+		float* cflag = xch + 9 * 128;          // empty column of the blend: its diagonal entry (partial_rwr.py:96-97)
+		const int td = threadIdx.x - 128;      // 0..255 among the drain warps
+		const long long lo_plane = (long long)p.ncell * p.a_cell_stride;
+		// this thread's row of P in the shared-memory operand: k row m of n group h; 16-byte chunk i at (i ^ (m & 7))
+		uint8_t* prow = pbuf + h * (128 * 128) + (m >> 3) * 1024 + (m & 7) * 128;
+		long long ch = 0;
+		for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x) {
+			// first-order block A[32q + r][s + 64h + 32c + lane], r = 0..31, from the two planes: COALESCED (a warp reads one
+			// 64-byte row segment per plane and instruction)
+			const __half* ablk = p.Ahi + (long long)cell * p.a_cell_stride + (long long)(q * 32) * p.ld16 + p.s + h * 64 + lane;
+			// ---- A (independent of S2: runs under the S2 MMAs): column sums of the first-order block; the block itself is
+			// transposed to one row per lane through the staging tile (word (r, j) at r*32 + (j ^ r)) and parked in TMEM
+#pragma unroll 1
+			for (int c = 0; c < 2; ++c) {
+				const bool colok = h * 64 + c * 32 + lane < p.nb;
+				float v[32];
+#pragma unroll
+				for (int r = 0; r < 32; ++r) {
+					float x = 0.f;
+					if (colok && q * 32 + r < p.nb) {
+						const __half* e = ablk + (long long)r * p.ld16 + c * 32;
+						x = (__half2float(e[0]) + __half2float(e[lo_plane])) * sa_inv;
+					}
+					v[r] = x;
+				}
+				float cs = 0.f;
+#pragma unroll
+				for (int r = 0; r < 32; ++r) cs += v[r];
+				colpart[q * 128 + h * 64 + c * 32 + lane] = cs;
+				if (lane == 0) tma_store_wait_read();  // the tile may still feed an X store
+				__syncwarp();
+#pragma unroll
+				for (int r = 0; r < 32; ++r) tile_s[r * 32 + (lane ^ r)] = v[r];
+				__syncwarp();
+				uint32_t fu[32];
+#pragma unroll
+				for (int j = 0; j < 32; ++j) fu[j] = __float_as_uint(tile_s[lane * 32 + (j ^ lane)]);
+				__syncwarp();
+				tmem_st32(tmem + lane_addr + TM_PARK + (uint32_t)(h * 64 + c * 32), fu);
+			}
+			tmem_st_wait();
+			if (td == 0) FH_TRACE(26);
+			drain_sync();
+			if (td < 128) cs1raw[td] = (colpart[td] + colpart[128 + td]) + (colpart[256 + td] + colpart[384 + td]);
+			// ---- B: S2 row (this warp's 64 columns), chunks summed with round-to-nearest adds
+			float sum[64];
+#pragma unroll
+			for (int j = 0; j < 64; ++j) sum[j] = 0.f;
+			const int nchunk = (nkw + CHUNK_KB - 1) / CHUNK_KB;
+			for (int chunk = 0; chunk < nchunk; ++chunk, ++ch) {
+				const int cb = (int)(ch & 1);
+				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+				for (int c = 0; c < 2; ++c) {
+					uint32_t v[32];
+					tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 64 + c * 32), v);
+#pragma unroll
+					for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(v[j]);
+				}
+				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&acc_empty[cb]);
+			}
+			if (td == 0) FH_TRACE(16);
+			// second-order affinity without its diagonal; S2 is symmetric, so its column sums are row sums
+			float rs = 0.f;
+#pragma unroll
+			for (int j = 0; j < 64; ++j) {
+				const int col = h * 64 + j;
+				const float x = (m < p.nb && col < p.nb && col != m) ? sum[j] * s2_scale : 0.f;
+				sum[j] = x;
+				rs += x;
+			}
+			rowsum[h * 128 + m] = rs;
+			drain_sync();
+			if (td == 0) FH_TRACE(17);
+			// per column j: P[i][j] = (3/4 f/(cs1+eps) + 1/4 h/(cs2+eps)) / (csl+eps) = f w1[j] + h w2[j]. The column
+			// sum of the blend is taken analytically, csl = 3/4 cs1/(cs1+eps) + 1/4 cs2/(cs2+eps) (the reference
+			// sums the rounded entries: same value to fp32 rounding), partial_rwr.py:88-97
+			if (td < 128) {
+				const float c1 = cs1raw[td], c2 = rowsum[td] + rowsum[128 + td];
+				const float r1 = 1.f / (c1 + EPS), r2 = 1.f / (c2 + EPS);
+				float csl = 0.75f * (c1 * r1) + 0.25f * (c2 * r2);
+				const bool empty_col = (csl == 0.f) && td < p.nb;  // unreachable after the 1e-8 floor; kept for parity
+				if (empty_col) csl = 1.f;
+				const float rl = 1.f / (csl + EPS);
+				w1[td] = 0.75f * r1 * rl;
+				w2[td] = 0.25f * r2 * rl;
+				cflag[td] = empty_col ? rl : 0.f;
+			}
+			drain_sync();
+			if (td == 0) FH_TRACE(18);
+			// ---- C: P -> shared-memory B operand of the chain (hi / lo halves); Q_1 = 0.5 P + 0.5 I -> TMEM
+#pragma unroll
+			for (int c = 0; c < 2; ++c) {
+				uint32_t fu[32];
+				tmem_ld32(tmem + lane_addr + TM_PARK + (uint32_t)(h * 64 + c * 32), fu);
+				float pv[32];
+#pragma unroll
+				for (int j = 0; j < 32; ++j) {
+					const int col = h * 64 + c * 32 + j;
+					float x = __uint_as_float(fu[j]) * w1[col] + sum[c * 32 + j] * w2[col];  // 0 outside nb x nb
+					if (m == col) x += cflag[col];
+					pv[j] = x;
+				}
+				if (chain) {
+#pragma unroll
+					for (int g = 0; g < 4; ++g) {  // 8 columns = one 16-byte chunk per plane
+						uint4 vh, vl;
+						f16_split2(pv[8 * g] * QS, pv[8 * g + 1] * QS, vh.x, vl.x);
+						f16_split2(pv[8 * g + 2] * QS, pv[8 * g + 3] * QS, vh.y, vl.y);
+						f16_split2(pv[8 * g + 4] * QS, pv[8 * g + 5] * QS, vh.z, vl.z);
+						f16_split2(pv[8 * g + 6] * QS, pv[8 * g + 7] * QS, vh.w, vl.w);
+						const int off = ((c * 4 + g) ^ (m & 7)) * 16;
+						*reinterpret_cast<uint4*>(prow + off) = vh;
+						*reinterpret_cast<uint4*>(prow + P_PLANE + off) = vl;
+					}
+				}
+#pragma unroll
+				for (int j = 0; j < 32; ++j) pv[j] = 0.5f * pv[j] + ((m == h * 64 + c * 32 + j && m < p.nb) ? 0.5f : 0.f);
+				store_q_chunk(c, pv);
+			}
+			if (chain) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of P -> UMMA
+			publish_q();
+			if (td == 0) FH_TRACE(19);
+			if (chain) {
+				drain_sync();
+				if (td == 0) mbar_arrive(p_written);
+			}
+			for (int step = 1; step < p.k; ++step) {
+				const int cb = (int)(ch & 1);
+				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				if (td == 0 && step == 1) FH_TRACE(27);
+#pragma unroll
+				for (int c = 0; c < 2; ++c) {
+					uint32_t v[32];
+					tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 64 + c * 32), v);
+					float qv[32];
+#pragma unroll
+					for (int j = 0; j < 32; ++j) {
+						const int col = h * 64 + c * 32 + j;
+						float r = (0.5f * QS_INV2) * __uint_as_float(v[j]);
+						if (m == col && m < p.nb) r += 0.5f;
+						qv[j] = col < n_step ? r : 0.f;  // accumulator columns beyond the MMA's N were never written
+					}
+					store_q_chunk(c, qv);  // every MMA that read the old Q completed before acc_full fired
+				}
+				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&acc_empty[cb]);
+				++ch;
+				publish_q();
+				if (td == 0 && step == 1) FH_TRACE(28);
+			}
+			if (td == 0) FH_TRACE(20);
+			for (int nt = 0; nt < NT; ++nt) {
+				const int cb = (int)(ch & 1);
+				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				float xs[64];
+#pragma unroll
+				for (int c = 0; c < 2; ++c) {
+					uint32_t v[32];
+					tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 64 + c * 32), v);
+#pragma unroll
+					for (int j = 0; j < 32; ++j) xs[c * 32 + j] = __uint_as_float(v[j]) * x_scale;
+				}
+				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&acc_empty[cb]);
+				++ch;
+				if (td == 0) FH_TRACE(21 + nt);
+				// each lane lays its row into the warp's staging tile in the 128-byte-swizzle pattern (16-byte chunk g
+				// of row r at g ^ (r & 7): four wavefronts per 512-byte store, the minimum), one TMA store per
+				// 32 x 32 chunk; rows >= nb and columns >= ldw are clipped by the tensor map
+#pragma unroll
+				for (int c = 0; c < 2; ++c) {
+					const int n0 = nt * BN + h * 64 + c * 32;
+					if (lane == 0) tma_store_wait_read();
+					__syncwarp();
+					float4* rowp = reinterpret_cast<float4*>(tile_s) + lane * 8;
+#pragma unroll
+					for (int g = 0; g < 8; ++g)
+						rowp[g ^ (lane & 7)] = make_float4(xs[c * 32 + 4 * g], xs[c * 32 + 4 * g + 1], xs[c * 32 + 4 * g + 2], xs[c * 32 + 4 * g + 3]);
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					__syncwarp();
+					if (lane == 0 && n0 < p.ldw && q * 32 < p.nb) {
+						tma_store_3d(&tmO, tile_s, n0, q * 32, cell);
+						tma_store_commit();
+					}
+				}
+			}
+			if (td == 0) FH_TRACE(25);
+		}
+		if (lane == 0) tma_store_wait_all();
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	if (warp == 2) {
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+	}
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+
+// Ahi: two binary16 planes (hi, then lo at + ncell * a_cell_stride halves) of (ncell, nb, ld16) conv'd panels scaled as
+// described at the top (written by densify_conv_kernel<.., true>); amax: the device word that fixes the scale;
+// out: cell c at out + c * out_cell_stride, rows of ldw floats (16-byte aligned). Returns FH_ERR_UNSUPPORTED (nothing
+// launched) when the shape is outside the kernel's range - the caller runs the TF32 kernels.
+int fh_rwr_chain16(const void* Ahi, const unsigned* amax, float* out, int nb, int w, int ldw, int ld16, int s, int k,
+                   int ncell, long long a_cell_stride, long long out_cell_stride, void* stream) {
+	if (ncell <= 0) return FH_OK;
+	if (nb > BM || k < 1 || (ldw & 3) || (ld16 & 7) || (a_cell_stride & 7) || !aligned16(Ahi) || !aligned16(out) ||
+	    (out_cell_stride & 3)) {
+		fh_set_error("fh_rwr_chain16: shape outside the fused kernel (nb <= 128, k >= 1, 16-byte aligned rows)");
+		return FH_ERR_UNSUPPORTED;
+	}
+	static int num_sms = 0;
+	if (!num_sms) {
+		int dev = 0;
+		FH_CUDA(cudaGetDevice(&dev));
+		FH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+	}
+	const int grid = ncell < num_sms ? ncell : num_sms;
+	CUtensorMap tk, ta, to;
+	// the contiguous extent is the LOGICAL width, so pad columns and rows beyond nb read as zeros whatever the buffers hold
+	bool ok = make_map16(&tk, Ahi, w, nb, ld16, 2LL * ncell, a_cell_stride, BK, BM) &&
+	          make_map16(&ta, Ahi, w, nb, ld16, 2LL * ncell, a_cell_stride, 64, BK) &&
+	          make_map(&to, out, ldw, nb, ldw, ncell, out_cell_stride, 32, 32, false);
+	if (!ok) {
+		fh_set_error("fh_rwr_chain16: cuTensorMapEncodeTiled failed");
+		return FH_ERR_UNSUPPORTED;
+	}
+	Chain16P p;
+	p.nb = nb; p.w = w; p.ldw = ldw; p.ld16 = ld16; p.k = k; p.ncell = ncell;
+	p.a_cell_stride = a_cell_stride; p.out_cell_stride = out_cell_stride;
+	p.Ahi = (const __half*)Ahi; p.amax = amax; p.s = s; p.out = out;
+	cudaStream_t st = (cudaStream_t)stream;
+	static int trace_on = -1;
+	if (trace_on < 0) { const char* e = getenv("FH_CHAIN_TRACE"); trace_on = (e && e[0] == '1') ? 1 : 0; }
+	p.trace = nullptr;
+	if (trace_on) {
+		FH_CUDA(cudaMalloc(&p.trace, 32 * sizeof(long long)));
+		FH_CUDA(cudaMemsetAsync(p.trace, 0, 32 * sizeof(long long), st));
+	}
+	static bool attr_set = false;
+	if (!attr_set) {
+		FH_CUDA(cudaFuncSetAttribute(rwr_chain16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+		attr_set = true;
+	}
+	const int tmr = fh_time_begin(FH_TIME_RWR_CHAIN, st);
+	rwr_chain16_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tk, ta, to, p);
+	fh_time_end(tmr, st);
+	FH_LAUNCH_CHECK();
+	if (trace_on) {  // debug only: synchronises and prints the phase stamps (SM clocks relative to stamp 8)
+		long long h[32];
+		FH_CUDA(cudaMemcpyAsync(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost, st));
+		FH_CUDA(cudaStreamSynchronize(st));
+		FH_CUDA(cudaFree(p.trace));
+		long long t0 = h[8] ? h[8] : h[0];
+		fprintf(stderr, "[chain16 trace] nb=%d w=%d k=%d:", nb, w, k);
+		for (int i = 0; i < 32; ++i)
+			if (h[i]) fprintf(stderr, " %d:%lld", i, (i == 5 || i == 6 || i == 13 || i == 14) ? h[i] : h[i] - t0);  // 5/6/13/14: summed waits
+		fprintf(stderr, "\n");
+	}
+	return FH_OK;
+}

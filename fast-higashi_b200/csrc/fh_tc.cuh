@@ -125,6 +125,52 @@ __device__ __forceinline__ uint32_t tf32_lo(float v) {
 	return tf32_rn(__float_as_uint(v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u)));
 }
 
+
+// ---- kind::f16 (binary16 operands, fp32 accumulate), layouts confirmed on a B200 by scripts/umma_f16_probe.cu:
+// K-major SWIZZLE_128B rows of 64 halves (K = 16 step = +32 B) / SWIZZLE_64B rows of 32 halves; MN-major SWIZZLE_128B
+// (64-wide n groups LBO apart, 8-row k groups SBO = 1024 B apart, K = 16 step = +2048 B); A from TMEM = two halves per
+// 32-bit column, even k in the low half (K = 16 step = +8 columns).
+// instruction descriptor: c_format F32 [4,6) = 1, a/b_format F16 = 0
+__device__ __forceinline__ uint32_t make_idesc_f16(bool a_mn, bool b_mn, int n, int m) {
+	return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"setp.ne.b32 p, %4, 0;\n"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+		"}\n" ::"r"(tmem_d),
+		"l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+		: "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"setp.ne.b32 p, %4, 0;\n"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+		"}\n" ::"r"(tmem_d),
+		"r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+		: "memory");
+}
+// 32 lanes x 16 columns of registers -> TMEM
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+	asm volatile(
+		"tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+		"{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+		"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+		"r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+		: "memory");
+}
+// 3xFP16 split of a (pre-scaled) pair: hi = rn16(x), lo = rn16(x - hi); returns the two packed pairs (first value in the low half)
+__device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+	asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+	float fa, fb;
+	asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}\n" : "=f"(fa), "=f"(fb) : "r"(hi));
+	asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - fb), "f"(a - fa));
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -154,5 +200,18 @@ inline bool make_map(CUtensorMap* m, const float* base, long long contig_extent,
 	return r == CUDA_SUCCESS;
 }
 
+// binary16 tensor (two planes folded into the batch dimension by the caller): box_contig <= 64 halves (128-byte swizzle)
+inline bool make_map16(CUtensorMap* m, const void* base, long long contig_extent, long long rows, long long row_stride,
+              long long batch, long long batch_stride, int box_contig, int box_rows) {
+	EncodeFn enc = get_encode();
+	if (!enc) return false;
+	cuuint64_t dims[3] = {(cuuint64_t)contig_extent, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
+	cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)batch_stride * 2};
+	cuuint32_t box[3] = {(cuuint32_t)box_contig, (cuuint32_t)box_rows, 1};
+	cuuint32_t es[3] = {1, 1, 1};
+	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return r == CUDA_SUCCESS;
+}
 
 }  // namespace fh_tc

@@ -432,7 +432,7 @@ def test_rwr_fused_chain_kernel(k):
 	assert _lib.lib().fh_tc_fallback_count() == fb0  # the tensor-core path really ran
 
 
-@pytest.mark.parametrize("env", [{"FH_RWR_FUSED": "1"}, {"FH_RWR_FUSED": "0"}, {"FH_CHAIN_DEBUG": "2"}])
+@pytest.mark.parametrize("env", [{"FH_RWR_F16": "0"}, {"FH_RWR_FUSED": "1"}, {"FH_RWR_FUSED": "0"}, {"FH_RWR_F16": "0", "FH_CHAIN_DEBUG": "2"}])
 def test_rwr_alternative_paths(env):
 	"""The library reads its path switches once per process, so the other RWR paths are exercised in a child
 	process: chain-only fusion (S2 / transition as separate kernels), the per-op tcgen05 GEMM chain, and the
