@@ -47,7 +47,7 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
                     const float* __restrict__ dense_in, long long in_cell_stride,
                     int cell0, int nb, int w, int ldw, int do_conv,
                     float* __restrict__ out, long long out_cell_stride,
-                    int ld16, long long lo_plane, const unsigned* __restrict__ amax) {
+                    int ld16, long long lo_plane, const unsigned* __restrict__ amax, int pad16) {
 	extern __shared__ __align__(16) float smem[];
 	const int tp = ldw + 8;
 	float* tile = smem;                                   // (RT+2) x tp
@@ -135,7 +135,8 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 	// the columns on them, one 128-bit global store per output row (ncu on the one-column version: issue slots 87 % busy,
 	// ALU the busiest pipe - the kernel was instruction bound at 2.2 TB/s, not memory bound).
 	float* dst = out + (long long)cell * out_cell_stride;
-	__half* dst16 = reinterpret_cast<__half*>(out) + (long long)cell * out_cell_stride;  // OUT16: strides in halves
+	// OUT16: strides in halves; window column c at plane column c + pad16 (pad16 = 0 or 4 leading zero columns)
+	__half* dst16 = reinterpret_cast<__half*>(out) + (long long)cell * out_cell_stride + pad16;
 	float sa = 1.f;
 	if (OUT16) {
 		const unsigned abits = max(*amax, __float_as_uint(FH_FLOOR));
@@ -182,8 +183,10 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 						o.y = m1 ? fmaxf(((h0.y + h1.y) + h2.y) * (1.0f / 9.0f), FH_FLOOR) : 0.f;
 						o.z = m2 ? fmaxf(((h0.z + h1.z) + h2.z) * (1.0f / 9.0f), FH_FLOOR) : 0.f;
 						o.w = m3 ? fmaxf(((h0.w + h1.w) + h2.w) * (1.0f / 9.0f), FH_FLOOR) : 0.f;
-						if (OUT16) store4_16(drow16 + (long long)k * ld16, lo_plane, o, sa);
-						else *reinterpret_cast<float4*>(drow + (long long)k * ldw) = o;
+						if (OUT16) {
+							store4_16(drow16 + (long long)k * ld16, lo_plane, o, sa);
+							if (pad16 && c == 0) store4_16(drow16 + (long long)k * ld16 - 4, lo_plane, make_float4(0.f, 0.f, 0.f, 0.f), 0.f);
+						} else *reinterpret_cast<float4*>(drow + (long long)k * ldw) = o;
 						h0 = h1; h1 = h2;
 					}
 				}
@@ -195,8 +198,10 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 			__half* drow16 = dst16 + (long long)(r0 + tr) * ld16;
 			const float4* trow = reinterpret_cast<const float4*>(tile + (tr + 1) * tp + 4);
 			for (int q = lane; q < ngrp; q += 32) {  // pad columns hold the background's zeros
-				if (OUT16) store4_16(drow16 + 4 * q, lo_plane, trow[q], sa);
-				else drow[q] = trow[q];
+				if (OUT16) {
+					store4_16(drow16 + 4 * q, lo_plane, trow[q], sa);
+					if (pad16 && q == 0) store4_16(drow16 - 4, lo_plane, make_float4(0.f, 0.f, 0.f, 0.f), 0.f);
+				} else drow[q] = trow[q];
 			}
 		}
 	}
@@ -401,6 +406,7 @@ csr_absmax_kernel(const int32_t* __restrict__ rowptr, const float* __restrict__ 
 }  // namespace
 extern "C" void fh_count_tc_fallback(void);
 size_t fh_rwr_chain_scratch_bytes();
+int fh_rwr_chain16_pad(int s);
 int fh_rwr_chain16(const void* Ahi, const unsigned* amax, float* out, int nb, int w, int ldw, int ld16, int s, int k,
                    int ncell, long long a_cell_stride, long long out_cell_stride, void* stream);
 int fh_rwr_chain(const float* P, const float* A, float* out, int nb, int w, int ldw, int ldp, int s, int k, int ncell,
@@ -420,7 +426,7 @@ RwrWs carve(const fh_rwr_desc* d, void* ws) {
 	RwrWs r;
 	const int ldp = (d->nb + 3) & ~3;
 	// the conv'd panel: fp32 rows of ldw floats, or two binary16 planes with rows of round_up(w, 8) halves
-	size_t a = align_up((size_t)d->ncell * d->nb * ((d->ldw + 7) & ~7) * 4, 256);
+	size_t a = align_up((size_t)d->ncell * d->nb * ((d->ldw + 4 + 7) & ~7) * 4, 256);
 	size_t p = align_up((size_t)d->ncell * d->nb * ldp * 4, 256);
 	char* b = (char*)ws;
 	r.A = (float*)b; b += a;
@@ -605,11 +611,11 @@ int launch_densify(const fh_rwr_desc* d, bool from_dense, const int32_t* rowptr,
 	if (from_dense) {
 		if (smem > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(densify_conv_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		densify_conv_kernel<true, false><<<grid, 256, smem, st>>>(nullptr, nullptr, nullptr, 0, dense_in, in_cs, 0, d->nb, d->w,
-		                                                         d->ldw, do_conv, out, out_cs, 0, 0, nullptr);
+		                                                         d->ldw, do_conv, out, out_cs, 0, 0, nullptr, 0);
 	} else {
 		if (smem > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(densify_conv_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		densify_conv_kernel<false, false><<<grid, 256, smem, st>>>(rowptr, col, val, d->nnz, nullptr, 0, d->cell0, d->nb, d->w,
-		                                                          d->ldw, do_conv, out, out_cs, 0, 0, nullptr);
+		                                                          d->ldw, do_conv, out, out_cs, 0, 0, nullptr, 0);
 	}
 	fh_time_end(tmr, st);
 	FH_LAUNCH_CHECK();
@@ -648,8 +654,9 @@ extern "C" int fh_rwr_batched(const fh_rwr_desc* d, const int32_t* rowptr, const
 	RwrWs ws = carve(d, workspace);
 	// forced step count without do_col on the tensor cores (every call of the ALS sweep): 3xFP16 fused kernel
 	if (d->use_tensor_cores && d->k >= 1 && !d->do_col && d->nb <= 128 && rwr_fused_level() >= 2 && rwr_f16_enabled() &&
-	    ((uintptr_t)out & 15) == 0 && (out_cell_stride & 3) == 0) {
-		const int ld16 = (d->ldw + 7) & ~7;
+	    ((uintptr_t)out & 15) == 0 && (out_cell_stride & 3) == 0 && (d->s & 3) == 0) {
+		const int pad16 = fh_rwr_chain16_pad(d->s);  // 0 or 4: the diagonal block starts at a multiple of 8 plane columns
+		const int ld16 = (d->ldw + pad16 + 7) & ~7;
 		const long long acs16 = (long long)d->nb * ld16;
 		FH_CUDA(cudaMemsetAsync(ws.amax, 0, 4, st));
 		csr_absmax_kernel<<<296, 256, 0, st>>>(rowptr, val, (long long)d->cell0 * d->nb, (long long)(d->cell0 + d->ncell) * d->nb, ws.amax);
@@ -659,7 +666,7 @@ extern "C" int fh_rwr_batched(const fh_rwr_desc* d, const int32_t* rowptr, const
 		dim3 grid(fh_cdiv(d->nb, RT), d->ncell);
 		const int tmr = fh_time_begin(FH_TIME_DENSIFY, st);
 		densify_conv_kernel<false, true><<<grid, 256, smem, st>>>(rowptr, col, val, d->nnz, nullptr, 0, d->cell0, d->nb, d->w, d->ldw,
-		                                                         conv, ws.A, acs16, ld16, (long long)d->ncell * acs16, ws.amax);
+		                                                         conv, ws.A, acs16, ld16, (long long)d->ncell * acs16, ws.amax, pad16);
 		fh_time_end(tmr, st);
 		FH_LAUNCH_CHECK();
 		rc = fh_rwr_chain16(ws.A, ws.amax, out, d->nb, d->w, d->ldw, ld16, d->s, d->k, d->ncell, acs16, out_cell_stride, st);

@@ -14,7 +14,11 @@
 //     shared-memory operand (MN-major SWIZZLE_128B, conflict-free 16-byte stores) - no global scratch round trip;
 //   * Q (scaled by 2^14) lives in TENSOR MEMORY as packed halves (two per 32-bit column) and is the A operand of every
 //     MMA of the chain and of X = Q A.
-// TMEM (512 columns): Q_hi [0,64) | Q_lo [64,128) | parked first-order block [128,256) | accumulators [256,384) [384,512)
+//   * the first-order block A[:, s:s+nb] is TMA-loaded (both planes) into the shared-memory region that P will occupy:
+//     the K-major tile of a 64-column box and the MN-major P operand put row m of column half h at the same 128 bytes,
+//     so every drain thread turns its own row of the block into its own row of P in place (no transposes through
+//     staging tiles, no global loads in the drain warps: those cost 14k of a cell's 47k cycles in the first version).
+// TMEM (512 columns): Q_hi [0,64) | Q_lo [64,128) | free [128,256) | accumulators [256,384) [384,512)
 // Roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 drain.
 // Accumulation control as in fh_gemm_tc.cu: S2 chunks of K = 128 alternate between the two accumulators and are summed in
 // registers with round-to-nearest adds; the chain's and X's products have K = nb <= 128.
@@ -31,17 +35,18 @@ constexpr int SLOT_BYTES = 2 * PLANE_BYTES;     // hi | lo
 constexpr int SLOTS = 3;
 constexpr int P_PLANE = 128 * 128 * 2;          // P hi (or lo): [n group (2)][k row (128)][128 B]
 constexpr int EPI_BYTES = 8 * 32 * 32 * 4;      // 8 drain warps x (32 x 32 floats)
-constexpr int XCH_FLOATS = 10 * 128;            // column partials [4][128], row sums [2][128], cs1 / w1 / w2 / flag [128]
+constexpr int XCH_FLOATS = 22 * 128;            // column partials [16][128], row sums [2][128], cs1 / w1 / w2 / flag [128]
 constexpr int NTHREADS = 384;
 constexpr int SMEM_BYTES = SLOTS * SLOT_BYTES + 2 * P_PLANE + EPI_BYTES + XCH_FLOATS * 4 + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int CHUNK_KB = 2;                     // S2: k-blocks (K = 128) accumulated in TMEM before a drain
 constexpr float EPS = 1e-15f;                   // partial_rwr.py:88-97
-constexpr uint32_t TM_QHI = 0, TM_QLO = 64, TM_PARK = 128, TM_ACC = 256;
+constexpr uint32_t TM_QHI = 0, TM_QLO = 64, TM_ACC = 256;
 constexpr float QS = 16384.f;                   // scale of Q and P (entries in [0, 1])
-constexpr float QS_INV2 = 1.f / (16384.f * 16384.f);
+constexpr float QS_INV = 1.f / 16384.f;
 
 struct Chain16P {
 	int nb, w, ldw, ld16, k, ncell;
+	int pad;               // plane column of window column 0: (s + pad) % 8 == 0 (TMA box starts must be 16-byte aligned)
 	long long a_cell_stride, out_cell_stride;  // halves / floats
 	const __half* Ahi;     // planes: hi at Ahi, lo at Ahi + ncell * a_cell_stride
 	const unsigned* amax;  // bits of the largest (floored) CSR value of the block: fixes the panel's scale
@@ -71,13 +76,15 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 	uint64_t* acc_empty = bars + 2 * SLOTS + 2;   // [2] accumulator drained     (count 8: drain warps)
 	uint64_t* q_ready = bars + 2 * SLOTS + 4;     // Q hi / lo stored in TMEM    (count 8: drain warps)
 	uint64_t* p_written = bars + 2 * SLOTS + 5;   // P of the current cell is in shared memory (count 1)
-	uint32_t* tmem_holder = (uint32_t*)(bars + 2 * SLOTS + 6);
+	uint64_t* f_full = bars + 2 * SLOTS + 6;      // first-order block landed in the P region (count 1 + tx)
+	uint64_t* f_free = bars + 2 * SLOTS + 7;      // P region no longer read: chain MMAs done (tcgen05.commit) / k = 1: drain
+	uint32_t* tmem_holder = (uint32_t*)(bars + 2 * SLOTS + 8);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int nkb = (p.nb + BK - 1) / BK;         // k-blocks of the bin dimension (K of X = Q A)
-	const int NT = (p.ldw + BN - 1) / BN;         // 128-column tiles of the window
-	const int nkw = (p.w + BK - 1) / BK;          // k-blocks of the window (K of S2)
-	const int n_last = (p.ldw - (NT - 1) * BN + 15) & ~15;  // MMA width of the last window tile (multiple of 16)
+	const int NT = (p.ldw + p.pad + BN - 1) / BN; // 128-column tiles of the (shifted) window
+	const int nkw = (p.w + p.pad + BK - 1) / BK;  // k-blocks of the (shifted) window (K of S2; the pad columns are zeros)
+	const int n_last = (p.ldw + p.pad - (NT - 1) * BN + 15) & ~15;  // MMA width of the last window tile (multiple of 16)
 	const int box_last = (n_last + 63) / 64;                // its 64-column TMA boxes
 	const int n_step = (p.nb + 15) & ~15;                   // MMA width / K extent of the chain's products
 	const bool chain = p.k > 1;
@@ -91,6 +98,8 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 		mbar_init(&acc_empty[0], 8); mbar_init(&acc_empty[1], 8);
 		mbar_init(q_ready, 8);
 		mbar_init(p_written, 1);
+		mbar_init(f_full, 1);
+		mbar_init(f_free, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 0 && lane == 0) {
@@ -110,8 +119,17 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 	if (warp == 0) {
 		// ------------------------------------------------------------------ TMA producer
 		if (lane == 0) {
-			long long it = 0;
-			for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x) {
+			long long it = 0, ncell_done = 0;
+			// first-order block of a cell: two 64-column boxes per plane at window column s -> the P region
+			auto load_first_order = [&](int cell) {
+				mbar_expect_tx(f_full, 4 * PLANE_BYTES);
+				for (int g = 0; g < 2; ++g) {
+					tma_load_3d(pbuf + g * PLANE_BYTES, &tmK, f_full, p.s + p.pad + 64 * g, 0, cell);
+					tma_load_3d(pbuf + P_PLANE + g * PLANE_BYTES, &tmK, f_full, p.s + p.pad + 64 * g, 0, p.ncell + cell);
+				}
+			};
+			if ((int)blockIdx.x < p.ncell) load_first_order(blockIdx.x);
+			for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x, ++ncell_done) {
 				const int nslots = nkw + NT * nkb;
 				for (int j = 0; j < nslots; ++j, ++it) {
 					const int s = (int)(it % SLOTS);
@@ -142,6 +160,11 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 					}
 					if (j == nslots - 1) FH_TRACE(3);
 				}
+				// the next cell's first-order block, once this cell's chain no longer reads P (long past by now)
+				if (cell + (int)gridDim.x < p.ncell) {
+					mbar_wait(f_free, (uint32_t)(ncell_done & 1));
+					load_first_order(cell + gridDim.x);
+				}
 			}
 		}
 	} else if (warp == 1) {
@@ -171,7 +194,7 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 					if (p.trace && blockIdx.x == 0 && cell == 3 * (int)gridDim.x) { p.trace[6] += tw3 - tw2; p.trace[5] += clock64() - tw3; }
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 					const uint32_t hi = smem_u32(smem + s * SLOT_BYTES), lo = hi + PLANE_BYTES;
-					const int nk = min(BK, p.w - kb * BK);
+					const int nk = min(BK, p.w + p.pad - kb * BK);
 					const int nk4 = (nk + 15) >> 4;
 					for (int k4 = 0; k4 < nk4; ++k4) {
 						const uint64_t dh = make_desc(hi + k4 * 32, 16, 1024, 2), dl = make_desc(lo + k4 * 32, 16, 1024, 2);
@@ -211,6 +234,7 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 						++ch;
 						if (step == 1) FH_TRACE(29);
 					}
+					umma_commit(f_free);  // P is no longer read once these MMAs have completed
 				}
 				FH_TRACE(10);
 				mbar_wait(q_ready, (uint32_t)(qn & 1)); ++qn;   // Q_k
@@ -259,11 +283,11 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 		const unsigned abits = max(*p.amax, __float_as_uint(1e-8f));
 		const float sa_inv = __uint_as_float(((abits >> 23) - 13u) << 23);
 		const float s2_scale = sa_inv * sa_inv, x_scale = sa_inv * (1.f / QS);
-		// 32 values of Q (this thread's row, columns 64h + 32c ..) -> TMEM hi / lo halves, scaled by 2^14
+		// 32 values of Q ALREADY SCALED by 2^14 (this thread's row, columns 64h + 32c ..) -> TMEM hi / lo halves
 		auto store_q_chunk = [&](int c, const float (&qv)[32]) {
 			uint32_t hi[16], lo[16];
 #pragma unroll
-			for (int j = 0; j < 16; ++j) f16_split2(qv[2 * j] * QS, qv[2 * j + 1] * QS, hi[j], lo[j]);
+			for (int j = 0; j < 16; ++j) f16_split2(qv[2 * j], qv[2 * j + 1], hi[j], lo[j]);
 			tmem_st16(tmem + lane_addr + TM_QHI + (uint32_t)(h * 32 + c * 16), hi);
 			tmem_st16(tmem + lane_addr + TM_QLO + (uint32_t)(h * 32 + c * 16), lo);
 		};
@@ -274,55 +298,59 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 			if (lane == 0) mbar_arrive(q_ready);
 		};
 		auto drain_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };  // the 8 drain warps
-		float* colpart = xch;                  // [4][128] per-row-quarter column sums
-		float* rowsum = xch + 4 * 128;         // [2][128] S2 row sums of the two column halves
-		float* cs1raw = xch + 6 * 128;         // column sums of the first-order block
-		float* w1 = xch + 7 * 128;             // per-column weights of the first / second order parts of P
-		float* w2 = xch + 8 * 128;
-		float* cflag = xch + 9 * 128;          // empty column of the blend: its diagonal entry (partial_rwr.py:96-97)
+		float* colpart = xch;                  // [16][128] column sums of 8-row groups of the first-order block
+		float* rowsum = xch + 16 * 128;        // [2][128] S2 row sums of the two column halves
+		float* cs1raw = xch + 18 * 128;        // column sums of the first-order block
+		float* w1 = xch + 19 * 128;            // per-column weights of the first / second order parts of P
+		float* w2 = xch + 20 * 128;
+		float* cflag = xch + 21 * 128;         // empty column of the blend: its diagonal entry (partial_rwr.py:96-97)
 		const int td = threadIdx.x - 128;      // 0..255 among the drain warps
-		const long long lo_plane = (long long)p.ncell * p.a_cell_stride;
-		// this thread's row of P in the shared-memory operand: k row m of n group h; 16-byte chunk i at (i ^ (m & 7))
-		uint8_t* prow = pbuf + h * (128 * 128) + (m >> 3) * 1024 + (m & 7) * 128;
-		long long ch = 0;
-		for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x) {
-			// first-order block A[32q + r][s + 64h + 32c + lane], r = 0..31, from the two planes: COALESCED (a warp reads one
-			// 64-byte row segment per plane and instruction)
-			const __half* ablk = p.Ahi + (long long)cell * p.a_cell_stride + (long long)(q * 32) * p.ld16 + p.s + h * 64 + lane;
-			// ---- A (independent of S2: runs under the S2 MMAs): column sums of the first-order block; the block itself is
-			// transposed to one row per lane through the staging tile (word (r, j) at r*32 + (j ^ r)) and parked in TMEM
-#pragma unroll 1
-			for (int c = 0; c < 2; ++c) {
-				const bool colok = h * 64 + c * 32 + lane < p.nb;
-				float v[32];
+		// this thread's row of the first-order block / of P in the shared-memory operand: row m of column half h;
+		// 16-byte chunk i (8 columns) at (i ^ (m & 7)); lo plane P_PLANE bytes further
+		uint8_t* prow = pbuf + h * (128 * 128) + m * 128;
+		// column-sum pass: 8 columns (chunk ci of box cbx) of rows rg, rg + 16, ...
+		const int cbx = (td >> 3) & 1, ci = td & 7, rg = td >> 4;
+		auto halves_to_floats = [&](const uint4& vh, const uint4& vl, float (&f)[8]) {
+			const uint32_t hh[4] = {vh.x, vh.y, vh.z, vh.w}, ll[4] = {vl.x, vl.y, vl.z, vl.w};
 #pragma unroll
-				for (int r = 0; r < 32; ++r) {
-					float x = 0.f;
-					if (colok && q * 32 + r < p.nb) {
-						const __half* e = ablk + (long long)r * p.ld16 + c * 32;
-						x = (__half2float(e[0]) + __half2float(e[lo_plane])) * sa_inv;
-					}
-					v[r] = x;
-				}
-				float cs = 0.f;
-#pragma unroll
-				for (int r = 0; r < 32; ++r) cs += v[r];
-				colpart[q * 128 + h * 64 + c * 32 + lane] = cs;
-				if (lane == 0) tma_store_wait_read();  // the tile may still feed an X store
-				__syncwarp();
-#pragma unroll
-				for (int r = 0; r < 32; ++r) tile_s[r * 32 + (lane ^ r)] = v[r];
-				__syncwarp();
-				uint32_t fu[32];
-#pragma unroll
-				for (int j = 0; j < 32; ++j) fu[j] = __float_as_uint(tile_s[lane * 32 + (j ^ lane)]);
-				__syncwarp();
-				tmem_st32(tmem + lane_addr + TM_PARK + (uint32_t)(h * 64 + c * 32), fu);
+			for (int e = 0; e < 4; ++e) {
+				const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hh[e]));
+				const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&ll[e]));
+				f[2 * e] = (a.x + b.x) * sa_inv;
+				f[2 * e + 1] = (a.y + b.y) * sa_inv;
 			}
-			tmem_st_wait();
+		};
+		long long ch = 0, ncell_done = 0;
+		for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x, ++ncell_done) {
+			// ---- A (independent of S2: runs under the S2 MMAs): column sums of the first-order block from its
+			// shared-memory tile (rows >= nb and window columns >= w are the TMA's zeros; columns >= nb are masked)
+			mbar_wait(f_full, (uint32_t)(ncell_done & 1));
+			{
+				float acc[8];
+#pragma unroll
+				for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+				for (int t = 0; t < 8; ++t) {
+					const int r = rg + 16 * t;
+					const uint8_t* src = pbuf + cbx * PLANE_BYTES + r * 128 + ((ci ^ (r & 7)) * 16);
+					float f[8];
+					halves_to_floats(*reinterpret_cast<const uint4*>(src), *reinterpret_cast<const uint4*>(src + P_PLANE), f);
+#pragma unroll
+					for (int e = 0; e < 8; ++e) acc[e] += f[e];
+				}
+				float4* dstp = reinterpret_cast<float4*>(colpart + rg * 128 + cbx * 64 + ci * 8);
+				dstp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+				dstp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+			}
 			if (td == 0) FH_TRACE(26);
 			drain_sync();
-			if (td < 128) cs1raw[td] = (colpart[td] + colpart[128 + td]) + (colpart[256 + td] + colpart[384 + td]);
+			if (td < 128) {  // fixed summation order: deterministic
+				float a = 0.f;
+#pragma unroll
+				for (int g = 0; g < 16; g += 4)
+					a += (colpart[g * 128 + td] + colpart[(g + 1) * 128 + td]) + (colpart[(g + 2) * 128 + td] + colpart[(g + 3) * 128 + td]);
+				cs1raw[td] = td < p.nb ? a : 0.f;
+			}
 			// ---- B: S2 row (this warp's 64 columns), chunks summed with round-to-nearest adds
 			float sum[64];
 #pragma unroll
@@ -372,43 +400,42 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 			}
 			drain_sync();
 			if (td == 0) FH_TRACE(18);
-			// ---- C: P -> shared-memory B operand of the chain (hi / lo halves); Q_1 = 0.5 P + 0.5 I -> TMEM
+			// ---- C: this thread's row of the first-order block -> its row of P, IN PLACE in the shared-memory B operand of the
+			// chain (hi / lo halves scaled by 2^14); Q_1 = 0.5 P + 0.5 I -> TMEM
 #pragma unroll
 			for (int c = 0; c < 2; ++c) {
-				uint32_t fu[32];
-				tmem_ld32(tmem + lane_addr + TM_PARK + (uint32_t)(h * 64 + c * 32), fu);
 				float pv[32];
 #pragma unroll
-				for (int j = 0; j < 32; ++j) {
-					const int col = h * 64 + c * 32 + j;
-					float x = __uint_as_float(fu[j]) * w1[col] + sum[c * 32 + j] * w2[col];  // 0 outside nb x nb
-					if (m == col) x += cflag[col];
-					pv[j] = x;
-				}
-				if (chain) {
+				for (int g = 0; g < 4; ++g) {
+					const int off = ((c * 4 + g) ^ (m & 7)) * 16;
+					float f[8];
+					halves_to_floats(*reinterpret_cast<const uint4*>(prow + off), *reinterpret_cast<const uint4*>(prow + P_PLANE + off), f);
 #pragma unroll
-					for (int g = 0; g < 4; ++g) {  // 8 columns = one 16-byte chunk per plane
+					for (int e = 0; e < 8; ++e) {
+						const int col = h * 64 + c * 32 + 8 * g + e;
+						float x = col < p.nb ? f[e] * w1[col] + sum[c * 32 + 8 * g + e] * w2[col] : 0.f;  // rows >= nb: zeros
+						if (m == col) x += cflag[col];
+						pv[8 * g + e] = x * QS;
+					}
+					if (chain) {
 						uint4 vh, vl;
-						f16_split2(pv[8 * g] * QS, pv[8 * g + 1] * QS, vh.x, vl.x);
-						f16_split2(pv[8 * g + 2] * QS, pv[8 * g + 3] * QS, vh.y, vl.y);
-						f16_split2(pv[8 * g + 4] * QS, pv[8 * g + 5] * QS, vh.z, vl.z);
-						f16_split2(pv[8 * g + 6] * QS, pv[8 * g + 7] * QS, vh.w, vl.w);
-						const int off = ((c * 4 + g) ^ (m & 7)) * 16;
+						f16_split2(pv[8 * g], pv[8 * g + 1], vh.x, vl.x);
+						f16_split2(pv[8 * g + 2], pv[8 * g + 3], vh.y, vl.y);
+						f16_split2(pv[8 * g + 4], pv[8 * g + 5], vh.z, vl.z);
+						f16_split2(pv[8 * g + 6], pv[8 * g + 7], vh.w, vl.w);
 						*reinterpret_cast<uint4*>(prow + off) = vh;
 						*reinterpret_cast<uint4*>(prow + P_PLANE + off) = vl;
 					}
 				}
 #pragma unroll
-				for (int j = 0; j < 32; ++j) pv[j] = 0.5f * pv[j] + ((m == h * 64 + c * 32 + j && m < p.nb) ? 0.5f : 0.f);
+				for (int j = 0; j < 32; ++j) pv[j] = 0.5f * pv[j] + ((m == h * 64 + c * 32 + j && m < p.nb) ? 0.5f * QS : 0.f);
 				store_q_chunk(c, pv);
 			}
 			if (chain) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of P -> UMMA
 			publish_q();
 			if (td == 0) FH_TRACE(19);
-			if (chain) {
-				drain_sync();
-				if (td == 0) mbar_arrive(p_written);
-			}
+			drain_sync();
+			if (td == 0) mbar_arrive(chain ? p_written : f_free);  // k = 1: nothing else reads the region
 			for (int step = 1; step < p.k; ++step) {
 				const int cb = (int)(ch & 1);
 				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
@@ -422,8 +449,8 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 #pragma unroll
 					for (int j = 0; j < 32; ++j) {
 						const int col = h * 64 + c * 32 + j;
-						float r = (0.5f * QS_INV2) * __uint_as_float(v[j]);
-						if (m == col && m < p.nb) r += 0.5f;
+						float r = (0.5f * QS_INV) * __uint_as_float(v[j]);  // Q scaled by 2^14 = 0.5 acc / 2^14 (+ 0.5 * 2^14)
+						if (m == col && m < p.nb) r += 0.5f * QS;
 						qv[j] = col < n_step ? r : 0.f;  // accumulator columns beyond the MMA's N were never written
 					}
 					store_q_chunk(c, qv);  // every MMA that read the old Q completed before acc_full fired
@@ -458,7 +485,20 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 				// 32 x 32 chunk; rows >= nb and columns >= ldw are clipped by the tensor map
 #pragma unroll
 				for (int c = 0; c < 2; ++c) {
-					const int n0 = nt * BN + h * 64 + c * 32;
+					const int n0 = nt * BN + h * 64 + c * 32 - p.pad;  // window column of the chunk
+					if (n0 < 0) {
+						// the first chunk of a shifted window starts at column -pad: a TMA store may not start at a negative
+						// coordinate (illegal instruction, compute-sanitizer on a B200), so its 32 - pad valid columns leave
+						// through 128-bit stores, one row per lane (1 chunk of ~10 per row)
+						if (m < p.nb) {
+							float* xrow = p.out + (long long)cell * p.out_cell_stride + (long long)m * p.ldw;
+#pragma unroll
+							for (int g = 1; g < 8; ++g)
+								if (4 * g - p.pad + 4 <= p.ldw)
+									*reinterpret_cast<float4*>(xrow + 4 * g - p.pad) = make_float4(xs[4 * g], xs[4 * g + 1], xs[4 * g + 2], xs[4 * g + 3]);
+						}
+						continue;
+					}
 					if (lane == 0) tma_store_wait_read();
 					__syncwarp();
 					float4* rowp = reinterpret_cast<float4*>(tile_s) + lane * 8;
@@ -489,13 +529,17 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 }  // namespace
 
 // Ahi: two binary16 planes (hi, then lo at + ncell * a_cell_stride halves) of (ncell, nb, ld16) conv'd panels scaled as
-// described at the top (written by densify_conv_kernel<.., true>); amax: the device word that fixes the scale;
+// described at the top (written by densify_conv_kernel<.., true>), window column c at plane column c + pad with
+// pad = fh_rwr_chain16_pad(s) leading zero columns; amax: the device word that fixes the scale;
 // out: cell c at out + c * out_cell_stride, rows of ldw floats (16-byte aligned). Returns FH_ERR_UNSUPPORTED (nothing
 // launched) when the shape is outside the kernel's range - the caller runs the TF32 kernels.
+int fh_rwr_chain16_pad(int s) { return (8 - (s & 7)) & 7; }
+
 int fh_rwr_chain16(const void* Ahi, const unsigned* amax, float* out, int nb, int w, int ldw, int ld16, int s, int k,
                    int ncell, long long a_cell_stride, long long out_cell_stride, void* stream) {
 	if (ncell <= 0) return FH_OK;
-	if (nb > BM || k < 1 || (ldw & 3) || (ld16 & 7) || (a_cell_stride & 7) || !aligned16(Ahi) || !aligned16(out) ||
+	const int pad = fh_rwr_chain16_pad(s);
+	if (nb > BM || k < 1 || (pad & 3) || ld16 < ldw + pad || (ldw & 3) || (ld16 & 7) || (a_cell_stride & 7) || !aligned16(Ahi) || !aligned16(out) ||
 	    (out_cell_stride & 3)) {
 		fh_set_error("fh_rwr_chain16: shape outside the fused kernel (nb <= 128, k >= 1, 16-byte aligned rows)");
 		return FH_ERR_UNSUPPORTED;
@@ -509,15 +553,15 @@ int fh_rwr_chain16(const void* Ahi, const unsigned* amax, float* out, int nb, in
 	const int grid = ncell < num_sms ? ncell : num_sms;
 	CUtensorMap tk, ta, to;
 	// the contiguous extent is the LOGICAL width, so pad columns and rows beyond nb read as zeros whatever the buffers hold
-	bool ok = make_map16(&tk, Ahi, w, nb, ld16, 2LL * ncell, a_cell_stride, BK, BM) &&
-	          make_map16(&ta, Ahi, w, nb, ld16, 2LL * ncell, a_cell_stride, 64, BK) &&
+	bool ok = make_map16(&tk, Ahi, w + pad, nb, ld16, 2LL * ncell, a_cell_stride, BK, BM) &&
+	          make_map16(&ta, Ahi, w + pad, nb, ld16, 2LL * ncell, a_cell_stride, 64, BK) &&
 	          make_map(&to, out, ldw, nb, ldw, ncell, out_cell_stride, 32, 32, false);
 	if (!ok) {
 		fh_set_error("fh_rwr_chain16: cuTensorMapEncodeTiled failed");
 		return FH_ERR_UNSUPPORTED;
 	}
 	Chain16P p;
-	p.nb = nb; p.w = w; p.ldw = ldw; p.ld16 = ld16; p.k = k; p.ncell = ncell;
+	p.nb = nb; p.w = w; p.ldw = ldw; p.ld16 = ld16; p.k = k; p.ncell = ncell; p.pad = pad;
 	p.a_cell_stride = a_cell_stride; p.out_cell_stride = out_cell_stride;
 	p.Ahi = (const __half*)Ahi; p.amax = amax; p.s = s; p.out = out;
 	cudaStream_t st = (cudaStream_t)stream;
