@@ -19,7 +19,7 @@
 //     so every drain thread turns its own row of the block into its own row of P in place (no transposes through
 //     staging tiles, no global loads in the drain warps: those cost 14k of a cell's 47k cycles in the first version).
 // TMEM (512 columns): Q_hi [0,64) | Q_lo [64,128) | free [128,256) | accumulators [256,384) [384,512)
-// Roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 drain.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 drain (lane quarter x column quarter).
 // Accumulation control as in fh_gemm_tc.cu: S2 chunks of K = 128 alternate between the two accumulators and are summed in
 // registers with round-to-nearest adds; the chain's and X's products have K = nb <= 128.
 #include <cuda_fp16.h>
@@ -34,9 +34,9 @@ constexpr int PLANE_BYTES = BK * BN * 2;        // 16 KB: the hi (or lo) tile of
 constexpr int SLOT_BYTES = 2 * PLANE_BYTES;     // hi | lo
 constexpr int SLOTS = 3;
 constexpr int P_PLANE = 128 * 128 * 2;          // P hi (or lo): [n group (2)][k row (128)][128 B]
-constexpr int EPI_BYTES = 8 * 32 * 32 * 4;      // 8 drain warps x (32 x 32 floats)
-constexpr int XCH_FLOATS = 22 * 128;            // column partials [16][128], row sums [2][128], cs1 / w1 / w2 / flag [128]
-constexpr int NTHREADS = 384;
+constexpr int EPI_BYTES = 16 * 32 * 16 * 4;     // 16 drain warps x (32 rows x 16 floats)
+constexpr int XCH_FLOATS = 24 * 128;            // column partials [16][128], row sums [4][128], cs1 / w1 / w2 / flag [128]
+constexpr int NTHREADS = 640;
 constexpr int SMEM_BYTES = SLOTS * SLOT_BYTES + 2 * P_PLANE + EPI_BYTES + XCH_FLOATS * 4 + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int CHUNK_KB = 2;                     // S2: k-blocks (K = 128) accumulated in TMEM before a drain
 constexpr float EPS = 1e-15f;                   // partial_rwr.py:88-97
@@ -60,7 +60,7 @@ struct Chain16P {
 	} while (0)
 
 // tmK: the planes as K-major boxes of 64 window columns x 128 rows (S2); tmA: as MN-major boxes of 64 window columns x
-// 64 bin rows (B tiles of X = Q A); plane / cell folded: z = cell (hi), ncell + cell (lo); tmO: X as 32 x 32 store boxes
+// 64 bin rows (B tiles of X = Q A); plane / cell folded: z = cell (hi), ncell + cell (lo); tmO: X as store boxes of 32 rows x 16 columns
 __global__ void __launch_bounds__(NTHREADS, 1)
 rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmA,
                    const __grid_constant__ CUtensorMap tmO, Chain16P p) {
@@ -73,8 +73,8 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 	uint64_t* full = bars;                        // TMA landed                  (count 1 + tx)
 	uint64_t* empty = bars + SLOTS;               // MMAs reading the slot done  (tcgen05.commit)
 	uint64_t* acc_full = bars + 2 * SLOTS;        // [2] accumulator complete    (tcgen05.commit)
-	uint64_t* acc_empty = bars + 2 * SLOTS + 2;   // [2] accumulator drained     (count 8: drain warps)
-	uint64_t* q_ready = bars + 2 * SLOTS + 4;     // Q hi / lo stored in TMEM    (count 8: drain warps)
+	uint64_t* acc_empty = bars + 2 * SLOTS + 2;   // [2] accumulator drained     (count 16: drain warps)
+	uint64_t* q_ready = bars + 2 * SLOTS + 4;     // Q hi / lo stored in TMEM    (count 16: drain warps)
 	uint64_t* p_written = bars + 2 * SLOTS + 5;   // P of the current cell is in shared memory (count 1)
 	uint64_t* f_full = bars + 2 * SLOTS + 6;      // first-order block landed in the P region (count 1 + tx)
 	uint64_t* f_free = bars + 2 * SLOTS + 7;      // P region no longer read: chain MMAs done (tcgen05.commit) / k = 1: drain
@@ -95,8 +95,8 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 			mbar_init(&empty[s], 1);
 		}
 		mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-		mbar_init(&acc_empty[0], 8); mbar_init(&acc_empty[1], 8);
-		mbar_init(q_ready, 8);
+		mbar_init(&acc_empty[0], 16); mbar_init(&acc_empty[1], 16);
+		mbar_init(q_ready, 16);
 		mbar_init(p_written, 1);
 		mbar_init(f_full, 1);
 		mbar_init(f_free, 1);
@@ -274,50 +274,47 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 		}
 	} else if (warp >= 4) {
 		// ------------------------------------------------------------------ drain: accumulator -> P, Q / X
+		// 16 warps: lane quarter q (rows 32q ..) x column quarter h (columns 32h ..). The drain phases are chains of dependent
+		// ALU work between TMEM / shared-memory accesses (ncu: ~5 cycles per instruction and warp, the tensor pipe idle
+		// meanwhile), so they are spread over four warps per scheduler instead of two, 32 columns per thread.
 		const int q = warp & 3;             // TMEM lane quarter of this warp (rows 32q .. 32q+31)
-		const int h = (warp - 4) >> 2;      // column half (64 columns)
+		const int h = (warp - 4) >> 2;      // column quarter (32 columns)
 		const int m = q * 32 + lane;        // this thread's row
+		const bool diag_chunk = (q == h);   // warp-uniform: rows 32q.. meet columns 32h.. (column - first column = lane)
 		const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-		float* tile_s = (float*)(stagebuf + (warp - 4) * (32 * 32 * 4));
+		float* tile_s = (float*)(stagebuf + (warp - 4) * (32 * 16 * 4));  // one 32 x 16 staging buffer per warp
 		// the panel's scale: amax * sa in [2^13, 2^14)
 		const unsigned abits = max(*p.amax, __float_as_uint(1e-8f));
 		const float sa_inv = __uint_as_float(((abits >> 23) - 13u) << 23);
 		const float s2_scale = sa_inv * sa_inv, x_scale = sa_inv * (1.f / QS);
-		// 32 values of Q ALREADY SCALED by 2^14 (this thread's row, columns 64h + 32c ..) -> TMEM hi / lo halves
-		auto store_q_chunk = [&](int c, const float (&qv)[32]) {
-			uint32_t hi[16], lo[16];
-#pragma unroll
-			for (int j = 0; j < 16; ++j) f16_split2(qv[2 * j], qv[2 * j + 1], hi[j], lo[j]);
-			tmem_st16(tmem + lane_addr + TM_QHI + (uint32_t)(h * 32 + c * 16), hi);
-			tmem_st16(tmem + lane_addr + TM_QLO + (uint32_t)(h * 32 + c * 16), lo);
-		};
 		auto publish_q = [&]() {
 			tmem_st_wait();
 			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 			__syncwarp();
 			if (lane == 0) mbar_arrive(q_ready);
 		};
-		auto drain_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };  // the 8 drain warps
+		auto drain_sync = [&]() { asm volatile("bar.sync 1, 512;" ::: "memory"); };  // the 16 drain warps
 		float* colpart = xch;                  // [16][128] column sums of 8-row groups of the first-order block
-		float* rowsum = xch + 16 * 128;        // [2][128] S2 row sums of the two column halves
-		float* cs1raw = xch + 18 * 128;        // column sums of the first-order block
-		float* w1 = xch + 19 * 128;            // per-column weights of the first / second order parts of P
-		float* w2 = xch + 20 * 128;
-		float* cflag = xch + 21 * 128;         // empty column of the blend: its diagonal entry (partial_rwr.py:96-97)
-		const int td = threadIdx.x - 128;      // 0..255 among the drain warps
-		// this thread's row of the first-order block / of P in the shared-memory operand: row m of column half h;
-		// 16-byte chunk i (8 columns) at (i ^ (m & 7)); lo plane P_PLANE bytes further
-		uint8_t* prow = pbuf + h * (128 * 128) + m * 128;
-		// column-sum pass: 8 columns (chunk ci of box cbx) of rows rg, rg + 16, ...
-		const int cbx = (td >> 3) & 1, ci = td & 7, rg = td >> 4;
+		float* rowsum = xch + 16 * 128;        // [4][128] S2 row sums of the four column quarters
+		float* cs1raw = xch + 20 * 128;        // column sums of the first-order block
+		float* w1 = xch + 21 * 128;            // per-column weights of the first / second order parts of P
+		float* w2 = xch + 22 * 128;
+		float* cflag = xch + 23 * 128;         // empty column of the blend: its diagonal entry (partial_rwr.py:96-97)
+		const int td = threadIdx.x - 128;      // 0..511 among the drain warps
+		// this thread's row of the first-order block / of P in the shared-memory operand: row m of the 64-column group
+		// h >> 1; its 16-byte chunks (8 columns) 4 (h & 1) + g at (chunk ^ (m & 7)); lo plane P_PLANE bytes further
+		uint8_t* prow = pbuf + (h >> 1) * (128 * 128) + m * 128;
+		const int chunk0 = (h & 1) * 4;
+		// column-sum pass (threads 0..255): 8 columns (chunk ci of box cbx) of rows rg, rg + 16, ...
+		const int cbx = (td >> 3) & 1, ci = td & 7, rg = (td >> 4) & 15;
 		auto halves_to_floats = [&](const uint4& vh, const uint4& vl, float (&f)[8]) {
 			const uint32_t hh[4] = {vh.x, vh.y, vh.z, vh.w}, ll[4] = {vl.x, vl.y, vl.z, vl.w};
 #pragma unroll
 			for (int e = 0; e < 4; ++e) {
 				const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hh[e]));
 				const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&ll[e]));
-				f[2 * e] = (a.x + b.x) * sa_inv;
-				f[2 * e + 1] = (a.y + b.y) * sa_inv;
+				f[2 * e] = a.x + b.x;
+				f[2 * e + 1] = a.y + b.y;
 			}
 		};
 		long long ch = 0, ncell_done = 0;
@@ -325,7 +322,7 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 			// ---- A (independent of S2: runs under the S2 MMAs): column sums of the first-order block from its
 			// shared-memory tile (rows >= nb and window columns >= w are the TMA's zeros; columns >= nb are masked)
 			mbar_wait(f_full, (uint32_t)(ncell_done & 1));
-			{
+			if (td < 256) {
 				float acc[8];
 #pragma unroll
 				for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -338,6 +335,8 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 #pragma unroll
 					for (int e = 0; e < 8; ++e) acc[e] += f[e];
 				}
+#pragma unroll
+				for (int e = 0; e < 8; ++e) acc[e] *= sa_inv;
 				float4* dstp = reinterpret_cast<float4*>(colpart + rg * 128 + cbx * 64 + ci * 8);
 				dstp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
 				dstp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
@@ -351,22 +350,19 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 					a += (colpart[g * 128 + td] + colpart[(g + 1) * 128 + td]) + (colpart[(g + 2) * 128 + td] + colpart[(g + 3) * 128 + td]);
 				cs1raw[td] = td < p.nb ? a : 0.f;
 			}
-			// ---- B: S2 row (this warp's 64 columns), chunks summed with round-to-nearest adds
-			float sum[64];
+			// ---- B: S2 row (this warp's 32 columns), chunks summed with round-to-nearest adds
+			float sum[32];
 #pragma unroll
-			for (int j = 0; j < 64; ++j) sum[j] = 0.f;
+			for (int j = 0; j < 32; ++j) sum[j] = 0.f;
 			const int nchunk = (nkw + CHUNK_KB - 1) / CHUNK_KB;
 			for (int chunk = 0; chunk < nchunk; ++chunk, ++ch) {
 				const int cb = (int)(ch & 1);
 				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				uint32_t v[32];
+				tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 32), v);
 #pragma unroll
-				for (int c = 0; c < 2; ++c) {
-					uint32_t v[32];
-					tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 64 + c * 32), v);
-#pragma unroll
-					for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(v[j]);
-				}
+				for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(v[j]);
 				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 				__syncwarp();
 				if (lane == 0) mbar_arrive(&acc_empty[cb]);
@@ -374,12 +370,22 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 			if (td == 0) FH_TRACE(16);
 			// second-order affinity without its diagonal; S2 is symmetric, so its column sums are row sums
 			float rs = 0.f;
+			{
+				const float rscale = m < p.nb ? s2_scale : 0.f;  // rows beyond the block are zero anyway (TMA zero fill)
 #pragma unroll
-			for (int j = 0; j < 64; ++j) {
-				const int col = h * 64 + j;
-				const float x = (m < p.nb && col < p.nb && col != m) ? sum[j] * s2_scale : 0.f;
-				sum[j] = x;
-				rs += x;
+				for (int j = 0; j < 32; ++j) sum[j] *= rscale;
+				if (h * 32 + 32 > p.nb) {  // warp-uniform: only the quarters at / beyond the block's last column mask columns
+#pragma unroll
+					for (int j = 0; j < 32; ++j)
+						if (h * 32 + j >= p.nb) sum[j] = 0.f;
+				}
+				if (diag_chunk) {
+#pragma unroll
+					for (int j = 0; j < 32; ++j)
+						if (lane == j) sum[j] = 0.f;
+				}
+#pragma unroll
+				for (int j = 0; j < 32; ++j) rs += sum[j];
 			}
 			rowsum[h * 128 + m] = rs;
 			drain_sync();
@@ -388,48 +394,72 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 			// sum of the blend is taken analytically, csl = 3/4 cs1/(cs1+eps) + 1/4 cs2/(cs2+eps) (the reference
 			// sums the rounded entries: same value to fp32 rounding), partial_rwr.py:88-97
 			if (td < 128) {
-				const float c1 = cs1raw[td], c2 = rowsum[td] + rowsum[128 + td];
+				const float c1 = cs1raw[td], c2 = (rowsum[td] + rowsum[128 + td]) + (rowsum[256 + td] + rowsum[384 + td]);
 				const float r1 = 1.f / (c1 + EPS), r2 = 1.f / (c2 + EPS);
 				float csl = 0.75f * (c1 * r1) + 0.25f * (c2 * r2);
 				const bool empty_col = (csl == 0.f) && td < p.nb;  // unreachable after the 1e-8 floor; kept for parity
 				if (empty_col) csl = 1.f;
 				const float rl = 1.f / (csl + EPS);
-				w1[td] = 0.75f * r1 * rl;
-				w2[td] = 0.25f * r2 * rl;
-				cflag[td] = empty_col ? rl : 0.f;
+				// pre-scaled for the binary16 operand (x 2^14; w1 also undoes the panel's scale), 0 beyond the block
+				w1[td] = td < p.nb ? 0.75f * r1 * rl * (QS * sa_inv) : 0.f;
+				w2[td] = td < p.nb ? 0.25f * r2 * rl * QS : 0.f;
+				cflag[td] = empty_col ? rl * QS : 0.f;
 			}
 			drain_sync();
 			if (td == 0) FH_TRACE(18);
 			// ---- C: this thread's row of the first-order block -> its row of P, IN PLACE in the shared-memory B operand of the
-			// chain (hi / lo halves scaled by 2^14); Q_1 = 0.5 P + 0.5 I -> TMEM
-#pragma unroll
-			for (int c = 0; c < 2; ++c) {
-				float pv[32];
+			// chain (hi / lo halves scaled by 2^14); Q_1 = 0.5 P + 0.5 I -> TMEM. Away from the diagonal the halves of Q_1 are
+			// the halves of P times 0.5 (exact), so only the warps that hold a diagonal chunk split again.
+			{
+				uint32_t qh[16], ql[16];
+				const float cf = diag_chunk ? cflag[m] : 0.f;  // the diagonal entry of this thread's row
 #pragma unroll
 				for (int g = 0; g < 4; ++g) {
-					const int off = ((c * 4 + g) ^ (m & 7)) * 16;
+					const int off = ((chunk0 + g) ^ (m & 7)) * 16;
 					float f[8];
 					halves_to_floats(*reinterpret_cast<const uint4*>(prow + off), *reinterpret_cast<const uint4*>(prow + P_PLANE + off), f);
+					const int col0 = h * 32 + 8 * g;
+					const float4 wa = *reinterpret_cast<const float4*>(w1 + col0), wb = *reinterpret_cast<const float4*>(w1 + col0 + 4);
+					const float4 va = *reinterpret_cast<const float4*>(w2 + col0), vb = *reinterpret_cast<const float4*>(w2 + col0 + 4);
+					const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w}, vv[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+					float pv[8];
 #pragma unroll
-					for (int e = 0; e < 8; ++e) {
-						const int col = h * 64 + c * 32 + 8 * g + e;
-						float x = col < p.nb ? f[e] * w1[col] + sum[c * 32 + 8 * g + e] * w2[col] : 0.f;  // rows >= nb: zeros
-						if (m == col) x += cflag[col];
-						pv[8 * g + e] = x * QS;
+					for (int e = 0; e < 8; ++e) pv[e] = f[e] * ww[e] + sum[8 * g + e] * vv[e];  // rows >= nb: zeros
+					if (diag_chunk) {
+#pragma unroll
+						for (int e = 0; e < 8; ++e)
+							if (lane == 8 * g + e) pv[e] += cf;
 					}
+					uint4 vh, vl;
+					f16_split2(pv[0], pv[1], vh.x, vl.x);
+					f16_split2(pv[2], pv[3], vh.y, vl.y);
+					f16_split2(pv[4], pv[5], vh.z, vl.z);
+					f16_split2(pv[6], pv[7], vh.w, vl.w);
 					if (chain) {
-						uint4 vh, vl;
-						f16_split2(pv[8 * g], pv[8 * g + 1], vh.x, vl.x);
-						f16_split2(pv[8 * g + 2], pv[8 * g + 3], vh.y, vl.y);
-						f16_split2(pv[8 * g + 4], pv[8 * g + 5], vh.z, vl.z);
-						f16_split2(pv[8 * g + 6], pv[8 * g + 7], vh.w, vl.w);
 						*reinterpret_cast<uint4*>(prow + off) = vh;
 						*reinterpret_cast<uint4*>(prow + P_PLANE + off) = vl;
 					}
-				}
+					if (diag_chunk) {
 #pragma unroll
-				for (int j = 0; j < 32; ++j) pv[j] = 0.5f * pv[j] + ((m == h * 64 + c * 32 + j && m < p.nb) ? 0.5f * QS : 0.f);
-				store_q_chunk(c, pv);
+						for (int e = 0; e < 4; ++e) {
+							const float a = 0.5f * pv[2 * e] + ((lane == 8 * g + 2 * e && m < p.nb) ? 0.5f * QS : 0.f);
+							const float b = 0.5f * pv[2 * e + 1] + ((lane == 8 * g + 2 * e + 1 && m < p.nb) ? 0.5f * QS : 0.f);
+							f16_split2(a, b, qh[4 * g + e], ql[4 * g + e]);
+						}
+					} else {
+						const uint32_t ph[4] = {vh.x, vh.y, vh.z, vh.w}, pl[4] = {vl.x, vl.y, vl.z, vl.w};
+						const __half2 half2c = __floats2half2_rn(0.5f, 0.5f);
+#pragma unroll
+						for (int e = 0; e < 4; ++e) {
+							const __half2 a2 = __hmul2(*reinterpret_cast<const __half2*>(&ph[e]), half2c);
+							const __half2 b2 = __hmul2(*reinterpret_cast<const __half2*>(&pl[e]), half2c);
+							qh[4 * g + e] = *reinterpret_cast<const uint32_t*>(&a2);
+							ql[4 * g + e] = *reinterpret_cast<const uint32_t*>(&b2);
+						}
+					}
+				}
+				tmem_st16(tmem + lane_addr + TM_QHI + (uint32_t)(h * 16), qh);
+				tmem_st16(tmem + lane_addr + TM_QLO + (uint32_t)(h * 16), ql);
 			}
 			if (chain) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of P -> UMMA
 			publish_q();
@@ -441,19 +471,28 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 				if (td == 0 && step == 1) FH_TRACE(27);
-#pragma unroll
-				for (int c = 0; c < 2; ++c) {
+				{
 					uint32_t v[32];
-					tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 64 + c * 32), v);
+					tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 32), v);
 					float qv[32];
 #pragma unroll
-					for (int j = 0; j < 32; ++j) {
-						const int col = h * 64 + c * 32 + j;
-						float r = (0.5f * QS_INV) * __uint_as_float(v[j]);  // Q scaled by 2^14 = 0.5 acc / 2^14 (+ 0.5 * 2^14)
-						if (m == col && m < p.nb) r += 0.5f * QS;
-						qv[j] = col < n_step ? r : 0.f;  // accumulator columns beyond the MMA's N were never written
+					for (int j = 0; j < 32; ++j) qv[j] = (0.5f * QS_INV) * __uint_as_float(v[j]);  // Q scaled by 2^14 = 0.5 acc / 2^14 (+ 0.5 * 2^14 I)
+					if (diag_chunk) {
+#pragma unroll
+						for (int j = 0; j < 32; ++j)
+							if (lane == j && m < p.nb) qv[j] += 0.5f * QS;
 					}
-					store_q_chunk(c, qv);  // every MMA that read the old Q completed before acc_full fired
+					if (h * 32 + 32 > n_step) {  // accumulator columns beyond the MMA's N were never written
+#pragma unroll
+						for (int j = 0; j < 32; ++j)
+							if (h * 32 + j >= n_step) qv[j] = 0.f;
+					}
+					// every MMA that read the old Q completed before acc_full fired
+					uint32_t hi[16], lo[16];
+#pragma unroll
+					for (int j = 0; j < 16; ++j) f16_split2(qv[2 * j], qv[2 * j + 1], hi[j], lo[j]);
+					tmem_st16(tmem + lane_addr + TM_QHI + (uint32_t)(h * 16), hi);
+					tmem_st16(tmem + lane_addr + TM_QLO + (uint32_t)(h * 16), lo);
 				}
 				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 				__syncwarp();
@@ -467,33 +506,32 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 				const int cb = (int)(ch & 1);
 				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-				float xs[64];
-#pragma unroll
-				for (int c = 0; c < 2; ++c) {
+				if (td == 0) FH_TRACE(21 + nt);
+				float xs[32];
+				{
 					uint32_t v[32];
-					tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 64 + c * 32), v);
+					tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 32), v);
 #pragma unroll
-					for (int j = 0; j < 32; ++j) xs[c * 32 + j] = __uint_as_float(v[j]) * x_scale;
+					for (int j = 0; j < 32; ++j) xs[j] = __uint_as_float(v[j]) * x_scale;
 				}
 				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 				__syncwarp();
 				if (lane == 0) mbar_arrive(&acc_empty[cb]);
 				++ch;
-				if (td == 0) FH_TRACE(21 + nt);
-				// each lane lays its row into the warp's staging tile in the 128-byte-swizzle pattern (16-byte chunk g
-				// of row r at g ^ (r & 7): four wavefronts per 512-byte store, the minimum), one TMA store per
-				// 32 x 32 chunk; rows >= nb and columns >= ldw are clipped by the tensor map
+				// each lane lays 16 columns of its row into the warp's staging buffer in the 64-byte-swizzle pattern (16-byte
+				// chunk g of row r at g ^ ((r >> 1) & 3): conflict-free), one TMA store per 32 x 16 chunk; rows >= nb and
+				// columns >= ldw are clipped by the tensor map
 #pragma unroll
-				for (int c = 0; c < 2; ++c) {
-					const int n0 = nt * BN + h * 64 + c * 32 - p.pad;  // window column of the chunk
+				for (int cc = 0; cc < 2; ++cc) {
+					const int n0 = nt * BN + h * 32 + cc * 16 - p.pad;  // window column of the chunk
 					if (n0 < 0) {
 						// the first chunk of a shifted window starts at column -pad: a TMA store may not start at a negative
-						// coordinate (illegal instruction, compute-sanitizer on a B200), so its 32 - pad valid columns leave
-						// through 128-bit stores, one row per lane (1 chunk of ~10 per row)
+						// coordinate (illegal instruction, compute-sanitizer on a B200), so its 16 - pad valid columns leave
+						// through 128-bit stores, one row per lane
 						if (m < p.nb) {
 							float* xrow = p.out + (long long)cell * p.out_cell_stride + (long long)m * p.ldw;
 #pragma unroll
-							for (int g = 1; g < 8; ++g)
+							for (int g = 1; g < 4; ++g)
 								if (4 * g - p.pad + 4 <= p.ldw)
 									*reinterpret_cast<float4*>(xrow + 4 * g - p.pad) = make_float4(xs[4 * g], xs[4 * g + 1], xs[4 * g + 2], xs[4 * g + 3]);
 						}
@@ -501,10 +539,10 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 					}
 					if (lane == 0) tma_store_wait_read();
 					__syncwarp();
-					float4* rowp = reinterpret_cast<float4*>(tile_s) + lane * 8;
+					float4* rowp = reinterpret_cast<float4*>(tile_s) + lane * 4;
 #pragma unroll
-					for (int g = 0; g < 8; ++g)
-						rowp[g ^ (lane & 7)] = make_float4(xs[c * 32 + 4 * g], xs[c * 32 + 4 * g + 1], xs[c * 32 + 4 * g + 2], xs[c * 32 + 4 * g + 3]);
+					for (int g = 0; g < 4; ++g)
+						rowp[g ^ ((lane >> 1) & 3)] = make_float4(xs[cc * 16 + 4 * g], xs[cc * 16 + 4 * g + 1], xs[cc * 16 + 4 * g + 2], xs[cc * 16 + 4 * g + 3]);
 					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 					__syncwarp();
 					if (lane == 0 && n0 < p.ldw && q * 32 < p.nb) {
@@ -555,7 +593,7 @@ int fh_rwr_chain16(const void* Ahi, const unsigned* amax, float* out, int nb, in
 	// the contiguous extent is the LOGICAL width, so pad columns and rows beyond nb read as zeros whatever the buffers hold
 	bool ok = make_map16(&tk, Ahi, w + pad, nb, ld16, 2LL * ncell, a_cell_stride, BK, BM) &&
 	          make_map16(&ta, Ahi, w + pad, nb, ld16, 2LL * ncell, a_cell_stride, 64, BK) &&
-	          make_map(&to, out, ldw, nb, ldw, ncell, out_cell_stride, 32, 32, false);
+	          make_map_sw(&to, out, ldw, nb, ldw, ncell, out_cell_stride, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
 	if (!ok) {
 		fh_set_error("fh_rwr_chain16: cuTensorMapEncodeTiled failed");
 		return FH_ERR_UNSUPPORTED;

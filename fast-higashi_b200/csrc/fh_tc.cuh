@@ -70,6 +70,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // pull a tile into L2 ahead of its TMA load
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
@@ -186,6 +187,19 @@ inline EncodeFn get_encode() {
 }
 
 // operand viewed as (rows x contiguous) with an optional batch dimension
+inline bool make_map_sw(CUtensorMap* m, const float* base, long long contig_extent, long long rows, long long row_stride,
+              int batch, long long batch_stride, int box_contig, int box_rows, CUtensorMapSwizzle sw) {
+	EncodeFn enc = get_encode();
+	if (!enc) return false;
+	cuuint64_t dims[3] = {(cuuint64_t)contig_extent, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
+	long long bs = batch_stride > 0 ? batch_stride : row_stride * rows;
+	cuuint64_t strides[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)bs * 4};
+	cuuint32_t box[3] = {(cuuint32_t)box_contig, (cuuint32_t)box_rows, 1};
+	cuuint32_t es[3] = {1, 1, 1};
+	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                 sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return r == CUDA_SUCCESS;
+}
 inline bool make_map(CUtensorMap* m, const float* base, long long contig_extent, long long rows, long long row_stride,
               int batch, long long batch_stride, int box_contig, int box_rows, bool mn_major) {
 	EncodeFn enc = get_encode();
