@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcP p,
                float* __restrict__ C) {
 	extern __shared__ uint8_t smem_raw[];
-	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
 	uint8_t* stagebuf = smem + STAGES * STAGE_BYTES;           // 8 warps x 32 x 32 floats (epilogue transposes)
 	uint64_t* bars = (uint64_t*)(stagebuf + EPI_BYTES);
 	uint64_t* raw_full = bars;                 // TMA landed            (count 1 + tx)

@@ -76,7 +76,7 @@ rwr_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmS, ChainP p) {
 	constexpr int SLOTS = Cfg<PANEL>::SLOTS;
 	extern __shared__ uint8_t smem_raw[];
-	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
 	uint8_t* stagebuf = smem + SLOTS * SLOT_BYTES;
 	float* xch = (float*)(stagebuf + EPI_BYTES);
 	uint64_t* bars = (uint64_t*)(stagebuf + EPI_BYTES + (PANEL ? XCH_FLOATS * 4 : 0));

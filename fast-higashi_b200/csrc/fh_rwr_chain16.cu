@@ -18,10 +18,10 @@
 //     the K-major tile of a 64-column box and the MN-major P operand put row m of column half h at the same 128 bytes,
 //     so every drain thread turns its own row of the block into its own row of P in place (no transposes through
 //     staging tiles, no global loads in the drain warps: those cost 14k of a cell's 47k cycles in the first version).
-// TMEM (512 columns): Q_hi [0,64) | Q_lo [64,128) | free [128,256) | accumulators [256,384) [384,512)
+// TMEM (512 columns): Q_hi [0,64) | Q_lo [64,128) | S2 accumulator [128,256) | accumulators [256,384) [384,512)
 // Roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 drain (lane quarter x column quarter).
-// Accumulation control as in fh_gemm_tc.cu: S2 chunks of K = 128 alternate between the two accumulators and are summed in
-// registers with round-to-nearest adds; the chain's and X's products have K = nb <= 128.
+// Every product has K <= ~330 (S2) or K = nb <= 128 (chain, X): one accumulation in TMEM each (fh_gemm_tc.cu drains long-K
+// sums every 128 because the tensor core's accumulation truncates; at these K the effect is <= 2e-6).
 #include <cuda_fp16.h>
 #include "fh_tc.cuh"
 #include "../../include/fh_b200.h"
@@ -38,9 +38,8 @@ constexpr int EPI_BYTES = 16 * 32 * 16 * 4;     // 16 drain warps x (32 rows x 1
 constexpr int XCH_FLOATS = 24 * 128;            // column partials [16][128], row sums [4][128], cs1 / w1 / w2 / flag [128]
 constexpr int NTHREADS = 640;
 constexpr int SMEM_BYTES = SLOTS * SLOT_BYTES + 2 * P_PLANE + EPI_BYTES + XCH_FLOATS * 4 + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int CHUNK_KB = 2;                     // S2: k-blocks (K = 128) accumulated in TMEM before a drain
 constexpr float EPS = 1e-15f;                   // partial_rwr.py:88-97
-constexpr uint32_t TM_QHI = 0, TM_QLO = 64, TM_ACC = 256;
+constexpr uint32_t TM_QHI = 0, TM_QLO = 64, TM_S2 = 128, TM_ACC = 256;
 constexpr float QS = 16384.f;                   // scale of Q and P (entries in [0, 1])
 constexpr float QS_INV = 1.f / 16384.f;
 
@@ -65,7 +64,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmA,
                    const __grid_constant__ CUtensorMap tmO, Chain16P p) {
 	extern __shared__ uint8_t smem_raw[];
-	uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+	uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
 	uint8_t* pbuf = smem + SLOTS * SLOT_BYTES;                 // P hi | P lo
 	uint8_t* stagebuf = pbuf + 2 * P_PLANE;
 	float* xch = (float*)(stagebuf + EPI_BYTES);
@@ -78,7 +77,9 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 	uint64_t* p_written = bars + 2 * SLOTS + 5;   // P of the current cell is in shared memory (count 1)
 	uint64_t* f_full = bars + 2 * SLOTS + 6;      // first-order block landed in the P region (count 1 + tx)
 	uint64_t* f_free = bars + 2 * SLOTS + 7;      // P region no longer read: chain MMAs done (tcgen05.commit) / k = 1: drain
-	uint32_t* tmem_holder = (uint32_t*)(bars + 2 * SLOTS + 8);
+	uint64_t* s2_full = bars + 2 * SLOTS + 8;     // S2 of a cell complete in its own accumulator (tcgen05.commit)
+	uint64_t* s2_empty = bars + 2 * SLOTS + 9;    // ... and read by the drain warps (count 16)
+	uint32_t* tmem_holder = (uint32_t*)(bars + 2 * SLOTS + 10);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int nkb = (p.nb + BK - 1) / BK;         // k-blocks of the bin dimension (K of X = Q A)
@@ -100,6 +101,8 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 		mbar_init(p_written, 1);
 		mbar_init(f_full, 1);
 		mbar_init(f_free, 1);
+		mbar_init(s2_full, 1);
+		mbar_init(s2_empty, 16);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 0 && lane == 0) {
@@ -128,38 +131,45 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 					tma_load_3d(pbuf + P_PLANE + g * PLANE_BYTES, &tmK, f_full, p.s + p.pad + 64 * g, 0, p.ncell + cell);
 				}
 			};
-			if ((int)blockIdx.x < p.ncell) load_first_order(blockIdx.x);
-			for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x, ++ncell_done) {
-				const int nslots = nkw + NT * nkb;
-				for (int j = 0; j < nslots; ++j, ++it) {
+			// S2 tiles of a cell: one K-major box of 128 rows x 64 window columns per plane and slot
+			auto load_s2 = [&](int cell) {
+				for (int j = 0; j < nkw; ++j, ++it) {
 					const int s = (int)(it % SLOTS);
 					mbar_wait(&empty[s], (uint32_t)(((it / SLOTS) & 1) ^ 1));
 					uint8_t* dst = smem + s * SLOT_BYTES;
-					if (j < nkw) {  // S2: one K-major box of 128 rows x 64 window columns per plane
-						if (j == 0) FH_TRACE(0);
-						mbar_expect_tx(&full[s], SLOT_BYTES);
-						tma_load_3d(dst, &tmK, &full[s], j * BK, 0, cell);
-						tma_load_3d(dst + PLANE_BYTES, &tmK, &full[s], j * BK, 0, p.ncell + cell);
-						if (j == nkw - 1) {
-							FH_TRACE(1);
-							// next cell's panel -> L2 while this cell's transition and step chain keep the TMA unit idle
-							if (cell + (int)gridDim.x < p.ncell)
-								for (int jj = 0; jj < nkw; ++jj) {
-									tma_prefetch_3d(&tmK, jj * BK, 0, cell + gridDim.x);
-									tma_prefetch_3d(&tmK, jj * BK, 0, p.ncell + cell + gridDim.x);
-								}
-						}
-						continue;
+					mbar_expect_tx(&full[s], SLOT_BYTES);
+					tma_load_3d(dst, &tmK, &full[s], j * BK, 0, cell);
+					tma_load_3d(dst + PLANE_BYTES, &tmK, &full[s], j * BK, 0, p.ncell + cell);
+				}
+				// the panel after it -> L2 (its S2 loads follow one cell later)
+				if (cell + (int)gridDim.x < p.ncell)
+					for (int jj = 0; jj < nkw; ++jj) {
+						tma_prefetch_3d(&tmK, jj * BK, 0, cell + gridDim.x);
+						tma_prefetch_3d(&tmK, jj * BK, 0, p.ncell + cell + gridDim.x);
 					}
-					const int t = j - nkw, nt = t / nkb, kb = t % nkb;
+			};
+			// ring order = the MMA warp's order: S2(first); per cell: S2(next cell), then the X = Q A tiles of the cell
+			if ((int)blockIdx.x < p.ncell) {
+				load_first_order(blockIdx.x);
+				load_s2(blockIdx.x);
+			}
+			for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x, ++ncell_done) {
+				if (cell == blockIdx.x + 3 * (int)gridDim.x) FH_TRACE(0);
+				if (cell + (int)gridDim.x < p.ncell) load_s2(cell + gridDim.x);
+				FH_TRACE(1);
+				for (int t = 0; t < NT * nkb; ++t, ++it) {
+					const int s = (int)(it % SLOTS);
+					mbar_wait(&empty[s], (uint32_t)(((it / SLOTS) & 1) ^ 1));
+					uint8_t* dst = smem + s * SLOT_BYTES;
+					const int nt = t / nkb, kb = t % nkb;
 					const int nbox = (nt == NT - 1) ? box_last : BN / 64;  // the last window tile may be narrower
 					mbar_expect_tx(&full[s], 2 * nbox * (BK * 128));
 					for (int g = 0; g < nbox; ++g) {
 						tma_load_3d(dst + g * (BK * 128), &tmA, &full[s], nt * BN + 64 * g, kb * BK, cell);
 						tma_load_3d(dst + PLANE_BYTES + g * (BK * 128), &tmA, &full[s], nt * BN + 64 * g, kb * BK, p.ncell + cell);
 					}
-					if (j == nslots - 1) FH_TRACE(3);
 				}
+				FH_TRACE(3);
 				// the next cell's first-order block, once this cell's chain no longer reads P (long past by now)
 				if (cell + (int)gridDim.x < p.ncell) {
 					mbar_wait(f_free, (uint32_t)(ncell_done & 1));
@@ -176,38 +186,36 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 			const uint32_t idesc_xl = make_idesc_f16(false, true, n_last, BM);
 			const uint32_t p_hi = smem_u32(pbuf), p_lo = p_hi + P_PLANE;
 			long long it = 0, ch = 0, qn = 0, ncell_done = 0;
-			for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x, ++ncell_done) {
-				FH_TRACE(8);
-				// S2 = A A^T: the landed K-major tiles (SWIZZLE_128B: 128-byte rows, 8-row groups 1024 B apart, a K = 16
-				// step = +32 B) are both operands; accumulator chunks of CHUNK_KB k-blocks alternate buffers
+			// S2 = A A^T of the n-th cell of this CTA into its own accumulator: the landed K-major tiles (SWIZZLE_128B: 128-byte
+			// rows, 8-row groups 1024 B apart, a K = 16 step = +32 B) are both operands. K = w <= ~330 is accumulated in one go
+			// (the tensor core's truncating accumulation costs ~7e-9 K relative, 2e-6 here, on the quarter-weight term of P).
+			// It is issued ONE CELL AHEAD, at the top of the previous cell's transition, so that the tensor pipe works on it
+			// while the drain warps build that cell's P (they idle the pipe for ~9k of a cell's ~43k cycles otherwise).
+			auto issue_s2 = [&](long long n) {
+				mbar_wait(s2_empty, (uint32_t)((n & 1) ^ 1));  // the drain warps have read the previous cell's S2
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				const uint32_t acc = tmem + TM_S2;
 				for (int kb = 0; kb < nkw; ++kb, ++it) {
-					const int cb = (int)(ch & 1);
-					const long long tw2 = p.trace ? clock64() : 0;
-					if (kb % CHUNK_KB == 0) {
-						mbar_wait(&acc_empty[cb], (uint32_t)(((ch >> 1) & 1) ^ 1));
-						asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-					}
-					const long long tw3 = p.trace ? clock64() : 0;
-					const uint32_t acc = tmem + TM_ACC + (uint32_t)(cb * BN);
 					const int s = (int)(it % SLOTS);
 					mbar_wait(&full[s], (uint32_t)((it / SLOTS) & 1));
-					if (p.trace && blockIdx.x == 0 && cell == 3 * (int)gridDim.x) { p.trace[6] += tw3 - tw2; p.trace[5] += clock64() - tw3; }
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 					const uint32_t hi = smem_u32(smem + s * SLOT_BYTES), lo = hi + PLANE_BYTES;
 					const int nk = min(BK, p.w + p.pad - kb * BK);
 					const int nk4 = (nk + 15) >> 4;
 					for (int k4 = 0; k4 < nk4; ++k4) {
 						const uint64_t dh = make_desc(hi + k4 * 32, 16, 1024, 2), dl = make_desc(lo + k4 * 32, 16, 1024, 2);
-						umma_f16(acc, dl, dh, idesc_kk, ((kb % CHUNK_KB) | k4) ? 1u : 0u);  // small terms first
+						umma_f16(acc, dl, dh, idesc_kk, (kb | k4) ? 1u : 0u);  // small terms first
 						umma_f16(acc, dh, dl, idesc_kk, 1u);
 						umma_f16(acc, dh, dh, idesc_kk, 1u);
 					}
 					umma_commit(&empty[s]);
-					if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkw - 1) {
-						umma_commit(&acc_full[cb]);
-						++ch;
-					}
 				}
+				umma_commit(s2_full);
+			};
+			if ((int)blockIdx.x < p.ncell) issue_s2(0);
+			for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x, ++ncell_done) {
+				FH_TRACE(8);
+				if (cell + (int)gridDim.x < p.ncell) issue_s2(ncell_done + 1);
 				FH_TRACE(9);
 				if (chain) {
 					// Q_{t+1} = 0.5 Q_t P + 0.5 I: A = Q from TMEM (K = 16 step = +8 columns), B = P in shared memory (MN-major:
@@ -350,22 +358,18 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 					a += (colpart[g * 128 + td] + colpart[(g + 1) * 128 + td]) + (colpart[(g + 2) * 128 + td] + colpart[(g + 3) * 128 + td]);
 				cs1raw[td] = td < p.nb ? a : 0.f;
 			}
-			// ---- B: S2 row (this warp's 32 columns), chunks summed with round-to-nearest adds
+			// ---- B: S2 row (this warp's 32 columns)
 			float sum[32];
-#pragma unroll
-			for (int j = 0; j < 32; ++j) sum[j] = 0.f;
-			const int nchunk = (nkw + CHUNK_KB - 1) / CHUNK_KB;
-			for (int chunk = 0; chunk < nchunk; ++chunk, ++ch) {
-				const int cb = (int)(ch & 1);
-				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
+			{
+				mbar_wait(s2_full, (uint32_t)(ncell_done & 1));
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 				uint32_t v[32];
-				tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 32), v);
+				tmem_ld32(tmem + lane_addr + TM_S2 + (uint32_t)(h * 32), v);
 #pragma unroll
-				for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(v[j]);
+				for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(v[j]);
 				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 				__syncwarp();
-				if (lane == 0) mbar_arrive(&acc_empty[cb]);
+				if (lane == 0) mbar_arrive(s2_empty);
 			}
 			if (td == 0) FH_TRACE(16);
 			// second-order affinity without its diagonal; S2 is symmetric, so its column sums are row sums

@@ -88,7 +88,8 @@ def test_full_size_rwr_conserves_column_mass(use_tc):
 	500 kb, blocks of 115 rows with 215 / 315-column windows, density 0.05) where the oracle is too slow to be the
 	checker: the transition matrix P is column-stochastic, hence so is every Q_k = 1/2 Q_{k-1} P + 1/2 I, and the imputed
 	panel X = Q A has exactly the column sums of the convolved panel A (partial_rwr.py:84-138; 2e-7 on the oracle).
-	Also: X > 0, pad columns exactly 0, and a second call reproduces the first bit for bit."""
+	Also: X > 0, pad columns exactly 0, and a second call reproduces the first bit for bit. Tolerance 1e-5 of a column's
+	mass (plus, on the 3xFP16 tensor-core path, the floor-level resolution of the binary16 planes: see below)."""
 	from fasthigashi_b200 import synth
 	from fasthigashi_b200.partial_rwr import rwr_block_csr, pad4
 	from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset
@@ -109,7 +110,12 @@ def test_full_size_rwr_conserves_column_mass(use_tc):
 		assert torch.equal(X.reshape(ncell, -1), X2)
 		assert float(X[:, :, g.w:].abs().sum()) == 0.0 and bool((X[:, :, :g.w] > 0).all())
 		ca, cx = A.double().sum(1)[:, :g.w], X.double().sum(1)[:, :g.w]
-		assert float(((cx - ca).abs() / ca).max()) < 1e-5
+		# tensor-core path (3xFP16, fh_rwr_chain16.cu): the operand planes are binary16 pairs of the panel scaled to
+		# [2^13, 2^14), i.e. 22 bits relative to an entry down to 2^-14 of the block's largest value and an ABSOLUTE
+		# resolution of 2^-25 / scale below that: an entry at the 1e-8 floor is carried to ~1e-3 relative (1e-11 absolute),
+		# which only shows in the columns whose whole mass is the floor (ca ~ nb * 1e-8)
+		floor_res = g.nb * 1e-8 * 2e-3 if use_tc else 0.0
+		assert float(((cx - ca).abs() / (1e-5 * ca + floor_res)).max()) < 1.0
 
 
 def test_chrom_dataset_fetch_api():
