@@ -18,6 +18,13 @@
 //     the K-major tile of a 64-column box and the MN-major P operand put row m of column half h at the same 128 bytes,
 //     so every drain thread turns its own row of the block into its own row of P in place (no transposes through
 //     staging tiles, no global loads in the drain warps: those cost 14k of a cell's 47k cycles in the first version).
+//   * S2 of the NEXT cell is issued at the top of a cell's transition into its own TMEM accumulator, and the column sums of
+//     the first-order block come from a ones x F product: the tensor pipe works while the drain warps build P.
+// Measured on a B200 (FH_CHAIN_TRACE=1, nb = 115, w = 315, k = 4, SM cycles per cell): 47k in the first version -> 37k
+// (3xTF32 kernel: 64k). What a cell costs now: S2 (next cell) ~10k under the transition (~14k: the drain warps' shared-memory
+// traffic for P competes with the UMMA operand reads, both at the 128 B/clk limit), 3 chain steps 3 x 3.1k (24 MMAs ~2k +
+// drain ~1k), X = Q A ~9.5k (epilogue paced: TMEM read, staging writes, TMA stores) + 3k tail. Shared-memory bytes per cell
+// (operand reads + TMA + staging) ~2.1 MB = 16k cycles at 128 B/clk: the floor of this design.
 // TMEM (512 columns): Q_hi [0,64) | Q_lo [64,128) | S2 accumulator [128,256) | accumulators [256,384) [384,512)
 // Roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 drain (lane quarter x column quarter).
 // Every product has K <= ~330 (S2) or K = nb <= 128 (chain, X): one accumulation in TMEM each (fh_gemm_tc.cu drains long-K
@@ -35,9 +42,10 @@ constexpr int SLOT_BYTES = 2 * PLANE_BYTES;     // hi | lo
 constexpr int SLOTS = 3;
 constexpr int P_PLANE = 128 * 128 * 2;          // P hi (or lo): [n group (2)][k row (128)][128 B]
 constexpr int EPI_BYTES = 16 * 32 * 16 * 4;     // 16 drain warps x (32 rows x 16 floats)
-constexpr int XCH_FLOATS = 24 * 128;            // column partials [16][128], row sums [4][128], cs1 / w1 / w2 / flag [128]
+constexpr int XCH_FLOATS = 8 * 128;             // row sums [4][128], cs1 / w1 / w2 / flag [128]
+constexpr int ONES_BYTES = 4096;                // 128 x 16 halves of 1.0: the A operand of the column-sum MMAs
 constexpr int NTHREADS = 640;
-constexpr int SMEM_BYTES = SLOTS * SLOT_BYTES + 2 * P_PLANE + EPI_BYTES + XCH_FLOATS * 4 + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = SLOTS * SLOT_BYTES + 2 * P_PLANE + EPI_BYTES + XCH_FLOATS * 4 + ONES_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr float EPS = 1e-15f;                   // partial_rwr.py:88-97
 constexpr uint32_t TM_QHI = 0, TM_QLO = 64, TM_S2 = 128, TM_ACC = 256;
 constexpr float QS = 16384.f;                   // scale of Q and P (entries in [0, 1])
@@ -68,7 +76,8 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 	uint8_t* pbuf = smem + SLOTS * SLOT_BYTES;                 // P hi | P lo
 	uint8_t* stagebuf = pbuf + 2 * P_PLANE;
 	float* xch = (float*)(stagebuf + EPI_BYTES);
-	uint64_t* bars = (uint64_t*)(stagebuf + EPI_BYTES + XCH_FLOATS * 4);
+	uint8_t* ones = stagebuf + EPI_BYTES + XCH_FLOATS * 4;
+	uint64_t* bars = (uint64_t*)(ones + ONES_BYTES);
 	uint64_t* full = bars;                        // TMA landed                  (count 1 + tx)
 	uint64_t* empty = bars + SLOTS;               // MMAs reading the slot done  (tcgen05.commit)
 	uint64_t* acc_full = bars + 2 * SLOTS;        // [2] accumulator complete    (tcgen05.commit)
@@ -110,6 +119,8 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 		asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
 		asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmO) : "memory");
 	}
+	for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(ones)[i] = 0x3C003C00u;  // (1.0, 1.0)
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	if (warp == 2) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512) : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -215,6 +226,23 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 			if ((int)blockIdx.x < p.ncell) issue_s2(0);
 			for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x, ++ncell_done) {
 				FH_TRACE(8);
+				{
+					// column sums of the first-order block on the tensor core: ones (128 x K) x F (K = rows, MN-major, the layout P
+					// will have) -> every accumulator row holds the column sums (hi and lo planes summed); 2 nb / 16 MMAs instead
+					// of a pass over the block by the drain warps (3k cycles of their critical path)
+					mbar_wait(f_full, (uint32_t)(ncell_done & 1));
+					const int cb = (int)(ch & 1);
+					mbar_wait(&acc_empty[cb], (uint32_t)(((ch >> 1) & 1) ^ 1));
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					const uint32_t acc = tmem + TM_ACC + (uint32_t)(cb * BN);
+					const uint64_t da = make_desc(smem_u32(ones), 128, 256, 0);  // no swizzle: 8-row x 16-byte core matrices
+					for (int ks = 0; ks < (n_step >> 4); ++ks) {
+						umma_f16(acc, da, make_desc(p_lo + ks * 2048, 128 * 128, 1024, 2), idesc_st, ks ? 1u : 0u);
+						umma_f16(acc, da, make_desc(p_hi + ks * 2048, 128 * 128, 1024, 2), idesc_st, 1u);
+					}
+					umma_commit(&acc_full[cb]);
+					++ch;
+				}
 				if (cell + (int)gridDim.x < p.ncell) issue_s2(ncell_done + 1);
 				FH_TRACE(9);
 				if (chain) {
@@ -250,17 +278,13 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 				FH_TRACE(11);
 				for (int nt = 0; nt < NT; ++nt) {
 					const int cb = (int)(ch & 1);
-					const long long tw1 = p.trace ? clock64() : 0;
 					mbar_wait(&acc_empty[cb], (uint32_t)(((ch >> 1) & 1) ^ 1));
-					if (p.trace && blockIdx.x == 0 && cell == 3 * (int)gridDim.x) p.trace[14] += clock64() - tw1;
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 					const uint32_t acc = tmem + TM_ACC + (uint32_t)(cb * BN);
 					const uint32_t idesc = nt == NT - 1 ? idesc_xl : idesc_x;
 					for (int kb = 0; kb < nkb; ++kb, ++it) {
 						const int s = (int)(it % SLOTS);
-						const long long tw0 = p.trace ? clock64() : 0;
 						mbar_wait(&full[s], (uint32_t)((it / SLOTS) & 1));
-						if (p.trace && blockIdx.x == 0 && cell == 3 * (int)gridDim.x) p.trace[13] += clock64() - tw0;
 						asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 						const uint32_t hi = smem_u32(smem + s * SLOT_BYTES), lo = hi + PLANE_BYTES;
 						const int nk4 = (min(BK, n_step - kb * BK) + 15) >> 4;
@@ -302,19 +326,16 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 			if (lane == 0) mbar_arrive(q_ready);
 		};
 		auto drain_sync = [&]() { asm volatile("bar.sync 1, 512;" ::: "memory"); };  // the 16 drain warps
-		float* colpart = xch;                  // [16][128] column sums of 8-row groups of the first-order block
-		float* rowsum = xch + 16 * 128;        // [4][128] S2 row sums of the four column quarters
-		float* cs1raw = xch + 20 * 128;        // column sums of the first-order block
-		float* w1 = xch + 21 * 128;            // per-column weights of the first / second order parts of P
-		float* w2 = xch + 22 * 128;
-		float* cflag = xch + 23 * 128;         // empty column of the blend: its diagonal entry (partial_rwr.py:96-97)
+		float* rowsum = xch;                   // [4][128] S2 row sums of the four column quarters
+		float* cs1raw = xch + 4 * 128;         // column sums of the first-order block
+		float* w1 = xch + 5 * 128;             // per-column weights of the first / second order parts of P
+		float* w2 = xch + 6 * 128;
+		float* cflag = xch + 7 * 128;          // empty column of the blend: its diagonal entry (partial_rwr.py:96-97)
 		const int td = threadIdx.x - 128;      // 0..511 among the drain warps
 		// this thread's row of the first-order block / of P in the shared-memory operand: row m of the 64-column group
 		// h >> 1; its 16-byte chunks (8 columns) 4 (h & 1) + g at (chunk ^ (m & 7)); lo plane P_PLANE bytes further
 		uint8_t* prow = pbuf + (h >> 1) * (128 * 128) + m * 128;
 		const int chunk0 = (h & 1) * 4;
-		// column-sum pass (threads 0..255): 8 columns (chunk ci of box cbx) of rows rg, rg + 16, ...
-		const int cbx = (td >> 3) & 1, ci = td & 7, rg = (td >> 4) & 15;
 		auto halves_to_floats = [&](const uint4& vh, const uint4& vl, float (&f)[8]) {
 			const uint32_t hh[4] = {vh.x, vh.y, vh.z, vh.w}, ll[4] = {vl.x, vl.y, vl.z, vl.w};
 #pragma unroll
@@ -327,37 +348,29 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 		};
 		long long ch = 0, ncell_done = 0;
 		for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x, ++ncell_done) {
-			// ---- A (independent of S2: runs under the S2 MMAs): column sums of the first-order block from its
-			// shared-memory tile (rows >= nb and window columns >= w are the TMA's zeros; columns >= nb are masked)
+			// ---- A: column sums of the first-order block from the tensor core's ones x F product: all accumulator rows are
+			// equal, lane j of the quarter-0 warps keeps column 32h + j (rows >= nb and window columns >= w are the TMA's
+			// zeros; columns >= nb are masked)
 			mbar_wait(f_full, (uint32_t)(ncell_done & 1));
-			if (td < 256) {
-				float acc[8];
+			{
+				const int cb = (int)(ch & 1);
+				mbar_wait(&acc_full[cb], (uint32_t)((ch >> 1) & 1));
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				if (q == 0) {
+					uint32_t v[32];
+					tmem_ld32(tmem + TM_ACC + (uint32_t)(cb * BN + h * 32), v);
+					float cs = 0.f;
 #pragma unroll
-				for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-#pragma unroll
-				for (int t = 0; t < 8; ++t) {
-					const int r = rg + 16 * t;
-					const uint8_t* src = pbuf + cbx * PLANE_BYTES + r * 128 + ((ci ^ (r & 7)) * 16);
-					float f[8];
-					halves_to_floats(*reinterpret_cast<const uint4*>(src), *reinterpret_cast<const uint4*>(src + P_PLANE), f);
-#pragma unroll
-					for (int e = 0; e < 8; ++e) acc[e] += f[e];
+					for (int j = 0; j < 32; ++j)
+						if (lane == j) cs = __uint_as_float(v[j]);
+					cs1raw[h * 32 + lane] = h * 32 + lane < p.nb ? cs * sa_inv : 0.f;
 				}
-#pragma unroll
-				for (int e = 0; e < 8; ++e) acc[e] *= sa_inv;
-				float4* dstp = reinterpret_cast<float4*>(colpart + rg * 128 + cbx * 64 + ci * 8);
-				dstp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-				dstp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&acc_empty[cb]);
+				++ch;
 			}
 			if (td == 0) FH_TRACE(26);
-			drain_sync();
-			if (td < 128) {  // fixed summation order: deterministic
-				float a = 0.f;
-#pragma unroll
-				for (int g = 0; g < 16; g += 4)
-					a += (colpart[g * 128 + td] + colpart[(g + 1) * 128 + td]) + (colpart[(g + 2) * 128 + td] + colpart[(g + 3) * 128 + td]);
-				cs1raw[td] = td < p.nb ? a : 0.f;
-			}
 			// ---- B: S2 row (this warp's 32 columns)
 			float sum[32];
 			{
@@ -631,7 +644,7 @@ int fh_rwr_chain16(const void* Ahi, const unsigned* amax, float* out, int nb, in
 		long long t0 = h[8] ? h[8] : h[0];
 		fprintf(stderr, "[chain16 trace] nb=%d w=%d k=%d:", nb, w, k);
 		for (int i = 0; i < 32; ++i)
-			if (h[i]) fprintf(stderr, " %d:%lld", i, (i == 5 || i == 6 || i == 13 || i == 14) ? h[i] : h[i] - t0);  // 5/6/13/14: summed waits
+			if (h[i]) fprintf(stderr, " %d:%lld", i, h[i] - t0);
 		fprintf(stderr, "\n");
 	}
 	return FH_OK;
