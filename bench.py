@@ -230,7 +230,7 @@ def baseline_record(t, full_cells, kind, where):
 def build_roofline(per, kt, work, datasets, n_i, pk, dev, top):
 	"""`roofline` of the dominant kernel + `roofline_all` for the three stage groups SURVEY.md 8d names.
 	RWR: HBM bound per 8d (algorithmic bytes = block-CSR read + imputed panel written once), the tensor-pipe figure beside it
-	(the stage is compute bound at fp32 parity: ~170 flop per algorithmic byte, 3 TF32 MMAs per product).
+	(the stage is compute bound at fp32 parity: ~170 flop per algorithmic byte, three binary16 MMAs per product).
 	Contractions: tensor pipe (useful fp32-equivalent flops counted once; 3xTF32 executes 3x that).
 	Per-bin polar: fp64 pipe, against a DGEMM peak measured in this run.
 	achieved = algorithmic work per launch / average launch duration from CUDA events on the launching stream (kt);
@@ -256,15 +256,16 @@ def build_roofline(per, kt, work, datasets, n_i, pk, dev, top):
 		chain = per_launch("rwr_chain_kernel", work["rwr_bytes"], 1e9)
 		t_stage = rwr_flops / (per["rwr"] / 1e3) / 1e12
 		t_chain = per_launch("rwr_chain_kernel", rwr_flops, 1e12)
-		roof_all["rwr"] = {"bound": "hbm", "kernel": "rwr_chain_kernel (tcgen05 3xTF32 + TMA: A A^T, transition matrix, RWR steps with Q in TMEM, Q A)",
+		roof_all["rwr"] = {"bound": "hbm", "kernel": "rwr_chain16_kernel (tcgen05 kind::f16, 3xFP16 operand split, TMA-fed: A A^T, transition matrix, RWR steps with Q in TMEM, Q A)",
 		                   "achieved": chain if chain is not None else stage, "peak": pk["hbm"], "unit": "GB/s",
 		                   "frac": (chain if chain is not None else stage) / pk["hbm"], "stage_achieved": stage, "stage_frac": stage / pk["hbm"],
 		                   "stage": "densify_conv_kernel + rwr_chain_kernel",
 		                   "tensor_side": {"achieved": t_chain if t_chain is not None else t_stage, "stage_achieved": t_stage, "peak": pk["tensor"],
 		                                   "unit": "TFLOP/s", "frac": (t_chain if t_chain is not None else t_stage) / pk["tensor"],
 		                                   "note": "algorithmic fp32 flops (2 nb^2 w for A A^T, 2 nb^3 per step, 2 nb^2 w for Q A) against the measured dense "
-		                                           "bf16 peak; fp32-parity maths executes 3 TF32 MMAs per product on 128-padded tiles (~3.5x the algorithmic "
-		                                           "flops), which is why this stage is bound by the tensor pipe and not by HBM"}}
+		                                           "bf16 peak; fp32-parity maths executes three binary16 MMAs (hi hi + hi lo + lo hi) per product on 128-padded tiles "
+		                                           "(~3.5x the algorithmic flops): the stage is bound by the SM (tensor pipe, shared-memory operand bandwidth, the "
+		                                           "drain warps' fp32 work between the products), not by HBM"}}
 	gem = sum(per.get(k, 0.0) for k in ("p1_mttkrp", "p3_project", "p5_tensor"))
 	if gem > 0:
 		a = work["contraction_flops"] / (gem / 1e3) / 1e12

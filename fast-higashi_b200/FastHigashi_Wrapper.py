@@ -263,6 +263,10 @@ class FastHigashi:
 		n_batch = max(math.ceil(size / recommend_bs_bin), 1)
 		bs_bin_local = math.ceil(size / n_batch)
 		bs_cell = int(max_tensor_size / (bs_bin_local * (bs_bin_local + 2 * self.off_diag)))
+		# one fh_rwr call takes at most 65,535 cells and the auto-stop RWR of init_params / only_partial_rwr is one call per
+		# cell batch (partial_rwr.py:119-123 decides per batch): larger batches would be rejected by the library, so the rule
+		# is capped here (it only binds for > 65,535 cells on one GPU at low resolution, with 180 GB of HBM)
+		bs_cell = min(bs_cell, 65535)
 		ncell_eff = good_qc_num if self.filter else num_cell
 		n_cb = int(math.ceil(ncell_eff / max(bs_cell, 1)))
 		return bs_bin_local, min(int(math.ceil(ncell_eff / n_cb)), ncell_eff)

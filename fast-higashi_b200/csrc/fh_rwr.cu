@@ -408,7 +408,8 @@ extern "C" void fh_count_tc_fallback(void);
 size_t fh_rwr_chain_scratch_bytes();
 int fh_rwr_chain16_pad(int s);
 int fh_rwr_chain16(const void* Ahi, const unsigned* amax, float* out, int nb, int w, int ldw, int ld16, int s, int k,
-                   int ncell, long long a_cell_stride, long long out_cell_stride, void* stream);
+                   int ncell, long long a_cell_stride, long long out_cell_stride, const float* bin_cov, long long bin_cov_ld,
+                   void* stream);
 int fh_rwr_chain(const float* P, const float* A, float* out, int nb, int w, int ldw, int ldp, int s, int k, int ncell,
                  long long p_cell_stride, long long a_cell_stride, long long out_cell_stride, float* scratch,
                  void* stream);
@@ -652,8 +653,8 @@ extern "C" int fh_rwr_batched(const fh_rwr_desc* d, const int32_t* rowptr, const
 	             "fh_rwr_batched: workspace too small (%zu < %zu)", workspace_bytes, fh_rwr_workspace_bytes(d));
 	FH_CHECK_ARG(!d->do_col || bin_cov != nullptr, "fh_rwr_batched: do_col needs bin_cov");
 	RwrWs ws = carve(d, workspace);
-	// forced step count without do_col on the tensor cores (every call of the ALS sweep): 3xFP16 fused kernel
-	if (d->use_tensor_cores && d->k >= 1 && !d->do_col && d->nb <= 128 && rwr_fused_level() >= 2 && rwr_f16_enabled() &&
+	// forced step count on the tensor cores (every call of the ALS sweep; do_col from two steps on): 3xFP16 fused kernel
+	if (d->use_tensor_cores && d->k >= (d->do_col ? 2 : 1) && d->nb <= 128 && rwr_fused_level() >= 2 && rwr_f16_enabled() &&
 	    ((uintptr_t)out & 15) == 0 && (out_cell_stride & 3) == 0 && (d->s & 3) == 0) {
 		const int pad16 = fh_rwr_chain16_pad(d->s);  // 0 or 4: the diagonal block starts at a multiple of 8 plane columns
 		const int ld16 = (d->ldw + pad16 + 7) & ~7;
@@ -669,7 +670,8 @@ extern "C" int fh_rwr_batched(const fh_rwr_desc* d, const int32_t* rowptr, const
 		                                                         conv, ws.A, acs16, ld16, (long long)d->ncell * acs16, ws.amax, pad16);
 		fh_time_end(tmr, st);
 		FH_LAUNCH_CHECK();
-		rc = fh_rwr_chain16(ws.A, ws.amax, out, d->nb, d->w, d->ldw, ld16, d->s, d->k, d->ncell, acs16, out_cell_stride, st);
+		rc = fh_rwr_chain16(ws.A, ws.amax, out, d->nb, d->w, d->ldw, ld16, d->s, d->k, d->ncell, acs16, out_cell_stride,
+		                    d->do_col ? bin_cov : nullptr, bin_cov_ld, st);
 		if (rc == FH_OK) {
 			if (host_n_iter) *host_n_iter = d->k;
 			return FH_OK;

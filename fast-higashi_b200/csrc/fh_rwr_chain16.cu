@@ -42,7 +42,7 @@ constexpr int SLOT_BYTES = 2 * PLANE_BYTES;     // hi | lo
 constexpr int SLOTS = 3;
 constexpr int P_PLANE = 128 * 128 * 2;          // P hi (or lo): [n group (2)][k row (128)][128 B]
 constexpr int EPI_BYTES = 16 * 32 * 16 * 4;     // 16 drain warps x (32 rows x 16 floats)
-constexpr int XCH_FLOATS = 8 * 128;             // row sums [4][128], cs1 / w1 / w2 / flag [128]
+constexpr int XCH_FLOATS = 12 * 128;            // row sums [4][128], cs1 / w1 / w2 / flag [128], do_col: 1 / bin_cov [512]
 constexpr int ONES_BYTES = 4096;                // 128 x 16 halves of 1.0: the A operand of the column-sum MMAs
 constexpr int NTHREADS = 640;
 constexpr int SMEM_BYTES = SLOTS * SLOT_BYTES + 2 * P_PLANE + EPI_BYTES + XCH_FLOATS * 4 + ONES_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -59,6 +59,8 @@ struct Chain16P {
 	const unsigned* amax;  // bits of the largest (floored) CSR value of the block: fixes the panel's scale
 	int s;
 	float* out;
+	const float* bin_cov;  // do_col: [ncell][>= w] per-cell coverage of the window columns (row stride cov_ld), else nullptr
+	long long cov_ld;
 	long long* trace;      // FH_CHAIN_TRACE=1: clock64 stamps of CTA 0's 4th cell (debug)
 };
 #define FH_TRACE(slot)                                                         \
@@ -270,7 +272,8 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 						++ch;
 						if (step == 1) FH_TRACE(29);
 					}
-					umma_commit(f_free);  // P is no longer read once these MMAs have completed
+					if (!p.bin_cov) umma_commit(f_free);  // P is no longer read once these MMAs have completed (do_col: the drain
+					                                      // warps reuse the region for the transpose of Q and release it)
 				}
 				FH_TRACE(10);
 				mbar_wait(q_ready, (uint32_t)(qn & 1)); ++qn;   // Q_k
@@ -331,6 +334,7 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 		float* w1 = xch + 5 * 128;             // per-column weights of the first / second order parts of P
 		float* w2 = xch + 6 * 128;
 		float* cflag = xch + 7 * 128;          // empty column of the blend: its diagonal entry (partial_rwr.py:96-97)
+		float* rcov = xch + 8 * 128;           // do_col: 1 / bin_cov by (shifted) window column, <= 512
 		const int td = threadIdx.x - 128;      // 0..511 among the drain warps
 		// this thread's row of the first-order block / of P in the shared-memory operand: row m of the 64-column group
 		// h >> 1; its 16-byte chunks (8 columns) 4 (h & 1) + g at (chunk ^ (m & 7)); lo plane P_PLANE bytes further
@@ -407,6 +411,14 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 			rowsum[h * 128 + m] = rs;
 			drain_sync();
 			if (td == 0) FH_TRACE(17);
+			if (p.bin_cov) {  // do_col: 1 / bin_cov of this cell's window columns (partial_rwr.py:135), by shifted window column.
+				// After the cell's first drain barrier: no warp still reads the previous cell's table in its epilogue.
+				const float* cv = p.bin_cov + (long long)cell * p.cov_ld;
+				for (int i = td; i < NT * BN; i += 512) {
+					const int n = i - p.pad;
+					rcov[i] = (n >= 0 && n < p.w) ? 1.f / cv[n] : 0.f;
+				}
+			}
 			// per column j: P[i][j] = (3/4 f/(cs1+eps) + 1/4 h/(cs2+eps)) / (csl+eps) = f w1[j] + h w2[j]. The column
 			// sum of the blend is taken analytically, csl = 3/4 cs1/(cs1+eps) + 1/4 cs2/(cs2+eps) (the reference
 			// sums the rounded entries: same value to fp32 rounding), partial_rwr.py:88-97
@@ -504,6 +516,31 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 						for (int j = 0; j < 32; ++j)
 							if (h * 32 + j >= n_step) qv[j] = 0.f;
 					}
+					if (p.bin_cov && step == p.k - 1) {
+						// do_col (partial_rwr.py:131-134): Q <- rownorm(max((Q + Q^T) / 2, 0)). The transpose goes through the P
+						// region (dead: the chain's MMAs have completed) as a 128 x 128 fp32 tile, 16-byte chunk c of row r at
+						// c ^ (r & 7): conflict-free row writes and conflict-free column reads.
+						float* tq = reinterpret_cast<float*>(pbuf);
+#pragma unroll
+						for (int g = 0; g < 8; ++g)
+							*reinterpret_cast<float4*>(tq + m * 128 + (((8 * h + g) ^ (m & 7)) << 2)) = make_float4(qv[4 * g], qv[4 * g + 1], qv[4 * g + 2], qv[4 * g + 3]);
+						drain_sync();
+						float prs = 0.f;
+#pragma unroll
+						for (int j = 0; j < 32; ++j) {
+							const int r = h * 32 + j;  // Q^T[m][r] = Q[r][m]
+							const float t = tq[r * 128 + ((((m >> 2) ^ (r & 7)) << 2) | (m & 3))];
+							qv[j] = fmaxf(0.5f * (qv[j] + t), 0.f);
+							prs += qv[j];
+						}
+						rowsum[h * 128 + m] = prs;
+						drain_sync();  // every transposed read is done: the region may take the next cell's first-order block
+						if (td == 0) mbar_arrive(f_free);
+						const float tot = ((rowsum[m] + rowsum[128 + m]) + (rowsum[256 + m] + rowsum[384 + m])) * QS_INV + EPS;
+						const float rinv = 1.f / tot;
+#pragma unroll
+						for (int j = 0; j < 32; ++j) qv[j] *= rinv;  // (S / 2^14) / (sum / 2^14 + eps) * 2^14
+					}
 					// every MMA that read the old Q completed before acc_full fired
 					uint32_t hi[16], lo[16];
 #pragma unroll
@@ -530,6 +567,13 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 					tmem_ld32(tmem + lane_addr + TM_ACC + (uint32_t)(cb * BN + h * 32), v);
 #pragma unroll
 					for (int j = 0; j < 32; ++j) xs[j] = __uint_as_float(v[j]) * x_scale;
+					if (p.bin_cov) {
+#pragma unroll
+						for (int g = 0; g < 8; ++g) {
+							const float4 rc = *reinterpret_cast<const float4*>(rcov + nt * BN + h * 32 + 4 * g);
+							xs[4 * g] *= rc.x; xs[4 * g + 1] *= rc.y; xs[4 * g + 2] *= rc.z; xs[4 * g + 3] *= rc.w;
+						}
+					}
 				}
 				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 				__syncwarp();
@@ -586,15 +630,19 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 // Ahi: two binary16 planes (hi, then lo at + ncell * a_cell_stride halves) of (ncell, nb, ld16) conv'd panels scaled as
 // described at the top (written by densify_conv_kernel<.., true>), window column c at plane column c + pad with
 // pad = fh_rwr_chain16_pad(s) leading zero columns; amax: the device word that fixes the scale;
+// bin_cov (do_col, partial_rwr.py:131-135; nullptr otherwise): [ncell][>= w] coverage of the window columns;
 // out: cell c at out + c * out_cell_stride, rows of ldw floats (16-byte aligned). Returns FH_ERR_UNSUPPORTED (nothing
 // launched) when the shape is outside the kernel's range - the caller runs the TF32 kernels.
 int fh_rwr_chain16_pad(int s) { return (8 - (s & 7)) & 7; }
 
 int fh_rwr_chain16(const void* Ahi, const unsigned* amax, float* out, int nb, int w, int ldw, int ld16, int s, int k,
-                   int ncell, long long a_cell_stride, long long out_cell_stride, void* stream) {
+                   int ncell, long long a_cell_stride, long long out_cell_stride, const float* bin_cov, long long bin_cov_ld,
+                   void* stream) {
 	if (ncell <= 0) return FH_OK;
 	const int pad = fh_rwr_chain16_pad(s);
-	if (nb > BM || k < 1 || (pad & 3) || ld16 < ldw + pad || (ldw & 3) || (ld16 & 7) || (a_cell_stride & 7) || !aligned16(Ahi) || !aligned16(out) ||
+	// do_col (bin_cov != nullptr): the symmetrisation runs in the last chain step's drain (k >= 2); the reciprocal coverage
+	// table holds 512 shifted window columns
+	if ((bin_cov && (k < 2 || ((ldw + pad + BN - 1) / BN) * BN > 512)) || nb > BM || k < 1 || (pad & 3) || ld16 < ldw + pad || (ldw & 3) || (ld16 & 7) || (a_cell_stride & 7) || !aligned16(Ahi) || !aligned16(out) ||
 	    (out_cell_stride & 3)) {
 		fh_set_error("fh_rwr_chain16: shape outside the fused kernel (nb <= 128, k >= 1, 16-byte aligned rows)");
 		return FH_ERR_UNSUPPORTED;
@@ -619,6 +667,7 @@ int fh_rwr_chain16(const void* Ahi, const unsigned* amax, float* out, int nb, in
 	p.nb = nb; p.w = w; p.ldw = ldw; p.ld16 = ld16; p.k = k; p.ncell = ncell; p.pad = pad;
 	p.a_cell_stride = a_cell_stride; p.out_cell_stride = out_cell_stride;
 	p.Ahi = (const __half*)Ahi; p.amax = amax; p.s = s; p.out = out;
+	p.bin_cov = bin_cov; p.cov_ld = bin_cov_ld;
 	cudaStream_t st = (cudaStream_t)stream;
 	static int trace_on = -1;
 	if (trace_on < 0) { const char* e = getenv("FH_CHAIN_TRACE"); trace_on = (e && e[0] == '1') ? 1 : 0; }

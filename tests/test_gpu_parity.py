@@ -432,6 +432,45 @@ def test_rwr_fused_chain_kernel(k):
 	assert _lib.lib().fh_tc_fallback_count() == fb0  # the tensor-core path really ran
 
 
+@pytest.mark.parametrize("k", [2, 4])
+def test_rwr_fused_chain_kernel_do_col(k):
+	"""do_col inside the fused 3xFP16 kernel (partial_rwr.py:131-135: Q <- rownorm(max((Q + Q^T) / 2, 0)) through a transpose
+	in shared memory in the last step's drain, 1 / bin_cov per window column in the epilogue): more cells than SMs, blocks
+	with and without the shifted window, a coverage table with an infinite entry, against the CPU oracle and the fp32
+	CUDA-core chain."""
+	import math
+	from fasthigashi_b200 import synth, _lib
+	from fasthigashi_b200.partial_rwr import rwr_block_csr, pad4
+	from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset
+	bins, ncell = [250, 90], 330
+	chroms, _ = synth.synth_dataset(bins, ncell, 0.10, off_diag=100, seed=5, num_cluster=4)
+	gen = torch.Generator().manual_seed(11)
+	fb0 = _lib.lib().fh_tc_fallback_count()
+	for ch in chroms:
+		n = ch["n"]
+		bb = math.ceil(n / max(math.ceil(n / 128), 1))
+		mk = lambda device: Chrom_Dataset(Sparse(ch["indices"], ch["values"], ch["shape"]), bs_bin=bb, bs_cell=ncell, compact=True,
+		                                  flank=100, chrom=ch["chrom"], resolution=1000000, device=device)
+		ds_c, ds_g = mk("cpu"), mk(DEV)
+		cov = torch.rand(ncell, n, generator=gen) + 0.5
+		cov[1, :5] = float("inf")
+		for b, g in enumerate(ds_c.geoms):
+			ldw = pad4(g.w)
+			out = torch.full((ncell, g.nb * ldw), float("nan"), device=DEV)
+			ref32 = torch.full((ncell, g.nb * ldw), float("nan"), device=DEV)
+			rwr_block_csr(ds_g, b, 0, ncell, out, g.nb * ldw, k, True, True, True, bin_cov=cov.to(DEV), use_tc=True)
+			rwr_block_csr(ds_g, b, 0, ncell, ref32, g.nb * ldw, k, True, True, True, bin_cov=cov.to(DEV), use_tc=False)
+			got = out.view(ncell, g.nb, ldw)
+			assert torch.isfinite(got).all()
+			assert float(got[:, :, g.w:].abs().sum()) == 0.0
+			per_cell = (got - ref32.view(ncell, g.nb, ldw)).flatten(1).norm(dim=1) / ref32.view(ncell, -1).norm(dim=1)
+			assert float(per_cell.max()) < 1e-5, (n, b, int(per_cell.argmax()))
+			sel = [0, 1, 147, 148, 149, 296, 329]
+			ref, _ = O.partial_rwr(O.densify_block(ds_c, b, 0, ncell)[sel], g.s, g.e, True, True, True, cov[sel][:, g.col0:g.col0 + g.w], k)
+			assert rel_fro(got[sel][:, :, :g.w].cpu().numpy(), ref.numpy()) < 1e-5, (n, b)
+	assert _lib.lib().fh_tc_fallback_count() == fb0  # the fused tensor-core kernel took do_col itself
+
+
 @pytest.mark.parametrize("env", [{"FH_RWR_F16": "0"}, {"FH_RWR_FUSED": "1"}, {"FH_RWR_FUSED": "0"}, {"FH_RWR_F16": "0", "FH_CHAIN_DEBUG": "2"}])
 def test_rwr_alternative_paths(env):
 	"""The library reads its path switches once per process, so the other RWR paths are exercised in a child
