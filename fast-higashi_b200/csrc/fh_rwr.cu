@@ -24,8 +24,8 @@ constexpr int RT = 32;  // output rows per CTA in densify/conv
 __host__ __device__ inline size_t densify_smem_bytes(int ldw) { return (size_t)((RT + 2) * (ldw + 8) + RT + 4) * 4; }
 
 // OUT16: the panel leaves as two binary16 planes (hi = rn16(s x), lo = rn16(s x - hi); rows of ld16 halves, the lo plane
-// lo_plane halves after the hi plane) for the 3xFP16 kernel (fh_rwr_chain16.cu); s is the power of two that brings *amax
-// (the largest floored CSR value of the block: an upper bound of every panel entry) into [2^13, 2^14).
+// lo_plane halves after the hi plane) for the 3xFP16 kernel (fh_rwr_chain16.cu); s is the power of two that brings amax[cell]
+// (the largest floored CSR value of the cell's rows of the block: an upper bound of every entry of its panel) into [2^13, 2^14).
 __device__ __forceinline__ void split_pair16(float a, float b, unsigned& hi, unsigned& lo) {
 	asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
 	float fa, fb;
@@ -139,7 +139,7 @@ densify_conv_kernel(const int32_t* __restrict__ rowptr, const int16_t* __restric
 	__half* dst16 = reinterpret_cast<__half*>(out) + (long long)cell * out_cell_stride + pad16;
 	float sa = 1.f;
 	if (OUT16) {
-		const unsigned abits = max(*amax, __float_as_uint(FH_FLOOR));
+		const unsigned abits = max(amax[cell], __float_as_uint(FH_FLOOR));
 		sa = __uint_as_float((267u - (abits >> 23)) << 23);
 	}
 	const int rows = min(RT, nb - r0);
@@ -382,24 +382,23 @@ sqnorm_kernel(const float* __restrict__ x, const float* __restrict__ y, long lon
 	if (threadIdx.x == 0) atomicAdd(acc, a);
 }
 
-// largest floored value of the CSR rows [row0, row1) -> *amax (bits of a non-negative float: integer order = float order)
-__global__ void __launch_bounds__(256)
-csr_absmax_kernel(const int32_t* __restrict__ rowptr, const float* __restrict__ val, long long row0, long long row1,
+// per cell: largest floored value of its CSR rows of the block -> amax[cell] (bits of a non-negative float; 0 = no entries).
+// One CTA per cell (a cell's slice is a few thousand entries): no atomics, no initialisation pass.
+__global__ void __launch_bounds__(128)
+csr_absmax_kernel(const int32_t* __restrict__ rowptr, const float* __restrict__ val, int cell0, int nb,
                   unsigned* __restrict__ amax) {
-	__shared__ float red[8];
-	const long long lo = rowptr[row0], hi = rowptr[row1];
+	__shared__ float red[4];
+	const long long r0 = (long long)(cell0 + blockIdx.x) * nb;
+	const int lo = rowptr[r0], hi = rowptr[r0 + nb];
 	float m = 0.f;
-	for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x)
-		m = fmaxf(m, __ldg(val + i));
+	for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) m = fmaxf(m, __ldg(val + i));
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
 	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
 	__syncthreads();
-	if (threadIdx.x < 8) {
-		m = red[threadIdx.x];
-#pragma unroll
-		for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
-		if (threadIdx.x == 0 && m > 0.f) atomicMax(amax, __float_as_uint(fmaxf(m, FH_FLOOR)));
+	if (threadIdx.x == 0) {
+		m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+		amax[blockIdx.x] = m > 0.f ? __float_as_uint(fmaxf(m, FH_FLOOR)) : 0u;
 	}
 }
 
@@ -436,7 +435,7 @@ RwrWs carve(const fh_rwr_desc* d, void* ws) {
 	r.Q1 = (float*)b; b += p;
 	r.delta = (float*)b; b += align_up((size_t)d->ncell * 4, 256);
 	r.scratch = (float*)b; b += align_up(fh_rwr_chain_scratch_bytes(), 256);
-	r.amax = (unsigned*)b; b += 256;
+	r.amax = (unsigned*)b; b += align_up((size_t)d->ncell * 4, 256);  // 3xFP16 path: one scale word per cell
 	r.bytes = (size_t)(b - (char*)ws);
 	return r;
 }
@@ -659,8 +658,7 @@ extern "C" int fh_rwr_batched(const fh_rwr_desc* d, const int32_t* rowptr, const
 		const int pad16 = fh_rwr_chain16_pad(d->s);  // 0 or 4: the diagonal block starts at a multiple of 8 plane columns
 		const int ld16 = (d->ldw + pad16 + 7) & ~7;
 		const long long acs16 = (long long)d->nb * ld16;
-		FH_CUDA(cudaMemsetAsync(ws.amax, 0, 4, st));
-		csr_absmax_kernel<<<296, 256, 0, st>>>(rowptr, val, (long long)d->cell0 * d->nb, (long long)(d->cell0 + d->ncell) * d->nb, ws.amax);
+		csr_absmax_kernel<<<d->ncell, 128, 0, st>>>(rowptr, val, d->cell0, d->nb, ws.amax);
 		FH_LAUNCH_CHECK();
 		const size_t smem = densify_smem_bytes(d->ldw);
 		if (smem > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(densify_conv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

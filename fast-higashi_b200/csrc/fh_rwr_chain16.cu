@@ -7,8 +7,8 @@
 // half the shared-memory bytes per operand (scripts/split_precision_study.py: operand error 1.2e-7 on the RWR chain).
 // What that changes in the data flow:
 //   * the conv'd panel arrives ALREADY SPLIT: densify_conv_kernel<.., true> (fh_rwr.cu) writes it as two binary16 planes
-//     (same bytes as fp32), scaled by the power of two that brings the block's largest CSR value into [2^13, 2^14)
-//     (device word `amax`); TMA lands the tiles in the layouts the MMAs read (K-major SWIZZLE_128B for S2, MN-major
+//     (same bytes as fp32), scaled per cell by the power of two that brings its largest CSR value into [2^13, 2^14)
+//     (device words `amax[cell]`); TMA lands the tiles in the layouts the MMAs read (K-major SWIZZLE_128B for S2, MN-major
 //     SWIZZLE_128B for X = Q A) - there are no splitter warps and no generic-proxy pass over the ring;
 //   * P never leaves the SM: the drain warps write its hi / lo tiles (scaled by 2^14) straight into a dedicated
 //     shared-memory operand (MN-major SWIZZLE_128B, conflict-free 16-byte stores) - no global scratch round trip;
@@ -56,7 +56,7 @@ struct Chain16P {
 	int pad;               // plane column of window column 0: (s + pad) % 8 == 0 (TMA box starts must be 16-byte aligned)
 	long long a_cell_stride, out_cell_stride;  // halves / floats
 	const __half* Ahi;     // planes: hi at Ahi, lo at Ahi + ncell * a_cell_stride
-	const unsigned* amax;  // bits of the largest (floored) CSR value of the block: fixes the panel's scale
+	const unsigned* amax;  // [ncell] bits of the largest (floored) CSR value of each cell's slice: fixes that panel's scale
 	int s;
 	float* out;
 	const float* bin_cov;  // do_col: [ncell][>= w] per-cell coverage of the window columns (row stride cov_ld), else nullptr
@@ -318,10 +318,7 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 		const bool diag_chunk = (q == h);   // warp-uniform: rows 32q.. meet columns 32h.. (column - first column = lane)
 		const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
 		float* tile_s = (float*)(stagebuf + (warp - 4) * (32 * 16 * 4));  // one 32 x 16 staging buffer per warp
-		// the panel's scale: amax * sa in [2^13, 2^14)
-		const unsigned abits = max(*p.amax, __float_as_uint(1e-8f));
-		const float sa_inv = __uint_as_float(((abits >> 23) - 13u) << 23);
-		const float s2_scale = sa_inv * sa_inv, x_scale = sa_inv * (1.f / QS);
+		float sa_inv, s2_scale, x_scale;  // the current cell's panel scale (amax[cell] * sa in [2^13, 2^14)) undone
 		auto publish_q = [&]() {
 			tmem_st_wait();
 			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -352,6 +349,12 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 		};
 		long long ch = 0, ncell_done = 0;
 		for (int cell = blockIdx.x; cell < p.ncell; cell += gridDim.x, ++ncell_done) {
+			{
+				const unsigned abits = max(p.amax[cell], __float_as_uint(1e-8f));
+				sa_inv = __uint_as_float(((abits >> 23) - 13u) << 23);
+				s2_scale = sa_inv * sa_inv;
+				x_scale = sa_inv * (1.f / QS);
+			}
 			// ---- A: column sums of the first-order block from the tensor core's ones x F product: all accumulator rows are
 			// equal, lane j of the quarter-0 warps keeps column 32h + j (rows >= nb and window columns >= w are the TMA's
 			// zeros; columns >= nb are masked)
@@ -629,7 +632,7 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 // Ahi: two binary16 planes (hi, then lo at + ncell * a_cell_stride halves) of (ncell, nb, ld16) conv'd panels scaled as
 // described at the top (written by densify_conv_kernel<.., true>), window column c at plane column c + pad with
-// pad = fh_rwr_chain16_pad(s) leading zero columns; amax: the device word that fixes the scale;
+// pad = fh_rwr_chain16_pad(s) leading zero columns; amax: [ncell] device words that fix the scales;
 // bin_cov (do_col, partial_rwr.py:131-135; nullptr otherwise): [ncell][>= w] coverage of the window columns;
 // out: cell c at out + c * out_cell_stride, rows of ldw floats (16-byte aligned). Returns FH_ERR_UNSUPPORTED (nothing
 // launched) when the shape is outside the kernel's range - the caller runs the TF32 kernels.

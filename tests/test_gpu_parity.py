@@ -432,6 +432,34 @@ def test_rwr_fused_chain_kernel(k):
 	assert _lib.lib().fh_tc_fallback_count() == fb0  # the tensor-core path really ran
 
 
+def test_rwr_fused_chain_kernel_cell_scales():
+	"""The binary16 planes of the 3xFP16 kernel carry one power-of-two scale PER CELL (from the cell's largest CSR value), so
+	cells whose values differ by eight decades in one launch - and a cell without any contact - keep the per-cell 1e-5 of the
+	fp32 CUDA-core chain."""
+	from fasthigashi_b200 import synth
+	from fasthigashi_b200.partial_rwr import rwr_block_csr, pad4
+	from fasthigashi_b200.sparse_for_schic import Sparse, Chrom_Dataset
+	ncell = 200
+	chroms, _ = synth.synth_dataset([250], ncell, 0.10, off_diag=100, seed=9, num_cluster=4)
+	ch = chroms[0]
+	idx, val = torch.as_tensor(np.asarray(ch["indices"])), torch.as_tensor(np.asarray(ch["values"])).clone()
+	cell = idx[2]
+	val[cell == 3] *= 1e4
+	val[cell == 5] *= 1e-4
+	keep = cell != 7  # cell 7: no contacts at all
+	ds = Chrom_Dataset(Sparse(idx[:, keep], val[keep], ch["shape"]), bs_bin=125, bs_cell=ncell, compact=True, flank=100,
+	                   chrom="chr1", resolution=1000000, device=DEV)
+	for b, g in enumerate(ds.geoms):
+		ldw = pad4(g.w)
+		out = torch.full((ncell, g.nb * ldw), float("nan"), device=DEV)
+		ref32 = torch.full((ncell, g.nb * ldw), float("nan"), device=DEV)
+		rwr_block_csr(ds, b, 0, ncell, out, g.nb * ldw, 3, True, True, False, use_tc=True)
+		rwr_block_csr(ds, b, 0, ncell, ref32, g.nb * ldw, 3, True, True, False, use_tc=False)
+		assert torch.isfinite(out).all()
+		per_cell = (out - ref32).norm(dim=1) / ref32.norm(dim=1)
+		assert float(per_cell.max()) < 1e-5, (b, int(per_cell.argmax()), float(per_cell.max()))
+
+
 @pytest.mark.parametrize("k", [2, 4])
 def test_rwr_fused_chain_kernel_do_col(k):
 	"""do_col inside the fused 3xFP16 kernel (partial_rwr.py:131-135: Q <- rownorm(max((Q + Q^T) / 2, 0)) through a transpose
