@@ -36,6 +36,7 @@ constexpr int EPI_BYTES = 8 * 32 * 32 * 4;       // epilogue transposes: 8 drain
 constexpr uint32_t TM_A = 2 * BN;                // TMEM: accumulators [0, 2 BN), then per stage A_hi (32 cols) | A_lo (32 cols)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NTHREADS = 512;
+constexpr int TURN_TILES = 8192, TURN_SLOTS = 64;  // split-K turn counters: tiles per launch, launches in flight
 #ifndef FH_GEMM_CHUNK_KB
 #define FH_GEMM_CHUNK_KB 4                       // compile-time knob for A/B builds (FH_NVCC_EXTRA, scripts/gpu_session.sh)
 #endif
@@ -49,7 +50,8 @@ struct TcP {
 	const float* cscale; long long cscale_batch; int cscale_recip;
 	int a_bcast, b_bcast;  // operand shared by all batch items (batch stride 0)
 	int vec_ok;            // C rows are 16-byte aligned: 128-bit epilogue accesses allowed
-	int ksplit, kb_per_split;  // split-K: work item = (tile, k range); partial sums are atomically added to C
+	int ksplit, kb_per_split;  // split-K: work item = (tile, k range); partial sums are added to C with fp32 atomics, or
+	int* turn;             // (FH_GEMM_SPLITK_ORDERED=1) in the order of the ranges: one turn counter per output tile, zero between launches
 	int dbg;               // FH_TC_DEBUG bits (timing experiments only, results wrong): 1 no C stores, 2 no split, 4 no MMA
 };
 
@@ -289,6 +291,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 			float* Cb = C + (long long)bz * p.batch_c;
 			const float* cs = p.cscale ? p.cscale + (long long)bz * p.cscale_batch : nullptr;
 			const int cg = lane & 7, ro = lane >> 3;
+			// split-K: the k ranges of a tile add their partial sums to C in the order of the ranges (range 0 stores
+			// beta C + x, range s waits for range s - 1): a fixed summation order, bit-reproducible, no atomics and no
+			// zero-fill. The ranges of a tile are consecutive work items, i.e. they run on neighbouring CTAs of the same
+			// wave (all CTAs of the persistent grid are resident, and a range only ever waits for a lower work item, so the
+			// wait cannot deadlock); only the drain warps wait - the CTA's loads and MMAs for its next item go on.
+			float beta_t = p.beta;
+			const bool ordered = p.ksplit > 1 && p.turn != nullptr;  // else FH_GEMM_SPLITK_ORDERED=0: fp32 atomics onto beta C
+			if (ordered) {
+				if (ksm > 0) {
+					beta_t = 1.f;
+					if (lane == 0) {
+						const volatile int* tp = p.turn + tl;
+						while (*tp != ksm) __nanosleep(64);
+					}
+					__syncwarp();
+					__threadfence();  // acquire: the previous range's stores to C are visible
+				}
+			}
 #pragma unroll
 			for (int c = 0; c < 2; ++c) {
 				__syncwarp();
@@ -319,26 +339,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 							if (cs) x[e] = p.cscale_recip ? x[e] / csv[e] : x[e] * csv[e];
 						}
 						float* cp = Cb + (long long)r * p.ldc + n;
-						if (p.ksplit > 1) {  // split-K partial: C already holds beta*C (host), add atomically
+						if (p.ksplit > 1 && !ordered) {
 #pragma unroll
 							for (int e = 0; e < 4; ++e)
 								if (n + e < p.N) atomicAdd(cp + e, x[e]);
 						} else if (vec) {
-							if (p.beta != 0.f) {
+							if (beta_t != 0.f) {
 								const float4 o = *reinterpret_cast<const float4*>(cp);
-								x[0] += p.beta * o.x; x[1] += p.beta * o.y; x[2] += p.beta * o.z; x[3] += p.beta * o.w;
+								x[0] += beta_t * o.x; x[1] += beta_t * o.y; x[2] += beta_t * o.z; x[3] += beta_t * o.w;
 							}
 							*reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
 						} else {
 #pragma unroll
 							for (int e = 0; e < 4; ++e)
 								if (n + e < p.N) {
-									if (p.beta != 0.f) x[e] += p.beta * cp[e];
+									if (beta_t != 0.f) x[e] += beta_t * cp[e];
 									cp[e] = x[e];
 								}
 						}
 					}
 				}
+			}
+			if (ordered) {
+				__threadfence();  // release: this range's stores to C before the turn moves on
+				asm volatile("bar.sync 2, 256;" ::: "memory");  // all eight drain warps have stored their part
+				if (threadIdx.x == 256) p.turn[tl] = (ksm + 1 == p.ksplit) ? 0 : ksm + 1;  // the last range leaves the counter at zero
 			}
 		}
 	}
@@ -392,12 +417,16 @@ int fh_gemm_tc(const fh_gemm_desc* d, const float* A, const float* B, float* C, 
 		FH_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
 	}
 	// long-K problems with few output tiles (P3: cells x 256 outputs, K = nb*ldw ~ 36k): split K so every SM
-	// has work; partial sums are added with fp32 atomics (C pre-scaled by beta here)
+	// has work; partial sums are added with fp32 atomics (C pre-scaled by beta here) or, on request, in the order of the k ranges
 	static int dbg = -1;
 	if (dbg < 0) { const char* e = getenv("FH_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
 	p.dbg = dbg;
+	static int ordered_splitk = -1;
+	// FH_GEMM_SPLITK_ORDERED=1: bit-reproducible split-K (the k ranges of a tile take turns on C); default 0: fp32 atomics
+	// (measured at config 2: the ordered mode costs 2.5 ms of a 134 ms sweep - P5 +1.4, P3 +0.7, CP-ALS +0.4)
+	if (ordered_splitk < 0) { const char* e = getenv("FH_GEMM_SPLITK_ORDERED"); ordered_splitk = e ? atoi(e) : 0; }
 	const int nkb_h = fh_cdiv(d->K, BK);
-	p.ksplit = 1; p.kb_per_split = nkb_h;
+	p.ksplit = 1; p.kb_per_split = nkb_h; p.turn = nullptr;
 	// ... and, for any long-K problem, so that the work items fill whole waves of the persistent grid: 196 output tiles
 	// on 148 SMs (P3 at 12,500 cells) are two waves of which the second is a third full; split 3 ways they are four full ones
 	if (nkb_h >= 64 && !d->cscale && d->epilogue == FH_EPI_NONE && (d->beta == 0.0 || d->beta == 1.0)) {
@@ -405,20 +434,34 @@ int fh_gemm_tc(const fh_gemm_desc* d, const float* A, const float* B, float* C, 
 		double best = (double)fh_cdiv(total_tiles, num_sms);  // waves, in units of one unsplit tile
 		for (int c = 2; c <= 8 && nkb_h / c >= 32; ++c) {
 			const double cost = (double)fh_cdiv(total_tiles * c, num_sms) / c;
-			if (cost < best * 0.93) { best = cost; ks = c; }  // atomics + the zero-fill must be paid for
+			if (cost < best * 0.93) { best = cost; ks = c; }  // the ordered read-modify-write of C must be paid for
 		}
 		if (total_tiles * 2 <= num_sms + 12) {  // few tiles: as before, one work item per SM at least
 			int k2 = (int)(num_sms / total_tiles);
 			if (k2 > nkb_h / 32) k2 = nkb_h / 32;
+			if (ordered_splitk && k2 > 8) k2 = 8;  // the ranges of a tile take turns on C: many short ranges would queue behind
+			                                       // each other (the CP-ALS products of this shape run on up to 11 streams anyway)
 			if (k2 > ks) ks = k2;
 		}
-		if (ks > 1) {
+		if (ks > 1 && !ordered_splitk) {  // FH_GEMM_SPLITK_ORDERED=0: zero-fill (beta = 0) + fp32 atomics, any summation order
 			p.kb_per_split = (fh_cdiv(nkb_h, ks) + CHUNK_KB - 1) / CHUNK_KB * CHUNK_KB;
 			p.ksplit = fh_cdiv(nkb_h, p.kb_per_split);
 			if (d->beta == 0.0)
 				for (int b = 0; b < d->batch; ++b)
 					FH_CUDA(cudaMemset2DAsync(C + (long long)b * d->batch_c, (size_t)d->ldc * 4, 0, (size_t)d->N * 4, (size_t)d->M, (cudaStream_t)stream));
 			p.beta = 0.f;
+		} else if (ks > 1 && total_tiles <= TURN_TILES) {
+			p.kb_per_split = (fh_cdiv(nkb_h, ks) + CHUNK_KB - 1) / CHUNK_KB * CHUNK_KB;
+			p.ksplit = fh_cdiv(nkb_h, p.kb_per_split);
+			// turn counters: TURN_SLOTS regions handed out round robin, so that split-K launches in flight on different
+			// streams (CP-ALS runs on up to 11) never share one; every launch leaves its counters at zero
+			static int* turn_base = nullptr;
+			static unsigned turn_seq = 0;
+			if (!turn_base) {
+				FH_CUDA(cudaMalloc(&turn_base, (size_t)TURN_SLOTS * TURN_TILES * sizeof(int)));
+				FH_CUDA(cudaMemset(turn_base, 0, (size_t)TURN_SLOTS * TURN_TILES * sizeof(int)));
+			}
+			p.turn = turn_base + (size_t)(turn_seq++ % TURN_SLOTS) * TURN_TILES;
 		}
 	}
 	const long long work = total_tiles * p.ksplit;

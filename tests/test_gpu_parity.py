@@ -383,17 +383,40 @@ def test_fasthigashi_wrapper_end_to_end(tmp_path):
 
 @pytest.mark.parametrize("beta", [0.0, 1.0])
 def test_gemm_tcgen05_split_k(beta):
-	"""Long-K / few-tile shape (the P3 accumulation M += X W): split-K work items with atomic partial sums."""
+	"""Long-K / few-tile shapes (the P3 accumulation M += X W): split-K work items whose partial sums are added to C with fp32
+	atomics (default) or, with FH_GEMM_SPLITK_ORDERED=1, in the order of the k ranges - then the result is the same bit for
+	bit on every run (checked in a child process by test_gemm_split_k_ordered_is_bit_reproducible); also a shape with more
+	work items than SMs, so that a k range waits for a range of an earlier wave."""
 	L = _lib()
 	g = torch.Generator().manual_seed(11)
-	M, N, K = 200, 256, 4100
-	A, B, C0 = torch.randn(M, K + 0, generator=g), torch.randn(K, N, generator=g), torch.randn(M, N, generator=g)
-	lda = (K + 3) // 4 * 4
-	Ad = torch.zeros(M, lda); Ad[:, :K] = A
-	ref = A.double() @ B.double() + beta * C0.double()
-	Cd = C0.clone().to(DEV)
-	L.gemm(Ad.to(DEV), B.to(DEV), Cd, M, N, K, (lda, 1), (N, 1), N, beta=beta, dtype=L.GEMM_TF32X3)
-	assert rel_fro(Cd.cpu().numpy(), ref.numpy()) < 2e-6
+	for M, N, K in [(200, 256, 4100), (12000, 256, 6200)]:
+		A, B, C0 = torch.randn(M, K + 0, generator=g), torch.randn(K, N, generator=g), torch.randn(M, N, generator=g)
+		lda = (K + 3) // 4 * 4
+		Ad = torch.zeros(M, lda); Ad[:, :K] = A
+		ref = A.double() @ B.double() + beta * C0.double()
+		Adev, Bdev = Ad.to(DEV), B.to(DEV)
+		runs = []
+		for _ in range(3):
+			Cd = C0.clone().to(DEV)
+			L.gemm(Adev, Bdev, Cd, M, N, K, (lda, 1), (N, 1), N, beta=beta, dtype=L.GEMM_TF32X3)
+			runs.append(Cd)
+		assert rel_fro(runs[0].cpu().numpy(), ref.numpy()) < 2e-6
+		if os.environ.get("FH_GEMM_SPLITK_ORDERED") == "1":
+			assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+
+
+def test_gemm_split_k_ordered_is_bit_reproducible():
+	"""The library reads FH_GEMM_SPLITK_ORDERED once per process: the ordered split-K is exercised in a child process."""
+	import subprocess
+	import sys
+	e = dict(os.environ)
+	e["FH_GEMM_SPLITK_ORDERED"] = "1"
+	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
+	                    "-k", "test_gemm_tcgen05_split_k or test_cp_als_matches_reference_fixture", "-p", "no:cacheprovider"], env=e, cwd=root,
+	                   capture_output=True, text=True, timeout=600)
+	assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+	assert "3 passed" in r.stdout, r.stdout[-2000:]
 
 
 @pytest.mark.parametrize("k", [1, 2, 4])
