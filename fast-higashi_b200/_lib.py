@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfh_b200.so")
 
 GEMM_F32, GEMM_F32_ACC64, GEMM_F64, GEMM_F32xF64_F32, GEMM_TF32X3, GEMM_F64xF32_F32 = 0, 1, 2, 3, 4, 5
-EPI_NONE, EPI_DIAG_ADD = 0, 1
+EPI_NONE, EPI_DIAG_ADD, EPI_SYMMETRIC = 0, 1, 2
 
 
 class GemmDesc(C.Structure):

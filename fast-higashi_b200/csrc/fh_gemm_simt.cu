@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(GemmP p, const TA* __restrict__ A, const TB* __restrict__ B, TC* __restrict__ C) {
 	constexpr int NT = 256;
 	static_assert((BM / TM) * (BN / TN) == NT, "tile/thread mismatch");
+	static_assert(BM == BN, "FH_EPI_SYMMETRIC mirrors square tiles");
 	constexpr int PA = 4, PB = 4;
 	__shared__ __align__(16) TAcc As[BK][BM + PA];
 	__shared__ __align__(16) TAcc Bs[BK][BN + PB];
@@ -33,6 +34,8 @@ gemm_simt_kernel(GemmP p, const TA* __restrict__ A, const TB* __restrict__ B, TC
 	const int kbeg = (blockIdx.z % p.splits) * p.kchunk;
 	const int kend = min(p.K, kbeg + p.kchunk);
 	const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+	const bool sym = p.epilogue == FH_EPI_SYMMETRIC;  // square tiles (BM == BN): tiles below the diagonal are mirror images
+	if (sym && blockIdx.x < blockIdx.y) return;
 	const int tid = threadIdx.x;
 	const int tx = tid % (BN / TN), ty = tid / (BN / TN);
 	A += (long long)b * p.batch_a;
@@ -106,6 +109,7 @@ gemm_simt_kernel(GemmP p, const TA* __restrict__ A, const TB* __restrict__ B, TC
 			if (p.splits > 1) { atomicAdd(&C[off], (TC)v); continue; }
 			if (p.beta != 0.0) v += (TAcc)p.beta * (TAcc)C[off];
 			C[off] = (TC)v;
+			if (sym && blockIdx.x > blockIdx.y) C[(long long)n * p.ldc + m] = (TC)v;
 		}
 	}
 }
@@ -170,6 +174,8 @@ extern "C" int fh_gemm_batched(const fh_gemm_desc* d, const void* A, const void*
 	p.alpha = d->alpha; p.beta = d->beta; p.epilogue = d->epilogue; p.diag = d->diag;
 	p.kscale = d->kscale; p.kscale_batch = d->kscale_batch;
 	p.cscale = d->cscale; p.cscale_batch = d->cscale_batch; p.cscale_recip = d->cscale_recip;
+	// FH_EPI_SYMMETRIC only where it is implemented and meaningful; otherwise the full product
+	if (p.epilogue == FH_EPI_SYMMETRIC && (d->M != d->N || d->beta != 0.0 || d->cscale || d->dtype == FH_GEMM_TF32X3)) p.epilogue = FH_EPI_NONE;
 	cudaStream_t st = (cudaStream_t)stream;
 	switch (d->dtype) {
 		case FH_GEMM_F32: return launch<float, float, float, float>(p, A, B, C, st);

@@ -472,10 +472,10 @@ class Fast_Higashi_core:
 				Gb = G_all[off + lo * ns * ns:off + hi * ns * ns]
 				if ldw >= r:
 					_lib.gemm(temp[lo:hi], temp[lo:hi], Gb, ns, ns, ldw, (1, rp), (rp, 1), ns, batch=hi - lo,
-					          batch_strides=(ldw * rp, ldw * rp, ns * ns), dtype=_lib.GEMM_F32_ACC64)
+					          batch_strides=(ldw * rp, ldw * rp, ns * ns), dtype=_lib.GEMM_F32_ACC64, epilogue=_lib.EPI_SYMMETRIC)
 				else:
 					_lib.gemm(temp[lo:hi], temp[lo:hi], Gb, ns, ns, r, (rp, 1), (1, rp), ns, batch=hi - lo,
-					          batch_strides=(ldw * rp, ldw * rp, ns * ns), dtype=_lib.GEMM_F32_ACC64)
+					          batch_strides=(ldw * rp, ldw * rp, ns * ns), dtype=_lib.GEMM_F32_ACC64, epilogue=_lib.EPI_SYMMETRIC)
 			self._toc("polar_bins", t)
 
 		pending, nblk = None, 0
@@ -529,7 +529,8 @@ class Fast_Higashi_core:
 				if hi > lo:
 					nn = ns * ns
 					WTb, Mb = WT_all[off + lo * nn:off + hi * nn], G_all[off + lo * nn:off + hi * nn]
-					_lib.gemm(WTb, WTb, Mb, ns, ns, ns, (1, ns), (ns, 1), ns, batch=hi - lo, batch_strides=(nn, nn, nn), dtype=_lib.GEMM_F64)
+					_lib.gemm(WTb, WTb, Mb, ns, ns, ns, (1, ns), (ns, 1), ns, batch=hi - lo, batch_strides=(nn, nn, nn), dtype=_lib.GEMM_F64,
+					          epilogue=_lib.EPI_SYMMETRIC)  # G^{-1/2} = WT^T WT: symmetric, the tiles below the diagonal are mirrored
 		if tab["world"] > 1:
 			self._allreduce(G_all)
 			self._allreduce(tab["ssum"])

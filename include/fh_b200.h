@@ -45,7 +45,9 @@ enum { FH_GEMM_F32 = 0,         /* fp32 in/out, fp32 accumulate (CUDA cores)    
        FH_GEMM_F32xF64_F32 = 3, /* A fp32, B fp64, fp64 accumulate, fp32 out              */
        FH_GEMM_TF32X3 = 4,      /* fp32 in/out on tcgen05 tensor cores, 3xTF32 split      */
        FH_GEMM_F64xF32_F32 = 5 };/* A fp64, B fp32, fp64 accumulate, fp32 out              */
-enum { FH_EPI_NONE = 0, FH_EPI_DIAG_ADD = 1 };
+enum { FH_EPI_NONE = 0, FH_EPI_DIAG_ADD = 1,
+       FH_EPI_SYMMETRIC = 2 };  /* the caller guarantees C = C^T (B = A^T, M = N, beta = 0): only the tiles on and above the
+                                  diagonal are computed, the others are their mirror images (CUDA-core kernels; elsewhere = NONE) */
 
 typedef struct fh_gemm_desc {
 	int M, N, K, batch;

@@ -55,6 +55,26 @@ def test_gemm_epilogues():
 	assert rel_fro(Cd.cpu().numpy(), ref.numpy()) < 1e-6
 
 
+def test_gemm_symmetric_output():
+	"""FH_EPI_SYMMETRIC (the fp64 Grams T^T T and G^{-1/2} = WT^T WT of the per-bin polar step): only the tiles on and above
+	the diagonal are computed and mirrored - bit-identical to the full product, symmetric bit for bit, both tile sizes."""
+	L = _lib()
+	g = torch.Generator().manual_seed(5)
+	for n, K, bt in [(144, 316, 7), (137, 300, 5), (100, 64, 3), (31, 40, 2)]:
+		T = torch.randn(bt, K, n + 3, generator=g).to(DEV)  # rows of pitch n + 3
+		for dtype, src in ((L.GEMM_F32_ACC64, T), (L.GEMM_F64, T.double())):
+			full = torch.zeros(bt, n, n, dtype=torch.float64, device=DEV)
+			sym = torch.full((bt, n, n), float("nan"), dtype=torch.float64, device=DEV)
+			args = (n, n, K, (1, n + 3), (n + 3, 1), n)
+			L.gemm(src, src, full, *args, batch=bt, batch_strides=(K * (n + 3), K * (n + 3), n * n), dtype=dtype)
+			L.gemm(src, src, sym, *args, batch=bt, batch_strides=(K * (n + 3), K * (n + 3), n * n), dtype=dtype, epilogue=L.EPI_SYMMETRIC)
+			assert torch.equal(sym, sym.transpose(1, 2))
+			up = torch.triu(torch.ones(n, n, dtype=torch.bool, device=DEV))
+			assert torch.equal(sym[:, up], full[:, up])
+			ref = torch.matmul(src.double()[:, :, :n].transpose(1, 2), src.double()[:, :, :n])
+			assert rel_fro(sym.cpu().numpy(), ref.cpu().numpy()) < 1e-12
+
+
 def test_densify_bit_exact():
 	from fasthigashi_b200.partial_rwr import densify_block
 	for ds_c, ds_g in zip(load_small_dataset(good_qc_num=44, bs_cell=20), load_small_dataset(good_qc_num=44, bs_cell=20, device=DEV)):
