@@ -475,6 +475,28 @@ def test_rwr_fused_chain_kernel(k):
 	assert _lib.lib().fh_tc_fallback_count() == fb0  # the tensor-core path really ran
 
 
+@pytest.mark.parametrize("bs_bin", [8, 17, 20, 64])
+def test_rwr_fused_chain_kernel_small_blocks(bs_bin):
+	"""The fused kernels on blocks far below a tile (6 ... 64 rows, windows of 20 ... 90 columns, a last block of a few rows,
+	diagonal offsets that are and are not multiples of 4 - the latter take the 3xTF32 kernel), five steps, fewer cells than
+	SMs: against the oracle, do_col on and off."""
+	from fasthigashi_b200.partial_rwr import rwr_block_csr, pad4
+	cpu = load_small_dataset(bs_bin=bs_bin)
+	gpu = load_small_dataset(bs_bin=bs_bin, device=DEV)
+	gen = torch.Generator().manual_seed(3)
+	for ds_c, ds_g in zip(cpu, gpu):
+		cov = torch.rand(48, ds_c.num_bin, generator=gen) + 0.5
+		for b, g in enumerate(ds_c.geoms):
+			for do_col in (False, True):
+				ldw = pad4(g.w)
+				out = torch.full((48, g.nb * ldw), float("nan"), device=DEV)
+				rwr_block_csr(ds_g, b, 0, 48, out, g.nb * ldw, 5, True, True, do_col, bin_cov=cov.to(DEV), use_tc=True)
+				ref, _ = O.partial_rwr(O.densify_block(ds_c, b, 0, 48), g.s, g.e, True, True, do_col, cov[:, g.col0:g.col0 + g.w], 5)
+				got = out.view(48, g.nb, ldw).cpu()
+				assert rel_fro(got[:, :, :g.w].numpy(), ref.numpy()) < 1e-5, (bs_bin, b, g.nb, g.w, g.s, do_col)
+				assert float(got[:, :, g.w:].abs().sum()) == 0.0
+
+
 def test_rwr_fused_chain_kernel_cell_scales():
 	"""The binary16 planes of the 3xFP16 kernel carry one power-of-two scale PER CELL (from the cell's largest CSR value), so
 	cells whose values differ by eight decades in one launch - and a cell without any contact - keep the per-cell 1e-5 of the
