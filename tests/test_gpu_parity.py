@@ -432,9 +432,9 @@ def test_gemm_split_k_ordered_is_bit_reproducible():
 	e = dict(os.environ)
 	e["FH_GEMM_SPLITK_ORDERED"] = "1"
 	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-	r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
-	                    "-k", "test_gemm_tcgen05_split_k or test_cp_als_matches_reference_fixture", "-p", "no:cacheprovider"], env=e, cwd=root,
-	                   capture_output=True, text=True, timeout=600)
+	tp = os.path.join(root, "tests", "test_gpu_parity.py")
+	r = subprocess.run([sys.executable, "-m", "pytest", tp + "::test_gemm_tcgen05_split_k", tp + "::test_cp_als_matches_reference_fixture",
+	                    "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"], env=e, cwd=root, capture_output=True, text=True, timeout=600)
 	assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 	assert "3 passed" in r.stdout, r.stdout[-2000:]
 
@@ -574,9 +574,9 @@ def test_rwr_alternative_paths(env):
 	e = dict(os.environ)
 	e.update(env)
 	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-	r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
-	                    "-k", "test_rwr_fused_chain_kernel and 4 and not do_col", "-p", "no:cacheprovider"], env=e, cwd=root, capture_output=True, text=True,
-	                   timeout=600)
+	# the exact node id: a -k expression would also pick up every later test whose name or parameters contain its words
+	r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py") + "::test_rwr_fused_chain_kernel[4]",
+	                    "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"], env=e, cwd=root, capture_output=True, text=True, timeout=600)
 	assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 	assert "1 passed" in r.stdout, r.stdout[-2000:]
 
