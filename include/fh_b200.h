@@ -83,12 +83,14 @@ typedef struct fh_rwr_desc {
 	int do_conv, do_rwr, do_col;
 	int cell0;     /* first cell: CSR row of (cell c, row r) is rowptr[(cell0+c)*nb + r]       */
 	int ncell;     /* cells imputed by this call                                              */
-	int use_tensor_cores; /* 1: tcgen05 3xTF32 GEMMs, 0: CUDA-core fp32 GEMMs                 */
+	int use_tensor_cores; /* 1: tcgen05 (fused 3xFP16 / 3xTF32 kernels, 3xTF32 GEMMs), 0: CUDA-core fp32 GEMMs */
 	long long nnz; /* total entries of col/val (bounds the 128-bit vector loads)               */
 } fh_rwr_desc;
 
 size_t fh_rwr_workspace_bytes(const fh_rwr_desc* d);
 /* out: (ncell, nb, ldw) fp32, cell stride out_cell_stride floats; pad columns [w, ldw) are 0.
+ * Forced step counts on the tensor cores run as ONE fused kernel per call when nb <= 128 (3xFP16 operand pairs, do_col included
+ * from two steps on; FH_RWR_F16=0 / FH_RWR_FUSED select the 3xTF32 kernel or the per-step kernels): INTEGRATION.md.
  * bin_cov: [ncell][>=w] per-cell coverage of the window columns (row stride bin_cov_ld), only
  * read when do_col. host_n_iter (may be NULL): receives the RWR step count the reference would
  * return (auto mode: applied steps - 1; forced mode: k). Auto mode synchronises the stream. */
