@@ -13,7 +13,7 @@ cells. Here both factorisations work on the rank-local cell rows and exchange on
   * `sharded_svd_gram`       thin SVD of a tall cell-sharded matrix through its all-reduced Gram
     (fp64 eigh), for the joint embedding (cells x sum r).
 
-Plain torch tensor algebra (cuBLAS / cuSOLVER on the device): this is one-off initialisation, not
+Plain torch tensor algebra (GEMMs plus k x k Cholesky / eigh factorisations): one-off initialisation, not
 the sweep. Works on any device and with `group=None` (single process), which is how the CPU tests
 check it against an exact SVD and against sklearn. The default `init_params` path keeps the
 reference's host SVD (bit-reproducible with its seed); this module is the `init_svd="device"` option.
@@ -28,6 +28,17 @@ def _allreduce(t, group):
 	return t
 
 
+def _small_cholesky(G):
+	"""Lower Cholesky factor of a k x k matrix (k ~ 150), on the host: cuSOLVER's potrf / syevd take tens of milliseconds on
+	matrices of this size, LAPACK well under one (measured: the 22 per-chromosome SVDs of init_params 1.8 s -> see DESIGN 7)."""
+	return torch.linalg.cholesky(G.cpu()).to(G.device)
+
+
+def _small_eigh(G):
+	lam, W = torch.linalg.eigh(G.cpu())
+	return lam.to(G.device), W.to(G.device)
+
+
 def _orthonormalize_sharded(Y, group):
 	"""Q with orthonormal columns spanning the (row-sharded) Y: two rounds of Cholesky-QR in fp64, the
 	k x k Gram all-reduced. A tiny ridge keeps the factorisation defined for rank-deficient sketches."""
@@ -35,9 +46,24 @@ def _orthonormalize_sharded(Y, group):
 		G = _allreduce(Y.T @ Y, group)
 		G = (G + G.T) * 0.5
 		ridge = torch.finfo(G.dtype).eps * G.diagonal().max().clamp_min(1e-300) * G.shape[0]
-		L = torch.linalg.cholesky(G + ridge * torch.eye(G.shape[0], dtype=G.dtype, device=G.device))
+		L = _small_cholesky(G + ridge * torch.eye(G.shape[0], dtype=G.dtype, device=G.device))
 		Y = torch.linalg.solve_triangular(L, Y.T, upper=False).T
 	return Y
+
+
+def _svd_wide_gram(B):
+	"""Thin SVD of the wide k x m matrix B (k ~ 150 sketch rows, m = thousands of features) through eigh of its k x k Gram
+	in fp64: B = Uh diag(S) Vt. Both tall-skinny factorisations of the range finder (the QR of the features x k power
+	iterate and this SVD) went through cuSOLVER's geqrf / gesvd, which took ~50 ms per chromosome whatever the cell count
+	(1.1 s of a 1.4 s init at 2,500 cells); as GEMMs + a k x k eigh they are a few ms. The Gram squares the condition
+	number: the relative error of component i is ~eps (S_0 / S_i)^2, 1e-10 for the leading components kept here."""
+	G = B @ B.T
+	lam, W = _small_eigh((G + G.T) * 0.5)
+	lam, W = lam.flip(0), W.flip(1)
+	S = lam.clamp_min(0).sqrt()
+	floor = S[0] * 1e-12 if S.numel() else S
+	Vt = (W.T @ B) / S.clamp_min(floor)[:, None]
+	return W, S, Vt
 
 
 @torch.no_grad()
@@ -45,22 +71,24 @@ def sharded_truncated_svd(F_local, n_components, n_iter=2, n_oversamples=10, gro
 	"""Rank-`n_components` randomized SVD of F = [F_0; F_1; ...] (rows = cells, sharded over the ranks
 	of `group`). Returns (U_local * S, S, Vt): the embedding rows of the local cells (what
 	`TruncatedSVD.fit_transform` returns), the singular values and the right singular vectors
-	(replicated). The random test matrix comes from a seeded CPU generator, so every rank draws the
-	same one and a run is reproducible for a given world size."""
+	(replicated). The random test matrix comes from a seeded generator of F's device, so every rank draws
+	the same one and a run is reproducible for a given world size."""
 	F = F_local.to(torch.float64)
 	n_feat = F.shape[1]
 	k = min(int(n_components) + int(n_oversamples), n_feat)
-	gen = torch.Generator().manual_seed(int(seed))
-	omega = torch.randn(n_feat, k, generator=gen, dtype=torch.float64).to(F.device)
+	# drawn on the device of F (2.4 M doubles per chromosome from the CPU generator cost ~25 ms each): every rank seeds the
+	# same generator of the same device type, so all ranks still draw the same matrix
+	gen = torch.Generator(device=F.device).manual_seed(int(seed))
+	omega = torch.randn(n_feat, k, generator=gen, dtype=torch.float64, device=F.device)
 	Y = F @ omega
 	for _ in range(int(n_iter)):
 		# power iteration with the right factor re-orthonormalised (replicated, local QR): (F F^T)^q F Omega
 		Z = _allreduce(F.T @ Y, group)
-		Z, _ = torch.linalg.qr(Z)
+		Z = _orthonormalize_sharded(Z, None)           # replicated: Cholesky-QR2 without an exchange (see below)
 		Y = F @ Z
 	Q = _orthonormalize_sharded(Y, group)
 	B = _allreduce(Q.T @ F, group)                     # k x features, replicated
-	Uh, S, Vt = torch.linalg.svd(B, full_matrices=False)
+	Uh, S, Vt = _svd_wide_gram(B)
 	r = min(int(n_components), S.shape[0])
 	U = Q @ Uh[:, :r]
 	# deterministic signs (sklearn's svd_flip, v-based): largest |entry| of every right vector positive

@@ -140,7 +140,6 @@ class Fast_Higashi_core:
 	# I1: init_params, parafac2_intergrative.py:61-301
 	@torch.no_grad()
 	def init_params(self, schic, do_conv, do_rwr, do_col):
-		from sklearn.decomposition import TruncatedSVD
 		dev, R = self.device, self.rank
 		t0 = time.perf_counter()
 		sizes = [self.chrom2size[ds.chrom] for ds in self.schic]
@@ -157,6 +156,16 @@ class Fast_Higashi_core:
 		C = None
 		cstart = 0
 		self.bin_cov_list, self.bad_bin_cov_list, n_i_all = [], [], []
+		# FH_INIT_TIMING=1: where init_params spends its time (synchronises after every part; diagnostics only)
+		import os as _os, time as _time
+		_timing = _os.environ.get("FH_INIT_TIMING") == "1"
+		_acc = {"features (RWR auto-stop + coverage + pooling)": 0.0, "per-chromosome SVD": 0.0, "joint SVD": 0.0}
+
+		def _lap(key, t0):
+			if _timing:
+				torch.cuda.synchronize()
+				_acc[key] += _time.perf_counter() - t0
+			return _time.perf_counter()
 		for ci, ds in enumerate(self.schic):
 			nbad = ds.total_cell_num - ds.num_cell
 			# one coverage table for good then bad cells (rows follow the dataset's cell order)
@@ -203,9 +212,13 @@ class Fast_Higashi_core:
 							del x
 				return fstart
 
+			if _timing:
+				torch.cuda.synchronize()
+			_t = _time.perf_counter()
 			fstart = feature_pass(False, 0)
 			if do_col:
 				fstart = feature_pass(True, fstart)
+			_t = _lap("features (RWR auto-stop + coverage + pooling)", _t)
 			r = self.chrom2size[ds.chrom]
 			# host randomized SVD exactly as the reference (:257-258, numpy global RNG); with cell
 			# sharding the features are gathered to rank 0 (SURVEY.md 8e "init")
@@ -224,11 +237,13 @@ class Fast_Higashi_core:
 					dist.all_gather_object(gathered, f_host, group=self.group)
 					f_host = np.concatenate(gathered, 0)
 				if rank0:
+					from sklearn.decomposition import TruncatedSVD  # host route only: the import alone costs ~1.8 s
 					emb = TruncatedSVD(n_components=r, n_iter=2).fit_transform(f_host)
 					if C is None:
 						C = np.empty((f_host.shape[0], cum[-1]))
 					C[:, cstart:cstart + emb.shape[1]] = emb
 			cstart += r
+			_t = _lap("per-chromosome SVD", _t)
 			ni = torch.tensor([max(n_i_list) if n_i_list else 0], device=dev)
 			if dist is not None:
 				self._allreduce(ni, dist.ReduceOp.MAX)
@@ -241,6 +256,7 @@ class Fast_Higashi_core:
 			del feats
 		self.n_i = np.array(n_i_all)
 		self._log("rwr iters:", self.n_i)
+		_t = _time.perf_counter()
 		# joint SVD of the per-chromosome embeddings (:283-290); one-off, cuSOLVER through torch
 		if self.init_svd == "device":
 			meta, SVh = sharded_svd_gram(C, R, self.group if dist is not None else None)
@@ -273,6 +289,9 @@ class Fast_Higashi_core:
 			for t in self.A_dev + list(self.B_dict.values()):
 				dist.broadcast(t, src=src, group=self.group)
 		self.meta_embedding = meta
+		_lap("joint SVD", _t)
+		if _timing and rank0:
+			print("[init timing] total %.2f s: " % (time.perf_counter() - t0) + ", ".join("%s %.2f s" % kv for kv in _acc.items()), flush=True)
 		self._log(f"time elapsed: {time.perf_counter() - t0:.2f}")
 		self._log("finish init")
 
@@ -618,12 +637,22 @@ class Fast_Higashi_core:
 		"""Everything `fit` does before its sweep loop (:551-632)."""
 		dev, R = self.device, self.rank
 		_lib.require_cuda(getattr(self, "device", "cpu"), "Fast_Higashi_core (call .to('cuda') first)")
+		_timing = os.environ.get("FH_INIT_TIMING") == "1"  # diagnostics: synchronises between the parts
+		_tp = [time.perf_counter()]
+
+		def _mark(what):
+			if _timing:
+				torch.cuda.synchronize()
+				_tp.append(time.perf_counter())
+				print("[prepare timing] %s %.2f s" % (what, _tp[-1] - _tp[-2]), flush=True)
 		self._setup(schic, size_ratio, size_list)
 		self._log("empty params initialized")
+		_mark("_setup")
 		if state is not None:
 			self.load_state(*state)
 		elif run_init:
 			self.init_params(schic, do_conv, do_rwr, do_col)
+		_mark("init_params / load_state")
 		self._flags = (do_conv, do_rwr, do_col)
 		self.projection_dev = [[torch.zeros(g.nb, pad4(g.w), pad4(self.chrom2size[ds.chrom]), dtype=torch.float32, device=dev)
 		                        for g in ds.geoms] for ds in self.schic]
@@ -637,6 +666,7 @@ class Fast_Higashi_core:
 		self._xnorm = None
 		self.re_trace, self.sweep_seconds, self.loss_terms = [], [], []
 		self._rec_errors = []
+		_mark("buffers + core norms")
 
 	def sweep_once(self, n_iter_parafac=1):
 		"""One iteration of the reference's outer loop (:635-737): projections + V update + projected
