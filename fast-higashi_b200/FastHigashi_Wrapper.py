@@ -453,20 +453,22 @@ class FastHigashi:
 	def _reduce(self, embedding, dim, svd):
 		"""TruncatedSVD(n_components=dim).fit_transform(embedding): sklearn on the host (reference behaviour, :767,:872) or
 		the same randomized algorithm on the device (dist_svd.py; matters from ~100k cells on)."""
+		if svd == "auto":  # the reference's host route (same numpy RNG stream) up to 20,000 cells, the device above - as init_svd
+			svd = "host" if (embedding.shape[0] <= 20000 or not torch.cuda.is_available()) else "device"
 		if svd == "host":
 			from sklearn.decomposition import TruncatedSVD
 			return TruncatedSVD(n_components=dim).fit_transform(embedding)
 		if svd != "device":
-			raise ValueError("svd must be 'host' or 'device'")
+			raise ValueError("svd must be 'auto', 'host' or 'device'")
 		from .dist_svd import sharded_truncated_svd
 		dev = getattr(self, "device", "cpu")
 		emb, _, _ = sharded_truncated_svd(torch.as_tensor(embedding, dtype=torch.float64).to(dev), dim, n_iter=5,
 		                                  seed=int(np.random.randint(0, 2 ** 31 - 1)))
 		return emb.cpu().numpy()
 
-	def fetch_cell_embedding(self, final_dim=None, restore_order=False, svd="host"):
-		"""FastHigashi_Wrapper.py:750-789 (host numpy/sklearn post-processing, as in the reference; `svd="device"` runs the
-		two truncated SVDs on the GPU)."""
+	def fetch_cell_embedding(self, final_dim=None, restore_order=False, svd="auto"):
+		"""FastHigashi_Wrapper.py:750-789. `svd`: "host" = numpy / sklearn post-processing exactly as the reference, "device" =
+		the two truncated SVDs on the GPU (dist_svd.py), "auto" (default) = host up to 20,000 cells, device above."""
 		print("fetching embedding")
 		from sklearn.preprocessing import quantile_transform, normalize
 		final_dim = self.rank if final_dim is None else final_dim
