@@ -87,7 +87,7 @@ rwr_chain16_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 	uint64_t* q_ready = bars + 2 * SLOTS + 4;     // Q hi / lo stored in TMEM    (count 16: drain warps)
 	uint64_t* p_written = bars + 2 * SLOTS + 5;   // P of the current cell is in shared memory (count 1)
 	uint64_t* f_full = bars + 2 * SLOTS + 6;      // first-order block landed in the P region (count 1 + tx)
-	uint64_t* f_free = bars + 2 * SLOTS + 7;      // P region no longer read: chain MMAs done (tcgen05.commit) / k = 1: drain
+	uint64_t* f_free = bars + 2 * SLOTS + 7;      // P region no longer read: chain MMAs done (tcgen05.commit) / k = 1, do_col: drain
 	uint64_t* s2_full = bars + 2 * SLOTS + 8;     // S2 of a cell complete in its own accumulator (tcgen05.commit)
 	uint64_t* s2_empty = bars + 2 * SLOTS + 9;    // ... and read by the drain warps (count 16)
 	uint32_t* tmem_holder = (uint32_t*)(bars + 2 * SLOTS + 10);
