@@ -433,3 +433,52 @@ def test_distributed_wrapper_on_two_gloo_ranks(fake, tmp_path):
 				# the auto-stop is per cell batch, so a slab may stop one step earlier or later than the full batch
 				assert np.linalg.norm(p[k] - ref[k]) <= 0.05 * np.linalg.norm(ref[k])
 	assert res[0][8]                                   # rank 0 wrote results_all*.pkl
+
+
+def test_transform_with_other_flags_never_reuses_the_fitted_maps(fake):
+	"""`transform(do_col=...)` with flags other than fit's (round-1 advisor item): the imputed maps of the last sweep and the
+	kept Z = X^T V are dropped and every block is imputed again with the new flags - the embedding equals that of a core
+	that was fitted to the same factors and transformed with those flags from scratch (cache='run' as well)."""
+	g = np.load(os.path.join(GOLDEN, "core_col.npz"))
+	good = int(g["good_qc_num"])
+	out = {}
+	for cache in ("sweep", "run"):
+		core = _core(int(g["rank"]), 12, [1000000], cache=cache)
+		ds = load_small_dataset(good_qc_num=good, bs_cell=int(g["bs_cell"]))
+		core.fit(ds, 0.3, 2, 1, True, True, False, 0.0, verbose=False, state=_state(g, 3, 3))     # fitted with do_col=False
+		fake.calls.clear()
+		_, (_, _, _, V_same), _ = core.transform()                                                    # fit's flags
+		same_calls = fake.calls["rwr_batched"]
+		fake.calls.clear()
+		_, (_, _, _, V_col), _ = core.transform(do_col=True)                                          # other flags: re-impute
+		assert fake.calls["rwr_batched"] > same_calls or cache == "sweep"
+		assert core._X_flags == (True, True, True) and not core._Z_valid
+		out[cache] = (V_same.numpy().copy(), V_col.numpy().copy())
+		assert rel_fro(out[cache][1], out[cache][0]) > 1e-3                                           # do_col changes the maps
+	assert rel_fro(out["run"][1], out["sweep"][1]) < 1e-5 and rel_fro(out["run"][0], out["sweep"][0]) < 1e-5
+	# from scratch: same factors, only the do_col transform
+	core = _core(int(g["rank"]), 12, [1000000])
+	ds = load_small_dataset(good_qc_num=good, bs_cell=int(g["bs_cell"]))
+	core.fit(ds, 0.3, 2, 1, True, True, False, 0.0, verbose=False, state=_state(g, 3, 3))
+	core.release()
+	_, (_, _, _, V_ref), _ = core.transform(do_col=True)
+	assert rel_fro(V_ref.numpy(), out["sweep"][1]) < 1e-5
+
+
+def test_load_state_without_bad_cell_coverage_gives_them_a_zero_column_scale(fake):
+	"""The reference stores 0 for "no coverage table of the bad-QC cells"; a do_col transform then reads rows of inf
+	(column scale 1 / bin_cov = 0) for them instead of running past the end of the good cells' table (advisor item)."""
+	g = np.load(os.path.join(GOLDEN, "core_col.npz"))
+	good = int(g["good_qc_num"])
+	assert good < 48
+	st = list(_state(g, 3, 3))
+	st[5] = [0, 0, 0]
+	core = _core(int(g["rank"]), 12, [1000000])
+	ds = load_small_dataset(good_qc_num=good, bs_cell=int(g["bs_cell"]))
+	core.fit(ds, 0.3, 1, 1, True, True, True, 0.0, verbose=False, state=tuple(st))
+	for ci, d in enumerate(core.schic):
+		cov = core._cov_all[ci]
+		assert tuple(cov.shape) == (d.total_cell_num, d.num_bin)
+		assert torch.isinf(cov[d.num_cell:]).all() and torch.equal(cov[:d.num_cell], core.bin_cov_list[ci])
+	_, (_, _, _, V), _ = core.transform()
+	assert tuple(V.shape) == (48, int(g["rank"])) and torch.isfinite(V).all()
