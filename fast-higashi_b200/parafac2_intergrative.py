@@ -532,6 +532,16 @@ class Fast_Higashi_core:
 				pending = (work, ci, b, T1, Bp)
 		if pending is not None:
 			finish_block(pending)
+		# Streaming input (bench.py's end-to-end leg, a caller that re-stages cells between sweeps): phase A holds the only
+		# reads of the block-CSR in a sweep (phases C and P5 reuse the imputed X), so from here on the caller may overwrite
+		# the datasets' device arrays with the NEXT sweep's input. `inputs_consumed_hook(event)` is called once per sweep with
+		# an event recorded on the compute stream behind the last RWR launch; an upload stream that waits for it overlaps
+		# the rest of this sweep (per-bin polar, P3, P4, P5, CP-ALS) instead of starting after the sweep's final read-back.
+		hook = getattr(self, "inputs_consumed_hook", None)
+		if hook is not None:
+			consumed = torch.cuda.Event()
+			consumed.record()
+			hook(consumed)
 		# ---- phase B: G^{-1/2} of all bins of all chromosomes at once (P2b)
 		t = self._tic()
 		if tab["world"] > 1:

@@ -482,3 +482,29 @@ def test_load_state_without_bad_cell_coverage_gives_them_a_zero_column_scale(fak
 		assert torch.isinf(cov[d.num_cell:]).all() and torch.equal(cov[:d.num_cell], core.bin_cov_list[ci])
 	_, (_, _, _, V), _ = core.transform()
 	assert tuple(V.shape) == (48, int(g["rank"])) and torch.isfinite(V).all()
+
+
+def test_inputs_consumed_hook_fires_behind_the_last_csr_read_of_a_sweep(fake, monkeypatch):
+	"""`inputs_consumed_hook` (streaming input: bench.py's end-to-end leg uploads the next step's block-CSR from it): called
+	once per sweep, after every RWR call of the sweep - the only readers of the block-CSR - and before the per-bin polar;
+	phases C / P5 reuse the imputed X, so nothing reads the CSR after the hook (cache='sweep' and 'run')."""
+	class _Event:
+		def record(self, *a):
+			self.recorded = True
+	monkeypatch.setattr(torch.cuda, "Event", _Event)
+	g = np.load(os.path.join(GOLDEN, "core_nocol.npz"))
+	for cache in ("sweep", "run"):
+		fake.calls.clear()
+		core = _core(int(g["rank"]), 12, [1000000], cache=cache)
+		core.prepare(load_small_dataset(), 0.3, True, True, False, state=_state(g, 3, 3))
+		seen = []
+		core.inputs_consumed_hook = lambda ev: seen.append((getattr(ev, "recorded", False), fake.calls.get("rwr_batched", 0),
+		                                                    fake.calls.get("polar_isqrt_multi", 0)))
+		after = []
+		for t in range(3):
+			core.sweep_once(1)
+			after.append(fake.calls["rwr_batched"])
+		assert len(seen) == 3 and all(s[0] for s in seen)
+		assert [s[1] for s in seen] == after                      # no RWR call (no CSR read) after the hook within a sweep
+		assert [s[2] for s in seen] == [0, 1, 2]                  # fired before the sweep's polar stage
+		assert after[0] > 0 and (after[2] == 3 * after[0] if cache == "sweep" else after[2] == after[0])
