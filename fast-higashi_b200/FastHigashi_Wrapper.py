@@ -28,7 +28,6 @@ import json
 import math
 import os
 import pickle
-import sys
 import time
 
 import numpy as np

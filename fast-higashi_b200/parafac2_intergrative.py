@@ -26,7 +26,7 @@ import torch
 
 from . import _lib
 from .partial_rwr import rwr_block_csr, pad4, cells_per_chunk
-from .project2orthogonal import polar_batched, polar_tall
+from .project2orthogonal import polar_tall
 from .parafac_integrative import cp_als_, core_sqnorm_accum
 from .sparse_for_schic import Chrom_Dataset
 from .sharding import polar_bin_range

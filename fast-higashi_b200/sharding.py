@@ -2,7 +2,6 @@
 slab of cells for ALL chromosomes; A, B, D, U, Y are replicated; T1, Y, the R x R Gram of
 SVD_term^T and two scalars are all-reduced every sweep; the per-bin polar problems (which depend only
 on all-reduced data) are partitioned across ranks and their inverse square roots exchanged."""
-import numpy as np
 
 
 def cell_slab(total_cells, world_size, rank):
