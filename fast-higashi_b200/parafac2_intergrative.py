@@ -41,6 +41,10 @@ def _as_block_csr(ds, device):
 	raise TypeError("schic entries must be Chrom_Dataset objects (ours or the reference's)")
 
 
+MAX_POLAR_SIDE = 160  # fh_polar.cu kMaxGram: a Gram matrix of that side (fp64) fills the 227 KB of shared memory
+MAX_CP_RANK = 169     # fh_cp.cu: (r (r | 1) + r) * 8 bytes of shared memory for the r x r SPD inverse
+
+
 class Fast_Higashi_core:
 	HOST_INIT_MAX_CELLS = 20000  # init_svd="auto": above this (or when cell-sharded) the init SVDs stay on the device
 
@@ -121,6 +125,7 @@ class Fast_Higashi_core:
 					raise EOFError
 				chrom2size[ds.chrom] = size
 		self.chrom2size = chrom2size
+		self._check_limits()
 		self.chrom2num_bin = {}
 		self.chrom2id = {c: [] for c in chrom2size}
 		for ci, ds in enumerate(self.schic):
@@ -135,6 +140,19 @@ class Fast_Higashi_core:
 				pass
 		self.num_cell = self.schic[0].num_cell
 		self.total_cell_num = self.schic[0].total_cell_num
+
+	def _check_limits(self):
+		"""The library's size limits (INTEGRATION.md "Limits"), checked BEFORE init_params spends its RWR passes: the per-bin
+		polar step keeps a Gram matrix of side min(window, r) in shared memory (fh_polar.cu: <= 160) and the inner CP-ALS an
+		r x r fp64 SPD inverse (fh_cp.cu: r <= 169). The reference has no such limit (rank 256 with dim1 > 0.64 on human chr1
+		at 500 kb gives r > 160): fail here with the way out instead of at the first sweep."""
+		for ds in self.schic:
+			r = self.chrom2size[ds.chrom]
+			side = max(min(pad4(g.w), r) for g in ds.geoms)
+			if side > MAX_POLAR_SIDE or r > MAX_CP_RANK:
+				raise ValueError("%s at %d bp: per-chromosome rank r = %d (Gram side %d of the per-bin polar step) exceeds this library's limits "
+				                 "(Gram side <= %d, r <= %d); lower size_ratio / dim1 (r = int(bins * dim1 * resolution / 1e6)) or pass size_list"
+				                 % (ds.chrom, ds.resolution, r, side, MAX_POLAR_SIDE, MAX_CP_RANK))
 
 	# ------------------------------------------------------------------------------------------
 	# I1: init_params, parafac2_intergrative.py:61-301

@@ -508,3 +508,24 @@ def test_inputs_consumed_hook_fires_behind_the_last_csr_read_of_a_sweep(fake, mo
 		assert [s[1] for s in seen] == after                      # no RWR call (no CSR read) after the hook within a sweep
 		assert [s[2] for s in seen] == [0, 1, 2]                  # fired before the sweep's polar stage
 		assert after[0] > 0 and (after[2] == 3 * after[0] if cache == "sweep" else after[2] == after[0])
+
+
+def test_size_limits_are_checked_before_init(fake):
+	"""The library's limits on the per-chromosome rank (per-bin polar: Gram side min(window, r) <= 160; inner CP-ALS: r <= 169)
+	stop a run in _setup - before init_params' RWR passes - with a ValueError that names the chromosome and the way out; the
+	reference has no such limit (rank 256, dim1 > 0.64 at 500 kb). Sizes inside the limits pass."""
+	from types import SimpleNamespace as NS
+	from fasthigashi_b200 import parafac2_intergrative as P
+	core = _core(256, 12, [1000000])
+	ds = load_small_dataset()
+	with pytest.raises(ValueError, match="chr1.*r <= 169"):
+		core._setup(ds, 0.3, [200, 200, 200])          # narrow windows (Gram side = window), but r beyond the CP-ALS limit
+	core._setup(ds, 0.3, [165, 165, 165])              # Gram side = window width < 160, r <= 169: fine
+	assert core.chrom2size["chr1"] == 165
+	# a 500 kb chr1 block (115 rows, window 315) at dim1 = 0.7: r = int(499 * 0.7 * 0.5) = 174 -> Gram side 174
+	core.schic = [NS(chrom="chr1", resolution=500000, geoms=[NS(w=215), NS(w=315)])]
+	core.chrom2size = {"chr1": 161}
+	with pytest.raises(ValueError, match="Gram side 161"):
+		core._check_limits()
+	core.chrom2size = {"chr1": P.MAX_POLAR_SIDE}
+	core._check_limits()
