@@ -86,3 +86,14 @@ def test_reference_arm_other_ranks_exit_without_work():
 	p = _run_reference_arm({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, "--gpus", "2", "--steps", "1", "--warmup", "1")
 	assert p.returncode == 0, p.stderr[-2000:]
 	assert [l for l in p.stdout.splitlines() if l.strip()] == ["NO_PRODUCT_LIB"]
+
+
+def test_b200_arm_fails_loudly_without_a_gpu():
+	"""No CPU fallback: on a box without a CUDA device the product arm stops with an assertion instead of timing anything."""
+	import torch
+	if torch.cuda.is_available():
+		pytest.skip("a CUDA device is present")
+	p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+	                   cwd=ROOT, timeout=900)
+	assert p.returncode != 0 and "needs a CUDA device (no CPU fallback)" in p.stderr
+	assert not [l for l in p.stdout.splitlines() if l.startswith("{")]
