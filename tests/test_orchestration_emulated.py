@@ -196,15 +196,18 @@ def _sharded_worker(rank, world, port, q, do_col, good, bs_cell, init_svd):
 	dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("do_col,good,bs_cell,init_svd", [(False, -1, 24, "host"), (True, 44, 22, "host"), (False, -1, 24, "device")])
-def test_two_rank_gloo_run_equals_single_process(do_col, good, bs_cell, init_svd):
+@pytest.mark.parametrize("do_col,good,bs_cell,init_svd,world", [(False, -1, 24, "host", 2), (True, 44, 22, "host", 2), (False, -1, 24, "device", 2),
+                                                                (True, -1, 16, "host", 3)])
+def test_two_rank_gloo_run_equals_single_process(do_col, good, bs_cell, init_svd, world):
 	"""The whole cell-sharded run (init with features gathered to rank 0 and the MAX of the RWR step counts, all-reduced
 	T1 / Gram / Y, per-bin polar problems partitioned over the ranks, factor broadcast, transform with bad-QC cells) on two
 	gloo ranks against the same run in one process: same n_i, loss trace to 1e-6, identical factors on both ranks,
 	embeddings of all cells in the unsharded order. `bs_cell` is chosen so that the good-cell batches of the single process
 	are the two slabs: the reference's auto-stop in `init_params` is per CELL BATCH (partial_rwr.py:119-123), so the init
 	features - and with them the whole run - depend on the batch composition (1e-4 on the loss with other batch sizes).
-	init_svd='device': the init SVDs stay cell-sharded (dist_svd.py: only sketches and k x k Grams are all-reduced)."""
+	init_svd='device': the init SVDs stay cell-sharded (dist_svd.py: only sketches and k x k Grams are all-reduced).
+	world = 3: uneven shares of the per-bin polar problems (blocks of 32 / 26 / 6 ... rows over three ranks), one chromosome's
+	CP-ALS per rank, 16-cell slabs."""
 	import torch.multiprocessing as mp
 	f, undo = fake_abi.install()
 	try:
@@ -219,16 +222,17 @@ def test_two_rank_gloo_run_equals_single_process(do_col, good, bs_cell, init_svd
 	ctx = mp.get_context("spawn")
 	q = ctx.Queue()
 	port = _free_port()
-	procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q, do_col, good, bs_cell, init_svd)) for r in range(2)]
+	procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, q, do_col, good, bs_cell, init_svd)) for r in range(world)]
 	for p in procs: p.start()
 	res = sorted([q.get(timeout=180) for _ in procs], key=lambda r: r[0])
 	for p in procs: p.join(timeout=60)
 	for r in res:
 		assert r[1] == n_i1
 		assert np.allclose(r[2], re1, rtol=1e-6), (r[2], re1)
-	for a, b in zip(res[0][4] + res[0][5], res[1][4] + res[1][5]):
-		assert np.array_equal(a, b)                                      # replicas stay bit-identical
-	assert np.array_equal(res[0][3], res[1][3])
+	for other in res[1:]:
+		for a, b in zip(res[0][4] + res[0][5], other[4] + other[5]):
+			assert np.array_equal(a, b)                                  # replicas stay bit-identical
+		assert np.array_equal(res[0][3], other[3])
 	V2 = res[0][3]
 	assert V2.shape == tuple(V1.shape)
 	E1 = O.embed_all(V1.numpy(), [d.numpy() for d in D1])
