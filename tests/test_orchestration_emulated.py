@@ -241,6 +241,47 @@ def test_two_rank_gloo_run_equals_single_process(do_col, good, bs_cell, init_svd
 		assert abs(np.corrcoef(E1[:, j], E2[:, j])[0, 1]) > 0.9999
 
 
+def _sharded_multires_worker(rank, world, port, q):
+	import torch.distributed as dist
+	os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+	dist.init_process_group("gloo", rank=rank, world_size=world)
+	torch.set_num_threads(2)
+	fake_abi.install()
+	from fasthigashi_b200.sharding import shard_datasets, cell_slab
+	from fasthigashi_b200.parafac2_intergrative import Fast_Higashi_core
+	ds, g = load_multires_dataset()
+	nchrom = len(g["chrom2size"])
+	lo, hi = cell_slab(ds[0].num_cell, world, rank)
+	st = _state(g, len(ds), nchrom)
+	st = (st[0], st[1], st[2], st[3][lo:hi], [c[lo:hi] for c in st[4]], st[5], st[6])   # V rows and coverage rows of the slab
+	core = Fast_Higashi_core(int(g["rank"]), int(g["off_diag"]), [int(r) for r in g["res"]], group=dist.group.WORLD).to("cpu")
+	core.fit(shard_datasets(ds, world, rank), 0.3, 2, 1, True, True, False, 0.0, verbose=False, state=st)
+	q.put((rank, list(core.re_trace), [core.projected_tensor_list[c].numpy() for c in core.chrom2size],
+	       [a.numpy() for a in core.A_list] + [core.B_dict[c].numpy() for c in core.chrom2size] + [core.D_dict[c].numpy() for c in core.chrom2size]))
+	dist.destroy_process_group()
+
+
+def test_two_rank_gloo_multi_resolution_lockstep():
+	"""The multi-resolution path cell-sharded over two gloo ranks (stacked bins of a chromosome's resolutions all-reduced as one
+	projected tensor, one CP-ALS per chromosome on its owner rank, the stacked A rows split back and exchanged), in lock-step
+	from the reference's state: the reference's losses <= 1e-4, its projected tensors, identical replicas."""
+	import torch.multiprocessing as mp
+	_, g = load_multires_dataset()
+	ctx = mp.get_context("spawn")
+	q = ctx.Queue()
+	port = _free_port()
+	procs = [ctx.Process(target=_sharded_multires_worker, args=(r, 2, port, q)) for r in range(2)]
+	for p in procs: p.start()
+	res = sorted([q.get(timeout=240) for _ in procs], key=lambda r: r[0])
+	for p in procs: p.join(timeout=60)
+	for r in res:
+		assert np.max(np.abs(np.array(r[1]) - g["re"][:2]) / g["re"][:2]) < 1e-4, (r[1], g["re"][:2])
+		for c, Y in enumerate(r[2]):
+			assert rel_fro(Y, g["t1_Y%d" % c]) < 1e-3
+	for a, b in zip(res[0][2] + res[0][3], res[1][2] + res[1][3]):
+		assert np.array_equal(a, b)
+
+
 def test_headline_job_script_runs_end_to_end(fake):
 	"""scripts/headline_run.py (init + S sweeps + transform on per-rank synthetic slabs, the north star's full job) at a toy
 	size: the JSON fields exist, the loss decreases, one RWR pass per sweep plus the one of transform's cache refresh."""
