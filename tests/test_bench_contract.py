@@ -96,3 +96,28 @@ def test_b200_arm_fails_loudly_without_a_gpu():
 	                   cwd=ROOT, timeout=900)
 	assert p.returncode != 0 and "needs a CUDA device (no CPU fallback)" in p.stderr
 	assert not [l for l in p.stdout.splitlines() if l.startswith("{")]
+
+
+def test_roofline_object_of_the_dominant_kernel(config2_geometry):
+	"""`roofline` describes the kernel with the largest per-kernel total of a sweep: bound / achieved / peak / unit / frac = achieved / peak,
+	`traffic` = that kernel's dram bytes per launch from the committed ncu capture (profiles/r02_ncu_traffic.json), the RWR stage reported
+	against the HBM peak with its tensor side beside it. Per-stage and per-kernel times are the final record's."""
+	bench, bins, ds = config2_geometry
+	work = bench.algorithmic_work(ds, bench.RANK)
+	pk = bench.peaks()
+	per = {"rwr": 39.0, "p1_mttkrp": 3.2, "p3_project": 19.0, "p5_tensor": 17.7, "cp_als": 5.3, "polar_cells": 1.6}
+	kt = {"densify_conv_kernel": {"ms_per_sweep": 8.7, "launches_per_sweep": 99}, "rwr_chain_kernel": {"ms_per_sweep": 28.6, "launches_per_sweep": 99},
+	      "gemm_tc_kernel": {"ms_per_sweep": 39.0, "launches_per_sweep": 422}, "chol_jacobi_rb_kernel": {"ms_per_sweep": 34.9, "launches_per_sweep": 5}}
+	roof, roof_all = bench.build_roofline(per, kt, work, ds, [4] * len(ds), pk, "cpu", "rwr")
+	assert roof["dominant_kernel"] == "gemm_tc_kernel" and roof["bound"] == "tensor" and roof["unit"] == "TFLOP/s"
+	assert roof["peak"] == pk["tensor"] and roof["frac"] == pytest.approx(roof["achieved"] / roof["peak"])
+	assert roof["achieved"] == pytest.approx(work["contraction_flops"] / (39.9e-3) / 1e12)
+	traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+	assert roof["traffic"] == traffic["gemm_tc_kernel"]["dram_bytes_per_launch"] and "ncu" in roof["traffic_source"]
+	r = roof_all["rwr"]
+	assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] == pk["hbm"]
+	assert r["achieved"] == pytest.approx(work["rwr_bytes"] / 28.6e-3 / 1e9) and r["stage_achieved"] == pytest.approx(work["rwr_bytes"] / 39.0e-3 / 1e9)
+	assert r["frac"] == pytest.approx(r["achieved"] / pk["hbm"]) and r["tensor_side"]["unit"] == "TFLOP/s"
+	kt["rwr_chain_kernel"]["ms_per_sweep"] = 50.0
+	roof, _ = bench.build_roofline(per, kt, work, ds, [4] * len(ds), pk, "cpu", "rwr")
+	assert roof["dominant_kernel"] == "rwr_chain_kernel" and roof["bound"] == "hbm" and roof["traffic"] == traffic["rwr_chain_kernel"]["dram_bytes_per_launch"]
