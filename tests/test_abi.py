@@ -102,3 +102,73 @@ def _bad_gemm():
 	d = _lib.GemmDesc()
 	d.M = d.N = d.K = 4; d.batch = 1; d.sa_m, d.sa_k, d.sb_k, d.sb_n, d.ldc, d.alpha = 2, 2, 4, 1, 4, 1.0
 	return d
+
+
+def _prototypes(header="fh_b200.h"):
+	"""{name: [parameter declarations]} of every `fh_*` function the header declares (comments stripped)."""
+	src = open(os.path.join(ROOT, "include", header)).read()
+	src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+	src = re.sub(r"//[^\n]*", "", src)
+	out = {}
+	for m in re.finditer(r"\b(fh_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", src, flags=re.S):
+		params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+		out[m.group(1)] = [] if params in ([""], ["void"]) else params
+	return out
+
+
+def _c_class(decl):
+	if "*" in decl:
+		return "ptr"
+	for prefix, cls in (("long long", "i64"), ("int64_t", "i64"), ("size_t", "size"), ("double", "f64"), ("int32_t", "int"), ("int", "int")):
+		if decl.startswith(prefix):
+			return cls
+	raise AssertionError("unclassified parameter: " + decl)
+
+
+def _py_class(t):
+	import ctypes as C
+	if t in (C.c_void_p, C.c_char_p) or hasattr(t, "_type_") and not isinstance(t._type_, str):
+		return "ptr"
+	return {C.c_longlong: "i64", C.c_int64: "i64", C.c_size_t: "size", C.c_double: "f64", C.c_int: "int", C.c_int32: "int"}[t]
+
+
+def test_host_ctypes_prototypes_agree_with_the_header():
+	"""The same check for libfh_host.so (include/fh_host.h against ingest.py)."""
+	from fasthigashi_b200 import ingest
+	L = ingest.lib()
+	protos = _prototypes("fh_host.h")
+	assert set(protos) == set(ingest.EXPORTS)
+	checked = 0
+	for name, params in protos.items():
+		at = getattr(getattr(L, name), "argtypes", None)
+		if at is None:
+			assert not params, name
+			continue
+		assert len(at) == len(params), (name, len(at), params)
+		for t, decl in zip(at, params):
+			assert _py_class(t) == _c_class(decl), (name, decl, t)
+		checked += 1
+	assert checked >= 6
+
+
+def test_ctypes_prototypes_agree_with_the_header():
+	"""The Python binding (`_lib.py`: argtypes) against the C prototypes of include/fh_b200.h: same argument count for every entry
+	point that has argtypes, and the same coarse class per argument (pointer / 64-bit integer / int / size_t / double) - an edit
+	of one side without the other would pass garbage through ctypes silently."""
+	import ctypes as C
+	from fasthigashi_b200 import _lib
+	L = _lib.lib()
+	protos = _prototypes()
+	assert set(protos) == set(_lib.EXPORTS)
+
+	checked = 0
+	for name, params in protos.items():
+		at = getattr(getattr(L, name), "argtypes", None)
+		if at is None:
+			assert not params or name in ("fh_rwr_workspace_bytes",), name    # parameterless getters need no argtypes
+			continue
+		assert len(at) == len(params), (name, len(at), params)
+		for t, decl in zip(at, params):
+			assert _py_class(t) == _c_class(decl), (name, decl, t)
+		checked += 1
+	assert checked >= 18
